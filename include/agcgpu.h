@@ -1,0 +1,169 @@
+/*
+ * agcgpu.h -- C ABI of libagcgpu.so: the B200 (sm_100a) implementation of AGC's compression hot path.
+ *
+ * The reference (refresh-bio/agc v3.2.2) has no plugin/FFI seam on the compress side; the seam is the set of
+ * internal calls that CAGCCompressor / CSegment make per contig and per segment.  Each entry point below names the
+ * reference call site it replaces (paths relative to the reference tree).  INTEGRATION.md shows the binding a
+ * maintainer adds on the reference side.
+ *
+ * Conventions: plain pointers and sizes only (no C++/torch types); every function returns 0 on success and a
+ * negative AGCGPU_E* code on failure, agcgpu_last_error() gives the message; the caller owns host buffers, the
+ * context owns device memory and streams; no exception crosses the boundary.  There is NO CPU fallback:
+ * without a usable sm_100 device agcgpu_create() fails.
+ *
+ * Sequence representation on the device: bases are kept 2-bit packed (4 bases / byte, first base in the two most
+ * significant bits -- the same layout as the reference's 4-per-byte "tuples", src/common/segment.h:73-138) plus a
+ * sorted exception list (position, code) for every non-ACGT symbol, so the store is lossless.
+ */
+#ifndef AGCGPU_H
+#define AGCGPU_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden */
+#endif
+
+#define AGCGPU_OK            0
+#define AGCGPU_ECUDA        -1   /* CUDA runtime error */
+#define AGCGPU_EINVAL       -2   /* bad argument */
+#define AGCGPU_ENOMEM       -3   /* host or device allocation failed / capacity exceeded */
+#define AGCGPU_EOVERFLOW    -4   /* caller-provided output buffer too small */
+#define AGCGPU_ENODEV       -5   /* no sm_100 device */
+#define AGCGPU_EUNSUPPORTED -6   /* input outside the implemented envelope (fails loudly, never falls back) */
+
+typedef struct agcgpu_ctx agcgpu_ctx;
+
+/* Compression parameters: CAGCCompressor::Create arguments (src/core/agc_compressor.cpp:2273-2288) */
+typedef struct {
+    uint32_t kmer_length;        /* -k, 17..32 */
+    uint32_t min_match_len;      /* -l, 15..32 */
+    uint32_t segment_size;       /* -s */
+    uint32_t pack_cardinality;   /* -b */
+    int32_t  device;             /* CUDA device ordinal */
+    uint32_t reserved;
+} agcgpu_params;
+
+/* One segment cut out of a contig: what compress_contig hands to add_segment
+ * (src/core/agc_compressor.cpp:2019-2048).  front/back are the CKmer words (src/core/kmer.h:21-31) of the
+ * terminal splitters, left-aligned; has_* = CKmer::is_full(). */
+typedef struct {
+    uint32_t contig;             /* index into the resident contig batch */
+    uint32_t has_front;
+    uint32_t has_back;
+    uint32_t reserved;
+    uint64_t start;              /* first base, in preprocessed contig coordinates */
+    uint64_t len;
+    uint64_t front_dir, front_rc;
+    uint64_t back_dir, back_rc;
+} agcgpu_cut;
+
+/* A segment of a resident contig, optionally reverse-complemented (reverse_complement_copy,
+ * src/common/agc_basic.cpp:280-316) -- the `contig_t` argument of CSegment::add / estimate / get_coding_cost. */
+typedef struct {
+    uint32_t contig;
+    uint32_t is_rc;
+    uint64_t start;
+    uint32_t len;
+    uint32_t group_id;           /* reference-segment group to code against */
+    uint32_t bound;              /* estimate only: CLZDiff_V2::Estimate bound (src/common/lz_diff.cpp:868) */
+    uint32_t reserved;
+} agcgpu_seg_req;
+
+/* Result of the hash-assign kernel for one cut (the common branches of CAGCCompressor::add_segment,
+ * src/core/agc_compressor.cpp:1287-1313 + map_segments.find 1363). */
+typedef struct {
+    uint64_t key1, key2;         /* (min,max) canonical splitter pair; ~0 where a splitter is missing */
+    int32_t  group_id;           /* >= 0: known group; -1: pair not in the map (host decides: new group / split) */
+    uint32_t is_rc;              /* store reverse-complemented */
+    uint32_t klass;              /* 0 both splitters, 1 front only, 2 back only, 3 none */
+    uint32_t reserved;
+} agcgpu_assign;
+
+typedef struct {
+    uint64_t kernel_launches;    /* kernels of this library launched since agcgpu_create */
+    uint64_t h2d_bytes, d2h_bytes;
+    uint64_t device_bytes_in_use;
+    uint64_t lz_alg_bytes;       /* sum over LZ requests of ceil(n/4)+ceil(m/4)+e of the last LZ batch */
+    float    last_lz_kernel_ms;  /* device time of the last LZ kernel (CUDA events on the library stream) */
+    float    last_scan_kernel_ms;
+    float    reserved[2];
+} agcgpu_stats;
+
+/* ---- lifetime ------------------------------------------------------------------------------------------------- */
+/* ctor/dtor of the device side of CAGCCompressor (agc_compressor.h:540-764). */
+int agcgpu_create(const agcgpu_params* params, agcgpu_ctx** out_ctx);
+void agcgpu_destroy(agcgpu_ctx* ctx);
+const char* agcgpu_last_error(const agcgpu_ctx* ctx);     /* ctx may be NULL: error of the last failed create */
+int agcgpu_sync(agcgpu_ctx* ctx);                         /* wait for all work queued on the library stream */
+void* agcgpu_stream(agcgpu_ctx* ctx);                     /* cudaStream_t the kernels are launched on (for event timing) */
+int agcgpu_get_stats(agcgpu_ctx* ctx, agcgpu_stats* out);
+
+/* ---- splitters -------------------------------------------------------------------------------------------------- */
+/* determine_splitters (src/core/agc_compressor.cpp:428-563): raw FASTA bodies of the reference sample in
+ * (newlines included, as CGenomeIO::ReadContigRaw returns them) -> sorted splitter list out.  The contigs are
+ * uploaded by this call; they do not stay resident.  Also installs the set (as agcgpu_set_splitters). */
+int agcgpu_determine_splitters(agcgpu_ctx* ctx, const uint8_t* raw, const uint64_t* raw_offsets, uint32_t n_contigs,
+                               uint64_t* out_splitters, uint64_t cap, uint64_t* out_n);
+/* hs_splitters / bloom_splitters fill (agc_compressor.cpp:543-555; append: 339-351; -a: 1191-1209) */
+int agcgpu_set_splitters(agcgpu_ctx* ctx, const uint64_t* splitters, uint64_t n);
+
+/* ---- contig batch: preprocess + scan ---------------------------------------------------------------------------- */
+/* preprocess_raw_contig (agc_compressor.cpp:907-951) + compress_contig's scan loop (1997-2051) for a batch of
+ * contigs.  raw = concatenated raw bodies, contig i = raw[raw_offsets[i] .. raw_offsets[i+1]).  The preprocessed
+ * contigs replace the previous resident batch.  out_contig_len[i] = number of symbols after preprocessing.
+ * cuts come out ordered by (contig, start). */
+int agcgpu_scan_contigs(agcgpu_ctx* ctx, const uint8_t* raw, const uint64_t* raw_offsets, uint32_t n_contigs,
+                        uint64_t* out_contig_len, agcgpu_cut* out_cuts, uint64_t cap_cuts, uint64_t* out_n_cuts);
+/* Same, input already resident on the device (raw_dev = device pointer); used by bench.py for the HBM-resident
+ * timing and by pipelines that ingest through their own pinned staging. */
+int agcgpu_scan_contigs_dev(agcgpu_ctx* ctx, const void* raw_dev, uint64_t raw_bytes, const uint64_t* raw_offsets,
+                            uint32_t n_contigs, uint64_t* out_contig_len, agcgpu_cut* out_cuts, uint64_t cap_cuts,
+                            uint64_t* out_n_cuts);
+/* get_part (agc_compressor.cpp:2085-2091) / reverse_complement_copy: download symbols (1 byte each) of a segment */
+int agcgpu_get_segment(agcgpu_ctx* ctx, uint32_t contig, uint64_t start, uint32_t len, uint32_t is_rc, uint8_t* out);
+
+/* ---- hash-assign ------------------------------------------------------------------------------------------------ */
+/* map_segments updates (store_segments, agc_compressor.cpp:1007-1012) */
+int agcgpu_map_insert(agcgpu_ctx* ctx, const uint64_t* key1, const uint64_t* key2, const int32_t* group_id, uint64_t n);
+/* add_segment's key construction + map_segments.find for a batch of cuts (agc_compressor.cpp:1287-1313,1363) */
+int agcgpu_assign_cuts(agcgpu_ctx* ctx, const agcgpu_cut* cuts, uint64_t n, agcgpu_assign* out);
+
+/* ---- reference segments and LZ-diff ----------------------------------------------------------------------------- */
+/* CLZDiffBase::Prepare + prepare_index (src/common/lz_diff.cpp:48-149,375-428), called from CSegment::add for the
+ * first sequence of a group (src/common/segment.cpp:41-47).  Batch form: reference i of group req[i].group_id is
+ * the (possibly reverse-complemented) resident segment req[i]. */
+int agcgpu_group_put_reference_batch(agcgpu_ctx* ctx, const agcgpu_seg_req* reqs, uint32_t n);
+/* Same from host symbols (append path: CSegment::unpack, src/common/segment.cpp:528) */
+int agcgpu_group_put_reference(agcgpu_ctx* ctx, uint32_t group_id, const uint8_t* symbols, uint32_t len);
+/* hash-table slots of a group's index, widened to u32 (0xFFFFFFFF = empty): for layout-parity tests */
+int agcgpu_group_get_index(agcgpu_ctx* ctx, uint32_t group_id, uint32_t* out_slots, uint64_t cap, uint64_t* out_ht_size);
+
+/* CLZDiff_V2::Encode (lz_diff.cpp:669-798) as called from CSegment::add (segment.cpp:59).
+ * out_offsets has n+1 entries; delta i = out[out_offsets[i] .. out_offsets[i+1]). */
+int agcgpu_lz_encode_batch(agcgpu_ctx* ctx, const agcgpu_seg_req* reqs, uint32_t n,
+                           uint8_t* out, uint64_t out_cap, uint64_t* out_offsets);
+/* CLZDiff_V2::Estimate (lz_diff.cpp:839-946) as called from CSegment::estimate (agc_compressor.cpp:1705,1733,1757) */
+int agcgpu_lz_estimate_batch(agcgpu_ctx* ctx, const agcgpu_seg_req* reqs, uint32_t n, uint32_t* out);
+/* CLZDiffBase::GetCodingCostVector (lz_diff.cpp:159-284) as called from CSegment::get_coding_cost
+ * (agc_compressor.cpp:1540-1571).  out has req->len entries. */
+int agcgpu_lz_cost_vector(agcgpu_ctx* ctx, const agcgpu_seg_req* req, int prefix_costs, uint32_t* out);
+
+/* ---- packing of reference segments ------------------------------------------------------------------------------ */
+/* CSegment::store_in_archive(ref) up to the zstd call (src/common/segment.h:218-255): periodicity probe and
+ * bytes2tuples (73-138).  For group i: out_use_tuples[i] = 1 -> payload = tuples (zstd level 13, marker 1),
+ * 0 -> payload = raw symbols (zstd level 19, marker 0).  Payload i = out[out_offsets[i] .. out_offsets[i+1]). */
+int agcgpu_pack_ref_batch(agcgpu_ctx* ctx, const uint32_t* group_ids, uint32_t n, uint8_t* out, uint64_t out_cap,
+                          uint64_t* out_offsets, uint8_t* out_use_tuples);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,4 @@
+#!/bin/bash
+# helper for gpurun: run the GPU test-suite and keep the log
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q 2>&1 | tail -40 | tee gpurun_out/pytest_gpu.log
