@@ -1,0 +1,59 @@
+// capi.cpp -- C facade over agc_b200::CAGCCompressor (include/agcgpu.h, "CAGCCompressor facade")
+#include "compressor.h"
+#include <string>
+
+struct agcgpu_compressor { agc_b200::CAGCCompressor impl; std::string err; };
+static thread_local std::string g_err;
+
+extern "C" {
+
+int agcgpu_compressor_create(const char* out_file, uint32_t pack_cardinality, uint32_t kmer_length, const char* reference_file,
+                             uint32_t segment_size, uint32_t min_match_len, int concatenated_genomes, int adaptive_compression,
+                             uint32_t verbosity, uint32_t no_threads, double fallback_frac, int device,
+                             const char* dump_parts_path, agcgpu_compressor** out)
+{
+    if (!out_file || !reference_file || !out) { g_err = "null argument"; return AGCGPU_EINVAL; }
+    agcgpu_compressor* c = new agcgpu_compressor();
+    c->impl.SetAppMode(false);
+    c->impl.SetDevice(device);
+    if (dump_parts_path && *dump_parts_path) c->impl.SetDumpParts(dump_parts_path);
+    if (!c->impl.Create(out_file, pack_cardinality, kmer_length, reference_file, segment_size, min_match_len,
+                        concatenated_genomes != 0, adaptive_compression != 0, verbosity, no_threads, fallback_frac)) {
+        g_err = c->impl.LastError();
+        delete c;
+        return AGCGPU_EUNSUPPORTED;
+    }
+    *out = c;
+    return 0;
+}
+
+int agcgpu_compressor_add_sample_files(agcgpu_compressor* c, const char* const* sample_names, const char* const* file_names,
+                                       uint32_t n, uint32_t no_threads)
+{
+    if (!c || (n && (!sample_names || !file_names))) return AGCGPU_EINVAL;
+    std::vector<std::pair<std::string, std::string>> v;
+    for (uint32_t i = 0; i < n; ++i) v.emplace_back(sample_names[i], file_names[i]);
+    return c->impl.AddSampleFiles(v, no_threads) ? 0 : AGCGPU_ECUDA;
+}
+
+int agcgpu_compressor_add_cmd_line(agcgpu_compressor* c, const char* cmd_line)
+{
+    if (!c || !cmd_line) return AGCGPU_EINVAL;
+    c->impl.AddCmdLine(cmd_line);
+    return 0;
+}
+
+int agcgpu_compressor_close(agcgpu_compressor* c, uint32_t no_threads)
+{
+    if (!c) return AGCGPU_EINVAL;
+    bool ok = c->impl.Close(no_threads);
+    if (!ok) g_err = c->impl.LastError();
+    delete c;
+    return ok ? 0 : AGCGPU_ECUDA;
+}
+
+const char* agcgpu_compressor_last_error(const agcgpu_compressor* c) { return c ? c->impl.LastError().c_str() : g_err.c_str(); }
+uint64_t agcgpu_compressor_total_bases(const agcgpu_compressor* c) { return c ? c->impl.TotalBases() : 0; }
+agcgpu_ctx* agcgpu_compressor_ctx(agcgpu_compressor* c) { return c ? c->impl.Ctx() : nullptr; }
+
+}

@@ -1,0 +1,908 @@
+// compressor.cpp -- see compressor.h.  Reference citations are relative to /root/reference.
+#include "compressor.h"
+#include <zlib.h>
+#include <algorithm>
+#include <cstring>
+#include <iostream>
+#include <numeric>
+#include <set>
+
+namespace agc_b200 {
+
+// =====================================================================================================================
+// CArchive (output side), src/common/archive.cpp
+// =====================================================================================================================
+bool CArchive::Open(const std::string& file_name)
+{
+    if (f) return false;
+    f = fopen(file_name.c_str(), "wb");
+    if (!f) return false;
+    setvbuf(f, nullptr, _IOFBF, 32 << 20);
+    f_offset = 0;
+    return true;
+}
+
+size_t CArchive::write_varint(uint64_t x)
+{
+    int no_bytes = 0;
+    for (uint64_t tmp = x; tmp; tmp >>= 8) ++no_bytes;
+    putc(no_bytes, f);
+    for (int i = no_bytes; i; --i) putc((int)((x >> ((i - 1) * 8)) & 0xff), f);
+    return (size_t)no_bytes + 1;
+}
+
+int CArchive::RegisterStream(const std::string& name)
+{
+    auto p = rm_streams.find(name);
+    if (p != rm_streams.end()) return p->second;
+    int id = (int)v_streams.size();
+    v_streams.emplace_back();
+    v_streams[id].stream_name = name;
+    rm_streams[name] = id;
+    return id;
+}
+
+bool CArchive::AddPart(int stream_id, const std::vector<uint8_t>& data, uint64_t metadata)
+{
+    v_streams[stream_id].parts.push_back(part_t{ f_offset, data.size() });
+    f_offset += write_varint(metadata);
+    if (!data.empty()) fwrite(data.data(), 1, data.size(), f);
+    f_offset += data.size();
+    return true;
+}
+
+bool CArchive::AddPartBuffered(int stream_id, std::vector<uint8_t>&& data, uint64_t metadata)
+{
+    m_buffer[stream_id].emplace_back(std::move(data), metadata);
+    return true;
+}
+
+bool CArchive::FlushOutBuffers()
+{
+    for (auto& x : m_buffer)
+        for (auto& y : x.second) AddPart(x.first, y.first, y.second);
+    m_buffer.clear();
+    return true;
+}
+
+bool CArchive::Close()
+{
+    if (!f) return false;
+    FlushOutBuffers();
+    // footer: archive.cpp:142-169 (raw_size is never updated on the write path: always 0)
+    size_t footer_size = 0;
+    footer_size += write_varint(v_streams.size());
+    for (auto& s : v_streams) {
+        fwrite(s.stream_name.data(), 1, s.stream_name.size(), f); putc(0, f);
+        footer_size += s.stream_name.size() + 1;
+        footer_size += write_varint(s.parts.size());
+        footer_size += write_varint(s.raw_size);
+        for (auto& p : s.parts) { footer_size += write_varint(p.offset); footer_size += write_varint(p.size); }
+    }
+    for (int i = 0; i < 8; ++i) putc((int)((footer_size >> (8 * i)) & 0xff), f);     // io.h:371-380 WriteUInt little endian
+    bool ok = fclose(f) == 0;
+    f = nullptr;
+    return ok;
+}
+
+// =====================================================================================================================
+// CCollection_V3 (compression side), src/common/collection_v3.cpp + collection.h
+// =====================================================================================================================
+void CCollection_V3::set_params(uint32_t b, uint32_t s, uint32_t k) { batch_size = b; segment_size = s; kmer_length = k; }
+
+void CCollection_V3::append(std::vector<uint8_t>& data, uint32_t num)
+{
+    const uint32_t thr_1 = 1u << 7, thr_2 = thr_1 + (1u << 14), thr_3 = thr_2 + (1u << 21), thr_4 = thr_3 + (1u << 28);
+    if (num < thr_1) data.push_back((uint8_t)num);
+    else if (num < thr_2) { num -= thr_1; data.push_back((uint8_t)(0x80u + (num >> 8))); data.push_back((uint8_t)(num & 0xff)); }
+    else if (num < thr_3) { num -= thr_2; data.push_back((uint8_t)(0xC0u + (num >> 16))); data.push_back((uint8_t)((num >> 8) & 0xff)); data.push_back((uint8_t)(num & 0xff)); }
+    else if (num < thr_4) { num -= thr_3; data.push_back((uint8_t)(0xE0u + (num >> 24))); data.push_back((uint8_t)((num >> 16) & 0xff)); data.push_back((uint8_t)((num >> 8) & 0xff)); data.push_back((uint8_t)(num & 0xff)); }
+    else { num -= thr_4; data.push_back(0xF0u); data.push_back((uint8_t)((num >> 24) & 0xff)); data.push_back((uint8_t)((num >> 16) & 0xff)); data.push_back((uint8_t)((num >> 8) & 0xff)); data.push_back((uint8_t)(num & 0xff)); }
+}
+void CCollection_V3::append(std::vector<uint8_t>& data, const std::string& s)
+{
+    data.insert(data.end(), s.begin(), s.end());
+    data.push_back(0);
+}
+
+static std::string extract_contig_name(const std::string& s)      // collection.cpp:17-27
+{
+    auto p = s.begin();
+    for (; p != s.end(); ++p)
+        if ((*p < '0') && (*p == ' ' || *p == '\n' || *p == '\r' || *p == '\t')) break;
+    return std::string(s.begin(), p);
+}
+
+bool CCollection_V3::register_sample_contig(const std::string& sample_name, const std::string& contig_name)
+{
+    std::string stored = sample_name;
+    if (sample_name.empty()) stored = extract_contig_name(contig_name);
+    if (stored != prev_sample_name) {
+        if (sample_ids.count(stored)) return false;
+        uint32_t id = (uint32_t)sample_ids.size();
+        sample_ids[stored] = id;
+        sample_desc.emplace_back();
+        sample_desc.back().name = stored;
+        prev_sample_name = stored;
+    }
+    sample_desc.back().contigs.emplace_back();
+    sample_desc.back().contigs.back().name = contig_name;
+    return true;
+}
+
+void CCollection_V3::add_segment_placed(uint32_t sample_id, uint32_t contig_idx, uint32_t place, const segment_desc_t& d)
+{
+    // add_segments_placed looks the contig up by name and takes the first match (collection_v3.cpp:790-803)
+    auto& contigs = sample_desc[sample_id].contigs;
+    const std::string& nm = contigs[contig_idx].name;
+    for (auto& x : contigs)
+        if (x.name == nm) {
+            if (place >= x.segments.size()) x.segments.resize((size_t)place + 1);
+            x.segments[place] = d;
+            break;
+        }
+}
+
+void CCollection_V3::serialize_sample_names(std::vector<uint8_t>& v) const
+{
+    append(v, (uint32_t)sample_desc.size());
+    for (auto& x : sample_desc) append(v, x.name);
+}
+
+std::vector<std::string> CCollection_V3::split_string(const std::string& s)
+{
+    std::vector<std::string> comp;
+    auto p = s.begin();
+    while (true) {
+        auto q = std::find(p, s.end(), ' ');
+        comp.emplace_back(p, q);
+        if (q == s.end()) break;
+        p = q + 1;
+    }
+    return comp;
+}
+
+std::string CCollection_V3::encode_split(const std::vector<std::string>& prev, const std::vector<std::string>& curr)
+{
+    std::string enc;
+    for (size_t i = 0; i < curr.size(); ++i) {
+        if (prev[i] == curr[i]) enc.push_back((char)-127);
+        else if (prev[i].size() != curr[i].size()) enc.append(curr[i]);
+        else {
+            signed char cnt = 0;
+            for (size_t j = 0; j < curr[i].size(); ++j) {
+                if (prev[i][j] == curr[i][j]) {
+                    if (cnt == 100) { enc.push_back((char)-cnt); cnt = 1; } else ++cnt;
+                } else {
+                    if (cnt) { enc.push_back((char)-cnt); cnt = 0; }
+                    enc.push_back(curr[i][j]);
+                }
+            }
+            if (cnt) enc.push_back((char)-cnt);
+        }
+        enc.push_back(' ');
+    }
+    enc.pop_back();
+    return enc;
+}
+
+void CCollection_V3::serialize_contig_names(std::vector<uint8_t>& v, uint32_t id_from, uint32_t id_to) const
+{
+    append(v, id_to - id_from);
+    for (uint32_t s = id_from; s < id_to; ++s) {
+        const auto& sd = sample_desc[s];
+        append(v, (uint32_t)sd.contigs.size());
+        std::vector<std::string> prev_split, curr_split;
+        for (auto& x : sd.contigs) {
+            curr_split = split_string(x.name);
+            if (curr_split.size() != prev_split.size()) append(v, x.name);
+            else append(v, encode_split(prev_split, curr_split));
+            prev_split = std::move(curr_split);
+        }
+    }
+}
+
+static uint64_t zigzag_encode(uint64_t x_curr, uint64_t x_prev)      // utils.h:123-132
+{
+    if (x_curr < x_prev) return 2 * (x_prev - x_curr) - 1u;
+    if (x_curr < 2 * x_prev) return 2 * (x_curr - x_prev);
+    return x_curr;
+}
+
+void CCollection_V3::serialize_contig_details(std::vector<uint8_t> (&v)[5], uint32_t id_from, uint32_t id_to)
+{
+    append(v[0], id_to - id_from);
+    v_in_group_ids.clear();
+    auto get_igi = [&](uint32_t pos) -> int { return pos >= v_in_group_ids.size() ? -1 : v_in_group_ids[pos]; };
+    auto set_igi = [&](uint32_t pos, int val) {
+        if (pos >= v_in_group_ids.size()) v_in_group_ids.resize((size_t)((int)(pos * 1.2) + 1), -1);
+        v_in_group_ids[pos] = val;
+    };
+    for (uint32_t s = id_from; s < id_to; ++s) {
+        auto& sd = sample_desc[s];
+        append(v[0], (uint32_t)sd.contigs.size());
+        uint32_t pred_raw_length = segment_size + kmer_length;
+        for (auto& x : sd.contigs) {
+            append(v[0], (uint32_t)x.segments.size());
+            for (auto& seg : x.segments) {
+                int prev = get_igi(seg.group_id);
+                uint32_t e_in;
+                if (prev == -1) e_in = (uint32_t)(int)seg.in_group_id;
+                else if (seg.in_group_id == 0) e_in = 0;
+                else if ((int)seg.in_group_id == prev + 1) e_in = 1;
+                else e_in = (uint32_t)zigzag_encode(seg.in_group_id, (uint64_t)(prev + 1)) + 1u;
+                uint32_t e_raw = (uint32_t)zigzag_encode(seg.raw_length, pred_raw_length);
+                append(v[1], seg.group_id);
+                append(v[2], e_in);
+                append(v[3], e_raw);
+                append(v[4], (uint32_t)seg.is_rev_comp);
+                if ((int)seg.in_group_id > prev && seg.in_group_id > 0) set_igi(seg.group_id, (int)seg.in_group_id);
+            }
+        }
+    }
+}
+
+void CCollection_V3::clear_batch(uint32_t id_from, uint32_t id_to)
+{
+    for (uint32_t s = id_from; s < id_to; ++s) { sample_desc[s].contigs.clear(); sample_desc[s].contigs.shrink_to_fit(); }
+}
+
+// =====================================================================================================================
+// CGenomeIO: read_contig_raw (src/core/genome_io.cpp:206-250)
+// =====================================================================================================================
+bool CGenomeIO::Open(const std::string& file_name)
+{
+    Close();
+    gz = gzopen(file_name.c_str(), "rb");
+    if (!gz) return false;
+    gzbuffer((gzFile)gz, 1 << 20);
+    buf.resize(8 << 20);
+    pos = filled = 0; at_eof = false;
+    return true;
+}
+void CGenomeIO::Close() { if (gz) { gzclose((gzFile)gz); gz = nullptr; } }
+bool CGenomeIO::fill()
+{
+    if (pos < filled) { memmove(buf.data(), buf.data() + pos, filled - pos); filled -= pos; pos = 0; }
+    else pos = filled = 0;
+    if (at_eof) return filled != 0;
+    int r = gzread((gzFile)gz, buf.data() + filled, (unsigned)(buf.size() - filled));
+    if (r <= 0) { at_eof = true; return filled != 0; }
+    filled += (size_t)r;
+    return filled != 0;
+}
+bool CGenomeIO::ReadContigRaw(std::string& id, std::vector<uint8_t>& contig)
+{
+    if (!gz) return false;
+    id.clear(); contig.clear();
+    while (true) {
+        if (pos >= filled) if (!fill()) return false;
+        uint8_t c = buf[pos++];
+        if (c == '\n' || c == '\r') break;
+        id.push_back((char)c);
+    }
+    if (!id.empty()) id.erase(id.begin());
+    while (true) {
+        uint8_t* b = buf.data() + pos; uint8_t* e = buf.data() + filled;
+        uint8_t* p = (uint8_t*)memchr(b, '>', (size_t)(e - b));
+        if (p) { contig.insert(contig.end(), b, p); pos = (size_t)(p - buf.data()); break; }
+        contig.insert(contig.end(), b, e);
+        pos = filled;
+        if (!fill()) break;
+    }
+    return !id.empty() && !contig.empty();
+}
+
+// =====================================================================================================================
+// CAGCCompressor
+// =====================================================================================================================
+static const uint32_t NO_RAW_GROUPS = 16;       // agc_basic.h:79
+static const uint64_t EMPTY = ~0ull;
+
+CAGCCompressor::CAGCCompressor() {}
+CAGCCompressor::~CAGCCompressor()
+{
+    if (working) Close(1);
+    if (ctx) agcgpu_destroy(ctx);
+    if (dump_f) fclose(dump_f);
+}
+
+bool CAGCCompressor::fail(const std::string& msg)
+{
+    last_error = msg;
+    if (is_app_mode) std::cerr << msg << std::endl;
+    return false;
+}
+bool CAGCCompressor::gpu_ok(int rc, const char* what)
+{
+    if (rc == 0) return true;
+    return fail(std::string(what) + ": " + agcgpu_last_error(ctx));
+}
+
+std::string CAGCCompressor::ss_base(uint32_t n) const       // utils.cpp:30-66 (file version 3: "x" + base64)
+{
+    static const char dig[] = "0123456789ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz_#";
+    std::string res = "x";
+    do { res.push_back(dig[n & 0x3fu]); n /= 64; } while (n);
+    return res;
+}
+
+void CAGCCompressor::add_job(PartJob&& j)
+{
+    j.seq = job_seq++;
+    jobs.emplace_back(std::move(j));
+}
+
+bool CAGCCompressor::Create(const std::string& file_name, uint32_t _pack_cardinality, uint32_t _kmer_length,
+                            const std::string& reference_file_name, uint32_t _segment_size, uint32_t _min_match_len,
+                            bool _concatenated_genomes, bool _adaptive_compression, uint32_t _verbosity, uint32_t, double fallback_frac)
+{
+    if (working) return false;
+    pack_cardinality = _pack_cardinality; kmer_length = _kmer_length; min_match_len = _min_match_len;
+    segment_size = _segment_size; verbosity = _verbosity;
+    concatenated_genomes = _concatenated_genomes; adaptive_compression = _adaptive_compression;
+    if (concatenated_genomes || adaptive_compression || fallback_frac != 0.0)
+        return fail("agc-b200: -c / -a / -f are not implemented on the GPU path yet (refusing rather than falling back)");
+    agcgpu_params prm; memset(&prm, 0, sizeof prm);
+    prm.kmer_length = kmer_length; prm.min_match_len = min_match_len; prm.segment_size = segment_size;
+    prm.pack_cardinality = pack_cardinality; prm.device = device;
+    int rc = agcgpu_create(&prm, &ctx);
+    if (rc) return fail(std::string("agcgpu_create: ") + agcgpu_last_error(nullptr));
+
+    // determine_splitters (agc_compressor.cpp:428-563)
+    {
+        CGenomeIO gio;
+        if (!gio.Open(reference_file_name)) return fail("Cannot open file: " + reference_file_name);
+        std::vector<uint8_t> raw, contig; std::vector<uint64_t> offs{ 0 };
+        std::string id;
+        while (gio.ReadContigRaw(id, contig)) { raw.insert(raw.end(), contig.begin(), contig.end()); offs.push_back(raw.size()); }
+        if (verbosity > 0 && is_app_mode) std::cerr << "Determination of splitters\n";
+        uint64_t cap = raw.size() / std::max<uint32_t>(segment_size, 1) + 2 * offs.size() + 64, n = 0;
+        splitters.resize(cap);
+        if (raw.empty()) raw.push_back(0);
+        if (!gpu_ok(agcgpu_determine_splitters(ctx, raw.data(), offs.data(), (uint32_t)offs.size() - 1, splitters.data(), cap, &n), "determine_splitters"))
+            return false;
+        splitters.resize(n);
+        if (verbosity > 1 && is_app_mode) std::cerr << "No. of splitters: " << n << std::endl;
+    }
+    if (!dump_path.empty()) {
+        dump_f = fopen(dump_path.c_str(), "wb");
+        if (!dump_f) return fail("cannot open dump file " + dump_path);
+    }
+    if (!out_archive.Open(file_name)) return fail("Cannot create archive " + file_name);
+    working = true;
+    collection.set_params(pack_cardinality, segment_size, kmer_length);
+    collection_samples_id = out_archive.RegisterStream("collection-samples");      // collection_v3.cpp:38-45
+    collection_contig_id = out_archive.RegisterStream("collection-contigs");
+    collection_details_id = out_archive.RegisterStream("collection-details");
+    map_segments[std::make_pair(EMPTY, EMPTY)] = 0;                               // agc_compressor.cpp:2307
+    v_segments.resize(NO_RAW_GROUPS);
+    for (no_segments = 0; no_segments < NO_RAW_GROUPS; ++no_segments) {             // 2311-2321
+        GroupState& g = v_segments[no_segments];
+        g.exists = true;
+        g.stream_delta = out_archive.RegisterStream(ss_base(no_segments) + "d");
+        g.no_seqs = 1;
+        g.pack.emplace_back(std::vector<uint8_t>{ 0x7f });
+    }
+    collection.reset_prev_sample_name();
+    epoch = 0; processed_samples = 0;
+    return true;
+}
+
+void CAGCCompressor::AddCmdLine(const std::string& cmd_line) { cmd_lines.emplace_back(cmd_line, ""); }   // never serialized in v3
+
+// CSegment::store_in_archive(pack) (segment.h:258-280): deltas (or raw sequences) each followed by 0xFF, zstd level 17
+void CAGCCompressor::store_pack(uint32_t group_id, GroupState& g, uint64_t ep)
+{
+    PartJob j; j.epoch = ep; j.kind = 0;
+    if (g.stream_delta < 0) g.stream_delta = out_archive.RegisterStream(ss_base(group_id) + "d");
+    j.stream_id = g.stream_delta;
+    std::vector<uint8_t> pack;
+    size_t sz = 0; for (auto& x : g.pack) sz += x.size() + 1;
+    pack.reserve(sz);
+    for (auto& x : g.pack) { pack.insert(pack.end(), x.begin(), x.end()); pack.push_back(0xff); }
+    j.raw_size = pack.size();
+    j.tasks.emplace_back(); j.tasks[0].level = 17; j.tasks[0].raw = pack;
+    j.fallback_raw = std::move(pack);
+    add_job(std::move(j));
+    g.pack.clear();
+}
+
+void CAGCCompressor::store_contig_batch(uint32_t id_from, uint32_t id_to, uint64_t ep)      // collection_v3.cpp:682-703
+{
+    PartJob jn; jn.epoch = ep; jn.kind = 2; jn.stream_id = collection_contig_id;
+    jn.tasks.emplace_back(); jn.tasks[0].level = 18;
+    collection.serialize_contig_names(jn.tasks[0].raw, id_from, id_to);
+    jn.raw_size = jn.tasks[0].raw.size();
+    PartJob jd; jd.epoch = ep; jd.kind = 3; jd.stream_id = collection_details_id; jd.raw_size = 0;
+    std::vector<uint8_t> v[5];
+    collection.serialize_contig_details(v, id_from, id_to);
+    for (int i = 0; i < 5; ++i) { jd.tasks.emplace_back(); jd.tasks[i].level = 19; jd.tasks[i].raw = std::move(v[i]); }
+    add_job(std::move(jn));
+    add_job(std::move(jd));
+    collection.clear_batch(id_from, id_to);
+}
+
+bool CAGCCompressor::compress_tasks(std::vector<ZTask*>& tasks)
+{
+    if (tasks.empty()) return true;
+    std::vector<uint64_t> offs(tasks.size() + 1, 0);
+    std::vector<int32_t> levels(tasks.size());
+    for (size_t i = 0; i < tasks.size(); ++i) { offs[i + 1] = offs[i] + tasks[i]->raw.size(); levels[i] = tasks[i]->level; }
+    std::vector<uint8_t> src(offs.back() + 1);
+    for (size_t i = 0; i < tasks.size(); ++i) if (!tasks[i]->raw.empty()) memcpy(src.data() + offs[i], tasks[i]->raw.data(), tasks[i]->raw.size());
+    uint64_t cap = offs.back() + offs.back() / 128 + 1024 * (tasks.size() + 1);
+    std::vector<uint8_t> dst(cap);
+    std::vector<uint64_t> doffs(tasks.size() + 1, 0);
+    if (!gpu_ok(agcgpu_zstd_compress_batch(ctx, src.data(), offs.data(), levels.data(), (uint32_t)tasks.size(), dst.data(), cap, doffs.data()),
+                "zstd_compress_batch")) return false;
+    for (size_t i = 0; i < tasks.size(); ++i) tasks[i]->packed.assign(dst.begin() + doffs[i], dst.begin() + doffs[i + 1]);
+    return true;
+}
+
+static void dump_u64(FILE* f, uint64_t v) { fwrite(&v, 8, 1, f); }
+static void dump_bytes(FILE* f, const void* p, size_t n) { dump_u64(f, n); if (n) fwrite(p, 1, n, f); }
+
+// write all pending parts in the reference's flush order: (registration epoch, stream id, call order)
+bool CAGCCompressor::flush_jobs(bool)
+{
+    if (jobs.empty()) return true;
+    std::stable_sort(jobs.begin(), jobs.end(), [](const PartJob& a, const PartJob& b) {
+        if (a.epoch != b.epoch) return a.epoch < b.epoch;
+        if (a.stream_id != b.stream_id) return a.stream_id < b.stream_id;
+        return a.seq < b.seq; });
+    if (dump_f) {
+        for (auto& j : jobs) {
+            fwrite("PART", 1, 4, dump_f);
+            dump_u64(dump_f, (uint64_t)j.stream_id); dump_u64(dump_f, j.epoch); dump_u64(dump_f, (uint64_t)j.kind); dump_u64(dump_f, j.raw_size);
+            dump_u64(dump_f, j.tasks.size());
+            for (auto& t : j.tasks) { dump_u64(dump_f, (uint64_t)t.level); dump_bytes(dump_f, t.raw.data(), t.raw.size()); }
+            dump_bytes(dump_f, j.fallback_raw.data(), j.fallback_raw.size());
+        }
+        jobs.clear();
+        return true;
+    }
+    std::vector<ZTask*> tasks;
+    for (auto& j : jobs) for (auto& t : j.tasks) tasks.push_back(&t);
+    if (!compress_tasks(tasks)) return false;
+    for (auto& j : jobs) {
+        if (j.kind == 0 || j.kind == 1) {                       // add_to_archive / add_to_archive_tuples (segment.h:172-215)
+            auto& pk = j.tasks[0].packed;
+            if ((uint32_t)pk.size() + 1u < (uint32_t)j.fallback_raw.size()) {
+                pk.push_back((uint8_t)j.kind);
+                out_archive.AddPart(j.stream_id, pk, j.fallback_raw.size());
+            } else out_archive.AddPart(j.stream_id, j.fallback_raw, 0);
+        } else if (j.kind == 2) out_archive.AddPart(j.stream_id, j.tasks[0].packed, j.raw_size);
+        else {                                                  // store_batch_contig_details (collection_v3.cpp:225-257)
+            std::vector<uint8_t> v;
+            for (auto& t : j.tasks) { CCollection_V3::append(v, (uint32_t)t.raw.size()); CCollection_V3::append(v, (uint32_t)t.packed.size()); }
+            for (auto& t : j.tasks) v.insert(v.end(), t.packed.begin(), t.packed.end());
+            out_archive.AddPart(j.stream_id, v, 0);
+        }
+    }
+    jobs.clear();
+    return true;
+}
+
+bool CAGCCompressor::AddSampleFiles(std::vector<std::pair<std::string, std::string>> files, uint32_t)
+{
+    if (!working) return false;
+    if (files.empty()) return true;
+    std::vector<std::vector<uint8_t>> raws;
+    std::vector<BatchContig> owners;
+    uint64_t raw_in_batch = 0;
+    for (auto& sf : files) {
+        collection.reset_prev_sample_name();
+        CGenomeIO gio;
+        if (!gio.Open(sf.second)) { std::cerr << "Cannot open file: " << sf.second << std::endl; continue; }
+        std::string id; std::vector<uint8_t> contig;
+        bool any_read = false, any_added = false;
+        while (gio.ReadContigRaw(id, contig)) {
+            any_read = true;
+            if (collection.register_sample_contig(sf.first, id)) {
+                uint32_t sid = (uint32_t)collection.sample_desc.size() - 1;
+                owners.push_back(BatchContig{ sid, (uint32_t)collection.sample_desc[sid].contigs.size() - 1 });
+                raw_in_batch += contig.size();
+                raws.emplace_back(std::move(contig));
+                contig.clear();
+                any_added = true;
+            } else std::cerr << "Error: Pair sample_name:contig_name " << sf.first << ":" << id << " is already in the archive!\n";
+        }
+        if (!any_read) std::cerr << "Warning: Pair sample_name:file_path " << sf.first << ":" << sf.second << " contains no contigs and will not be included in the archive!\n";
+        if (!any_added) std::cerr << "Warning: Pair sample_name:file_path " << sf.first << ":" << sf.second << " contains only contigs already present in the archive!\n";
+        if (raw_in_batch >= batch_bases) { if (!process_batch(raws, owners)) return false; raws.clear(); owners.clear(); raw_in_batch = 0; }
+    }
+    if (!raws.empty()) if (!process_batch(raws, owners)) return false;
+    if (processed_samples % pack_cardinality != 0)                                     // agc_compressor.cpp:2258-2259
+        store_contig_batch((processed_samples / pack_cardinality) * pack_cardinality, processed_samples, epoch);
+    ++epoch;
+    return flush_jobs(false);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// One device batch = whole samples.  scan -> (per sample, in order) add_segment + registration -> LZ batch -> bookkeeping
+// ---------------------------------------------------------------------------------------------------------------------
+bool CAGCCompressor::process_batch(std::vector<std::vector<uint8_t>>& raws, std::vector<BatchContig>& owners)
+{
+    const uint32_t nc = (uint32_t)raws.size();
+    std::vector<uint64_t> offs(nc + 1, 0);
+    for (uint32_t i = 0; i < nc; ++i) offs[i + 1] = offs[i] + raws[i].size();
+    std::vector<uint8_t> cat(offs[nc] + 1);
+    for (uint32_t i = 0; i < nc; ++i) { memcpy(cat.data() + offs[i], raws[i].data(), raws[i].size()); std::vector<uint8_t>().swap(raws[i]); }
+    std::vector<uint64_t> clen(nc + 1);
+    uint64_t cap_cuts = offs[nc] / std::max<uint32_t>(segment_size / 4, 16) + 4ull * nc + 64, n_cuts = 0;
+    std::vector<agcgpu_cut> cuts(cap_cuts);
+    int rc = agcgpu_scan_contigs(ctx, cat.data(), offs.data(), nc, clen.data(), cuts.data(), cap_cuts, &n_cuts);
+    if (rc == AGCGPU_EOVERFLOW && n_cuts > cap_cuts) {
+        cap_cuts = n_cuts + 16; cuts.resize(cap_cuts);
+        rc = agcgpu_scan_contigs(ctx, cat.data(), offs.data(), nc, clen.data(), cuts.data(), cap_cuts, &n_cuts);
+    }
+    if (!gpu_ok(rc, "scan_contigs")) return false;
+    cuts.resize(n_cuts);
+    std::vector<uint8_t>().swap(cat);
+    for (uint32_t i = 0; i < nc; ++i) total_bases += clen[i];
+
+    // cut ranges per contig
+    std::vector<uint64_t> cut_first(nc + 1, 0);
+    { uint64_t p = 0; for (uint32_t c = 0; c < nc; ++c) { cut_first[c] = p; while (p < n_cuts && cuts[p].contig == c) ++p; } cut_first[nc] = p; }
+
+    // device-side hash-assign of every cut against the current map; redone after each registration that changes the map
+    std::vector<agcgpu_assign> assign(n_cuts);
+    auto run_assign = [&](uint64_t from_cut) -> bool {
+        if (from_cut >= n_cuts) return true;
+        return gpu_ok(agcgpu_assign_cuts(ctx, cuts.data() + from_cut, n_cuts - from_cut, assign.data() + from_cut), "assign_cuts");
+    };
+    if (!run_assign(0)) return false;
+
+    struct RegGroup { uint32_t group; std::vector<Item> items; };
+    struct SampleReg { uint32_t sample_id; std::vector<RegGroup> groups; };
+    std::vector<SampleReg> regs;
+
+    auto canon = [](uint64_t d, uint64_t r) { return d < r ? d : r; };
+    auto seg_req = [&](uint32_t bc, uint64_t start, uint32_t len, bool is_rc, uint32_t group, uint32_t bound) {
+        agcgpu_seg_req q; q.contig = bc; q.is_rc = is_rc; q.start = start; q.len = len; q.group_id = group; q.bound = bound; q.reserved = 0; return q; };
+
+    // find_cand_segment_with_one_splitter (agc_compressor.cpp:1630-1808)
+    auto one_splitter = [&](uint64_t kdir, uint64_t krc, uint32_t bc, uint64_t start, uint32_t len, bool dir_is_rc,
+                            std::pair<uint64_t, uint64_t>& best_pk, bool& is_best_rc) -> bool {
+        const uint64_t kd = canon(kdir, krc);
+        const bool dir_oriented = kdir <= krc;
+        best_pk = std::make_pair(EMPTY, EMPTY); is_best_rc = false;
+        uint64_t best_est = len < 16 ? len : len - 16u;
+        auto p = map_segments_terminators.find(kd);
+        if (p != map_segments_terminators.end()) {
+            struct Cand { uint64_t a, b; bool rc; uint32_t group; };
+            std::vector<Cand> cands;
+            for (auto ck : p->second) {
+                Cand c;
+                if (ck < kd) { c.a = ck; c.b = kd; c.rc = true; } else { c.a = kd; c.b = ck; c.rc = false; }
+                c.group = (uint32_t)map_segments[std::make_pair(c.a, c.b)];
+                cands.push_back(c);
+            }
+            std::vector<agcgpu_seg_req> rq;
+            for (auto& c : cands) rq.push_back(seg_req(bc, start, len, c.rc ? !dir_is_rc : dir_is_rc, c.group, (uint32_t)best_est));
+            std::vector<uint32_t> est(rq.size());
+            if (!rq.empty() && !gpu_ok(agcgpu_lz_estimate_batch(ctx, rq.data(), (uint32_t)rq.size(), est.data()), "lz_estimate")) return false;
+            for (size_t i = 0; i < cands.size(); ++i) if ((uint64_t)est[i] < best_est) best_est = est[i];
+            for (size_t i = 0; i < cands.size(); ++i) {
+                auto cpk = std::make_pair(cands[i].a, cands[i].b);
+                if (est[i] < best_est || (est[i] == best_est && cpk < best_pk) || (est[i] == best_est && cpk == best_pk && !cands[i].rc)) {
+                    best_est = est[i]; best_pk = cpk; is_best_rc = cands[i].rc;
+                }
+            }
+        }
+        if (best_pk == std::make_pair(EMPTY, EMPTY)) {
+            if (dir_oriented) best_pk = std::make_pair(kd, EMPTY);
+            else { best_pk = std::make_pair(EMPTY, kd); is_best_rc = true; }
+        }
+        return true;
+    };
+
+    // find_cand_segment_with_missing_middle_splitter (agc_compressor.cpp:1502-1627); dir_is_rc tells which orientation
+    // of the resident segment plays "segment_dir"
+    auto missing_middle = [&](uint64_t k1d, uint64_t k2d, uint32_t bc, uint64_t start, uint32_t len, bool dir_is_rc,
+                              uint64_t& middle, uint32_t& best_pos) -> bool {
+        middle = EMPTY; best_pos = 0;
+        auto pf = map_segments_terminators.find(k1d), pb = map_segments_terminators.find(k2d);
+        if (pf == map_segments_terminators.end() || pb == map_segments_terminators.end()) return true;
+        std::vector<uint64_t> shared;
+        std::set_intersection(pf->second.begin(), pf->second.end(), pb->second.begin(), pb->second.end(), std::back_inserter(shared));
+        shared.erase(std::remove(shared.begin(), shared.end(), EMPTY), shared.end());
+        if (shared.empty()) return true;
+        uint64_t mid = shared.front();
+        uint32_t g1 = (uint32_t)map_segments[std::minmax(k1d, mid)], g2 = (uint32_t)map_segments[std::minmax(mid, k2d)];
+        std::vector<uint32_t> c1(len), c2(len);
+        agcgpu_seg_req q;
+        if (k1d < mid) {
+            q = seg_req(bc, start, len, dir_is_rc, g1, 0);
+            if (!gpu_ok(agcgpu_lz_cost_vector(ctx, &q, 1, c1.data()), "lz_cost_vector")) return false;
+        } else {
+            q = seg_req(bc, start, len, !dir_is_rc, g1, 0);
+            if (!gpu_ok(agcgpu_lz_cost_vector(ctx, &q, 0, c1.data()), "lz_cost_vector")) return false;
+            std::reverse(c1.begin(), c1.end());
+        }
+        std::partial_sum(c1.begin(), c1.end(), c1.begin());
+        if (mid < k2d) {
+            q = seg_req(bc, start, len, dir_is_rc, g2, 0);
+            if (!gpu_ok(agcgpu_lz_cost_vector(ctx, &q, 0, c2.data()), "lz_cost_vector")) return false;
+            std::partial_sum(c2.rbegin(), c2.rend(), c2.rbegin());
+        } else {
+            q = seg_req(bc, start, len, !dir_is_rc, g2, 0);
+            if (!gpu_ok(agcgpu_lz_cost_vector(ctx, &q, 1, c2.data()), "lz_cost_vector")) return false;
+            std::partial_sum(c2.begin(), c2.end(), c2.begin());
+            std::reverse(c2.begin(), c2.end());
+        }
+        uint32_t best_sum = ~0u, bp = 0;
+        for (uint32_t i = 0; i < len; ++i) { uint32_t cs = c1[i] + c2[i]; if (cs < best_sum) { best_sum = cs; bp = i; } }
+        if (bp < kmer_length + 1u) bp = 0;
+        if ((size_t)bp + kmer_length + 1u > len) bp = len;
+        middle = mid; best_pos = bp;
+        return true;
+    };
+
+    uint32_t ci = 0;
+    while (ci < nc) {
+        const uint32_t sid = owners[ci].sample_id;
+        uint32_t cj = ci;
+        while (cj < nc && owners[cj].sample_id == sid) ++cj;
+        std::vector<Item> known, fresh;
+        // ---- add_segment for every cut of the sample (agc_compressor.cpp:1275-1499)
+        for (uint32_t bc = ci; bc < cj; ++bc) {
+            uint32_t part_no = 0;
+            const std::string* cname = &collection.sample_desc[sid].contigs[owners[bc].contig_idx].name;
+            for (uint64_t x = cut_first[bc]; x < cut_first[bc + 1]; ++x) {
+                const agcgpu_cut& cut = cuts[x];
+                const agcgpu_assign& as = assign[x];
+                Item it; it.sample_id = sid; it.contig_idx = owners[bc].contig_idx; it.seg_part_no = part_no; it.batch_contig = bc;
+                it.start = cut.start; it.len = (uint32_t)cut.len; it.contig_name = cname; it.is_rc = false; it.group = -1;
+                std::pair<uint64_t, uint64_t> pk(EMPTY, EMPTY);
+                bool store_rc = false, have_second = false;
+                Item it2 = it;
+                const uint64_t fc = canon(cut.front_dir, cut.front_rc), bcn = canon(cut.back_dir, cut.back_rc);
+                if (!cut.has_front && !cut.has_back) pk = std::make_pair(EMPTY, EMPTY);
+                else if (cut.has_front && cut.has_back) { pk = std::make_pair(as.key1, as.key2); store_rc = as.is_rc; }
+                else if (cut.has_front) {
+                    if (!one_splitter(cut.front_dir, cut.front_rc, bc, it.start, it.len, false, pk, store_rc)) return false;
+                } else {
+                    bool store_dir = false;      // kmer = kmer_back with swap_dir_rc; "segment_dir" is the reverse complement
+                    if (!one_splitter(cut.back_rc, cut.back_dir, bc, it.start, it.len, true, pk, store_dir)) return false;
+                    store_rc = !store_dir;
+                }
+                // map_segments.find(pk): the device hash-assign already answered it for the two-splitter / no-splitter classes
+                auto p = map_segments.end();
+                bool found = false;
+                if (as.klass == 0 || as.klass == 3) { found = as.group_id >= 0; if (found) p = map_segments.find(pk); }
+                else { p = map_segments.find(pk); found = p != map_segments.end(); }
+                if (found && p == map_segments.end()) return fail("internal: device and host segment maps disagree");
+                int32_t segment_id = -1, segment_id2 = -1;
+                if (p == map_segments.end() && pk.first != EMPTY && pk.second != EMPTY &&
+                    map_segments_terminators.count(pk.first) && map_segments_terminators.count(pk.second)) {
+                    if (fc == bcn) { if (!(cut.front_dir <= cut.front_rc)) store_rc = true; }
+                    else {
+                        uint64_t k1d = fc, k2d = bcn; bool use_rc = false;
+                        if (k1d > k2d) { std::swap(k1d, k2d); use_rc = true; }
+                        uint64_t mid; uint32_t bp;
+                        if (!missing_middle(k1d, k2d, bc, it.start, it.len, use_rc, mid, bp)) return false;
+                        if (mid != EMPTY) {
+                            uint32_t left = bp, right = it.len - bp;
+                            if (left == 0) { store_rc = (mid < k2d) ? use_rc : !use_rc; pk = std::minmax(mid, k2d); }
+                            else if (right == 0) { store_rc = (k1d < mid) ? use_rc : !use_rc; pk = std::minmax(k1d, mid); }
+                            else {
+                                if (use_rc) std::swap(left, right);
+                                uint32_t seg2_start = left - kmer_length / 2;
+                                it2.start = it.start + seg2_start; it2.len = it.len - seg2_start; it2.seg_part_no = part_no + 1;
+                                it.len = seg2_start + kmer_length;
+                                if (fc < mid) { store_rc = false; pk = std::make_pair(fc, mid); } else { store_rc = true; pk = std::make_pair(mid, fc); }
+                                segment_id = map_segments.at(pk);
+                                std::pair<uint64_t, uint64_t> pk2;
+                                if (mid < bcn) { it2.is_rc = false; pk2 = std::make_pair(mid, bcn); } else { it2.is_rc = true; pk2 = std::make_pair(bcn, mid); }
+                                segment_id2 = map_segments.at(pk2);
+                                it2.k1 = pk2.first; it2.k2 = pk2.second; it2.group = segment_id2;
+                                have_second = true;
+                            }
+                        }
+                    }
+                    p = map_segments.find(pk);
+                }
+                it.is_rc = store_rc; it.k1 = pk.first; it.k2 = pk.second;
+                if (p == map_segments.end()) { it.group = -1; fresh.push_back(it); }
+                else { it.group = have_second ? segment_id : p->second; known.push_back(it); if (have_second) known.push_back(it2); }
+                part_no += have_second ? 2 : 1;
+            }
+        }
+        // ---- register_segments (agc_compressor.cpp:954-971): canonical order = (sample, contig name, part) (agc_compressor.h:112-119)
+        auto item_less = [](const Item& a, const Item& b) {
+            if (*a.contig_name != *b.contig_name) return *a.contig_name < *b.contig_name;
+            return a.seg_part_no < b.seg_part_no; };
+        std::stable_sort(fresh.begin(), fresh.end(), item_less);
+        fresh.erase(std::unique(fresh.begin(), fresh.end(), [](const Item& a, const Item& b) {
+            return *a.contig_name == *b.contig_name && a.seg_part_no == b.seg_part_no; }), fresh.end());    // std::set semantics
+        SampleReg reg; reg.sample_id = sid;
+        std::map<uint32_t, std::vector<Item>> by_group;
+        for (auto& it : known) by_group[(uint32_t)it.group].push_back(it);
+        for (auto& kv : by_group) std::sort(kv.second.begin(), kv.second.end(), item_less);            // sort_known
+        std::map<std::pair<uint64_t, uint64_t>, uint32_t> m_kmers;                                      // process_new (agc_compressor.h:384-415)
+        uint32_t group_id = no_segments;
+        for (auto& it : fresh) { auto key = std::make_pair(it.k1, it.k2); if (!m_kmers.count(key)) m_kmers[key] = group_id++; }
+        const uint32_t no_new = group_id - no_segments;
+        for (auto& it : fresh) { it.group = (int32_t)m_kmers[std::make_pair(it.k1, it.k2)]; by_group[(uint32_t)it.group].push_back(it); }
+        if (v_segments.size() < group_id) v_segments.resize(group_id);
+        std::vector<uint64_t> ins_k1, ins_k2; std::vector<int32_t> ins_g;
+        std::vector<agcgpu_seg_req> new_refs;
+        for (uint32_t i = 0; i < no_new; ++i) {
+            GroupState& g = v_segments[no_segments + i];
+            g.stream_ref = out_archive.RegisterStream(ss_base(no_segments + i) + "r");              // RegisterStreams, 960-961
+            g.stream_delta = out_archive.RegisterStream(ss_base(no_segments + i) + "d");
+        }
+        // distribute_segments(0, 0, 16) (agc_compressor.h:417-435): the first n - ceil(n/16) items go round-robin to groups 1..15
+        {
+            auto g0 = by_group.find(0);
+            if (g0 != by_group.end()) {
+                std::vector<Item> all = std::move(g0->second), keep;
+                uint32_t n = (uint32_t)all.size(), dest = 0, taken = 0;
+                for (uint32_t i = 0; i < n; ++i) {
+                    if (dest != 0) { Item it = all[taken++]; it.group = (int32_t)dest; by_group[dest].push_back(it); }
+                    if (++dest == NO_RAW_GROUPS) dest = 0;
+                }
+                keep.assign(all.begin() + taken, all.end());
+                if (keep.empty()) by_group.erase(0); else by_group[0] = std::move(keep);
+            }
+        }
+        // store_segments part 1 (agc_compressor.cpp:1001-1027): group creation, map_segments / terminators update
+        bool map_changed = false;
+        for (auto& kv : by_group) {
+            GroupState& g = v_segments[kv.first];
+            if (!g.exists) {
+                g.exists = true;
+                const Item& first = kv.second.front();
+                auto key = std::make_pair(first.k1, first.k2);
+                auto pm = map_segments.find(key);
+                if (pm == map_segments.end()) map_segments[key] = (int32_t)kv.first; else if (pm->second > (int32_t)kv.first) pm->second = (int32_t)kv.first;
+                if (first.k1 != EMPTY && first.k2 != EMPTY) {
+                    auto& t1 = map_segments_terminators[first.k1]; t1.push_back(first.k2); std::sort(t1.begin(), t1.end());
+                    if (first.k1 != first.k2) { auto& t2 = map_segments_terminators[first.k2]; t2.push_back(first.k1); std::sort(t2.begin(), t2.end()); }
+                }
+                ins_k1.push_back(first.k1); ins_k2.push_back(first.k2); ins_g.push_back((int32_t)kv.first);
+                new_refs.push_back(seg_req(first.batch_contig, first.start, first.len, first.is_rc, kv.first, 0));
+                g.ref_size = first.len + 1;
+                map_changed = true;
+            }
+            reg.groups.push_back(RegGroup{ kv.first, std::move(kv.second) });
+        }
+        no_segments += no_new;
+        if (map_changed) {
+            if (!gpu_ok(agcgpu_map_insert(ctx, ins_k1.data(), ins_k2.data(), ins_g.data(), ins_g.size()), "map_insert")) return false;
+            if (!gpu_ok(agcgpu_group_put_reference_batch(ctx, new_refs.data(), (uint32_t)new_refs.size()), "put_reference")) return false;
+            if (!run_assign(cut_first[cj])) return false;
+        }
+        regs.push_back(std::move(reg));
+        ci = cj;
+    }
+
+    // ---- one LZ batch for the whole device batch: everything except each group's first sequence (its reference)
+    std::vector<agcgpu_seg_req> lz;
+    std::vector<uint32_t> ref_groups;
+    {
+        std::vector<uint8_t> seen_ref(v_segments.size(), 0);
+        for (uint32_t g = 0; g < v_segments.size(); ++g) seen_ref[g] = v_segments[g].no_seqs > 0;
+        for (auto& reg : regs) for (auto& rg : reg.groups) {
+            if (rg.group < NO_RAW_GROUPS) continue;
+            for (auto& it : rg.items) {
+                if (!seen_ref[rg.group]) { seen_ref[rg.group] = 1; ref_groups.push_back(rg.group); continue; }
+                lz.push_back(seg_req(it.batch_contig, it.start, it.len, it.is_rc, rg.group, 0));
+            }
+        }
+    }
+    std::vector<uint8_t> deltas; std::vector<uint64_t> doffs(lz.size() + 1, 0);
+    if (!lz.empty()) {
+        uint64_t cap = 64; for (auto& q : lz) cap += (uint64_t)q.len * 3 / 2 + 32;
+        // the ABI wants a buffer large enough for the worst case; typical deltas are ~1% of that, so try small first
+        uint64_t try_cap = std::max<uint64_t>(cap / 16, 1 << 20);
+        deltas.resize(try_cap);
+        int rc2 = agcgpu_lz_encode_batch(ctx, lz.data(), (uint32_t)lz.size(), deltas.data(), try_cap, doffs.data());
+        if (rc2 == AGCGPU_EOVERFLOW) { deltas.resize(cap); rc2 = agcgpu_lz_encode_batch(ctx, lz.data(), (uint32_t)lz.size(), deltas.data(), cap, doffs.data()); }
+        if (!gpu_ok(rc2, "lz_encode_batch")) return false;
+    }
+    // reference payloads (tuples or raw symbols) of the groups created in this batch
+    std::vector<uint8_t> refpay; std::vector<uint64_t> roffs(ref_groups.size() + 1, 0); std::vector<uint8_t> ruse(ref_groups.size() + 1, 0);
+    if (!ref_groups.empty()) {
+        uint64_t cap = 64; for (auto g : ref_groups) cap += v_segments[g].ref_size + 2;
+        refpay.resize(cap);
+        if (!gpu_ok(agcgpu_pack_ref_batch(ctx, ref_groups.data(), (uint32_t)ref_groups.size(), refpay.data(), cap, roffs.data(), ruse.data()), "pack_ref_batch")) return false;
+    }
+
+    // ---- store_segments part 2 (CSegment::add / add_raw, segment.cpp:14-80) in sample order + collection placement
+    size_t lz_i = 0, ref_i = 0;
+    for (auto& reg : regs) {
+        for (auto& rg : reg.groups) {
+            GroupState& g = v_segments[rg.group];
+            for (auto& it : rg.items) {
+                uint32_t in_group_id;
+                if (rg.group < NO_RAW_GROUPS) {                                   // add_raw
+                    if (g.pack.size() == pack_cardinality) store_pack(rg.group, g, epoch);
+                    std::vector<uint8_t> sym(it.len ? it.len : 1);
+                    if (!gpu_ok(agcgpu_get_segment(ctx, it.batch_contig, it.start, it.len, it.is_rc, sym.data()), "get_segment")) return false;
+                    sym.resize(it.len);
+                    ++g.no_seqs; g.pack.emplace_back(std::move(sym));
+                    in_group_id = g.no_seqs - 1;
+                } else if (g.no_seqs == 0) {                                      // first sequence = reference (segment.cpp:39-48)
+                    if (ref_i >= ref_groups.size() || ref_groups[ref_i] != rg.group) return fail("internal: reference order mismatch");
+                    PartJob j; j.epoch = epoch; j.stream_id = g.stream_ref; j.kind = ruse[ref_i] ? 1 : 0;
+                    j.tasks.emplace_back(); j.tasks[0].level = ruse[ref_i] ? 13 : 19;
+                    j.tasks[0].raw.assign(refpay.begin() + roffs[ref_i], refpay.begin() + roffs[ref_i + 1]);
+                    j.raw_size = it.len;
+                    // fallback ("packed+1 >= raw"): the raw symbols; only tiny references can hit it
+                    if (ruse[ref_i]) { j.fallback_raw.resize(it.len ? it.len : 1); if (!gpu_ok(agcgpu_get_segment(ctx, it.batch_contig, it.start, it.len, it.is_rc, j.fallback_raw.data()), "get_segment")) return false; j.fallback_raw.resize(it.len); }
+                    else j.fallback_raw = j.tasks[0].raw;
+                    add_job(std::move(j));
+                    ++ref_i; ++g.no_seqs;
+                    in_group_id = 0;
+                } else {
+                    if (g.pack.size() == pack_cardinality) store_pack(rg.group, g, epoch);
+                    std::vector<uint8_t> delta(deltas.begin() + doffs[lz_i], deltas.begin() + doffs[lz_i + 1]);
+                    ++lz_i;
+                    if (delta.empty()) in_group_id = 0;                            // IMPROVED_LZ_ENCODING (segment.cpp:61-64)
+                    else {
+                        auto p = std::find(g.pack.begin(), g.pack.end(), delta);
+                        if (p != g.pack.end()) in_group_id = g.no_seqs - (uint32_t)std::distance(p, g.pack.end());
+                        else { g.pack.emplace_back(std::move(delta)); ++g.no_seqs; in_group_id = g.no_seqs - 1; }
+                    }
+                }
+                segment_desc_t d; d.group_id = rg.group; d.in_group_id = in_group_id; d.is_rev_comp = it.is_rc; d.raw_length = it.len;
+                collection.add_segment_placed(it.sample_id, it.contig_idx, it.seg_part_no, d);
+            }
+        }
+        ++processed_samples;                                                       // agc_compressor.cpp:1162-1179
+        if (processed_samples % pack_cardinality == 0) store_contig_batch(processed_samples - pack_cardinality, processed_samples, epoch);
+        ++epoch;
+    }
+    return flush_jobs(false);
+}
+
+bool CAGCCompressor::Close(uint32_t)
+{
+    if (!working) return false;
+    working = false;
+    // close_compression (agc_compressor.cpp:2094-2114): CSegment::finish for all groups, flush, metadata
+    for (uint32_t i = 0; i < no_segments; ++i) if (!v_segments[i].pack.empty()) store_pack(i, v_segments[i], epoch);
+    ++epoch;
+    if (!flush_jobs(true)) return false;
+    auto a32 = [](std::vector<uint8_t>& v, uint32_t x) { for (int i = 0; i < 4; ++i) { v.push_back(x & 0xff); x >>= 8; } };
+    auto a64 = [](std::vector<uint8_t>& v, uint64_t x) { for (int i = 0; i < 8; ++i) { v.push_back(x & 0xff); x >>= 8; } };
+    auto astr = [](std::vector<uint8_t>& v, const std::string& s) { v.insert(v.end(), s.begin(), s.end()); v.push_back(0); };
+    std::vector<uint8_t> v_params; a32(v_params, kmer_length); a32(v_params, min_match_len); a32(v_params, pack_cardinality); a32(v_params, segment_size);
+    std::vector<uint8_t> v_spl; for (auto x : splitters) a64(v_spl, x);                     // already sorted (agc_compressor.cpp:220-226)
+    std::vector<uint8_t> v_map;                                                            // std::map iterates sorted (232-252)
+    for (auto& x : map_segments) { a64(v_map, x.first.first); a64(v_map, x.first.second); a32(v_map, (uint32_t)x.second); }
+    // collection-samples (collection_v3.cpp:155-165), file_type_info (agc_compressor.cpp:286-300, fields 53-59)
+    PartJob js; js.epoch = epoch; js.kind = 2; js.stream_id = collection_samples_id; js.tasks.emplace_back(); js.tasks[0].level = 19;
+    collection.serialize_sample_names(js.tasks[0].raw); js.raw_size = js.tasks[0].raw.size();
+    std::map<std::string, std::string> fti;
+    fti["producer"] = "agc"; fti["producer_version_major"] = "3"; fti["producer_version_minor"] = "2"; fti["producer_version_build"] = "20260326.1";
+    fti["file_version_major"] = "3"; fti["file_version_minor"] = "0";
+    fti["comment"] = "AGC (Assembled Genomes Compressor) v. 3.2.2 [build 20260326.1]";
+    std::vector<uint8_t> v_fti; for (auto& x : fti) { astr(v_fti, x.first); astr(v_fti, x.second); }
+    if (dump_f) {
+        auto dump_imm = [&](const char* name, const std::vector<uint8_t>& d, uint64_t meta) {
+            fwrite("IMMD", 1, 4, dump_f); dump_bytes(dump_f, name, strlen(name)); dump_u64(dump_f, meta); dump_bytes(dump_f, d.data(), d.size()); };
+        dump_imm("params", v_params, 0); dump_imm("splitters", v_spl, splitters.size()); dump_imm("segment-splitters", v_map, map_segments.size());
+        dump_imm("file_type_info", v_fti, fti.size());
+        add_job(std::move(js)); flush_jobs(true);
+        for (const char* nm : { "params", "splitters", "segment-splitters", "file_type_info" }) out_archive.RegisterStream(nm);
+        for (size_t i = 0; i < out_archive.NoStreams(); ++i) { fwrite("STRM", 1, 4, dump_f); dump_bytes(dump_f, out_archive.StreamName(i).data(), out_archive.StreamName(i).size()); }
+        fclose(dump_f); dump_f = nullptr;
+        out_archive.Close();
+        return true;
+    }
+    out_archive.AddPart(out_archive.RegisterStream("params"), v_params, 0);
+    out_archive.AddPart(out_archive.RegisterStream("splitters"), v_spl, splitters.size());
+    out_archive.AddPart(out_archive.RegisterStream("segment-splitters"), v_map, map_segments.size());
+    // collection-samples is *buffered* (AddPartBuffered) while file_type_info is written immediately, so it lands last
+    std::vector<ZTask*> t{ &js.tasks[0] };
+    if (!compress_tasks(t)) return false;
+    out_archive.AddPart(out_archive.RegisterStream("file_type_info"), v_fti, fti.size());
+    out_archive.AddPart(collection_samples_id, js.tasks[0].packed, js.raw_size);
+    return out_archive.Close();
+}
+
+}  // namespace agc_b200

@@ -1,0 +1,55 @@
+// agc-b200: `create` sub-command with the reference CLI's flags (src/app/application.cpp:125-169; defaults from
+// src/app/application.h:24-84).  Everything per-base runs on the GPU through libagcgpu.
+#include "compressor.h"
+#include <cstdlib>
+#include <cstring>
+#include <filesystem>
+#include <fstream>
+#include <iostream>
+#include <unordered_set>
+
+static void remove_common_suffixes(std::string& s)        // application.cpp:606-630
+{
+    const char* suf[] = { ".fna", ".gz", ".fa", ".fasta" };
+    while (true) {
+        bool removed = false;
+        for (auto x : suf) {
+            size_t l = strlen(x);
+            if (s.length() <= l) continue;
+            if (s.compare(s.length() - l, l, x) == 0) { s.resize(s.length() - l); removed = true; break; }
+        }
+        if (!removed) break;
+    }
+}
+
+int main(int argc, char** argv)
+{
+    if (argc < 3 || std::string(argv[1]) != "create") {
+        std::cerr << "usage: agc-b200 create [-k 31] [-l 20] [-s 60000] [-b 50] [-t n] [-v n] [-i list] [-d] [--device n] [--dump-parts file] -o out.agc ref.fa [samples...]\n";
+        return 1;
+    }
+    uint32_t k = 31, l = 20, s = 60000, b = 50, t = 1, v = 0; bool a = false, c = false; double f = 0.0; int dev = 0;
+    std::string out, list, dump;
+    std::vector<std::string> inputs;
+    for (int i = 2; i < argc; ++i) {
+        std::string x = argv[i];
+        auto next = [&]() -> const char* { if (i + 1 >= argc) { std::cerr << "missing value for " << x << "\n"; exit(1); } return argv[++i]; };
+        if (x == "-k") k = (uint32_t)atoi(next()); else if (x == "-l") l = (uint32_t)atoi(next()); else if (x == "-s") s = (uint32_t)atoi(next());
+        else if (x == "-b") b = (uint32_t)atoi(next()); else if (x == "-t") t = (uint32_t)atoi(next()); else if (x == "-v") v = (uint32_t)atoi(next());
+        else if (x == "-o") out = next(); else if (x == "-i") list = next(); else if (x == "-a") a = true; else if (x == "-c") c = true;
+        else if (x == "-d") {} else if (x == "-f") f = atof(next()); else if (x == "--device") dev = atoi(next()); else if (x == "--dump-parts") dump = next();
+        else inputs.push_back(x);
+    }
+    if (!list.empty()) { std::ifstream in(list); std::string ln; while (std::getline(in, ln)) if (!ln.empty()) inputs.push_back(ln); }
+    if (out.empty() || inputs.empty()) { std::cerr << "need -o and at least the reference FASTA\n"; return 1; }
+    { std::vector<std::string> u; std::unordered_set<std::string> seen; for (auto& x : inputs) if (seen.insert(x).second) u.push_back(x); inputs.swap(u); }
+    agc_b200::CAGCCompressor agc;
+    agc.SetDevice(dev);
+    if (!dump.empty()) agc.SetDumpParts(dump);
+    if (!agc.Create(out, b, k, inputs.front(), s, l, c, a, v, t, f)) { std::cerr << "Cannot create archive " << out << std::endl; return 1; }
+    std::vector<std::pair<std::string, std::string>> files;
+    for (auto& fn : inputs) { std::string nm = std::filesystem::path(fn).stem().string(); remove_common_suffixes(nm); files.emplace_back(nm, fn); }
+    bool r = agc.AddSampleFiles(files, t);
+    r &= agc.Close(t);
+    return r ? 0 : 1;
+}

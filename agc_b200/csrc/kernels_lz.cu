@@ -596,6 +596,7 @@ __global__ void __launch_bounds__(32) k_ref_probe_packed(const GroupRefDev* __re
 {
     if (blockIdx.x >= n) return;
     const GroupRefDev g = groups[ids[blockIdx.x]];
+    if (g.flags & GRF_DIRTY) return;
     const uint64_t* R = (const uint64_t*)g.packed;
     const uint32_t lane = threadIdx.x, m = g.m;
     bool periodic = false;
@@ -623,6 +624,7 @@ __global__ void k_ref_tuples_packed(const GroupRefDev* __restrict__ groups, cons
 {
     if (blockIdx.y >= n) return;
     const GroupRefDev g = groups[ids[blockIdx.y]];
+    if (g.flags & GRF_DIRTY) return;
     uint32_t full = g.m / 4, total = full + 2;
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
@@ -631,6 +633,41 @@ __global__ void k_ref_tuples_packed(const GroupRefDev* __restrict__ groups, cons
     else if (i == full) { uint32_t r = g.m & 3u; v = r ? (uint8_t)(g.packed[full] >> (8 - 2 * r)) : 0; }
     else v = (uint8_t)((4u << 4) + (g.m & 3u));
     out[out_off[blockIdx.y] + i] = v;
+}
+
+// same probe on 1-byte symbols (references with non-ACGT symbols): cnt counts every equal pair, cur only ACGT positions
+// (segment.h:231-241); also returns the largest symbol (selects the tuple width, segment.h:73-91)
+__global__ void __launch_bounds__(32) k_ref_probe_bytes(const uint8_t* __restrict__ d, uint32_t m, uint8_t* __restrict__ use_tuples,
+                                                       uint8_t* __restrict__ max_sym)
+{
+    const uint32_t lane = threadIdx.x;
+    uint32_t me = 0;
+    for (uint32_t j = lane; j < m; j += 32) me = max(me, (uint32_t)d[j]);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) me = max(me, __shfl_xor_sync(FULL, me, o));
+    bool periodic = false;
+    for (uint32_t lag = 4; lag < 32 && !periodic; ++lag) {
+        if (m <= lag) break;
+        uint32_t cnt = 0, cur = 0;
+        for (uint32_t j = lane; j + lag < m; j += 32) { cnt += d[j] == d[j + lag]; cur += d[j] < 4; }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) { cnt += __shfl_xor_sync(FULL, cnt, o); cur += __shfl_xor_sync(FULL, cur, o); }
+        if (cur && 2ull * cnt >= cur) periodic = true;
+    }
+    if (lane == 0) { *use_tuples = periodic ? 0 : 1; *max_sym = (uint8_t)me; }
+}
+// bytes2tuples_impl<NO_BYTES, MULT> (segment.h:108-138) / raw + 0x10 marker (86-90)
+__global__ void k_ref_tuples_bytes(const uint8_t* __restrict__ d, uint32_t m, uint32_t nb, uint32_t mult, uint8_t* __restrict__ out)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (nb == 1) { if (i < m) out[i] = d[i]; else if (i == m) out[i] = 0x10; return; }
+    uint32_t full = m / nb;
+    if (i > full + 1) return;
+    uint32_t c = 0;
+    if (i < full) for (uint32_t j = 0; j < nb; ++j) c = c * mult + d[i * nb + j];
+    else if (i == full) for (uint32_t q = full * nb; q < m; ++q) c = c * mult + d[q];
+    else c = (nb << 4) + (m % nb);
+    out[i] = (uint8_t)c;
 }
 
 // ================================================================================================ host side
@@ -944,43 +981,61 @@ int agc_pack_refs(agcgpu_ctx* ctx, const uint32_t* group_ids, uint32_t n, uint8_
         uint32_t gid = group_ids[i];
         if (gid >= ctx->h_groups.size() || !(ctx->h_groups[gid].flags & GRF_PRESENT))
             return agc_fail(ctx, AGCGPU_EINVAL, "pack_ref: group %u has no reference", gid);
-        if (ctx->h_groups[gid].flags & GRF_DIRTY)
-            return agc_fail(ctx, AGCGPU_EUNSUPPORTED, "pack_ref: reference of group %u holds non-ACGT symbols (not implemented on device yet)", gid);
     }
-    if (int r = agc_reserve(ctx, ctx->scr_misc, (size_t)n * 16 + 64)) return r;
+    if (int r = agc_reserve(ctx, ctx->scr_misc, (size_t)n * 32 + 256)) return r;
     uint32_t* d_ids = (uint32_t*)ctx->scr_misc.p;
-    uint8_t* d_use = (uint8_t*)(d_ids + n);
-    uint64_t* d_off = (uint64_t*)((uint8_t*)ctx->scr_misc.p + (((size_t)n * 5 + 15) / 16) * 16);
-    if ((size_t)((uint8_t*)(d_off + n + 1) - (uint8_t*)ctx->scr_misc.p) > ctx->scr_misc.cap)
-        if (int r = agc_reserve(ctx, ctx->scr_misc, (size_t)n * 32 + 256, false)) return r;
-    d_ids = (uint32_t*)ctx->scr_misc.p; d_use = (uint8_t*)(d_ids + n);
-    d_off = (uint64_t*)((uint8_t*)ctx->scr_misc.p + (((size_t)n * 5 + 15) / 16) * 16);
+    uint64_t* d_off = (uint64_t*)((uint8_t*)ctx->scr_misc.p + (((size_t)n * 4 + 15) / 16) * 16);
+    uint8_t* d_use = (uint8_t*)(d_off + n + 1);
+    uint8_t* d_max = d_use + n;
     CK(cudaMemcpyAsync(d_ids, group_ids, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemsetAsync(d_use, 0, (size_t)2 * n, ctx->st));
     k_ref_probe_packed<<<n, 32, 0, ctx->st>>>((const GroupRefDev*)ctx->d_groups.p, d_ids, n, d_use);
     CKL();
-    CK(cudaMemcpyAsync(out_use_tuples, d_use, n, cudaMemcpyDeviceToHost, ctx->st));
-    CK(cudaStreamSynchronize(ctx->st));
-    uint32_t max_m = 0;
     for (uint32_t i = 0; i < n; ++i) {
         const GroupRefDev& g = ctx->h_groups[group_ids[i]];
-        off[i + 1] = off[i] + (out_use_tuples[i] ? (uint64_t)g.m / 4 + 2 : (uint64_t)g.m);
+        if (g.flags & GRF_DIRTY) { k_ref_probe_bytes<<<1, 32, 0, ctx->st>>>(g.codes, g.m, d_use + i, d_max + i); CKL(); }
+    }
+    std::vector<uint8_t> h_max(n);
+    CK(cudaMemcpyAsync(out_use_tuples, d_use, n, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(h_max.data(), d_max, n, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    uint32_t max_m = 0;
+    auto tuple_mode = [&](uint32_t i, uint32_t& nb, uint32_t& mult) {       // bytes2tuples (segment.h:73-91)
+        uint8_t me = (ctx->h_groups[group_ids[i]].flags & GRF_DIRTY) ? h_max[i] : 0;
+        if (me < 4) { nb = 4; mult = 4; } else if (me < 6) { nb = 3; mult = 6; } else if (me < 16) { nb = 2; mult = 16; } else { nb = 1; mult = 0; }
+    };
+    for (uint32_t i = 0; i < n; ++i) {
+        const GroupRefDev& g = ctx->h_groups[group_ids[i]];
+        uint32_t nb, mult; tuple_mode(i, nb, mult);
+        uint64_t sz = !out_use_tuples[i] ? (uint64_t)g.m : (nb == 1 ? (uint64_t)g.m + 1 : (uint64_t)g.m / nb + 2);
+        off[i + 1] = off[i] + sz;
         max_m = std::max(max_m, g.m);
     }
     if (off[n] > out_cap) return agc_fail(ctx, AGCGPU_EOVERFLOW, "pack_ref: need %llu bytes", (unsigned long long)off[n]);
     if (int r = agc_reserve(ctx, ctx->scr_dense, off[n] + 64)) return r;
+    uint8_t* dense = (uint8_t*)ctx->scr_dense.p;
     CK(cudaMemcpyAsync(d_off, off.data(), ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, ctx->st));
     for (uint32_t y0 = 0; y0 < n; y0 += 32768) {
         uint32_t ny = std::min<uint32_t>(32768, n - y0);
         dim3 grid((max_m / 4 + 2 + 255) / 256, ny);
-        k_ref_tuples_packed<<<grid, 256, 0, ctx->st>>>((const GroupRefDev*)ctx->d_groups.p, d_ids + y0, ny, d_off + y0, (uint8_t*)ctx->scr_dense.p);
+        k_ref_tuples_packed<<<grid, 256, 0, ctx->st>>>((const GroupRefDev*)ctx->d_groups.p, d_ids + y0, ny, d_off + y0, dense);
         CKL();
     }
-    // references that failed the probe are stored as raw symbols: expand on the device
-    for (uint32_t i = 0; i < n; ++i) if (!out_use_tuples[i]) {
+    for (uint32_t i = 0; i < n; ++i) {
         const GroupRefDev& g = ctx->h_groups[group_ids[i]];
-        if (g.m) { k_expand_ref<<<(g.m + 255) / 256, 256, 0, ctx->st>>>(g.packed, g.m, (uint8_t*)ctx->scr_dense.p + off[i], 0); CKL(); }
+        const bool dirty = g.flags & GRF_DIRTY;
+        if (!out_use_tuples[i]) {          // failed the probe: stored as raw symbols (level 19)
+            if (!g.m) continue;
+            if (dirty) CK(cudaMemcpyAsync(dense + off[i], g.codes, g.m, cudaMemcpyDeviceToDevice, ctx->st));
+            else { k_expand_ref<<<(g.m + 255) / 256, 256, 0, ctx->st>>>(g.packed, g.m, dense + off[i], 0); CKL(); }
+        } else if (dirty) {
+            uint32_t nb, mult; tuple_mode(i, nb, mult);
+            uint32_t total = nb == 1 ? g.m + 1 : g.m / nb + 2;
+            k_ref_tuples_bytes<<<(total + 255) / 256, 256, 0, ctx->st>>>(g.codes, g.m, nb, mult, dense + off[i]);
+            CKL();
+        }
     }
-    CK(cudaMemcpyAsync(out, ctx->scr_dense.p, off[n], cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(out, dense, off[n], cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
     ctx->stats.d2h_bytes += off[n] + n;
     memcpy(out_offsets, off.data(), ((size_t)n + 1) * 8);

@@ -160,6 +160,33 @@ int agcgpu_lz_cost_vector(agcgpu_ctx* ctx, const agcgpu_seg_req* req, int prefix
 int agcgpu_pack_ref_batch(agcgpu_ctx* ctx, const uint32_t* group_ids, uint32_t n, uint8_t* out, uint64_t out_cap,
                           uint64_t* out_offsets, uint8_t* out_use_tuples);
 
+/* ---- residual coder ---------------------------------------------------------------------------------------------- */
+/* ZSTD_compressCCtx(cctx, dst, cap, src, n, level) of the vendored zstd 1.5.5 (3rd_party/zstd/lib/compress/
+ * zstd_compress.c:5317) for a batch of independent inputs, as called from add_to_archive / add_to_archive_tuples
+ * (src/common/segment.h:176,201) and CCollection_V3::zstd_compress (src/common/collection_v3.cpp:139).
+ * Input i = src[src_offsets[i] .. src_offsets[i+1]), compressed at levels[i]; frame i = dst[dst_offsets[i] ..
+ * dst_offsets[i+1]).  Frames are byte-identical to libzstd 1.5.5's. */
+int agcgpu_zstd_compress_batch(agcgpu_ctx* ctx, const uint8_t* src, const uint64_t* src_offsets, const int32_t* levels,
+                               uint32_t n, uint8_t* dst, uint64_t dst_cap, uint64_t* dst_offsets);
+
+/* ---- CAGCCompressor facade (src/core/agc_compressor.h:754-763) for non-C++ callers -------------------------------- */
+typedef struct agcgpu_compressor agcgpu_compressor;
+/* CAGCCompressor::Create; dump_parts_path (may be NULL) = test hook writing every part's pre-zstd content */
+int agcgpu_compressor_create(const char* out_file, uint32_t pack_cardinality, uint32_t kmer_length, const char* reference_file,
+                             uint32_t segment_size, uint32_t min_match_len, int concatenated_genomes, int adaptive_compression,
+                             uint32_t verbosity, uint32_t no_threads, double fallback_frac, int device,
+                             const char* dump_parts_path, agcgpu_compressor** out);
+/* CAGCCompressor::AddSampleFiles */
+int agcgpu_compressor_add_sample_files(agcgpu_compressor* c, const char* const* sample_names, const char* const* file_names,
+                                       uint32_t n, uint32_t no_threads);
+/* CAGCCompressor::AddCmdLine */
+int agcgpu_compressor_add_cmd_line(agcgpu_compressor* c, const char* cmd_line);
+/* CAGCCompressor::Close, then frees the object */
+int agcgpu_compressor_close(agcgpu_compressor* c, uint32_t no_threads);
+const char* agcgpu_compressor_last_error(const agcgpu_compressor* c);   /* c may be NULL: last failed create */
+uint64_t agcgpu_compressor_total_bases(const agcgpu_compressor* c);
+agcgpu_ctx* agcgpu_compressor_ctx(agcgpu_compressor* c);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

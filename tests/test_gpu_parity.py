@@ -253,6 +253,11 @@ def test_pack_refs(dev_factory):
     refs = [rng.integers(0, 4, n).astype(np.uint8) for n in (0, 1, 2, 3, 4, 5, 17, 4096, 60031)]
     refs.append(np.tile(rng.integers(0, 4, 7).astype(np.uint8), 900))     # period 7 -> raw + level 19 (segment.h:251-254)
     refs.append(np.tile(rng.integers(0, 4, 40).astype(np.uint8), 200))    # period 40: not detected (lags 4..31 only)
+    r = rng.integers(0, 4, 5001).astype(np.uint8); r[100:130] = 4; refs.append(r)                 # N  -> 3 symbols / byte
+    r = rng.integers(0, 4, 5002).astype(np.uint8); r[7] = 5; r[4000:4003] = 4; refs.append(r)     # R  -> 3 / byte
+    r = rng.integers(0, 4, 5003).astype(np.uint8); r[9] = 11; refs.append(r)                      # B  -> 2 / byte
+    r = rng.integers(0, 4, 5004).astype(np.uint8); r[11] = 30; refs.append(r)                     # other -> raw + 0x10
+    r = np.full(3000, 4, np.uint8); r[::50] = 1; refs.append(r)                                    # N-rich and periodic
     dev.set_splitters(np.zeros(0, np.uint64))
     dev.scan_contigs([to_fasta_body(r) for r in refs])
     dev.put_references([(i, 0, len(r), False, 16 + i) for i, r in enumerate(refs)])

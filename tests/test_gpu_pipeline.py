@@ -1,0 +1,55 @@
+"""Whole-pipeline parity: agc-b200 create (GPU path) vs the reference binary (oracle/_ref/agc) on the same FASTA files.
+While the device residual coder is incomplete the comparison is made on the pre-zstd content of every part
+(--dump-parts vs the reference archive decoded with the reference's own libzstd); once agcgpu_zstd_compress_batch
+exists the archives are compared byte for byte."""
+import os
+import subprocess
+import sys
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import gen_data
+import agc_parts
+
+pytestmark = pytest.mark.gpu
+
+REF_AGC = os.path.join(ROOT, "oracle", "_ref", "agc")
+OUR_AGC = os.path.join(ROOT, "agc_b200", "bin", "agc-b200")
+
+
+def _run_both(tmp, files, flags):
+    ref_out = os.path.join(tmp, "ref.agc"); our_out = os.path.join(tmp, "our.agc"); dump = os.path.join(tmp, "our.dump")
+    subprocess.check_call([REF_AGC, "create", "-t", "4", "-o", ref_out] + flags + files, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    subprocess.check_call([OUR_AGC, "create", "-o", our_out, "--dump-parts", dump] + flags + files)
+    return agc_parts.compare_dump_to_archive(dump, ref_out)
+
+
+@pytest.mark.skipif(not os.path.exists(REF_AGC), reason="reference binary not built (make -f oracle/Makefile.ref)")
+@pytest.mark.parametrize("case", ["viral", "complex", "complex_n", "tiny", "smallpacks"])
+def test_parts_match_reference(tmp_path, case):
+    tmp = str(tmp_path)
+    if case == "viral":
+        files, _ = gen_data.viral(os.path.join(tmp, "d"), n_samples=40, ref_len=30000, p=0.01, seed=1)
+        flags = ["-k", "25"]
+    elif case == "complex":
+        files = gen_data.complex_collection(os.path.join(tmp, "d"), seed=5)
+        flags = ["-k", "21", "-s", "2000", "-b", "5"]
+    elif case == "complex_n":
+        files = gen_data.complex_collection(os.path.join(tmp, "d"), seed=6, with_n=True)
+        flags = ["-k", "31", "-s", "3000", "-l", "18", "-b", "4"]
+    elif case == "tiny":
+        rng = np.random.default_rng(3)
+        d = os.path.join(tmp, "d"); os.makedirs(d)
+        files = []
+        for i, nm in enumerate(["ref", "a", "b", "c"]):
+            fn = os.path.join(d, nm + ".fa")
+            gen_data.write_fasta(fn, [(f"{nm}{j}", rng.integers(0, 4, int(rng.integers(5, 28)), dtype=np.uint8)) for j in range(1 + i)])
+            files.append(fn)
+        flags = ["-k", "29", "-l", "22"]
+    else:
+        files, _ = gen_data.viral(os.path.join(tmp, "d"), n_samples=25, ref_len=9000, p=0.02, seed=9)
+        flags = ["-k", "17", "-s", "1000", "-b", "3", "-l", "15"]
+    bad = _run_both(tmp, files, flags)
+    assert not bad, "\n".join(bad[:10])

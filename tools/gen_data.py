@@ -1,0 +1,105 @@
+"""Synthetic genome collections: NumPy PCG64, reference = iid uniform ACGT, sample = reference with iid
+substitutions (+ optional indels / structural edits), FASTA upper-case, 80 columns, sample name = file stem."""
+import os
+import numpy as np
+
+LET = np.frombuffer(b"ACGTN", np.uint8)
+
+
+def write_fasta(path, contigs, width=80):
+    """contigs: list of (name, symbol array 0..4)"""
+    with open(path, "wb") as f:
+        for name, codes in contigs:
+            f.write(b">" + name.encode() + b"\n")
+            a = LET[np.asarray(codes, np.uint8)]
+            n = len(a)
+            if n == 0:
+                continue
+            full = (n // width) * width
+            if full:
+                rows = a[:full].reshape(-1, width)
+                out = np.empty((rows.shape[0], width + 1), np.uint8)
+                out[:, :width] = rows; out[:, width] = 10
+                f.write(out.tobytes())
+            if n > full:
+                f.write(a[full:].tobytes() + b"\n")
+
+
+def substitute(rng, ref, p):
+    t = ref.copy()
+    if p > 0 and len(t):
+        m = rng.random(len(t)) < p
+        t[m] = (t[m] + rng.integers(1, 4, int(m.sum()), dtype=np.uint8)) % 4
+    return t
+
+
+def indels(rng, t, n, maxlen=50):
+    t = list(t) if n else t
+    for _ in range(n):
+        pos = int(rng.integers(0, max(1, len(t))))
+        L = int(rng.integers(1, maxlen + 1))
+        if rng.random() < 0.5:
+            del t[pos:pos + L]
+        else:
+            t[pos:pos] = list(rng.integers(0, 4, L))
+    return np.asarray(t, np.uint8)
+
+
+def viral(out_dir, n_samples=1000, ref_len=30000, p=0.01, seed=1):
+    """config C2: one random reference, n_samples genomes with 1% SNPs, one contig each.  Returns file list (ref first)."""
+    os.makedirs(out_dir, exist_ok=True)
+    rng = np.random.default_rng(seed)
+    ref = rng.integers(0, 4, ref_len, dtype=np.uint8)
+    files = [os.path.join(out_dir, "ref.fa")]
+    write_fasta(files[0], [("ref_ctg1", ref)])
+    for i in range(n_samples):
+        fn = os.path.join(out_dir, f"s{i:04d}.fa")
+        write_fasta(fn, [(f"s{i:04d}_ctg1", substitute(rng, ref, p))])
+        files.append(fn)
+    return files, (n_samples + 1) * ref_len if p == 0 else None
+
+
+def complex_collection(out_dir, seed=5, n_samples=12, ctg_len=40000, n_ctg=3, with_n=False):
+    """small multi-contig collection that exercises the rare add_segment branches: deleted splitters (missing middle),
+    one-sided segments, reverse-complemented contigs, novel contigs without splitters, duplicated sequences"""
+    os.makedirs(out_dir, exist_ok=True)
+    rng = np.random.default_rng(seed)
+    ref = [rng.integers(0, 4, ctg_len + 1000 * i, dtype=np.uint8) for i in range(n_ctg)]
+    files = [os.path.join(out_dir, "ref.fa")]
+    write_fasta(files[0], [(f"chr{i + 1} some description", c) for i, c in enumerate(ref)])
+    for s in range(n_samples):
+        ctgs = []
+        for i, c in enumerate(ref):
+            t = substitute(rng, c, [0.0, 0.001, 0.01, 0.05][s % 4])
+            t = indels(rng, t, s % 3)
+            if s % 4 == 1 and len(t) > 9000:
+                a = int(rng.integers(1000, len(t) - 8000)); t = np.concatenate([t[:a], t[a + int(rng.integers(1500, 6000)):]])   # big deletion
+            if s % 5 == 2:
+                t = (3 - t[::-1]).astype(np.uint8)                     # reverse complement
+            if s % 6 == 3:
+                t = t[int(rng.integers(100, 3000)):len(t) - int(rng.integers(100, 3000))]   # trimmed ends
+            if with_n and s % 2 == 0 and len(t) > 5000:
+                a = int(rng.integers(0, len(t) - 600)); t = t.copy(); t[a:a + int(rng.integers(1, 500))] = 4
+            ctgs.append((f"smp{s}_chr{i + 1}", t))
+        if s % 3 == 0:
+            ctgs.append((f"smp{s}_novel", rng.integers(0, 4, int(rng.integers(50, 5000)), dtype=np.uint8)))
+        if s % 4 == 2:
+            ctgs.append((f"smp{s}_tiny", rng.integers(0, 4, 12, dtype=np.uint8)))
+        if s % 7 == 5:
+            ctgs = ctgs[::-1]
+        if s == n_samples - 1:
+            ctgs = [(f"smp{s}_copy{i}", c) for i, c in enumerate(ref)]   # identical to the reference: empty deltas
+        fn = os.path.join(out_dir, f"smp{s:02d}.fa")
+        write_fasta(fn, ctgs)
+        files.append(fn)
+    return files
+
+
+def total_bases(files):
+    n = 0
+    for fn in files:
+        with open(fn, "rb") as f:
+            for line in f:
+                if not line.startswith(b">"):
+                    n += len(line.rstrip(b"\r\n"))
+    return n
