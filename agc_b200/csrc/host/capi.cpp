@@ -36,6 +36,24 @@ int agcgpu_compressor_add_sample_files(agcgpu_compressor* c, const char* const* 
     return c->impl.AddSampleFiles(v, no_threads) ? 0 : AGCGPU_ECUDA;
 }
 
+int agcgpu_compressor_add_samples_memory(agcgpu_compressor* c, const char* const* sample_names, uint32_t n_samples,
+                                         const uint32_t* sample_of_contig, const char* const* contig_ids, uint32_t n_contigs,
+                                         const void* raw, const uint64_t* offsets, int raw_is_device)
+{
+    if (!c || !sample_names || !sample_of_contig || !contig_ids || !raw || !offsets) return AGCGPU_EINVAL;
+    std::vector<std::string> sn(sample_names, sample_names + n_samples), ci(contig_ids, contig_ids + n_contigs);
+    std::vector<uint32_t> soc(sample_of_contig, sample_of_contig + n_contigs);
+    for (auto s : soc) if (s >= n_samples) return AGCGPU_EINVAL;
+    return c->impl.AddSamplesFromMemory(sn, soc, ci, (const uint8_t*)raw, offsets, raw_is_device != 0) ? 0 : AGCGPU_ECUDA;
+}
+
+int agcgpu_compressor_set_discard_parts(agcgpu_compressor* c, int discard)
+{
+    if (!c) return AGCGPU_EINVAL;
+    c->impl.SetDiscardParts(discard != 0);
+    return 0;
+}
+
 int agcgpu_compressor_add_cmd_line(agcgpu_compressor* c, const char* cmd_line)
 {
     if (!c || !cmd_line) return AGCGPU_EINVAL;

@@ -401,7 +401,7 @@ void CAGCCompressor::store_pack(uint32_t group_id, GroupState& g, uint64_t ep)
     size_t sz = 0; for (auto& x : g.pack) sz += x.size() + 1;
     pack.reserve(sz);
     for (auto& x : g.pack) { pack.insert(pack.end(), x.begin(), x.end()); pack.push_back(0xff); }
-    j.raw_size = pack.size();
+    j.raw_size = pack.size(); j.fallback_size = pack.size();
     j.tasks.emplace_back(); j.tasks[0].level = 17; j.tasks[0].raw = pack;
     j.fallback_raw = std::move(pack);
     add_job(std::move(j));
@@ -451,6 +451,7 @@ bool CAGCCompressor::flush_jobs(bool)
         if (a.epoch != b.epoch) return a.epoch < b.epoch;
         if (a.stream_id != b.stream_id) return a.stream_id < b.stream_id;
         return a.seq < b.seq; });
+    if (discard_parts) { jobs.clear(); return true; }
     if (dump_f) {
         for (auto& j : jobs) {
             fwrite("PART", 1, 4, dump_f);
@@ -468,10 +469,13 @@ bool CAGCCompressor::flush_jobs(bool)
     for (auto& j : jobs) {
         if (j.kind == 0 || j.kind == 1) {                       // add_to_archive / add_to_archive_tuples (segment.h:172-215)
             auto& pk = j.tasks[0].packed;
-            if ((uint32_t)pk.size() + 1u < (uint32_t)j.fallback_raw.size()) {
+            if ((uint32_t)pk.size() + 1u < (uint32_t)j.fallback_size) {
                 pk.push_back((uint8_t)j.kind);
-                out_archive.AddPart(j.stream_id, pk, j.fallback_raw.size());
-            } else out_archive.AddPart(j.stream_id, j.fallback_raw, 0);
+                out_archive.AddPart(j.stream_id, pk, j.fallback_size);
+            } else {
+                if (j.fallback_raw.size() != j.fallback_size) return fail("internal: raw fallback of a large reference was not fetched");
+                out_archive.AddPart(j.stream_id, j.fallback_raw, 0);
+            }
         } else if (j.kind == 2) out_archive.AddPart(j.stream_id, j.tasks[0].packed, j.raw_size);
         else {                                                  // store_batch_contig_details (collection_v3.cpp:225-257)
             std::vector<uint8_t> v;
@@ -529,17 +533,43 @@ bool CAGCCompressor::process_batch(std::vector<std::vector<uint8_t>>& raws, std:
     for (uint32_t i = 0; i < nc; ++i) offs[i + 1] = offs[i] + raws[i].size();
     std::vector<uint8_t> cat(offs[nc] + 1);
     for (uint32_t i = 0; i < nc; ++i) { memcpy(cat.data() + offs[i], raws[i].data(), raws[i].size()); std::vector<uint8_t>().swap(raws[i]); }
+    return process_batch_raw(cat.data(), false, offs, owners);
+}
+
+bool CAGCCompressor::AddSamplesFromMemory(const std::vector<std::string>& sample_names, const std::vector<uint32_t>& sample_of_contig,
+                                          const std::vector<std::string>& contig_ids, const uint8_t* raw, const uint64_t* offsets, bool raw_is_device)
+{
+    if (!working) return false;
+    std::vector<BatchContig> owners;
+    uint32_t prev = ~0u;
+    for (size_t i = 0; i < contig_ids.size(); ++i) {
+        if (sample_of_contig[i] != prev) { collection.reset_prev_sample_name(); prev = sample_of_contig[i]; }
+        if (!collection.register_sample_contig(sample_names[sample_of_contig[i]], contig_ids[i]))
+            return fail("Error: Pair sample_name:contig_name " + sample_names[sample_of_contig[i]] + ":" + contig_ids[i] + " is already in the archive!");
+        uint32_t sid = (uint32_t)collection.sample_desc.size() - 1;
+        owners.push_back(BatchContig{ sid, (uint32_t)collection.sample_desc[sid].contigs.size() - 1 });
+    }
+    std::vector<uint64_t> offs(offsets, offsets + contig_ids.size() + 1);
+    if (!process_batch_raw(raw, raw_is_device, offs, owners)) return false;
+    if (processed_samples % pack_cardinality != 0)
+        store_contig_batch((processed_samples / pack_cardinality) * pack_cardinality, processed_samples, epoch);
+    ++epoch;
+    return flush_jobs(false);
+}
+
+bool CAGCCompressor::process_batch_raw(const uint8_t* cat, bool is_device, const std::vector<uint64_t>& offs, std::vector<BatchContig>& owners)
+{
+    const uint32_t nc = (uint32_t)owners.size();
     std::vector<uint64_t> clen(nc + 1);
     uint64_t cap_cuts = offs[nc] / std::max<uint32_t>(segment_size / 4, 16) + 4ull * nc + 64, n_cuts = 0;
     std::vector<agcgpu_cut> cuts(cap_cuts);
-    int rc = agcgpu_scan_contigs(ctx, cat.data(), offs.data(), nc, clen.data(), cuts.data(), cap_cuts, &n_cuts);
-    if (rc == AGCGPU_EOVERFLOW && n_cuts > cap_cuts) {
-        cap_cuts = n_cuts + 16; cuts.resize(cap_cuts);
-        rc = agcgpu_scan_contigs(ctx, cat.data(), offs.data(), nc, clen.data(), cuts.data(), cap_cuts, &n_cuts);
-    }
+    auto do_scan = [&]() {
+        return is_device ? agcgpu_scan_contigs_dev(ctx, cat, offs[nc], offs.data(), nc, clen.data(), cuts.data(), cap_cuts, &n_cuts)
+                         : agcgpu_scan_contigs(ctx, cat, offs.data(), nc, clen.data(), cuts.data(), cap_cuts, &n_cuts); };
+    int rc = do_scan();
+    if (rc == AGCGPU_EOVERFLOW && n_cuts > cap_cuts) { cap_cuts = n_cuts + 16; cuts.resize(cap_cuts); rc = do_scan(); }
     if (!gpu_ok(rc, "scan_contigs")) return false;
     cuts.resize(n_cuts);
-    std::vector<uint8_t>().swap(cat);
     for (uint32_t i = 0; i < nc; ++i) total_bases += clen[i];
 
     // cut ranges per contig
@@ -562,27 +592,55 @@ bool CAGCCompressor::process_batch(std::vector<std::vector<uint8_t>>& raws, std:
     auto seg_req = [&](uint32_t bc, uint64_t start, uint32_t len, bool is_rc, uint32_t group, uint32_t bound) {
         agcgpu_seg_req q; q.contig = bc; q.is_rc = is_rc; q.start = start; q.len = len; q.group_id = group; q.bound = bound; q.reserved = 0; return q; };
 
-    // find_cand_segment_with_one_splitter (agc_compressor.cpp:1630-1808)
-    auto one_splitter = [&](uint64_t kdir, uint64_t krc, uint32_t bc, uint64_t start, uint32_t len, bool dir_is_rc,
+    // find_cand_segment_with_one_splitter (agc_compressor.cpp:1630-1808).  The CSegment::estimate calls of ALL one-sided
+    // segments of the batch are issued as one agcgpu_lz_estimate_batch (re-issued after a registration changed the map).
+    struct Cand { uint64_t a, b; bool rc; uint32_t group; };
+    auto candidates_of = [&](uint64_t kd, std::vector<Cand>& cands) {
+        cands.clear();
+        auto p = map_segments_terminators.find(kd);
+        if (p == map_segments_terminators.end()) return;
+        for (auto ck : p->second) {
+            Cand c;
+            if (ck < kd) { c.a = ck; c.b = kd; c.rc = true; } else { c.a = kd; c.b = ck; c.rc = false; }
+            c.group = (uint32_t)map_segments[std::make_pair(c.a, c.b)];
+            cands.push_back(c);
+        }
+    };
+    std::vector<std::vector<uint32_t>> est_cache(n_cuts);
+    std::vector<uint8_t> est_valid(n_cuts, 0);
+    auto prefetch_estimates = [&](uint64_t from_cut) -> bool {
+        std::vector<agcgpu_seg_req> rq; std::vector<uint64_t> owner; std::vector<Cand> cands;
+        for (uint64_t x = from_cut; x < n_cuts; ++x) {
+            const agcgpu_cut& c = cuts[x];
+            est_valid[x] = 0; est_cache[x].clear();
+            if (c.has_front == c.has_back) continue;
+            const bool front = c.has_front != 0;
+            const uint64_t kd = front ? canon(c.front_dir, c.front_rc) : canon(c.back_dir, c.back_rc);
+            const bool dir_is_rc = !front;
+            const uint32_t len = (uint32_t)c.len;
+            const uint32_t bound = len < 16 ? len : len - 16u;
+            candidates_of(kd, cands);
+            for (auto& cd : cands) { rq.push_back(seg_req(c.contig, c.start, len, cd.rc ? !dir_is_rc : dir_is_rc, cd.group, bound)); owner.push_back(x); }
+            est_valid[x] = 1;
+        }
+        if (rq.empty()) return true;
+        std::vector<uint32_t> est(rq.size());
+        if (!gpu_ok(agcgpu_lz_estimate_batch(ctx, rq.data(), (uint32_t)rq.size(), est.data()), "lz_estimate")) return false;
+        for (size_t i = 0; i < rq.size(); ++i) est_cache[owner[i]].push_back(est[i]);
+        return true;
+    };
+    if (!prefetch_estimates(0)) return false;
+    auto one_splitter = [&](uint64_t x, uint64_t kdir, uint64_t krc, uint32_t len,
                             std::pair<uint64_t, uint64_t>& best_pk, bool& is_best_rc) -> bool {
         const uint64_t kd = canon(kdir, krc);
         const bool dir_oriented = kdir <= krc;
         best_pk = std::make_pair(EMPTY, EMPTY); is_best_rc = false;
         uint64_t best_est = len < 16 ? len : len - 16u;
-        auto p = map_segments_terminators.find(kd);
-        if (p != map_segments_terminators.end()) {
-            struct Cand { uint64_t a, b; bool rc; uint32_t group; };
-            std::vector<Cand> cands;
-            for (auto ck : p->second) {
-                Cand c;
-                if (ck < kd) { c.a = ck; c.b = kd; c.rc = true; } else { c.a = kd; c.b = ck; c.rc = false; }
-                c.group = (uint32_t)map_segments[std::make_pair(c.a, c.b)];
-                cands.push_back(c);
-            }
-            std::vector<agcgpu_seg_req> rq;
-            for (auto& c : cands) rq.push_back(seg_req(bc, start, len, c.rc ? !dir_is_rc : dir_is_rc, c.group, (uint32_t)best_est));
-            std::vector<uint32_t> est(rq.size());
-            if (!rq.empty() && !gpu_ok(agcgpu_lz_estimate_batch(ctx, rq.data(), (uint32_t)rq.size(), est.data()), "lz_estimate")) return false;
+        std::vector<Cand> cands;
+        candidates_of(kd, cands);
+        if (!cands.empty()) {
+            if (!est_valid[x] || est_cache[x].size() != cands.size()) return fail("internal: estimate cache out of date");
+            const std::vector<uint32_t>& est = est_cache[x];
             for (size_t i = 0; i < cands.size(); ++i) if ((uint64_t)est[i] < best_est) best_est = est[i];
             for (size_t i = 0; i < cands.size(); ++i) {
                 auto cpk = std::make_pair(cands[i].a, cands[i].b);
@@ -662,10 +720,10 @@ bool CAGCCompressor::process_batch(std::vector<std::vector<uint8_t>>& raws, std:
                 if (!cut.has_front && !cut.has_back) pk = std::make_pair(EMPTY, EMPTY);
                 else if (cut.has_front && cut.has_back) { pk = std::make_pair(as.key1, as.key2); store_rc = as.is_rc; }
                 else if (cut.has_front) {
-                    if (!one_splitter(cut.front_dir, cut.front_rc, bc, it.start, it.len, false, pk, store_rc)) return false;
+                    if (!one_splitter(x, cut.front_dir, cut.front_rc, it.len, pk, store_rc)) return false;
                 } else {
                     bool store_dir = false;      // kmer = kmer_back with swap_dir_rc; "segment_dir" is the reverse complement
-                    if (!one_splitter(cut.back_rc, cut.back_dir, bc, it.start, it.len, true, pk, store_dir)) return false;
+                    if (!one_splitter(x, cut.back_rc, cut.back_dir, it.len, pk, store_dir)) return false;
                     store_rc = !store_dir;
                 }
                 // map_segments.find(pk): the device hash-assign already answered it for the two-splitter / no-splitter classes
@@ -774,6 +832,7 @@ bool CAGCCompressor::process_batch(std::vector<std::vector<uint8_t>>& raws, std:
             if (!gpu_ok(agcgpu_map_insert(ctx, ins_k1.data(), ins_k2.data(), ins_g.data(), ins_g.size()), "map_insert")) return false;
             if (!gpu_ok(agcgpu_group_put_reference_batch(ctx, new_refs.data(), (uint32_t)new_refs.size()), "put_reference")) return false;
             if (!run_assign(cut_first[cj])) return false;
+            if (!prefetch_estimates(cut_first[cj])) return false;
         }
         regs.push_back(std::move(reg));
         ci = cj;
@@ -832,8 +891,10 @@ bool CAGCCompressor::process_batch(std::vector<std::vector<uint8_t>>& raws, std:
                     j.tasks[0].raw.assign(refpay.begin() + roffs[ref_i], refpay.begin() + roffs[ref_i + 1]);
                     j.raw_size = it.len;
                     // fallback ("packed+1 >= raw"): the raw symbols; only tiny references can hit it
-                    if (ruse[ref_i]) { j.fallback_raw.resize(it.len ? it.len : 1); if (!gpu_ok(agcgpu_get_segment(ctx, it.batch_contig, it.start, it.len, it.is_rc, j.fallback_raw.data()), "get_segment")) return false; j.fallback_raw.resize(it.len); }
-                    else j.fallback_raw = j.tasks[0].raw;
+                    // (tuples of >= 256 symbols are <= n/4+2 bytes: the zstd frame can never reach n-1 bytes, so no fetch)
+                    j.fallback_size = it.len;
+                    if (!ruse[ref_i]) j.fallback_raw = j.tasks[0].raw;
+                    else if (it.len < 256) { j.fallback_raw.resize(it.len ? it.len : 1); if (!gpu_ok(agcgpu_get_segment(ctx, it.batch_contig, it.start, it.len, it.is_rc, j.fallback_raw.data()), "get_segment")) return false; j.fallback_raw.resize(it.len); }
                     add_job(std::move(j));
                     ++ref_i; ++g.no_seqs;
                     in_group_id = 0;
@@ -882,6 +943,7 @@ bool CAGCCompressor::Close(uint32_t)
     fti["file_version_major"] = "3"; fti["file_version_minor"] = "0";
     fti["comment"] = "AGC (Assembled Genomes Compressor) v. 3.2.2 [build 20260326.1]";
     std::vector<uint8_t> v_fti; for (auto& x : fti) { astr(v_fti, x.first); astr(v_fti, x.second); }
+    if (discard_parts) { out_archive.Close(); return true; }
     if (dump_f) {
         auto dump_imm = [&](const char* name, const std::vector<uint8_t>& d, uint64_t meta) {
             fwrite("IMMD", 1, 4, dump_f); dump_bytes(dump_f, name, strlen(name)); dump_u64(dump_f, meta); dump_bytes(dump_f, d.data(), d.size()); };

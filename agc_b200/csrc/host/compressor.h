@@ -97,6 +97,7 @@ struct PartJob {
     uint64_t epoch; int stream_id; uint64_t seq;
     int kind;                // 0 plain (marker 0), 1 tuples (marker 1), 2 collection part (frame only), 3 collection details (5 frames)
     uint64_t raw_size;       // metadata when the packed form is kept
+    uint64_t fallback_size = 0;          // size of the un-coded form (the part's metadata when the coded form is kept)
     std::vector<uint8_t> fallback_raw;   // kinds 0/1: stored as is with metadata 0 when packed+1 >= raw (segment.h:180-187)
     std::vector<ZTask> tasks;
 };
@@ -109,6 +110,12 @@ public:
                 uint32_t segment_size, uint32_t min_match_len, bool concatenated_genomes, bool adaptive_compression,
                 uint32_t verbosity, uint32_t no_threads, double fallback_frac);
     bool AddSampleFiles(std::vector<std::pair<std::string, std::string>> v_sample_file_name, uint32_t no_threads);
+    // Same as AddSampleFiles for contigs that are already in memory (raw FASTA bodies as ReadContigRaw returns them):
+    // contig i = raw[offsets[i] .. offsets[i+1]) belongs to sample_of_contig[i]; `raw` is a host pointer, or a device
+    // pointer when raw_is_device (the HBM-resident entry used by bench.py).  Samples must be contiguous and ordered.
+    bool AddSamplesFromMemory(const std::vector<std::string>& sample_names, const std::vector<uint32_t>& sample_of_contig,
+                              const std::vector<std::string>& contig_ids, const uint8_t* raw, const uint64_t* offsets, bool raw_is_device);
+    void SetDiscardParts(bool d) { discard_parts = d; }              // bench hook: build every part, skip residual coder + file
     void AddCmdLine(const std::string& cmd_line);
     bool Close(uint32_t no_threads = 1);
 
@@ -141,6 +148,7 @@ private:
     bool fail(const std::string& msg);
     bool gpu_ok(int rc, const char* what);
     bool process_batch(std::vector<std::vector<uint8_t>>& raws, std::vector<BatchContig>& owners);
+    bool process_batch_raw(const uint8_t* cat, bool is_device, const std::vector<uint64_t>& offs, std::vector<BatchContig>& owners);
     bool flush_jobs(bool final_flush);
     bool compress_tasks(std::vector<ZTask*>& tasks);
     void add_job(PartJob&& j);
@@ -154,6 +162,7 @@ private:
     int device = 0;
     uint64_t batch_bases = 1ull << 30;
     std::string dump_path, last_error;
+    bool discard_parts = false;
     FILE* dump_f = nullptr;
 
     agcgpu_ctx* ctx = nullptr;

@@ -397,7 +397,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase)
 
 // ------------------------------------------------------------------------------------------------ LZ kernels
 template <int MODE>
-__global__ void __launch_bounds__(LZ_THREADS, 1) k_lz_packed(
+__global__ void __launch_bounds__(LZ_THREADS, 2) k_lz_packed(
     const uint64_t* __restrict__ P, const GroupRefDev* __restrict__ groups, const LzReqDev* __restrict__ reqs,
     const LzUnit* __restrict__ units, uint32_t mml, uint32_t stage_limit, uint8_t* __restrict__ slab,
     uint32_t* __restrict__ res, uint32_t* __restrict__ costv, int prefix, uint32_t* __restrict__ err)
@@ -408,7 +408,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lz_packed(
     const LzUnit u = units[blockIdx.x];
     const GroupRefDev g = groups[u.group];
     const uint32_t ht_bytes = g.ht_size * ((g.flags & GRF_SHORT) ? 2u : 4u);
-    const bool stage = (g.packed_bytes + ht_bytes <= stage_limit) && u.count >= 2;
+    const bool stage = (g.packed_bytes + ht_bytes <= stage_limit);
     const uint8_t* refp = g.packed;
     const void* htp = g.ht;
     if (threadIdx.x == 0) { next_req = 0; if (stage) mbar_init(&bar, 1); }
@@ -859,7 +859,8 @@ int agc_lz_run(agcgpu_ctx* ctx, int mode, const agcgpu_seg_req* reqs, uint32_t n
     }
     std::stable_sort(packed_reqs.begin(), packed_reqs.end(), [](const LzReqDev& a, const LzReqDev& b) { return a.group < b.group; });
     // units: requests of one group, at most UNIT_MAX per CTA; longest-first inside a group helps the tail
-    const uint32_t UNIT_MAX = 64;
+    // unit size: enough CTAs to cover every SM twice, at most one request per warp of a CTA
+    const uint32_t UNIT_MAX = (uint32_t)std::min<size_t>(16, std::max<size_t>(1, (packed_reqs.size() + 2 * (size_t)ctx->n_sm - 1) / (2 * (size_t)ctx->n_sm)));
     std::vector<LzUnit> units;
     size_t smem_need = 0;
     for (size_t a = 0; a < packed_reqs.size();) {

@@ -179,6 +179,14 @@ int agcgpu_compressor_create(const char* out_file, uint32_t pack_cardinality, ui
 /* CAGCCompressor::AddSampleFiles */
 int agcgpu_compressor_add_sample_files(agcgpu_compressor* c, const char* const* sample_names, const char* const* file_names,
                                        uint32_t n, uint32_t no_threads);
+/* AddSampleFiles for contigs already in memory: contig i = raw[offsets[i] .. offsets[i+1]) (raw FASTA body, as
+ * CGenomeIO::ReadContigRaw returns it) of sample sample_of_contig[i] (samples contiguous, in order).  raw is a host
+ * pointer, or a device pointer when raw_is_device != 0 (16-byte aligned, readable up to offsets[n] rounded up to 16). */
+int agcgpu_compressor_add_samples_memory(agcgpu_compressor* c, const char* const* sample_names, uint32_t n_samples,
+                                         const uint32_t* sample_of_contig, const char* const* contig_ids, uint32_t n_contigs,
+                                         const void* raw, const uint64_t* offsets, int raw_is_device);
+/* measurement hook: build every archive part but skip the residual coder and the file writes */
+int agcgpu_compressor_set_discard_parts(agcgpu_compressor* c, int discard);
 /* CAGCCompressor::AddCmdLine */
 int agcgpu_compressor_add_cmd_line(agcgpu_compressor* c, const char* cmd_line);
 /* CAGCCompressor::Close, then frees the object */
