@@ -1,0 +1,19 @@
+// TEST INFRASTRUCTURE ONLY: host build of agc_b200/csrc/zstd_enc.cuh so the CPU test-suite can diff the residual coder
+// against the reference's libzstd without a GPU.  The product (libagcgpu.so) only contains the device build.
+#include "../../agc_b200/csrc/zstd_enc.cuh"
+#include <cstdlib>
+#include <cstring>
+extern "C" {
+__attribute__((visibility("default"))) long ze_host_compress(const unsigned char* src, unsigned long n, int level, unsigned char* dst, unsigned long cap)
+{
+    ze::Params cp = ze::get_params(level, n);
+    if (!cp.supported) return -1;
+    ze::WorkSizes z = ze::work_sizes(cp);
+    unsigned char* mem = (unsigned char*)calloc(z.total + 64, 1);
+    int err = 0;
+    unsigned long r = ze::compress_frame(src, n, level, dst, cap, mem, &err);
+    free(mem);
+    return err ? -(long)err - 1 : (long)r;
+}
+__attribute__((visibility("default"))) unsigned long ze_host_bound(unsigned long n) { return ze::compress_bound(n); }
+}
