@@ -49,7 +49,7 @@ EXPORTED_SYMBOLS = [
     "agcgpu_determine_splitters", "agcgpu_set_splitters", "agcgpu_scan_contigs", "agcgpu_scan_contigs_dev",
     "agcgpu_get_segment", "agcgpu_map_insert", "agcgpu_assign_cuts", "agcgpu_group_put_reference_batch",
     "agcgpu_group_put_reference", "agcgpu_group_get_index", "agcgpu_lz_encode_batch", "agcgpu_lz_estimate_batch",
-    "agcgpu_lz_cost_vector", "agcgpu_pack_ref_batch",
+    "agcgpu_lz_cost_vector", "agcgpu_pack_ref_batch", "agcgpu_zstd_compress_batch",
 ]
 
 
@@ -95,6 +95,8 @@ def lib():
     L.agcgpu_lz_cost_vector.restype = C.c_int; L.agcgpu_lz_cost_vector.argtypes = [vp, C.POINTER(SegReq), C.c_int, u32p]
     L.agcgpu_pack_ref_batch.restype = C.c_int
     L.agcgpu_pack_ref_batch.argtypes = [vp, u32p, C.c_uint32, u8p, C.c_uint64, u64p, u8p]
+    L.agcgpu_zstd_compress_batch.restype = C.c_int
+    L.agcgpu_zstd_compress_batch.argtypes = [vp, u8p, u64p, i32p, C.c_uint32, u8p, C.c_uint64, u64p]
     _LIB = L
     return L
 
@@ -256,6 +258,19 @@ class Device:
         out = np.zeros(max(req[2], 1), np.uint32)
         self._ck(self.L.agcgpu_lz_cost_vector(self.h, arr, int(bool(prefix_costs)), _p(out, u32p)))
         return out[:req[2]].copy()
+
+    def zstd_compress(self, inputs, levels):
+        """ZSTD_compressCCtx(level) of every input on the device -> list of frames"""
+        offs = np.zeros(len(inputs) + 1, np.uint64)
+        if inputs:
+            offs[1:] = np.cumsum([len(x) for x in inputs])
+        src = np.frombuffer(b"".join(inputs), np.uint8).copy() if offs[-1] else np.zeros(1, np.uint8)
+        lv = np.ascontiguousarray(levels, np.int32)
+        cap = int(offs[-1]) + int(offs[-1]) // 128 + 1024 * (len(inputs) + 1)
+        dst = np.zeros(cap, np.uint8)
+        doffs = np.zeros(len(inputs) + 1, np.uint64)
+        self._ck(self.L.agcgpu_zstd_compress_batch(self.h, _p(src, u8p), _p(offs, u64p), _p(lv, i32p), len(inputs), _p(dst, u8p), cap, _p(doffs, u64p)))
+        return [dst[int(doffs[i]):int(doffs[i + 1])].tobytes() for i in range(len(inputs))]
 
     def pack_refs(self, group_ids, cap):
         ids = np.ascontiguousarray(group_ids, np.uint32)

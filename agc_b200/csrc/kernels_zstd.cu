@@ -1,9 +1,106 @@
-// kernels_zstd.cu -- residual coder (zstd 1.5.5 frame producer).  Placeholder until the device coder lands:
-// fails loudly (AGCGPU_EUNSUPPORTED) -- there is deliberately no host fallback.
+// kernels_zstd.cu -- residual coder on the device: agcgpu_zstd_compress_batch = ZSTD_compressCCtx(level) for a batch of
+// independent inputs.  The frame producer itself is zstd_enc.cuh (bit-identical to the reference's
+// vendored libzstd; see the header for the function-by-function citations).
+//
+// Mapping: one warp per input; inputs are independent so the batch is the parallel dimension (HPP scale: ~10^5 frames
+// per batch).  The optimal parser is a sequential dynamic program over a binary-tree match finder -- latency bound
+// pointer chasing -- so each warp runs it with warp-uniform control flow; tables live in a per-input workspace in HBM
+// (hash / chain tables are L2 resident for the <= 128 KB classes).  Largest inputs are scheduled first.
 #include "internal.cuh"
-extern "C" int agcgpu_zstd_compress_batch(agcgpu_ctx* ctx, const uint8_t*, const uint64_t*, const int32_t*, uint32_t,
-                                          uint8_t*, uint64_t, uint64_t*)
+#include "zstd_enc.cuh"
+#include <algorithm>
+#include <numeric>
+
+struct ZTaskDev {
+    const uint8_t* src; uint8_t* dst; uint8_t* mem;
+    uint64_t n, dst_cap;
+    int32_t level; int32_t err;
+    uint64_t out_size;
+};
+
+__global__ void __launch_bounds__(32) k_zstd(ZTaskDev* __restrict__ tasks, uint32_t n_tasks)
 {
-    if (!ctx) return AGCGPU_EINVAL;
-    return agc_fail(ctx, AGCGPU_EUNSUPPORTED, "agcgpu_zstd_compress_batch: device residual coder not built yet");
+    uint32_t t = blockIdx.x;
+    if (t >= n_tasks) return;
+    if (threadIdx.x != 0) return;
+    ZTaskDev& k = tasks[t];
+    int err = 0;
+    uint64_t r = ze::compress_frame(k.src, k.n, k.level, k.dst, k.dst_cap, k.mem, &err);
+    k.err = err; k.out_size = r;
+}
+
+extern "C" int agcgpu_zstd_compress_batch(agcgpu_ctx* ctx, const uint8_t* src, const uint64_t* src_offsets, const int32_t* levels,
+                                          uint32_t n, uint8_t* dst, uint64_t dst_cap, uint64_t* dst_offsets)
+{
+    if (!ctx || !src_offsets || !dst_offsets || (n && (!src || !levels || !dst))) return AGCGPU_EINVAL;
+    cudaSetDevice(ctx->dev);
+    dst_offsets[0] = 0;
+    if (n == 0) return 0;
+    // per-input parameters, workspace and output sizes
+    std::vector<uint64_t> ws(n), ob(n);
+    uint64_t total_src = src_offsets[n];
+    for (uint32_t i = 0; i < n; ++i) {
+        uint64_t len = src_offsets[i + 1] - src_offsets[i];
+        ze::Params cp = ze::get_params(levels[i], len);
+        if (!cp.supported)
+            return agc_fail(ctx, AGCGPU_EUNSUPPORTED, "zstd: input %u (level %d, %llu bytes) is outside the implemented envelope "
+                            "(levels 13/17/18/19; level 13 above 256 KB uses btlazy2)", i, levels[i], (unsigned long long)len);
+        ws[i] = (ze::work_sizes(cp).total + 255) / 256 * 256;
+        ob[i] = (ze::compress_bound(len) + 64 + 255) / 256 * 256;
+    }
+    // schedule: biggest inputs first; waves bounded by a workspace budget
+    std::vector<uint32_t> order(n);
+    std::iota(order.begin(), order.end(), 0u);
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+        return src_offsets[a + 1] - src_offsets[a] > src_offsets[b + 1] - src_offsets[b]; });
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    const uint64_t budget = std::max<uint64_t>((uint64_t)(free_b * 0.6), 512ull << 20);
+    if (int r = agc_reserve(ctx, ctx->scr_bytes, total_src + 64)) return r;
+    CK(cudaMemcpyAsync(ctx->scr_bytes.p, src, total_src, cudaMemcpyHostToDevice, ctx->st));
+    ctx->stats.h2d_bytes += total_src;
+    std::vector<uint64_t> out_size(n, 0);
+    std::vector<std::vector<uint8_t>> frames(n);
+    size_t pos = 0;
+    while (pos < n) {
+        size_t end = pos; uint64_t wsum = 0, osum = 0;
+        while (end < n && (end == pos || wsum + ws[order[end]] + osum + ob[order[end]] <= budget)) { wsum += ws[order[end]]; osum += ob[order[end]]; ++end; }
+        if (ws[order[pos]] + ob[order[pos]] > (uint64_t)free_b)
+            return agc_fail(ctx, AGCGPU_ENOMEM, "zstd: not enough device memory for one %llu-byte workspace", (unsigned long long)ws[order[pos]]);
+        uint32_t cnt = (uint32_t)(end - pos);
+        if (int r = agc_reserve(ctx, ctx->scr_out, wsum + 256)) return r;
+        if (int r = agc_reserve(ctx, ctx->scr_dense, osum + 256)) return r;
+        if (int r = agc_reserve(ctx, ctx->scr_req, cnt * sizeof(ZTaskDev))) return r;
+        CK(cudaMemsetAsync(ctx->scr_out.p, 0, wsum, ctx->st));
+        std::vector<ZTaskDev> tasks(cnt);
+        uint64_t wo = 0, oo = 0;
+        for (uint32_t j = 0; j < cnt; ++j) {
+            uint32_t i = order[pos + j];
+            ZTaskDev& k = tasks[j];
+            k.src = (const uint8_t*)ctx->scr_bytes.p + src_offsets[i]; k.n = src_offsets[i + 1] - src_offsets[i];
+            k.dst = (uint8_t*)ctx->scr_dense.p + oo; k.dst_cap = ob[i]; k.mem = (uint8_t*)ctx->scr_out.p + wo;
+            k.level = levels[i]; k.err = 0; k.out_size = 0;
+            wo += ws[i]; oo += ob[i];
+        }
+        CK(cudaMemcpyAsync(ctx->scr_req.p, tasks.data(), cnt * sizeof(ZTaskDev), cudaMemcpyHostToDevice, ctx->st));
+        CK(cudaDeviceSetLimit(cudaLimitStackSize, 16384));
+        k_zstd<<<cnt, 32, 0, ctx->st>>>((ZTaskDev*)ctx->scr_req.p, cnt);
+        CKL();
+        CK(cudaMemcpyAsync(tasks.data(), ctx->scr_req.p, cnt * sizeof(ZTaskDev), cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaStreamSynchronize(ctx->st));
+        for (uint32_t j = 0; j < cnt; ++j) {
+            uint32_t i = order[pos + j];
+            if (tasks[j].err) return agc_fail(ctx, AGCGPU_EUNSUPPORTED, "zstd: device coder failed on input %u (code %d)", i, tasks[j].err);
+            out_size[i] = tasks[j].out_size;
+            frames[i].resize(out_size[i]);
+            CK(cudaMemcpyAsync(frames[i].data(), tasks[j].dst, out_size[i], cudaMemcpyDeviceToHost, ctx->st));
+            ctx->stats.d2h_bytes += out_size[i];
+        }
+        CK(cudaStreamSynchronize(ctx->st));
+        pos = end;
+    }
+    for (uint32_t i = 0; i < n; ++i) dst_offsets[i + 1] = dst_offsets[i] + out_size[i];
+    if (dst_offsets[n] > dst_cap) return agc_fail(ctx, AGCGPU_EOVERFLOW, "zstd: need %llu output bytes", (unsigned long long)dst_offsets[n]);
+    for (uint32_t i = 0; i < n; ++i) if (out_size[i]) memcpy(dst + dst_offsets[i], frames[i].data(), out_size[i]);
+    return 0;
 }

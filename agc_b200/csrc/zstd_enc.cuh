@@ -146,6 +146,7 @@ struct Work {
     HufCT* tmpHuf;
     FseMeta* fseMeta; HufMeta* hufMeta;
     u32* partitions;         // 196+1
+    u32* dummySlot;          // sink for the binary-tree walks (must live in the same address space as the tables)
     int error;
 };
 
@@ -197,7 +198,7 @@ ZE_FN u32 lowest_match_index(const Work& w, u32 curr)             // ZSTD_getLow
 }
 
 // ZSTD_insertBt1 (zstd_opt.c:441-560), noDict
-ZE_FN u32 insert_bt1(Work& w, u32 curr, const u8* iend, u32 target, u32 mls)
+ZE_FN_NOINLINE u32 insert_bt1(Work& w, u32 curr, const u8* iend, u32 target, u32 mls)
 {
     const u8* base = w.src - w.baseOff;
     const u8* ip = base + curr;
@@ -209,7 +210,7 @@ ZE_FN u32 insert_bt1(Work& w, u32 curr, const u8* iend, u32 target, u32 mls)
     u32 btLow = btMask >= curr ? 0 : curr - btMask;
     u32* smallerPtr = bt + 2 * (curr & btMask);
     u32* largerPtr = smallerPtr + 1;
-    u32 dummy;
+    u32* const dummyPtr = w.dummySlot;
     u32 windowLow = lowest_match_index(w, target);
     u32 matchEndIdx = curr + 8 + 1;
     u32 bestLength = 8;
@@ -224,15 +225,16 @@ ZE_FN u32 insert_bt1(Work& w, u32 curr, const u8* iend, u32 target, u32 mls)
         if (ip + ml == iend) break;
         if (match[ml] < ip[ml]) {
             *smallerPtr = matchIndex; clSmaller = ml;
-            if (matchIndex <= btLow) { smallerPtr = &dummy; break; }
+            if (matchIndex <= btLow) { smallerPtr = dummyPtr; break; }
             smallerPtr = nextPtr + 1; matchIndex = nextPtr[1];
         } else {
             *largerPtr = matchIndex; clLarger = ml;
-            if (matchIndex <= btLow) { largerPtr = &dummy; break; }
+            if (matchIndex <= btLow) { largerPtr = dummyPtr + 1; break; }
             largerPtr = nextPtr; matchIndex = nextPtr[0];
         }
     }
-    *smallerPtr = *largerPtr = 0;
+    *largerPtr = 0;
+    *smallerPtr = 0;
     u32 positions = 0;
     if (bestLength > 384) { positions = bestLength - 384; if (positions > 192) positions = 192; }
     u32 adv = matchEndIdx - (curr + 8);
@@ -240,7 +242,7 @@ ZE_FN u32 insert_bt1(Work& w, u32 curr, const u8* iend, u32 target, u32 mls)
 }
 
 // ZSTD_updateTree_internal (zstd_opt.c:562-582)
-ZE_FN void update_tree(Work& w, u32 target, const u8* iend, u32 mls)
+ZE_FN_NOINLINE void update_tree(Work& w, u32 target, const u8* iend, u32 mls)
 {
     u32 idx = w.nextToUpdate;
     while (idx < target) idx += insert_bt1(w, idx, iend, target, mls);
@@ -248,7 +250,7 @@ ZE_FN void update_tree(Work& w, u32 target, const u8* iend, u32 mls)
 }
 
 // ZSTD_btGetAllMatches_internal + ZSTD_insertBtAndGetAllMatches (zstd_opt.c:590-820), noDict
-ZE_FN u32 get_all_matches(Work& w, Match* matches, u32* nextToUpdate3, const u8* ip, const u8* iLimit, const u32* rep, u32 ll0, u32 lengthToBeat)
+ZE_FN_NOINLINE u32 get_all_matches(Work& w, Match* matches, u32* nextToUpdate3, const u8* ip, const u8* iLimit, const u32* rep, u32 ll0, u32 lengthToBeat)
 {
     const u8* base = w.src - w.baseOff;
     u32 curr = (u32)(ip - base);
@@ -270,7 +272,7 @@ ZE_FN u32 get_all_matches(Work& w, Match* matches, u32* nextToUpdate3, const u8*
     u32* smallerPtr = bt + 2 * (curr & btMask);
     u32* largerPtr = smallerPtr + 1;
     u32 matchEndIdx = curr + 8 + 1;
-    u32 dummy;
+    u32* const dummyPtr = w.dummySlot;
     u32 mnum = 0;
     u32 nbCompares = 1u << w.cp.searchLog;
     u32 bestLength = lengthToBeat - 1;
@@ -323,15 +325,16 @@ ZE_FN u32 get_all_matches(Work& w, Match* matches, u32* nextToUpdate3, const u8*
         }
         if (match[ml] < ip[ml]) {
             *smallerPtr = matchIndex; clSmaller = ml;
-            if (matchIndex <= btLow) { smallerPtr = &dummy; break; }
+            if (matchIndex <= btLow) { smallerPtr = dummyPtr; break; }
             smallerPtr = nextPtr + 1; matchIndex = nextPtr[1];
         } else {
             *largerPtr = matchIndex; clLarger = ml;
-            if (matchIndex <= btLow) { largerPtr = &dummy; break; }
+            if (matchIndex <= btLow) { largerPtr = dummyPtr + 1; break; }
             largerPtr = nextPtr; matchIndex = nextPtr[0];
         }
     }
-    *smallerPtr = *largerPtr = 0;
+    *largerPtr = 0;
+    *smallerPtr = 0;
     w.nextToUpdate = matchEndIdx - 8;
     return mnum;
 }
@@ -346,13 +349,13 @@ ZE_FN void set_base_prices(Work& w, int optLevel)
     w.litSumBP = weight(w.litSum, optLevel); w.llSumBP = weight(w.llSum, optLevel);
     w.mlSumBP = weight(w.mlSum, optLevel); w.ofSumBP = weight(w.ofSum, optLevel);
 }
-ZE_FN u32 downscale(u32* t, u32 last, u32 shift, int base1)
+ZE_FN_NOINLINE u32 downscale(u32* t, u32 last, u32 shift, int base1)
 {
     u32 sum = 0;
     for (u32 s = 0; s <= last; ++s) { u32 b = base1 ? 1 : (t[s] > 0); u32 n = b + (t[s] >> shift); sum += n; t[s] = n; }
     return sum;
 }
-ZE_FN u32 scale_stats(u32* t, u32 last, u32 logTarget)
+ZE_FN_NOINLINE u32 scale_stats(u32* t, u32 last, u32 logTarget)
 {
     u32 prev = 0; for (u32 s = 0; s <= last; ++s) prev += t[s];
     u32 factor = prev >> logTarget;
@@ -360,7 +363,7 @@ ZE_FN u32 scale_stats(u32* t, u32 last, u32 logTarget)
     return downscale(t, last, highbit(factor), 1);
 }
 // ZSTD_rescaleFreqs (zstd_opt.c:140-258), no dictionary
-ZE_FN void rescale_freqs(Work& w, const u8* src, u32 srcSize, int optLevel)
+ZE_FN_NOINLINE void rescale_freqs(Work& w, const u8* src, u32 srcSize, int optLevel)
 {
     w.pricePredef = 0;
     if (w.llSum == 0) {
@@ -409,7 +412,7 @@ ZE_FN u32 match_price(const Work& w, u32 offBase, u32 ml, int optLevel)   // ZST
     price += BITCOST_MULT / 5;
     return price;
 }
-ZE_FN void update_stats(Work& w, u32 ll, const u8* lits, u32 offBase, u32 ml)
+ZE_FN_NOINLINE void update_stats(Work& w, u32 ll, const u8* lits, u32 offBase, u32 ml)
 {
     for (u32 u = 0; u < ll; ++u) w.litFreq[lits[u]] += 2;
     w.litSum += ll * 2;
@@ -418,7 +421,7 @@ ZE_FN void update_stats(Work& w, u32 ll, const u8* lits, u32 offBase, u32 ml)
     w.mlFreq[MLcode(ml - 3)]++; w.mlSum++;
 }
 // ZSTD_storeSeq (zstd_compress_internal.h:649-706)
-ZE_FN void store_seq(SeqStore& ss, u32 ll, const u8* lits, u32 offBase, u32 ml)
+ZE_FN_NOINLINE void store_seq(SeqStore& ss, u32 ll, const u8* lits, u32 offBase, u32 ml)
 {
     for (u32 i = 0; i < ll; ++i) ss.lit[i] = lits[i];
     ss.lit += ll;
@@ -608,7 +611,7 @@ ZE_FN u32 fse_optimal_table_log(u32 maxLog, u32 srcSize, u32 maxSym, u32 minus) 
     return tl;
 }
 // FSE_normalizeM2 (:366) ; returns false on failure
-ZE_FN bool fse_normalize_m2(i16* norm, u32 tableLog, const u32* count, u64 total, u32 maxSym, i16 lowProb)
+ZE_FN_NOINLINE bool fse_normalize_m2(i16* norm, u32 tableLog, const u32* count, u64 total, u32 maxSym, i16 lowProb)
 {
     const i16 NYA = -2;
     u32 distributed = 0, ToDistribute;
@@ -651,7 +654,7 @@ ZE_FN bool fse_normalize_m2(i16* norm, u32 tableLog, const u32* count, u64 total
     return true;
 }
 // FSE_normalizeCount (:450).  returns tableLog, 0 for the rle special case, ~0u on error
-ZE_FN u32 fse_normalize(i16* norm, u32 tableLog, const u32* count, u32 total, u32 maxSym, u32 useLowProb)
+ZE_FN_NOINLINE u32 fse_normalize(i16* norm, u32 tableLog, const u32* count, u32 total, u32 maxSym, u32 useLowProb)
 {
     if (tableLog == 0) tableLog = 11;
     if (tableLog < 5 || tableLog > 12) return ~0u;
@@ -677,7 +680,7 @@ ZE_FN u32 fse_normalize(i16* norm, u32 tableLog, const u32* count, u32 total, u3
     return tableLog;
 }
 // FSE_writeNCount_generic (:233), output buffer always large enough here.  returns size, 0 on error
-ZE_FN u32 fse_write_ncount(u8* out0, const i16* norm, u32 maxSym, u32 tableLog)
+ZE_FN_NOINLINE u32 fse_write_ncount(u8* out0, const i16* norm, u32 maxSym, u32 tableLog)
 {
     u8* out = out0;
     i32 nbBits, tableSize = 1 << tableLog, remaining, threshold;
@@ -712,7 +715,7 @@ ZE_FN u32 fse_write_ncount(u8* out0, const i16* norm, u32 maxSym, u32 tableLog)
     return (u32)(out - out0);
 }
 // FSE_buildCTable_wksp (:56).  tableSymbol scratch needs tableSize bytes, cumul maxSym+2 u16 (taken from `scratch`)
-ZE_FN void fse_build_ctable(FseCT& ct, const i16* norm, u32 maxSym, u32 tableLog, u8* scratch)
+ZE_FN_NOINLINE void fse_build_ctable(FseCT& ct, const i16* norm, u32 maxSym, u32 tableLog, u8* scratch)
 {
     u32 tableSize = 1u << tableLog, tableMask = tableSize - 1, step = (tableSize >> 1) + (tableSize >> 3) + 3, maxSV1 = maxSym + 1;
     u16* cumul = (u16*)scratch;                       // maxSV1 + 1 entries (<= 54)
@@ -749,7 +752,7 @@ ZE_FN void fse_build_ctable(FseCT& ct, const i16* norm, u32 maxSym, u32 tableLog
         }
     }
 }
-ZE_FN void fse_build_rle(FseCT& ct, u8 sym)              // FSE_buildCTable_rle (:531)
+ZE_FN_NOINLINE void fse_build_rle(FseCT& ct, u8 sym)              // FSE_buildCTable_rle (:531)
 {
     ct.tableLog = 0; ct.maxSym = sym; ct.state[0] = 0; ct.state[1] = 0; ct.dBits[sym] = 0; ct.dFind[sym] = 0;
 }
@@ -777,7 +780,7 @@ ZE_FN u32 fse_bit_cost(const FseCT& ct, u32 sym, u32 accuracyLog)   // FSE_bitCo
 }
 
 // ---------------------------------------------------------------------------------------------------- histogram (hist.c)
-ZE_FN u32 hist(u32* count, u32* maxSymPtr, const u8* src, u32 n)    // returns largest count, sets highest present symbol
+ZE_FN_NOINLINE u32 hist(u32* count, u32* maxSymPtr, const u8* src, u32 n)    // returns largest count, sets highest present symbol
 {
     u32 ms = *maxSymPtr;
     for (u32 i = 0; i <= ms; ++i) count[i] = 0;
@@ -792,12 +795,12 @@ ZE_FN u32 hist(u32* count, u32* maxSymPtr, const u8* src, u32 n)    // returns l
 
 // ---------------------------------------------------------------------------------------------------- Huffman (huf_compress.c)
 ZE_FN u32 huf_get_index(u32 c) { return c < 166 ? c : highbit(c) + 158; }       // HUF_getIndex (:497)
-ZE_FN void huf_insertion_sort(HufNode* a, i32 low, i32 high)
+ZE_FN_NOINLINE void huf_insertion_sort(HufNode* a, i32 low, i32 high)
 {
     i32 size = high - low + 1; a += low;
     for (i32 i = 1; i < size; ++i) { HufNode key = a[i]; i32 j = i - 1; while (j >= 0 && a[j].count < key.count) { a[j + 1] = a[j]; j--; } a[j + 1] = key; }
 }
-ZE_FN i32 huf_partition(HufNode* arr, i32 low, i32 high)
+ZE_FN_NOINLINE i32 huf_partition(HufNode* arr, i32 low, i32 high)
 {
     u32 pivot = arr[high].count; i32 i = low - 1;
     for (i32 j = low; j < high; j++) if (arr[j].count > pivot) { i++; HufNode t = arr[i]; arr[i] = arr[j]; arr[j] = t; }
@@ -805,7 +808,7 @@ ZE_FN i32 huf_partition(HufNode* arr, i32 low, i32 high)
     return i + 1;
 }
 // HUF_simpleQuickSort (:548) with its recursion unrolled onto an explicit stack (same visiting order => same result)
-ZE_FN void huf_quick_sort(HufNode* arr, i32 low0, i32 high0)
+ZE_FN_NOINLINE void huf_quick_sort(HufNode* arr, i32 low0, i32 high0)
 {
     i32 stk[160][2]; i32 sp = 0;
     stk[sp][0] = low0; stk[sp][1] = high0; sp++;
@@ -823,7 +826,7 @@ ZE_FN void huf_quick_sort(HufNode* arr, i32 low0, i32 high0)
 }
 
 // HUF_sort (:627): bucket sort by descending count (counts >= 166 share log2 buckets that are quick-sorted)
-ZE_FN void huf_sort(HufNode* huffNode, const u32* count, u32 maxSym, u32* rankPos /* 192*2: base, curr */)
+ZE_FN_NOINLINE void huf_sort(HufNode* huffNode, const u32* count, u32 maxSym, u32* rankPos /* 192*2: base, curr */)
 {
     u32 n1 = maxSym + 1;
     for (u32 i = 0; i < 192 * 2; ++i) rankPos[i] = 0;
@@ -840,7 +843,7 @@ ZE_FN void huf_sort(HufNode* huffNode, const u32* count, u32 maxSym, u32* rankPo
     }
 }
 // HUF_buildTree (:680). huffNode[-1] must be addressable (huffNode = table + 1)
-ZE_FN i32 huf_build_tree(HufNode* huffNode, u32 maxSym)
+ZE_FN_NOINLINE i32 huf_build_tree(HufNode* huffNode, u32 maxSym)
 {
     const i32 STARTNODE = 256;
     HufNode* huffNode0 = huffNode - 1;
@@ -865,7 +868,7 @@ ZE_FN i32 huf_build_tree(HufNode* huffNode, u32 maxSym)
     return nonNullRank;
 }
 // HUF_setMaxHeight (:340)
-ZE_FN u32 huf_set_max_height(HufNode* huffNode, u32 lastNonNull, u32 targetNbBits)
+ZE_FN_NOINLINE u32 huf_set_max_height(HufNode* huffNode, u32 lastNonNull, u32 targetNbBits)
 {
     u32 largestBits = huffNode[lastNonNull].nbBits;
     if (largestBits <= targetNbBits) return largestBits;
@@ -919,7 +922,7 @@ ZE_FN u32 huf_set_max_height(HufNode* huffNode, u32 lastNonNull, u32 targetNbBit
     return targetNbBits;
 }
 // HUF_buildCTable_wksp (:693) + HUF_buildCTableFromTree (:660). returns maxNbBits
-ZE_FN u32 huf_build_ctable(Work& w, HufCT& ct, const u32* count, u32 maxSym, u32 maxNbBits)
+ZE_FN_NOINLINE u32 huf_build_ctable(Work& w, HufCT& ct, const u32* count, u32 maxSym, u32 maxNbBits)
 {
     HufNode* huffNode0 = w.huffNode; HufNode* huffNode = huffNode0 + 1;
     if (maxNbBits == 0) maxNbBits = 11;
@@ -938,13 +941,13 @@ ZE_FN u32 huf_build_ctable(Work& w, HufCT& ct, const u32* count, u32 maxSym, u32
     }
     return maxNbBits;
 }
-ZE_FN u32 huf_estimate_size(const HufCT& ct, const u32* count, u32 maxSym)       // HUF_estimateCompressedSize (:722)
+ZE_FN_NOINLINE u32 huf_estimate_size(const HufCT& ct, const u32* count, u32 maxSym)       // HUF_estimateCompressedSize (:722)
 {
     u64 nbBits = 0;
     for (u32 s = 0; s <= maxSym; ++s) nbBits += (u64)ct.nbBits[s] * count[s];
     return (u32)(nbBits >> 3);
 }
-ZE_FN int huf_validate(const HufCT& ct, const u32* count, u32 maxSym)            // HUF_validateCTable (:733)
+ZE_FN_NOINLINE int huf_validate(const HufCT& ct, const u32* count, u32 maxSym)            // HUF_validateCTable (:733)
 {
     if (ct.maxSym < maxSym) return 0;
     int bad = 0;
@@ -952,7 +955,7 @@ ZE_FN int huf_validate(const HufCT& ct, const u32* count, u32 maxSym)           
     return !bad;
 }
 // FSE_compress_usingCTable_generic (fse_compress.c:556) -- only used for the Huffman weights.  returns 0 if not compressible
-ZE_FN u32 fse_compress_weights(u8* dst, u32 dstSize, const u8* src, u32 srcSize, const FseCT& ct)
+ZE_FN_NOINLINE u32 fse_compress_weights(u8* dst, u32 dstSize, const u8* src, u32 srcSize, const FseCT& ct)
 {
     const u8* ip = src + srcSize;
     BitW b; FseState s1, s2;
@@ -971,7 +974,7 @@ ZE_FN u32 fse_compress_weights(u8* dst, u32 dstSize, const u8* src, u32 srcSize,
     return bit_close(b);
 }
 // HUF_compressWeights (:128).  returns 0 = not compressible, 1 = rle, else size
-ZE_FN u32 huf_compress_weights(Work& w, u8* dst, u32 dstSize, const u8* wt, u32 wtSize)
+ZE_FN_NOINLINE u32 huf_compress_weights(Work& w, u8* dst, u32 dstSize, const u8* wt, u32 wtSize)
 {
     u32 maxSym = 12, tableLog = 6;
     u32 cnt[13]; i16 norm[13];
@@ -988,7 +991,7 @@ ZE_FN u32 huf_compress_weights(Work& w, u8* dst, u32 dstSize, const u8* wt, u32 
     return (u32)(op - dst);
 }
 // HUF_writeCTable_wksp (:226). dst must hold 129+ bytes. returns header size (0 on failure)
-ZE_FN u32 huf_write_ctable(Work& w, u8* dst, u32 maxDst, const HufCT& ct, u32 maxSym, u32 huffLog)
+ZE_FN_NOINLINE u32 huf_write_ctable(Work& w, u8* dst, u32 maxDst, const HufCT& ct, u32 maxSym, u32 huffLog)
 {
     u8 bitsToWeight[13]; u8* huffWeight = w.scratch + 768;     // 256 bytes
     bitsToWeight[0] = 0;
@@ -1003,7 +1006,7 @@ ZE_FN u32 huf_write_ctable(Work& w, u8* dst, u32 maxDst, const HufCT& ct, u32 ma
     return ((maxSym + 1) / 2) + 1;
 }
 // HUF_optimalTableLog (:1233)
-ZE_FN u32 huf_optimal_table_log(Work& w, u32 maxTableLog, u32 srcSize, u32 maxSym, HufCT& table, const u32* count, int optimalDepth)
+ZE_FN_NOINLINE u32 huf_optimal_table_log(Work& w, u32 maxTableLog, u32 srcSize, u32 maxSym, HufCT& table, const u32* count, int optimalDepth)
 {
     if (!optimalDepth) return fse_optimal_table_log(maxTableLog, srcSize, maxSym, 1);
     u8* dst = w.scratch + 256;           // 512 bytes
@@ -1022,7 +1025,7 @@ ZE_FN u32 huf_optimal_table_log(Work& w, u32 maxTableLog, u32 srcSize, u32 maxSy
     return optLog;
 }
 // HUF_compress1X_usingCTable_internal_body (:1003): the bit stream is the codes of src[n-1] .. src[0], then the end mark
-ZE_FN u32 huf_compress1x(u8* dst, u32 dstSize, const u8* src, u32 srcSize, const HufCT& ct)
+ZE_FN_NOINLINE u32 huf_compress1x(u8* dst, u32 dstSize, const u8* src, u32 srcSize, const HufCT& ct)
 {
     if (dstSize < 8) return 0;
     BitW b; if (!bit_init(b, dst, dstSize)) return 0;
@@ -1034,7 +1037,7 @@ ZE_FN u32 huf_compress1x(u8* dst, u32 dstSize, const u8* src, u32 srcSize, const
     return bit_close(b);
 }
 // HUF_compress4X_usingCTable_internal (:1068)
-ZE_FN u32 huf_compress4x(u8* dst, u32 dstSize, const u8* src, u32 srcSize, const HufCT& ct)
+ZE_FN_NOINLINE u32 huf_compress4x(u8* dst, u32 dstSize, const u8* src, u32 srcSize, const HufCT& ct)
 {
     u32 segmentSize = (srcSize + 3) / 4;
     const u8* ip = src; const u8* iend = src + srcSize;
@@ -1052,7 +1055,7 @@ ZE_FN u32 huf_compress4x(u8* dst, u32 dstSize, const u8* src, u32 srcSize, const
         op += c; }
     return (u32)(op - dst);
 }
-ZE_FN u32 huf_compress_ctable(u8* ostart, u8* op, u8* oend, const u8* src, u32 srcSize, int single, const HufCT& ct)   // HUF_compressCTable_internal (:1126)
+ZE_FN_NOINLINE u32 huf_compress_ctable(u8* ostart, u8* op, u8* oend, const u8* src, u32 srcSize, int single, const HufCT& ct)   // HUF_compressCTable_internal (:1126)
 {
     u32 c = single ? huf_compress1x(op, (u32)(oend - op), src, srcSize, ct) : huf_compress4x(op, (u32)(oend - op), src, srcSize, ct);
     if (c == 0) return 0;
@@ -1062,7 +1065,7 @@ ZE_FN u32 huf_compress_ctable(u8* ostart, u8* op, u8* oend, const u8* src, u32 s
 }
 // HUF_compress_internal (:1285) as called by ZSTD_compressLiterals (no preferRepeat: strategy >= lazy).
 // returns 0 = not compressible, 1 = single symbol (dst[0] = symbol), else size.  *repeat updated as in the reference.
-ZE_FN u32 huf_compress(Work& w, u8* dst, u32 dstSize, const u8* src, u32 srcSize, int single, HufCT& oldTable, i32* repeat,
+ZE_FN_NOINLINE u32 huf_compress(Work& w, u8* dst, u32 dstSize, const u8* src, u32 srcSize, int single, HufCT& oldTable, i32* repeat,
                        int optimalDepth, int suspectUncompressible)
 {
     u8* ostart = dst; u8* oend = dst + dstSize; u8* op = ostart;
@@ -1098,7 +1101,7 @@ ZE_FN u32 huf_compress(Work& w, u8* dst, u32 dstSize, const u8* src, u32 srcSize
 ZE_FN u32 min_gain(u32 srcSize, u32 strat) { u32 minlog = strat >= ST_BTULTRA ? strat - 1 : 6; return (srcSize >> minlog) + 2; }   // ZSTD_minGain
 
 // ---------------------------------------------------------------------------------------------------- literals (zstd_compress_literals.c)
-ZE_FN u32 no_compress_literals(u8* dst, const u8* src, u32 srcSize)
+ZE_FN_NOINLINE u32 no_compress_literals(u8* dst, const u8* src, u32 srcSize)
 {
     u32 fl = 1 + (srcSize > 31) + (srcSize > 4095);
     if (fl == 1) dst[0] = (u8)(SET_BASIC + (srcSize << 3));
@@ -1107,7 +1110,7 @@ ZE_FN u32 no_compress_literals(u8* dst, const u8* src, u32 srcSize)
     for (u32 i = 0; i < srcSize; ++i) dst[fl + i] = src[i];
     return srcSize + fl;
 }
-ZE_FN u32 rle_literals(u8* dst, const u8* src, u32 srcSize)
+ZE_FN_NOINLINE u32 rle_literals(u8* dst, const u8* src, u32 srcSize)
 {
     u32 fl = 1 + (srcSize > 31) + (srcSize > 4095);
     if (fl == 1) dst[0] = (u8)(SET_RLE + (srcSize << 3));
@@ -1117,7 +1120,7 @@ ZE_FN u32 rle_literals(u8* dst, const u8* src, u32 srcSize)
     return fl + 1;
 }
 // ZSTD_compressLiterals (:129)
-ZE_FN u32 compress_literals(Work& w, u8* dst, u32 dstCap, const u8* src, u32 srcSize, const Entropy& prev, Entropy& next, int suspectUncompressible)
+ZE_FN_NOINLINE u32 compress_literals(Work& w, u8* dst, u32 dstCap, const u8* src, u32 srcSize, const Entropy& prev, Entropy& next, int suspectUncompressible)
 {
     u32 strategy = w.cp.strategy;
     u32 lhSize = 3 + (srcSize >= 1024) + (srcSize >= 16384);
@@ -1148,7 +1151,7 @@ ZE_FN u32 compress_literals(Work& w, u8* dst, u32 dstCap, const u8* src, u32 src
 
 
 // ---------------------------------------------------------------------------------------------------- sequences (zstd_compress_sequences.c)
-ZE_FN u32 entropy_cost(const u32* count, u32 max, u32 total)               // ZSTD_entropyCost (:85)
+ZE_FN_NOINLINE u32 entropy_cost(const u32* count, u32 max, u32 total)               // ZSTD_entropyCost (:85)
 {
     u32 cost = 0;
     for (u32 s = 0; s <= max; ++s) {
@@ -1158,7 +1161,7 @@ ZE_FN u32 entropy_cost(const u32* count, u32 max, u32 total)               // ZS
     }
     return cost >> 8;
 }
-ZE_FN u64 fse_bit_cost_total(const FseCT& ct, const u32* count, u32 max)    // ZSTD_fseBitCost (:107) ; ~0 = error
+ZE_FN_NOINLINE u64 fse_bit_cost_total(const FseCT& ct, const u32* count, u32 max)    // ZSTD_fseBitCost (:107) ; ~0 = error
 {
     const u32 kAcc = 8; u64 cost = 0;
     if (ct.maxSym < max) return ~0ull;
@@ -1171,7 +1174,7 @@ ZE_FN u64 fse_bit_cost_total(const FseCT& ct, const u32* count, u32 max)    // Z
     }
     return cost >> kAcc;
 }
-ZE_FN u64 cross_entropy_cost(const i16* norm, u32 accuracyLog, const u32* count, u32 max)   // ZSTD_crossEntropyCost (:141)
+ZE_FN_NOINLINE u64 cross_entropy_cost(const i16* norm, u32 accuracyLog, const u32* count, u32 max)   // ZSTD_crossEntropyCost (:141)
 {
     u32 shift = 8 - accuracyLog; u64 cost = 0;
     for (u32 s = 0; s <= max; ++s) {
@@ -1180,7 +1183,7 @@ ZE_FN u64 cross_entropy_cost(const i16* norm, u32 accuracyLog, const u32* count,
     }
     return cost >> 8;
 }
-ZE_FN u64 ncount_cost(Work& w, const u32* count, u32 max, u32 nbSeq, u32 FSELog)              // ZSTD_NCountCost (:72)
+ZE_FN_NOINLINE u64 ncount_cost(Work& w, const u32* count, u32 max, u32 nbSeq, u32 FSELog)              // ZSTD_NCountCost (:72)
 {
     i16 norm[53];
     u32 tableLog = fse_optimal_table_log(FSELog, nbSeq, max, 2);
@@ -1189,7 +1192,7 @@ ZE_FN u64 ncount_cost(Work& w, const u32* count, u32 max, u32 nbSeq, u32 FSELog)
     return r ? r : ~0ull;
 }
 // ZSTD_selectEncodingType (:157) for strategy >= lazy
-ZE_FN int select_encoding_type(Work& w, i32* repeatMode, const u32* count, u32 max, u32 mostFrequent, u32 nbSeq, u32 FSELog,
+ZE_FN_NOINLINE int select_encoding_type(Work& w, i32* repeatMode, const u32* count, u32 max, u32 mostFrequent, u32 nbSeq, u32 FSELog,
                                const FseCT& prevCT, const i16* defaultNorm, u32 defaultNormLog, int isDefaultAllowed)
 {
     if (mostFrequent == nbSeq) {
@@ -1208,7 +1211,7 @@ ZE_FN int select_encoding_type(Work& w, i32* repeatMode, const u32* count, u32 m
     return SET_COMPRESSED;
 }
 // ZSTD_buildCTable (:243).  returns bytes written to op (NCount header / rle symbol); ~0u on error
-ZE_FN u32 build_ctable(Work& w, u8* op, FseCT& next, u32 FSELog, int type, u32* count, u32 max, const u8* codeTable, u32 nbSeq,
+ZE_FN_NOINLINE u32 build_ctable(Work& w, u8* op, FseCT& next, u32 FSELog, int type, u32* count, u32 max, const u8* codeTable, u32 nbSeq,
                        const i16* defaultNorm, u32 defaultNormLog, u32 defaultMax, const FseCT& prev)
 {
     switch (type) {
@@ -1228,7 +1231,7 @@ ZE_FN u32 build_ctable(Work& w, u8* op, FseCT& next, u32 FSELog, int type, u32* 
     }
 }
 // ZSTD_seqToCodes (zstd_compress.c:2679)
-ZE_FN void seq_to_codes(const SeqStore& ss)
+ZE_FN_NOINLINE void seq_to_codes(const SeqStore& ss)
 {
     u32 nbSeq = (u32)(ss.seq - ss.seqStart);
     for (u32 u = 0; u < nbSeq; u++) {
@@ -1241,7 +1244,7 @@ ZE_FN void seq_to_codes(const SeqStore& ss)
 }
 struct SeqStats { int LLtype, Offtype, MLtype; u32 size, lastCountSize; int err; };
 // ZSTD_buildSequencesStatistics (zstd_compress.c:2749)
-ZE_FN SeqStats build_seq_stats(Work& w, const SeqStore& ss, u32 nbSeq, const Entropy& prev, Entropy& next, u8* dst)
+ZE_FN_NOINLINE SeqStats build_seq_stats(Work& w, const SeqStore& ss, u32 nbSeq, const Entropy& prev, Entropy& next, u8* dst)
 {
     SeqStats st; st.lastCountSize = 0; st.err = 0; st.size = 0;
     u8* op = dst; u32* count = w.count;
@@ -1272,7 +1275,7 @@ ZE_FN SeqStats build_seq_stats(Work& w, const SeqStore& ss, u32 nbSeq, const Ent
     return st;
 }
 // ZSTD_encodeSequences_body (zstd_compress_sequences.c:292), 64-bit, no long offsets.  returns 0 if dst too small
-ZE_FN u32 encode_sequences(u8* dst, u64 cap, const Entropy& e, const SeqStore& ss, u32 nbSeq)
+ZE_FN_NOINLINE u32 encode_sequences(u8* dst, u64 cap, const Entropy& e, const SeqStore& ss, u32 nbSeq)
 {
     BitW b; FseState sML, sOF, sLL;
     if (!bit_init(b, dst, cap)) return 0;
@@ -1302,7 +1305,7 @@ ZE_FN u32 encode_sequences(u8* dst, u64 cap, const Entropy& e, const SeqStore& s
 }
 
 // ZSTD_entropyCompressSeqStore (zstd_compress.c:2874-3027). returns compressed block body size, 0 = "not compressed"
-ZE_FN u32 entropy_compress_seqstore(Work& w, const SeqStore& ss, const Entropy& prev, Entropy& next, u8* dst, u64 dstCap, u32 srcSize)
+ZE_FN_NOINLINE u32 entropy_compress_seqstore(Work& w, const SeqStore& ss, const Entropy& prev, Entropy& next, u8* dst, u64 dstCap, u32 srcSize)
 {
     u8* op = dst;
     u32 nbSeq = (u32)(ss.seq - ss.seqStart);
@@ -1335,7 +1338,7 @@ ZE_FN u32 entropy_compress_seqstore(Work& w, const SeqStore& ss, const Entropy& 
 
 // ---------------------------------------------------------------------------------------------------- block-split estimation (zstd_compress.c:3522-3860)
 // ZSTD_buildBlockEntropyStats_literals: returns desSize, sets hType
-ZE_FN u32 block_stats_literals(Work& w, const u8* src, u32 srcSize, const Entropy& prev, Entropy& next, HufMeta& hm, int optimalDepth)
+ZE_FN_NOINLINE u32 block_stats_literals(Work& w, const u8* src, u32 srcSize, const Entropy& prev, Entropy& next, HufMeta& hm, int optimalDepth)
 {
     u32 maxSym = 255, huffLog = 11;
     i32 repeat = prev.hufRepeat;
@@ -1361,7 +1364,7 @@ ZE_FN u32 block_stats_literals(Work& w, const u8* src, u32 srcSize, const Entrop
         return hSize;
     }
 }
-ZE_FN u32 estimate_literal(Work& w, const u8* lits, u32 litSize, const HufCT& huf, const HufMeta& hm, int writeEntropy)
+ZE_FN_NOINLINE u32 estimate_literal(Work& w, const u8* lits, u32 litSize, const HufCT& huf, const HufMeta& hm, int writeEntropy)
 {
     u32 maxSym = 255, hdr = 3 + (litSize >= 1024) + (litSize >= 16384), single = litSize < 256;
     if (hm.hType == SET_BASIC) return litSize;
@@ -1372,7 +1375,7 @@ ZE_FN u32 estimate_literal(Work& w, const u8* lits, u32 litSize, const HufCT& hu
     if (!single) est += 6;
     return est + hdr;
 }
-ZE_FN u64 estimate_symbol_type(Work& w, int type, const u8* codeTable, u32 nbSeq, u32 maxCode, const FseCT& ct, const u8* addBits,
+ZE_FN_NOINLINE u64 estimate_symbol_type(Work& w, int type, const u8* codeTable, u32 nbSeq, u32 maxCode, const FseCT& ct, const u8* addBits,
                                const i16* defaultNorm, u32 defaultNormLog)
 {
     u32 max = maxCode; u64 bits = 0;
@@ -1385,7 +1388,7 @@ ZE_FN u64 estimate_symbol_type(Work& w, int type, const u8* codeTable, u32 nbSeq
     return bits >> 3;
 }
 // ZSTD_buildEntropyStatisticsAndEstimateSubBlockSize (:3845). ~0 = error
-ZE_FN u64 estimate_subblock(Work& w, const SeqStore& ss)
+ZE_FN_NOINLINE u64 estimate_subblock(Work& w, const SeqStore& ss)
 {
     const Entropy& prev = w.bs[w.prevIdx]->e; Entropy& next = w.bs[w.prevIdx ^ 1]->e;
     HufMeta& hm = *w.hufMeta; FseMeta& fm = *w.fseMeta;
@@ -1407,20 +1410,20 @@ ZE_FN u64 estimate_subblock(Work& w, const SeqStore& ss)
     seqSize += fm.tablesSize;
     return seqSize + literalsSize + 3;
 }
-ZE_FN u32 count_lit_bytes(const SeqStore& ss)          // ZSTD_countSeqStoreLiteralsBytes (:3862)
+ZE_FN_NOINLINE u32 count_lit_bytes(const SeqStore& ss)          // ZSTD_countSeqStoreLiteralsBytes (:3862)
 {
     u32 n = (u32)(ss.seq - ss.seqStart), b = 0;
     for (u32 i = 0; i < n; ++i) { b += ss.seqStart[i].litLength; if (i == ss.longPos && ss.longType == 1) b += 0x10000; }
     return b;
 }
-ZE_FN u32 count_match_bytes(const SeqStore& ss)        // ZSTD_countSeqStoreMatchBytes (:3877)
+ZE_FN_NOINLINE u32 count_match_bytes(const SeqStore& ss)        // ZSTD_countSeqStoreMatchBytes (:3877)
 {
     u32 n = (u32)(ss.seq - ss.seqStart), b = 0;
     for (u32 i = 0; i < n; ++i) { b += ss.seqStart[i].mlBase + 3; if (i == ss.longPos && ss.longType == 2) b += 0x10000; }
     return b;
 }
 // ZSTD_deriveSeqStoreChunk (:3894)
-ZE_FN void derive_chunk(SeqStore& r, const SeqStore& o, u32 startIdx, u32 endIdx)
+ZE_FN_NOINLINE void derive_chunk(SeqStore& r, const SeqStore& o, u32 startIdx, u32 endIdx)
 {
     r = o;
     if (startIdx > 0) { r.seq = o.seqStart + startIdx; r.litStart += count_lit_bytes(r); }
@@ -1433,7 +1436,7 @@ ZE_FN void derive_chunk(SeqStore& r, const SeqStore& o, u32 startIdx, u32 endIdx
     r.llCode += startIdx; r.mlCode += startIdx; r.ofCode += startIdx;
 }
 // ZSTD_deriveBlockSplitsHelper (:4092) with its recursion on an explicit stack (in-order traversal keeps split order)
-ZE_FN u32 derive_block_splits(Work& w, u32* partitions, u32 nbSeq)
+ZE_FN_NOINLINE u32 derive_block_splits(Work& w, u32* partitions, u32 nbSeq)
 {
     if (nbSeq <= 4) return 0;
     u32 nsplits = 0;
@@ -1493,13 +1496,13 @@ ZE_FN_NOINLINE bool build_seqstore(Work& w, const u8* src, u32 srcSize)
     return true;
 }
 ZE_FN bool is_rle(const u8* src, u32 n) { for (u32 i = 1; i < n; ++i) if (src[i] != src[0]) return false; return true; }   // ZSTD_isRLE (:3469)
-ZE_FN u32 no_compress_block(u8* dst, const u8* src, u32 srcSize, u32 last)
+ZE_FN_NOINLINE u32 no_compress_block(u8* dst, const u8* src, u32 srcSize, u32 last)
 {
     wr24(dst, last + (0u << 1) + (srcSize << 3));
     for (u32 i = 0; i < srcSize; ++i) dst[3 + i] = src[i];
     return 3 + srcSize;
 }
-ZE_FN u32 rle_compress_block(u8* dst, u8 b, u32 srcSize, u32 last) { wr24(dst, last + (1u << 1) + (srcSize << 3)); dst[3] = b; return 4; }
+ZE_FN_NOINLINE u32 rle_compress_block(u8* dst, u8 b, u32 srcSize, u32 last) { wr24(dst, last + (1u << 1) + (srcSize << 3)); dst[3] = b; return 4; }
 ZE_FN void confirm(Work& w) { w.prevIdx ^= 1; }              // ZSTD_blockState_confirmRepcodesAndEntropyTables
 
 // ZSTD_resolveRepcodeToRawOffset (:3927) / ZSTD_seqStore_resolveOffCodes (:3959)
@@ -1509,7 +1512,7 @@ ZE_FN u32 resolve_rep_raw(const u32* rep, u32 offBase, u32 ll0)
     if (adj == 3) return rep[0] - 1;
     return rep[adj];
 }
-ZE_FN void resolve_off_codes(u32* dRep, u32* cRep, const SeqStore& ss, u32 nbSeq)
+ZE_FN_NOINLINE void resolve_off_codes(u32* dRep, u32* cRep, const SeqStore& ss, u32 nbSeq)
 {
     u32 longLit = ss.longType == 1 ? ss.longPos : nbSeq;
     for (u32 idx = 0; idx < nbSeq; ++idx) {
@@ -1525,7 +1528,7 @@ ZE_FN void resolve_off_codes(u32* dRep, u32* cRep, const SeqStore& ss, u32 nbSeq
     }
 }
 // ZSTD_compressSeqStore_singleBlock (:4002)
-ZE_FN u32 compress_seqstore_single(Work& w, const SeqStore& ss, u32* dRep, u32* cRep, u8* dst, u64 dstCap, const u8* src, u32 srcSize, u32 last, int isPartition)
+ZE_FN_NOINLINE u32 compress_seqstore_single(Work& w, const SeqStore& ss, u32* dRep, u32* cRep, u8* dst, u64 dstCap, const u8* src, u32 srcSize, u32 last, int isPartition)
 {
     u32 dRepOrig[3] = { dRep[0], dRep[1], dRep[2] };
     if (isPartition) resolve_off_codes(dRep, cRep, ss, (u32)(ss.seq - ss.seqStart));
@@ -1639,7 +1642,8 @@ ZE_FN_NOINLINE u64 compress_frame(const u8* src, u64 srcSize64, int level, u8* d
     p = (u8*)align_up((u64)p, 8);
     w.hufMeta = (HufMeta*)p; p += sizeof(HufMeta);
     p = (u8*)align_up((u64)p, 8);
-    w.partitions = (u32*)p;
+    w.partitions = (u32*)p; p += 4 * 200;
+    w.dummySlot = (u32*)p;
     reset_seqstore(w);
     w.hashLog3 = cp.minMatch == 3 ? (cp.windowLog < 17 ? cp.windowLog : 17) : 0;
     w.baseOff = 2; w.lowLimit = 2; w.dictLimit = 2; w.nextToUpdate = 2;

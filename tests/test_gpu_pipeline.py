@@ -53,3 +53,11 @@ def test_parts_match_reference(tmp_path, case):
         flags = ["-k", "17", "-s", "1000", "-b", "3", "-l", "15"]
     bad = _run_both(tmp, files, flags)
     assert not bad, "\n".join(bad[:10])
+    # and the real thing: the archive written through the device residual coder is byte-identical to the reference's
+    our = os.path.join(tmp, "our_full.agc")
+    subprocess.check_call([OUR_AGC, "create", "-o", our] + flags + files)
+    a = open(our, "rb").read(); b = open(os.path.join(tmp, "ref.agc"), "rb").read()
+    assert len(a) == len(b) and a == b, f"archives differ: {len(a)} vs {len(b)} bytes, first diff at {next((i for i, (x, y) in enumerate(zip(a, b)) if x != y), -1)}"
+    # the reference decompressor accepts it and returns the input
+    out = subprocess.run([REF_AGC, "getset", our, os.path.splitext(os.path.basename(files[-1]))[0]], capture_output=True).stdout
+    assert out == open(files[-1], "rb").read()
