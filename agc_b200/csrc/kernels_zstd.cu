@@ -10,6 +10,8 @@
 #include "zstd_enc.cuh"
 #include <algorithm>
 #include <numeric>
+#include <cstdio>
+#include <cstdlib>
 
 struct ZTaskDev {
     const uint8_t* src; uint8_t* dst; uint8_t* mem;
@@ -22,11 +24,11 @@ __global__ void __launch_bounds__(32) k_zstd(ZTaskDev* __restrict__ tasks, uint3
 {
     uint32_t t = blockIdx.x;
     if (t >= n_tasks) return;
-    if (threadIdx.x != 0) return;
-    ZTaskDev& k = tasks[t];
+    // all 32 lanes run the coder with identical scalar state (see zstd_enc.cuh); array-wide steps are split between them
+    ZTaskDev k = tasks[t];
     int err = 0;
     uint64_t r = ze::compress_frame(k.src, k.n, k.level, k.dst, k.dst_cap, k.mem, &err);
-    k.err = err; k.out_size = r;
+    if (threadIdx.x == 0) { tasks[t].err = err; tasks[t].out_size = r; }
 }
 
 extern "C" int agcgpu_zstd_compress_batch(agcgpu_ctx* ctx, const uint8_t* src, const uint64_t* src_offsets, const int32_t* levels,
@@ -84,10 +86,19 @@ extern "C" int agcgpu_zstd_compress_batch(agcgpu_ctx* ctx, const uint8_t* src, c
         }
         CK(cudaMemcpyAsync(ctx->scr_req.p, tasks.data(), cnt * sizeof(ZTaskDev), cudaMemcpyHostToDevice, ctx->st));
         CK(cudaDeviceSetLimit(cudaLimitStackSize, 16384));
+        CK(cudaEventRecord(ctx->ev0, ctx->st));
         k_zstd<<<cnt, 32, 0, ctx->st>>>((ZTaskDev*)ctx->scr_req.p, cnt);
         CKL();
+        CK(cudaEventRecord(ctx->ev1, ctx->st));
         CK(cudaMemcpyAsync(tasks.data(), ctx->scr_req.p, cnt * sizeof(ZTaskDev), cudaMemcpyDeviceToHost, ctx->st));
         CK(cudaStreamSynchronize(ctx->st));
+        {   float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+            ctx->stats.reserved[0] += ms;                           // total device time of the residual coder (ms)
+            if (getenv("AGCGPU_TRACE")) {
+                uint64_t tot = 0; for (uint32_t j = 0; j < cnt; ++j) tot += tasks[j].n;
+                fprintf(stderr, "[agcgpu] zstd wave: %u inputs, %llu bytes, largest %llu (level %d), kernel %.1f ms\n", cnt,
+                        (unsigned long long)tot, (unsigned long long)tasks[0].n, tasks[0].level, ms);
+            } }
         for (uint32_t j = 0; j < cnt; ++j) {
             uint32_t i = order[pos + j];
             if (tasks[j].err) return agc_fail(ctx, AGCGPU_EUNSUPPORTED, "zstd: device coder failed on input %u (code %d)", i, tasks[j].err);

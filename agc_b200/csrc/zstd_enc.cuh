@@ -9,6 +9,7 @@
 // scalar control flow is warp-uniform (every lane computes the same value), array-wide steps are lane-strided.
 #pragma once
 #include <stdint.h>
+#include <stddef.h>
 
 #if defined(__CUDACC__)
 #define ZE_FN __host__ __device__ __forceinline__
@@ -16,6 +17,30 @@
 #else
 #define ZE_FN inline
 #define ZE_FN_NOINLINE inline
+#endif
+
+// warp-cooperative helpers: on the device all 32 lanes of a warp run the coder with identical (uniform) scalar state and
+// split array-wide steps between them; on the host the same code runs with one "lane".
+#if defined(__CUDA_ARCH__)
+#define ZE_LANE (threadIdx.x & 31u)
+#define ZE_LANES 32u
+#define ze_ballot(p) __ballot_sync(0xffffffffu, (p))
+#define ze_shfl(v, l) __shfl_sync(0xffffffffu, (v), (l))
+#define ze_sync() __syncwarp()
+#define ze_ffs(m) ((unsigned)__ffs((int)(m)))
+#define ze_match_any(v) __match_any_sync(0xffffffffu, (v))
+#define ze_reduce_or(v) __reduce_or_sync(0xffffffffu, (v))
+#define ze_ctz64(x) ((unsigned)__ffsll((long long)(x)) - 1u)
+#else
+#define ZE_LANE 0u
+#define ZE_LANES 1u
+#define ze_ballot(p) ((p) ? 1u : 0u)
+#define ze_shfl(v, l) (v)
+#define ze_sync() ((void)0)
+#define ze_ffs(m) ((unsigned)__builtin_ffs((int)(m)))
+#define ze_match_any(v) 1u
+#define ze_reduce_or(v) (v)
+#define ze_ctz64(x) ((unsigned)__builtin_ctzll(x))
 #endif
 
 typedef uint8_t u8; typedef uint16_t u16; typedef uint32_t u32; typedef uint64_t u64; typedef int32_t i32; typedef int16_t i16;
@@ -147,6 +172,10 @@ struct Work {
     FseMeta* fseMeta; HufMeta* hufMeta;
     u32* partitions;         // 196+1
     u32* dummySlot;          // sink for the binary-tree walks (must live in the same address space as the tables)
+    // batched speculative tree walks (pw_*): one recorded read-only walk per lane for positions [pwBase, pwBase + pwCount)
+    u32* pwPath;             // ZE_LANES x PW_CAP x {matchIndex, matchLength | smaller << 31}
+    u32 pwBase, pwCount, pwDirty, pwEnd, pwBaseOff;     // uniform: covered positions, lanes whose bucket changed since, limits the walks assumed
+    u32 pwN, pwFlags, pwSame, pwFwd, pwHash;             // lane-private: entries, 1 = last entry reached iend / 2 = overflow, lanes in the same bucket, insertBt1's advance
     int error;
 };
 
@@ -156,12 +185,47 @@ ZE_FN void wr16(u8* p, u32 v) { p[0] = (u8)v; p[1] = (u8)(v >> 8); }
 ZE_FN void wr24(u8* p, u32 v) { p[0] = (u8)v; p[1] = (u8)(v >> 8); p[2] = (u8)(v >> 16); }
 ZE_FN void wr32(u8* p, u32 v) { p[0] = (u8)v; p[1] = (u8)(v >> 8); p[2] = (u8)(v >> 16); p[3] = (u8)(v >> 24); }
 
-// ZSTD_count (zstd_compress_internal.h:752-772): common prefix length of a and b, a bounded by lim
+// ZSTD_count (zstd_compress_internal.h:752-772): common prefix length of a and b, a bounded by lim.
+// Lane l compares bytes [4l, 4l+4) of each 4*LANES-byte step; the first lane that sees a mismatch (or the limit) decides.
+ZE_FN u32 ld32u(const u8* p)                                      // unaligned 4-byte little-endian load (may touch 3 bytes past p+3)
+{
+#if defined(__CUDA_ARCH__)
+    const u32* q = (const u32*)((uintptr_t)p & ~(uintptr_t)3);
+    return __funnelshift_r(q[0], q[1], 8u * (u32)((uintptr_t)p & 3u));
+#else
+    return (u32)p[0] | ((u32)p[1] << 8) | ((u32)p[2] << 16) | ((u32)p[3] << 24);
+#endif
+}
+ZE_FN u64 ld64u(const u8* p)                                      // unaligned 8-byte little-endian load (may touch 15 bytes past p)
+{
+#if defined(__CUDA_ARCH__)
+    const u64* q = (const u64*)((uintptr_t)p & ~(uintptr_t)7);
+    u32 sh = 8u * (u32)((uintptr_t)p & 7u);
+    u64 lo = q[0], hi = q[1];
+    return sh ? (lo >> sh) | (hi << (64 - sh)) : lo;
+#else
+    u64 v = 0; for (int i = 7; i >= 0; --i) v = (v << 8) | p[i]; return v;
+#endif
+}
 ZE_FN u32 count_eq(const u8* a, const u8* b, const u8* lim)
 {
-    const u8* s = a;
-    while (a < lim && *a == *b) { ++a; ++b; }
-    return (u32)(a - s);
+    if (a >= lim) return 0;
+    const u32 nmax = (u32)(lim - a);
+    for (u32 base = 0; base < nmax; base += 4 * ZE_LANES) {
+        u32 off = base + 4 * ZE_LANE, idx = 0;
+        bool stop = true;
+        if (off < nmax) {
+            u32 rem = nmax - off;
+            if (rem >= 4) {
+                u32 x = ld32u(a + off) ^ ld32u(b + off);
+                idx = x ? ((ze_ffs(x) - 1) >> 3) : 4;
+            } else { while (idx < rem && a[off + idx] == b[off + idx]) ++idx; }
+            stop = idx < 4;
+        }
+        u32 mk = ze_ballot(stop);
+        if (mk) { u32 L = ze_ffs(mk) - 1; return base + 4 * L + ze_shfl(idx, L); }
+    }
+    return nmax;
 }
 
 // ZSTD_hashPtr (zstd_compress_internal.h:825): mls 5 / 6 use the 64-bit multiplicative hashes, everything else hash4
@@ -241,11 +305,150 @@ ZE_FN_NOINLINE u32 insert_bt1(Work& w, u32 curr, const u8* iend, u32 target, u32
     return positions > adv ? positions : adv;
 }
 
+// ---- batched speculative walks ----------------------------------------------------------------------------------
+// The tree walk of ZSTD_insertBt1 / ZSTD_insertBtAndGetAllMatches is a chain of dependent steps, but the trees of different
+// hash buckets are disjoint, so walks of nearby positions commute unless they share a bucket.  pw_build lets each lane
+// walk one of the next ZE_LANES positions READ-ONLY on the current tree and record the visited (matchIndex, matchLength,
+// side) sequence; the recorded walk of position q is exactly what the sequential walk would see as long as no position
+// of the same bucket has been inserted in between (pwDirty).  The real operation then replays the record: inserts are
+// committed lane-parallel (pw_commit_insert), a query replays it with its own bestLength / break rules (get_all_matches).
+// Anything the record cannot stand for (bucket conflict, record overflow, positions near the window / tree-buffer edge)
+// takes the sequential walk, so the produced tree and matches are identical to the reference order of operations.
+static const u32 PW_CAP = 256;
+
+ZE_FN_NOINLINE void pw_build(Work& w, u32 pos, const u8* iend, u32 mls)
+{
+    const u8* base = w.src - w.baseOff;
+    const u32* bt = w.chainTable;
+    u32 btLog = w.cp.chainLog - 1, btMask = (1u << btLog) - 1;
+    u32 maxDist = 1u << w.cp.windowLog;
+    u32 endIdx = (u32)(iend - base);
+    w.pwBase = pos; w.pwDirty = 0; w.pwCount = 0; w.pwEnd = endIdx; w.pwBaseOff = w.baseOff;
+    w.pwN = 0; w.pwFlags = 0; w.pwSame = 0; w.pwFwd = 1; w.pwHash = 0;
+    // walk limits must not depend on the position: nothing may fall out of the window or of the tree buffer
+    if (endIdx > btMask || endIdx - w.lowLimit > maxDist || w.lowLimit < 1) return;
+    if (pos + 8 > endIdx) return;
+    u32 cnt = endIdx - 8 - pos + 1; if (cnt > ZE_LANES) cnt = ZE_LANES;
+    w.pwCount = cnt;
+    u32 q = pos + ZE_LANE; bool act = ZE_LANE < cnt;
+    const u8* ip = base + q;
+    u32 h = act ? hash_ptr(ip, w.cp.hashLog, mls) : 0xffffffffu - ZE_LANE;
+    w.pwHash = h;
+    w.pwSame = ze_match_any(h);
+    u32* path = w.pwPath + (size_t)ZE_LANE * (2 * PW_CAP);
+    u32 n = 0, flags = 0, nb = 1u << w.cp.searchLog;
+    u32 mi = act ? w.hashTable[h] : 0;
+    u32 clS = 0, clL = 0, ml = 0;
+    u32 bestI = 8, endI = q + 9;
+    const u32 windowLow = w.lowLimit;
+    const u32 remTot = endIdx - q;
+    if (mi < windowLow) act = false;
+    while (ze_ballot(act)) {
+        if (act) {
+            const u8* a = ip + ml; const u8* m = base + mi + ml;
+            u32 rem = remTot - ml, adv;
+            if (rem >= 8) { u64 x = ld64u(a) ^ ld64u(m); adv = x ? (ze_ctz64(x) >> 3) : 8; }
+            else { adv = 0; while (adv < rem && a[adv] == m[adv]) ++adv; }
+            ml += adv;
+            if (!(adv == 8 && rem > 8)) {                     // this step's match length is known
+                if (n == PW_CAP) { flags |= 2; act = false; }
+                else {
+                    if (ml > bestI) { bestI = ml; if (ml > endI - mi) endI = mi + ml; }
+                    if (ml == remTot) { path[2 * n] = mi; path[2 * n + 1] = ml; ++n; flags |= 1; act = false; }
+                    else {
+                        bool smaller = base[mi + ml] < ip[ml];
+                        path[2 * n] = mi; path[2 * n + 1] = ml | (smaller ? 0x80000000u : 0u); ++n;
+                        const u32* nextPtr = bt + 2 * (mi & btMask);
+                        if (smaller) { clS = ml; mi = nextPtr[1]; } else { clL = ml; mi = nextPtr[0]; }
+                        --nb;
+                        if (nb == 0 || mi < windowLow) act = false;
+                        ml = clS < clL ? clS : clL;
+                    }
+                }
+            }
+        }
+    }
+    w.pwN = n; w.pwFlags = flags;
+    u32 positions = 0;
+    if (bestI > 384) { positions = bestI - 384; if (positions > 192) positions = 192; }
+    u32 adv2 = endI - (q + 8);
+    w.pwFwd = positions > adv2 ? positions : adv2;
+    ze_sync();
+}
+
+// is the recorded walk of `pos` usable right now?  (re)builds the batch when pos is outside it or its bucket was touched
+ZE_FN_NOINLINE bool pw_ready(Work& w, u32 pos, const u8* iend, u32 mls)
+{
+    const u8* base = w.src - w.baseOff;
+    u32 endIdx = (u32)(iend - base);
+    if (w.pwCount && pos >= w.pwBase && pos - w.pwBase < w.pwCount && w.pwEnd == endIdx && w.pwBaseOff == w.baseOff) {
+        u32 l = pos - w.pwBase;
+        u32 fl = ze_shfl(w.pwFlags, l);
+        if (!((w.pwDirty >> l) & 1u)) return !(fl & 2u);
+    }
+    pw_build(w, pos, iend, mls);
+    if (!w.pwCount) return false;
+    return !(ze_shfl(w.pwFlags, 0) & 2u);
+}
+
+// replay this lane's recorded walk as ZSTD_insertBt1's tree update (lane-private; no warp-wide operations inside)
+ZE_FN_NOINLINE void pw_commit_insert(Work& w, u32 q)
+{
+    u32* bt = w.chainTable;
+    u32 btLog = w.cp.chainLog - 1, btMask = (1u << btLog) - 1;
+    const u32* path = w.pwPath + (size_t)ZE_LANE * (2 * PW_CAP);
+    u32* smallerPtr = bt + 2 * (q & btMask);
+    u32* largerPtr = smallerPtr + 1;
+    w.hashTable[w.pwHash] = q;
+    u32 n = w.pwN;
+    if (w.pwFlags & 1u) --n;                                  // the walk stopped on the entry that reached iend
+    for (u32 i = 0; i < n; ++i) {
+        u32 mi = path[2 * i], v = path[2 * i + 1];
+        u32* nextPtr = bt + 2 * (mi & btMask);
+        if (v >> 31) { *smallerPtr = mi; smallerPtr = nextPtr + 1; }
+        else { *largerPtr = mi; largerPtr = nextPtr; }
+    }
+    *largerPtr = 0;
+    *smallerPtr = 0;
+}
+
 // ZSTD_updateTree_internal (zstd_opt.c:562-582)
 ZE_FN_NOINLINE void update_tree(Work& w, u32 target, const u8* iend, u32 mls)
 {
     u32 idx = w.nextToUpdate;
-    while (idx < target) idx += insert_bt1(w, idx, iend, target, mls);
+    while (idx < target) {
+        if (!pw_ready(w, idx, iend, mls)) {                   // sequential walk
+            bool covered = w.pwCount && idx >= w.pwBase && idx - w.pwBase < w.pwCount;
+            u32 same = covered ? ze_shfl(w.pwSame, idx - w.pwBase) : 0;
+            idx += insert_bt1(w, idx, iend, target, mls);
+            w.pwDirty |= same;
+            continue;
+        }
+        // run of inserts covered by the batch: lanes [l0, hi)
+        u32 l0 = idx - w.pwBase, hi = w.pwCount;
+        if (target - w.pwBase < hi) hi = target - w.pwBase;
+        bool ok = !((w.pwDirty >> ZE_LANE) & 1u) && !(w.pwFlags & 2u);
+        u32 fwd = w.pwFwd;
+        u32 live = 0, cur = l0;
+        while (cur < hi) {                                    // follow insertBt1's skip chain through the lanes
+            u32 m = ze_ballot(ZE_LANE >= cur && ZE_LANE < hi && (fwd != 1 || !ok));
+            if (!m) { live |= (hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u)) & ~((1u << cur) - 1u); cur = hi; break; }
+            u32 f = ze_ffs(m) - 1;
+            live |= ((1u << f) - 1u) & ~((1u << cur) - 1u);
+            if (!ze_shfl((u32)ok, f)) { cur = f; break; }
+            live |= 1u << f;
+            cur = f + ze_shfl(fwd, f);
+        }
+        // a live lane that shares its bucket with an earlier live lane must see that lane's update first: cut there
+        u32 below = (1u << ZE_LANE) - 1u;
+        u32 conf = ze_ballot(((live >> ZE_LANE) & 1u) && (w.pwSame & live & below));
+        if (conf) { u32 c = ze_ffs(conf) - 1; live &= (1u << c) - 1u; cur = c; w.pwDirty |= 1u << c; }
+        bool mine = (live >> ZE_LANE) & 1u;
+        if (mine) pw_commit_insert(w, w.pwBase + ZE_LANE);
+        w.pwDirty |= ze_reduce_or(mine ? w.pwSame : 0u);
+        ze_sync();
+        idx = w.pwBase + cur;
+    }
     w.nextToUpdate = target;
 }
 
@@ -311,6 +514,33 @@ ZE_FN_NOINLINE u32 get_all_matches(Work& w, Match* matches, u32* nextToUpdate3, 
             }
         }
     }
+    if (pw_ready(w, curr, iLimit, mls)) {                     // replay the recorded walk under the query's rules
+        u32 lq = curr - w.pwBase;
+        u32 n = ze_shfl(w.pwN, lq), fl = ze_shfl(w.pwFlags, lq);
+        const u32* path = w.pwPath + (size_t)lq * (2 * PW_CAP);
+        bool usable = !((fl & 1u) && (path[2 * (n - 1) + 1] & 0x7fffffffu) <= bestLength);
+        if (usable) {
+            w.hashTable[h] = curr;
+            for (u32 i = 0; i < n; ++i) {
+                u32 mi = path[2 * i], v = path[2 * i + 1], ml = v & 0x7fffffffu;
+                if (ml > bestLength) {
+                    if (ml > matchEndIdx - mi) matchEndIdx = mi + ml;
+                    bestLength = ml;
+                    matches[mnum].off = (curr - mi) + 3; matches[mnum].len = ml; ++mnum;
+                    if ((ml > OPT_NUM) | (ip + ml == iLimit)) break;
+                }
+                u32* nextPtr = bt + 2 * (mi & btMask);
+                if (v >> 31) { *smallerPtr = mi; smallerPtr = nextPtr + 1; }
+                else { *largerPtr = mi; largerPtr = nextPtr; }
+            }
+            *largerPtr = 0;
+            *smallerPtr = 0;
+            w.nextToUpdate = matchEndIdx - 8;
+            w.pwDirty |= ze_shfl(w.pwSame, lq);
+            return mnum;
+        }
+    }
+    if (w.pwCount && curr >= w.pwBase && curr - w.pwBase < w.pwCount) w.pwDirty |= ze_shfl(w.pwSame, curr - w.pwBase);
     w.hashTable[h] = curr;
     for (; nbCompares && matchIndex >= matchLow; --nbCompares) {
         u32* nextPtr = bt + 2 * (matchIndex & btMask);
@@ -423,7 +653,8 @@ ZE_FN_NOINLINE void update_stats(Work& w, u32 ll, const u8* lits, u32 offBase, u
 // ZSTD_storeSeq (zstd_compress_internal.h:649-706)
 ZE_FN_NOINLINE void store_seq(SeqStore& ss, u32 ll, const u8* lits, u32 offBase, u32 ml)
 {
-    for (u32 i = 0; i < ll; ++i) ss.lit[i] = lits[i];
+    for (u32 i = ZE_LANE; i < ll; i += ZE_LANES) ss.lit[i] = lits[i];
+    ze_sync();
     ss.lit += ll;
     u32 pos = (u32)(ss.seq - ss.seqStart);
     if (ll > 0xFFFF) { ss.longType = 1; ss.longPos = pos; }
@@ -468,14 +699,17 @@ ZE_FN_NOINLINE u32 compress_block_opt(Work& w, u32* rep, const u8* src, u32 srcS
             if (!shortest) {
                 u32 pos;
                 for (pos = 1; pos < minMatch; pos++) { opt[pos].price = MAX_PRICE; opt[pos].mlen = 0; opt[pos].litlen = litlen + pos; }
-                for (u32 m = 0; m < nbMatches; m++) {
-                    u32 offBase = matches[m].off, end = matches[m].len;
-                    for (; pos <= end; pos++) {
-                        i32 mp = (i32)match_price(w, offBase, pos, optLevel);
-                        i32 sp = opt[0].price + mp;
-                        opt[pos].mlen = pos; opt[pos].off = offBase; opt[pos].litlen = 0;
-                        opt[pos].price = sp + (i32)ll_price(w, 0, optLevel);
+                {   const i32 ll0p = (i32)ll_price(w, 0, optLevel), p0 = opt[0].price;
+                    for (u32 m = 0; m < nbMatches; m++) {
+                        u32 offBase = matches[m].off, end = matches[m].len;
+                        for (u32 q = pos + ZE_LANE; q <= end; q += ZE_LANES) {          // lanes take different lengths
+                            i32 mp = (i32)match_price(w, offBase, q, optLevel);
+                            opt[q].mlen = q; opt[q].off = offBase; opt[q].litlen = 0;
+                            opt[q].price = p0 + mp + ll0p;
+                        }
+                        if (end >= pos) pos = end + 1;
                     }
+                    ze_sync();
                 }
                 last_pos = pos - 1;
                 opt[pos].price = MAX_PRICE;
@@ -533,13 +767,28 @@ ZE_FN_NOINLINE u32 compress_block_opt(Work& w, u32* rep, const u8* src, u32 srcS
                     for (u32 m = 0; m < nbMatches; m++) {
                         u32 offset = matches[m].off, lastML = matches[m].len;
                         u32 startML = m > 0 ? matches[m - 1].len + 1 : minMatch;
-                        for (u32 mlen = lastML; mlen >= startML; mlen--) {
-                            u32 pos = cur + mlen;
-                            i32 price = basePrice + (i32)match_price(w, offset, mlen, optLevel);
-                            if (pos > last_pos || price < opt[pos].price) {
-                                while (last_pos < pos) { last_pos++; opt[last_pos].price = MAX_PRICE; opt[last_pos].litlen = 1; }
-                                opt[pos].mlen = mlen; opt[pos].off = offset; opt[pos].litlen = 0; opt[pos].price = price;
-                            } else if (optLevel == 0) break;
+                        if (optLevel == 0) {                       // btopt: the early abort makes the scan order-dependent
+                            for (u32 mlen = lastML; mlen >= startML; mlen--) {
+                                u32 pos = cur + mlen;
+                                i32 price = basePrice + (i32)match_price(w, offset, mlen, optLevel);
+                                if (pos > last_pos || price < opt[pos].price) {
+                                    while (last_pos < pos) { last_pos++; opt[last_pos].price = MAX_PRICE; opt[last_pos].litlen = 1; }
+                                    opt[pos].mlen = mlen; opt[pos].off = offset; opt[pos].litlen = 0; opt[pos].price = price;
+                                } else break;
+                            }
+                        } else if (lastML >= startML) {            // btultra(2): every length is tried -> lanes take different lengths
+                            u32 top = cur + lastML;
+                            if (top > last_pos) {
+                                for (u32 q = last_pos + 1 + ZE_LANE; q <= top; q += ZE_LANES) { opt[q].price = MAX_PRICE; opt[q].litlen = 1; }
+                                ze_sync();
+                                last_pos = top;
+                            }
+                            for (u32 mlen = startML + ZE_LANE; mlen <= lastML; mlen += ZE_LANES) {
+                                u32 pos = cur + mlen;
+                                i32 price = basePrice + (i32)match_price(w, offset, mlen, optLevel);
+                                if (price < opt[pos].price) { opt[pos].mlen = mlen; opt[pos].off = offset; opt[pos].litlen = 0; opt[pos].price = price; }
+                            }
+                            ze_sync();
                         }
                     }
                 }
@@ -1107,7 +1356,8 @@ ZE_FN_NOINLINE u32 no_compress_literals(u8* dst, const u8* src, u32 srcSize)
     if (fl == 1) dst[0] = (u8)(SET_BASIC + (srcSize << 3));
     else if (fl == 2) wr16(dst, SET_BASIC + (1 << 2) + (srcSize << 4));
     else wr32(dst, SET_BASIC + (3 << 2) + (srcSize << 4));
-    for (u32 i = 0; i < srcSize; ++i) dst[fl + i] = src[i];
+    for (u32 i = ZE_LANE; i < srcSize; i += ZE_LANES) dst[fl + i] = src[i];
+    ze_sync();
     return srcSize + fl;
 }
 ZE_FN_NOINLINE u32 rle_literals(u8* dst, const u8* src, u32 srcSize)
@@ -1491,7 +1741,8 @@ ZE_FN_NOINLINE bool build_seqstore(Work& w, const u8* src, u32 srcSize)
         lastLL = compress_block_opt(w, next.rep, src, srcSize, 2);
     }
     {   const u8* ll = src + srcSize - lastLL;                    // ZSTD_storeLastLiterals
-        for (u32 i = 0; i < lastLL; ++i) w.ss.lit[i] = ll[i];
+        for (u32 i = ZE_LANE; i < lastLL; i += ZE_LANES) w.ss.lit[i] = ll[i];
+        ze_sync();
         w.ss.lit += lastLL; }
     return true;
 }
@@ -1499,7 +1750,8 @@ ZE_FN bool is_rle(const u8* src, u32 n) { for (u32 i = 1; i < n; ++i) if (src[i]
 ZE_FN_NOINLINE u32 no_compress_block(u8* dst, const u8* src, u32 srcSize, u32 last)
 {
     wr24(dst, last + (0u << 1) + (srcSize << 3));
-    for (u32 i = 0; i < srcSize; ++i) dst[3 + i] = src[i];
+    for (u32 i = ZE_LANE; i < srcSize; i += ZE_LANES) dst[3 + i] = src[i];
+    ze_sync();
     return 3 + srcSize;
 }
 ZE_FN_NOINLINE u32 rle_compress_block(u8* dst, u8 b, u32 srcSize, u32 last) { wr24(dst, last + (1u << 1) + (srcSize << 3)); dst[3] = b; return 4; }
@@ -1608,7 +1860,8 @@ ZE_FN WorkSizes work_sizes(const Params& cp)
     z.lits = align_up((u64)cp.blockSize + 64, 256);
     z.codes = align_up((u64)3 * (maxNbSeq + 2), 256);
     z.bstates = align_up(2 * sizeof(BlockState), 256);
-    z.misc = align_up(4 * 256 + sizeof(HufNode) * 520 + 4 * 192 * 2 + 1024 + sizeof(FseCT) + sizeof(HufCT) + sizeof(FseMeta) + sizeof(HufMeta) + 4 * 200 + 256, 256);
+    z.misc = align_up(4 * 256 + sizeof(HufNode) * 520 + 4 * 192 * 2 + 1024 + sizeof(FseCT) + sizeof(HufCT) + sizeof(FseMeta) + sizeof(HufMeta) + 4 * 200 + 256 + 16, 256)
+           + align_up((u64)4 * 32 * 2 * PW_CAP, 256);
     z.total = z.hash + z.chain + z.hash3 + z.opt + z.matches + z.freqs + z.seqs + z.lits + z.codes + z.bstates + z.misc;
     return z;
 }
@@ -1643,7 +1896,10 @@ ZE_FN_NOINLINE u64 compress_frame(const u8* src, u64 srcSize64, int level, u8* d
     w.hufMeta = (HufMeta*)p; p += sizeof(HufMeta);
     p = (u8*)align_up((u64)p, 8);
     w.partitions = (u32*)p; p += 4 * 200;
-    w.dummySlot = (u32*)p;
+    w.dummySlot = (u32*)p; p += 256;
+    p = (u8*)align_up((u64)p, 8);
+    w.pwPath = (u32*)p;
+    w.pwBase = w.pwCount = w.pwDirty = w.pwEnd = w.pwBaseOff = 0; w.pwN = w.pwFlags = w.pwSame = w.pwHash = 0; w.pwFwd = 1;
     reset_seqstore(w);
     w.hashLog3 = cp.minMatch == 3 ? (cp.windowLog < 17 ? cp.windowLog : 17) : 0;
     w.baseOff = 2; w.lowLimit = 2; w.dictLimit = 2; w.nextToUpdate = 2;

@@ -1,4 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-python bench.py --steps 3 --warmup 3 > gpurun_out/bench_ours.json 2> gpurun_out/bench_ours.err; tail -c 2500 gpurun_out/bench_ours.json; tail -5 gpurun_out/bench_ours.err
+python bench.py --steps 3 --warmup 3 > gpurun_out/bench_ours.json 2> gpurun_out/bench_ours.err; tail -c 2800 gpurun_out/bench_ours.json; tail -5 gpurun_out/bench_ours.err
