@@ -330,6 +330,7 @@ std::string CAGCCompressor::ss_base(uint32_t n) const       // utils.cpp:30-66 (
 void CAGCCompressor::add_job(PartJob&& j)
 {
     j.seq = job_seq++;
+    for (auto& t : j.tasks) pending_job_bytes += t.raw.size();
     jobs.emplace_back(std::move(j));
 }
 
@@ -444,9 +445,14 @@ static void dump_u64(FILE* f, uint64_t v) { fwrite(&v, 8, 1, f); }
 static void dump_bytes(FILE* f, const void* p, size_t n) { dump_u64(f, n); if (n) fwrite(p, 1, n, f); }
 
 // write all pending parts in the reference's flush order: (registration epoch, stream id, call order)
-bool CAGCCompressor::flush_jobs(bool)
+// Parts are independent residual-coder inputs, so they are queued and coded in as few device batches as possible
+// (every frame of a batch runs concurrently); the queue is drained when forced or when it holds flush_threshold bytes.
+// Registration epochs only grow, so one sorted drain writes the parts in the same order as many small ones would.
+bool CAGCCompressor::flush_jobs(bool force)
 {
-    if (jobs.empty()) return true;
+    if (jobs.empty() && extra_tasks.empty()) return true;
+    if (!force && !dump_f && !discard_parts && pending_job_bytes < flush_threshold) return true;
+    pending_job_bytes = 0;
     std::stable_sort(jobs.begin(), jobs.end(), [](const PartJob& a, const PartJob& b) {
         if (a.epoch != b.epoch) return a.epoch < b.epoch;
         if (a.stream_id != b.stream_id) return a.stream_id < b.stream_id;
@@ -465,6 +471,8 @@ bool CAGCCompressor::flush_jobs(bool)
     }
     std::vector<ZTask*> tasks;
     for (auto& j : jobs) for (auto& t : j.tasks) tasks.push_back(&t);
+    for (auto* t : extra_tasks) tasks.push_back(t);
+    extra_tasks.clear();
     if (!compress_tasks(tasks)) return false;
     for (auto& j : jobs) {
         if (j.kind == 0 || j.kind == 1) {                       // add_to_archive / add_to_archive_tuples (segment.h:172-215)
@@ -927,7 +935,6 @@ bool CAGCCompressor::Close(uint32_t)
     // close_compression (agc_compressor.cpp:2094-2114): CSegment::finish for all groups, flush, metadata
     for (uint32_t i = 0; i < no_segments; ++i) if (!v_segments[i].pack.empty()) store_pack(i, v_segments[i], epoch);
     ++epoch;
-    if (!flush_jobs(true)) return false;
     auto a32 = [](std::vector<uint8_t>& v, uint32_t x) { for (int i = 0; i < 4; ++i) { v.push_back(x & 0xff); x >>= 8; } };
     auto a64 = [](std::vector<uint8_t>& v, uint64_t x) { for (int i = 0; i < 8; ++i) { v.push_back(x & 0xff); x >>= 8; } };
     auto astr = [](std::vector<uint8_t>& v, const std::string& s) { v.insert(v.end(), s.begin(), s.end()); v.push_back(0); };
@@ -943,8 +950,9 @@ bool CAGCCompressor::Close(uint32_t)
     fti["file_version_major"] = "3"; fti["file_version_minor"] = "0";
     fti["comment"] = "AGC (Assembled Genomes Compressor) v. 3.2.2 [build 20260326.1]";
     std::vector<uint8_t> v_fti; for (auto& x : fti) { astr(v_fti, x.first); astr(v_fti, x.second); }
-    if (discard_parts) { out_archive.Close(); return true; }
+    if (discard_parts) { flush_jobs(true); out_archive.Close(); return true; }
     if (dump_f) {
+        if (!flush_jobs(true)) return false;
         auto dump_imm = [&](const char* name, const std::vector<uint8_t>& d, uint64_t meta) {
             fwrite("IMMD", 1, 4, dump_f); dump_bytes(dump_f, name, strlen(name)); dump_u64(dump_f, meta); dump_bytes(dump_f, d.data(), d.size()); };
         dump_imm("params", v_params, 0); dump_imm("splitters", v_spl, splitters.size()); dump_imm("segment-splitters", v_map, map_segments.size());
@@ -956,12 +964,12 @@ bool CAGCCompressor::Close(uint32_t)
         out_archive.Close();
         return true;
     }
+    extra_tasks.push_back(&js.tasks[0]);                        // coded in the same device batch as the last packs
+    if (!flush_jobs(true)) return false;
     out_archive.AddPart(out_archive.RegisterStream("params"), v_params, 0);
     out_archive.AddPart(out_archive.RegisterStream("splitters"), v_spl, splitters.size());
     out_archive.AddPart(out_archive.RegisterStream("segment-splitters"), v_map, map_segments.size());
     // collection-samples is *buffered* (AddPartBuffered) while file_type_info is written immediately, so it lands last
-    std::vector<ZTask*> t{ &js.tasks[0] };
-    if (!compress_tasks(t)) return false;
     out_archive.AddPart(out_archive.RegisterStream("file_type_info"), v_fti, fti.size());
     out_archive.AddPart(collection_samples_id, js.tasks[0].packed, js.raw_size);
     return out_archive.Close();

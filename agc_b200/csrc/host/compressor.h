@@ -178,6 +178,8 @@ private:
     uint32_t processed_samples = 0;
     uint64_t epoch = 0, job_seq = 0, total_bases = 0;
     std::vector<PartJob> jobs;
+    std::vector<ZTask*> extra_tasks;                             // coded with the next drain, written by their owner
+    uint64_t pending_job_bytes = 0, flush_threshold = 1ull << 30;
     std::vector<std::pair<std::string, std::string>> cmd_lines;
     int collection_samples_id = -1, collection_contig_id = -1, collection_details_id = -1;
 };

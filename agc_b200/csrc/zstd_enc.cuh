@@ -179,8 +179,6 @@ struct Work {
     int error;
 };
 
-ZE_FN u32 rd32(const u8* p) { return (u32)p[0] | ((u32)p[1] << 8) | ((u32)p[2] << 16) | ((u32)p[3] << 24); }
-ZE_FN u64 rd64(const u8* p) { return (u64)rd32(p) | ((u64)rd32(p + 4) << 32); }
 ZE_FN void wr16(u8* p, u32 v) { p[0] = (u8)v; p[1] = (u8)(v >> 8); }
 ZE_FN void wr24(u8* p, u32 v) { p[0] = (u8)v; p[1] = (u8)(v >> 8); p[2] = (u8)(v >> 16); }
 ZE_FN void wr32(u8* p, u32 v) { p[0] = (u8)v; p[1] = (u8)(v >> 8); p[2] = (u8)(v >> 16); p[3] = (u8)(v >> 24); }
@@ -207,6 +205,8 @@ ZE_FN u64 ld64u(const u8* p)                                      // unaligned 8
     u64 v = 0; for (int i = 7; i >= 0; --i) v = (v << 8) | p[i]; return v;
 #endif
 }
+ZE_FN u32 rd32(const u8* p) { return ld32u(p); }                // MEM_readLE32 / 64 on input text (reads may run a few bytes past p + 3 / p + 7)
+ZE_FN u64 rd64(const u8* p) { return ld64u(p); }
 ZE_FN u32 count_eq(const u8* a, const u8* b, const u8* lim)
 {
     if (a >= lim) return 0;

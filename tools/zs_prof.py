@@ -11,6 +11,12 @@ while sum(map(len, parts)) < n:
     t = ref.copy(); m = rng.random(len(t)) < 0.01; t[m] = (t[m] + rng.integers(1, 4, int(m.sum()))) % 4
     parts.append(z.encode(t) + b"\xff")
 raw = b"".join(parts)[:n]
+if len(sys.argv) > 3 and sys.argv[3] == "raw":                     # raw-group pack: near-copies of one sequence, 1 byte per base
+    ref = rng.integers(0, 4, 27000).astype(np.uint8); parts = []
+    while sum(map(len, parts)) < n:
+        t = ref.copy(); m = rng.random(len(t)) < 0.01; t[m] = (t[m] + rng.integers(1, 4, int(m.sum()))) % 4
+        parts.append(bytes(t))
+    raw = b"".join(parts)[:n]
 dev = agc_b200.Device(k=21, min_match_len=20)
 for r in range(reps):
     t0 = time.time(); out = dev.zstd_compress([raw], [17]); dt = time.time() - t0
