@@ -40,7 +40,7 @@ class Assign(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("device_bytes_in_use", C.c_uint64), ("lz_alg_bytes", C.c_uint64), ("last_lz_kernel_ms", C.c_float),
-                ("last_scan_kernel_ms", C.c_float), ("reserved", C.c_float * 2)]
+                ("last_scan_kernel_ms", C.c_float), ("zstd_kernel_ms", C.c_float), ("zstd_input_mb", C.c_float)]
 
 
 # every symbol include/agcgpu.h declares (tests/test_abi.py checks header <-> library <-> this list)

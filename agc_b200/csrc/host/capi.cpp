@@ -4,6 +4,7 @@
 
 struct agcgpu_compressor { agc_b200::CAGCCompressor impl; std::string err; };
 static thread_local std::string g_err;
+static agcgpu_stats g_last_stats = {};
 
 extern "C" {
 
@@ -66,6 +67,7 @@ int agcgpu_compressor_close(agcgpu_compressor* c, uint32_t no_threads)
     if (!c) return AGCGPU_EINVAL;
     bool ok = c->impl.Close(no_threads);
     if (!ok) g_err = c->impl.LastError();
+    if (c->impl.Ctx()) agcgpu_get_stats(c->impl.Ctx(), &g_last_stats);
     delete c;
     return ok ? 0 : AGCGPU_ECUDA;
 }
@@ -73,5 +75,6 @@ int agcgpu_compressor_close(agcgpu_compressor* c, uint32_t no_threads)
 const char* agcgpu_compressor_last_error(const agcgpu_compressor* c) { return c ? c->impl.LastError().c_str() : g_err.c_str(); }
 uint64_t agcgpu_compressor_total_bases(const agcgpu_compressor* c) { return c ? c->impl.TotalBases() : 0; }
 agcgpu_ctx* agcgpu_compressor_ctx(agcgpu_compressor* c) { return c ? c->impl.Ctx() : nullptr; }
+int agcgpu_compressor_last_stats(agcgpu_stats* out) { if (!out) return AGCGPU_EINVAL; *out = g_last_stats; return 0; }
 
 }

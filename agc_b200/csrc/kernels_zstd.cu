@@ -61,6 +61,7 @@ extern "C" int agcgpu_zstd_compress_batch(agcgpu_ctx* ctx, const uint8_t* src, c
     if (int r = agc_reserve(ctx, ctx->scr_bytes, total_src + 64)) return r;
     CK(cudaMemcpyAsync(ctx->scr_bytes.p, src, total_src, cudaMemcpyHostToDevice, ctx->st));
     ctx->stats.h2d_bytes += total_src;
+    ctx->stats.zstd_input_mb += (float)(total_src * 1e-6);
     std::vector<uint64_t> out_size(n, 0);
     std::vector<std::vector<uint8_t>> frames(n);
     size_t pos = 0;
@@ -93,7 +94,7 @@ extern "C" int agcgpu_zstd_compress_batch(agcgpu_ctx* ctx, const uint8_t* src, c
         CK(cudaMemcpyAsync(tasks.data(), ctx->scr_req.p, cnt * sizeof(ZTaskDev), cudaMemcpyDeviceToHost, ctx->st));
         CK(cudaStreamSynchronize(ctx->st));
         {   float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
-            ctx->stats.reserved[0] += ms;                           // total device time of the residual coder (ms)
+            ctx->stats.zstd_kernel_ms += ms;
             if (getenv("AGCGPU_TRACE")) {
                 uint64_t tot = 0; for (uint32_t j = 0; j < cnt; ++j) tot += tasks[j].n;
                 fprintf(stderr, "[agcgpu] zstd wave: %u inputs, %llu bytes, largest %llu (level %d), kernel %.1f ms\n", cnt,

@@ -5,7 +5,7 @@
 // function it restates (paths relative to 3rd_party/zstd/lib/compress unless noted).
 //
 // The code is written once for host and device (ZE_FN): the device build is what libagcgpu ships (kernels_zstd.cu);
-// the host build exists only so tests/ can diff it against libzstd_ref on a CPU box.  One *warp* works on one input:
+// the host build exists only so tests/ can diff it against the reference's libzstd on a CPU box.  One *warp* works on one input:
 // scalar control flow is warp-uniform (every lane computes the same value), array-wide steps are lane-strided.
 #pragma once
 #include <stdint.h>

@@ -161,6 +161,7 @@ def main():
     L.agcgpu_compressor_last_error.restype = C.c_char_p; L.agcgpu_compressor_last_error.argtypes = [vp]
     L.agcgpu_compressor_ctx.restype = vp; L.agcgpu_compressor_ctx.argtypes = [vp]
     L.agcgpu_compressor_total_bases.restype = C.c_uint64; L.agcgpu_compressor_total_bases.argtypes = [vp]
+    L.agcgpu_compressor_last_stats.restype = C.c_int; L.agcgpu_compressor_last_stats.argtypes = [C.POINTER(agc_b200.Stats)]
 
     tmp = tempfile.mkdtemp(prefix=f"agcbench{rank}_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
     try:
@@ -202,7 +203,11 @@ def main():
             if rc:
                 raise SystemExit("close failed: " + L.agcgpu_compressor_last_error(None).decode())
             torch.cuda.synchronize()
-            return time.perf_counter() - t0, stats
+            dt = time.perf_counter() - t0
+            L.agcgpu_compressor_last_stats(C.byref(st))          # counters incl. the residual coder, which runs inside close
+            for k in ("kernel_launches", "h2d_bytes", "d2h_bytes", "zstd_kernel_ms", "zstd_input_mb"):
+                stats[k] = getattr(st, k)
+            return dt, stats
 
         # is the device residual coder available?  (probe once; without it the step stops before zstd and says so)
         global RESIDUAL
@@ -263,6 +268,10 @@ def main():
                     "roofline": {"kernel": "k_lz_packed<0> (LZ-diff encode)", "bound": "hbm", "achieved": lz_gbs, "peak": peak, "unit": "GB/s",
                                  "frac": lz_gbs / peak, "traffic": traffic, "peak_source": peak_src,
                                  "algorithmic_bytes_per_launch": int(st_res["lz_alg_bytes"]), "kernel_ms": st_res["last_lz_kernel_ms"]},
+                    "residual_coder": {"kernel": "k_zstd (zstd frames, one warp per part)", "ms_per_step": float(st_res["zstd_kernel_ms"]),
+                                       "input_bytes_per_step": int(st_res["zstd_input_mb"] * 1e6),
+                                       "share_of_step": float(st_res["zstd_kernel_ms"]) / (sec_res * 1e3),
+                                       "note": "sequential optimal parse per frame: latency bound, not an HBM-roofline kernel (DESIGN.md section 5)"},
                     "cpu_baseline": cpu, "clocks": sampler.summary()}
             print(json.dumps(line))
     finally:

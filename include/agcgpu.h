@@ -91,7 +91,8 @@ typedef struct {
     uint64_t lz_alg_bytes;       /* sum over LZ requests of ceil(n/4)+ceil(m/4)+e of the last LZ batch */
     float    last_lz_kernel_ms;  /* device time of the last LZ kernel (CUDA events on the library stream) */
     float    last_scan_kernel_ms;
-    float    reserved[2];
+    float    zstd_kernel_ms;     /* device time spent in the residual coder since agcgpu_create (sum over batches) */
+    float    zstd_input_mb;      /* bytes handed to the residual coder since agcgpu_create, in 10^6 bytes */
 } agcgpu_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------------------------------- */
@@ -194,6 +195,8 @@ int agcgpu_compressor_close(agcgpu_compressor* c, uint32_t no_threads);
 const char* agcgpu_compressor_last_error(const agcgpu_compressor* c);   /* c may be NULL: last failed create */
 uint64_t agcgpu_compressor_total_bases(const agcgpu_compressor* c);
 agcgpu_ctx* agcgpu_compressor_ctx(agcgpu_compressor* c);
+/* counters of the compressor most recently closed in this process (its context is gone by then); measurement hook */
+int agcgpu_compressor_last_stats(agcgpu_stats* out);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

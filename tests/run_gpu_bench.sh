@@ -1,4 +1,7 @@
 #!/bin/bash
+# full GPU check: parity suite, smoke, then both bench arms (what the driver runs at round end)
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-python bench.py --steps 3 --warmup 3 > gpurun_out/bench_ours.json 2> gpurun_out/bench_ours.err; tail -c 2800 gpurun_out/bench_ours.json; tail -5 gpurun_out/bench_ours.err
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -2 gpurun_out/smoke.log
+python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; tail -c 600 gpurun_out/bench_ref.json
+python bench.py --steps 3 --warmup 3 > gpurun_out/bench_ours.json 2> gpurun_out/bench_ours.err; tail -c 3000 gpurun_out/bench_ours.json; tail -5 gpurun_out/bench_ours.err
