@@ -1,5 +1,8 @@
 // compressor.cpp -- see compressor.h.  Reference citations are relative to /root/reference.
 #include "compressor.h"
+#include <chrono>
+#include <cstdlib>
+#include <cstdio>
 #include <zlib.h>
 #include <algorithm>
 #include <cstring>
@@ -7,6 +10,12 @@
 #include <numeric>
 #include <set>
 
+// AGCGPU_TRACE=1: wall time of the host-visible phases on stderr (diagnostics only)
+struct PhaseTimer {
+    const char* name; std::chrono::steady_clock::time_point t0; bool on;
+    explicit PhaseTimer(const char* n) : name(n), t0(std::chrono::steady_clock::now()), on(getenv("AGCGPU_TRACE") != nullptr) {}
+    ~PhaseTimer() { if (on) fprintf(stderr, "[agcgpu] phase %-22s %8.1f ms\n", name, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count()); }
+};
 namespace agc_b200 {
 
 // =====================================================================================================================
@@ -347,6 +356,7 @@ bool CAGCCompressor::Create(const std::string& file_name, uint32_t _pack_cardina
     agcgpu_params prm; memset(&prm, 0, sizeof prm);
     prm.kmer_length = kmer_length; prm.min_match_len = min_match_len; prm.segment_size = segment_size;
     prm.pack_cardinality = pack_cardinality; prm.device = device;
+    PhaseTimer pt_create("create+splitters");
     int rc = agcgpu_create(&prm, &ctx);
     if (rc) return fail(std::string("agcgpu_create: ") + agcgpu_last_error(nullptr));
 
@@ -426,6 +436,7 @@ void CAGCCompressor::store_contig_batch(uint32_t id_from, uint32_t id_to, uint64
 
 bool CAGCCompressor::compress_tasks(std::vector<ZTask*>& tasks)
 {
+    PhaseTimer pt("residual coder batch");
     if (tasks.empty()) return true;
     std::vector<uint64_t> offs(tasks.size() + 1, 0);
     std::vector<int32_t> levels(tasks.size());
@@ -574,7 +585,7 @@ bool CAGCCompressor::process_batch_raw(const uint8_t* cat, bool is_device, const
     auto do_scan = [&]() {
         return is_device ? agcgpu_scan_contigs_dev(ctx, cat, offs[nc], offs.data(), nc, clen.data(), cuts.data(), cap_cuts, &n_cuts)
                          : agcgpu_scan_contigs(ctx, cat, offs.data(), nc, clen.data(), cuts.data(), cap_cuts, &n_cuts); };
-    int rc = do_scan();
+    int rc; { PhaseTimer pt("scan_contigs"); rc = do_scan(); }
     if (rc == AGCGPU_EOVERFLOW && n_cuts > cap_cuts) { cap_cuts = n_cuts + 16; cuts.resize(cap_cuts); rc = do_scan(); }
     if (!gpu_ok(rc, "scan_contigs")) return false;
     cuts.resize(n_cuts);
@@ -590,7 +601,8 @@ bool CAGCCompressor::process_batch_raw(const uint8_t* cat, bool is_device, const
         if (from_cut >= n_cuts) return true;
         return gpu_ok(agcgpu_assign_cuts(ctx, cuts.data() + from_cut, n_cuts - from_cut, assign.data() + from_cut), "assign_cuts");
     };
-    if (!run_assign(0)) return false;
+    { PhaseTimer pt("assign_cuts"); if (!run_assign(0)) return false; }
+    PhaseTimer pt_rest("add_segment..packs");
 
     struct RegGroup { uint32_t group; std::vector<Item> items; };
     struct SampleReg { uint32_t sample_id; std::vector<RegGroup> groups; };
@@ -930,6 +942,7 @@ bool CAGCCompressor::process_batch_raw(const uint8_t* cat, bool is_device, const
 
 bool CAGCCompressor::Close(uint32_t)
 {
+    PhaseTimer pt("close");
     if (!working) return false;
     working = false;
     // close_compression (agc_compressor.cpp:2094-2114): CSegment::finish for all groups, flush, metadata

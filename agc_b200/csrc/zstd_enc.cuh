@@ -205,6 +205,35 @@ ZE_FN u64 ld64u(const u8* p)                                      // unaligned 8
     u64 v = 0; for (int i = 7; i >= 0; --i) v = (v << 8) | p[i]; return v;
 #endif
 }
+ZE_FN void ld64w(const u8* p, u32& lo, u32& hi)                   // unaligned 8 bytes as two little-endian words (may touch 11 bytes past p)
+{
+#if defined(__CUDA_ARCH__)
+    const u32* q = (const u32*)((uintptr_t)p & ~(uintptr_t)3);
+    u32 sh = 8u * (u32)((uintptr_t)p & 3u);
+    u32 w0 = q[0], w1 = q[1], w2 = q[2];
+    lo = __funnelshift_r(w0, w1, sh); hi = __funnelshift_r(w1, w2, sh);
+#else
+    lo = (u32)p[0] | ((u32)p[1] << 8) | ((u32)p[2] << 16) | ((u32)p[3] << 24);
+    hi = (u32)p[4] | ((u32)p[5] << 8) | ((u32)p[6] << 16) | ((u32)p[7] << 24);
+#endif
+}
+struct U2 { u32 x, y; };
+ZE_FN U2 ld_pair(const u32* p)                                    // 8-byte aligned pair
+{
+#if defined(__CUDA_ARCH__)
+    uint2 v = *reinterpret_cast<const uint2*>(p); U2 r; r.x = v.x; r.y = v.y; return r;
+#else
+    U2 r; r.x = p[0]; r.y = p[1]; return r;
+#endif
+}
+ZE_FN void st_pair(u32* p, u32 x, u32 y)
+{
+#if defined(__CUDA_ARCH__)
+    *reinterpret_cast<uint2*>(p) = make_uint2(x, y);
+#else
+    p[0] = x; p[1] = y;
+#endif
+}
 ZE_FN u32 rd32(const u8* p) { return ld32u(p); }                // MEM_readLE32 / 64 on input text (reads may run a few bytes past p + 3 / p + 7)
 ZE_FN u64 rd64(const u8* p) { return ld64u(p); }
 ZE_FN u32 count_eq(const u8* a, const u8* b, const u8* lim)
@@ -343,23 +372,38 @@ ZE_FN_NOINLINE void pw_build(Work& w, u32 pos, const u8* iend, u32 mls)
     const u32 windowLow = w.lowLimit;
     const u32 remTot = endIdx - q;
     if (mi < windowLow) act = false;
+    U2 nx; nx.x = nx.y = 0;
+    bool fresh = true;                                            // children of `mi` not loaded yet
     while (ze_ballot(act)) {
         if (act) {
+            if (fresh) { nx = ld_pair(bt + 2 * (mi & btMask)); fresh = false; }   // both children, in flight with the text loads
             const u8* a = ip + ml; const u8* m = base + mi + ml;
-            u32 rem = remTot - ml, adv;
-            if (rem >= 8) { u64 x = ld64u(a) ^ ld64u(m); adv = x ? (ze_ctz64(x) >> 3) : 8; }
-            else { adv = 0; while (adv < rem && a[adv] == m[adv]) ++adv; }
-            ml += adv;
-            if (!(adv == 8 && rem > 8)) {                     // this step's match length is known
+            u32 rem = remTot - ml, ca = 0, cm = 0;
+            bool done;
+            if (rem >= 8) {
+                u32 alo, ahi, mlo, mhi;
+                ld64w(a, alo, ahi); ld64w(m, mlo, mhi);
+                u32 xlo = alo ^ mlo, xhi = ahi ^ mhi, adv;
+                if (xlo) { adv = (ze_ffs(xlo) - 1) >> 3; ca = (alo >> (8 * adv)) & 255u; cm = (mlo >> (8 * adv)) & 255u; }
+                else if (xhi) { u32 t = (ze_ffs(xhi) - 1) >> 3; adv = 4 + t; ca = (ahi >> (8 * t)) & 255u; cm = (mhi >> (8 * t)) & 255u; }
+                else adv = 8;
+                ml += adv;
+                done = adv < 8 || rem == 8;
+            } else {
+                u32 adv = 0; while (adv < rem && a[adv] == m[adv]) ++adv;
+                ml += adv; done = true;
+                if (adv < rem) { ca = a[adv]; cm = m[adv]; }
+            }
+            if (done) {                                           // this step's match length is known
                 if (n == PW_CAP) { flags |= 2; act = false; }
                 else {
                     if (ml > bestI) { bestI = ml; if (ml > endI - mi) endI = mi + ml; }
-                    if (ml == remTot) { path[2 * n] = mi; path[2 * n + 1] = ml; ++n; flags |= 1; act = false; }
+                    if (ml == remTot) { st_pair(path + 2 * n, mi, ml); ++n; flags |= 1; act = false; }
                     else {
-                        bool smaller = base[mi + ml] < ip[ml];
-                        path[2 * n] = mi; path[2 * n + 1] = ml | (smaller ? 0x80000000u : 0u); ++n;
-                        const u32* nextPtr = bt + 2 * (mi & btMask);
-                        if (smaller) { clS = ml; mi = nextPtr[1]; } else { clL = ml; mi = nextPtr[0]; }
+                        bool smaller = cm < ca;
+                        st_pair(path + 2 * n, mi, ml | (smaller ? 0x80000000u : 0u)); ++n;
+                        if (smaller) { clS = ml; mi = nx.y; } else { clL = ml; mi = nx.x; }
+                        fresh = true;
                         --nb;
                         if (nb == 0 || mi < windowLow) act = false;
                         ml = clS < clL ? clS : clL;
@@ -403,7 +447,8 @@ ZE_FN_NOINLINE void pw_commit_insert(Work& w, u32 q)
     u32 n = w.pwN;
     if (w.pwFlags & 1u) --n;                                  // the walk stopped on the entry that reached iend
     for (u32 i = 0; i < n; ++i) {
-        u32 mi = path[2 * i], v = path[2 * i + 1];
+        U2 e = ld_pair(path + 2 * i);
+        u32 mi = e.x, v = e.y;
         u32* nextPtr = bt + 2 * (mi & btMask);
         if (v >> 31) { *smallerPtr = mi; smallerPtr = nextPtr + 1; }
         else { *largerPtr = mi; largerPtr = nextPtr; }
@@ -522,7 +567,8 @@ ZE_FN_NOINLINE u32 get_all_matches(Work& w, Match* matches, u32* nextToUpdate3, 
         if (usable) {
             w.hashTable[h] = curr;
             for (u32 i = 0; i < n; ++i) {
-                u32 mi = path[2 * i], v = path[2 * i + 1], ml = v & 0x7fffffffu;
+                U2 e = ld_pair(path + 2 * i);
+                u32 mi = e.x, v = e.y, ml = v & 0x7fffffffu;
                 if (ml > bestLength) {
                     if (ml > matchEndIdx - mi) matchEndIdx = mi + ml;
                     bestLength = ml;
