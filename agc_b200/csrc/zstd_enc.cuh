@@ -374,40 +374,44 @@ ZE_FN_NOINLINE void pw_build(Work& w, u32 pos, const u8* iend, u32 mls)
     if (mi < windowLow) act = false;
     U2 nx; nx.x = nx.y = 0;
     bool fresh = true;                                            // children of `mi` not loaded yet
+    // lanes diverge only on rare events; the common step is straight-line selects so the warp issues it once for all lanes
     while (ze_ballot(act)) {
         if (act) {
             if (fresh) { nx = ld_pair(bt + 2 * (mi & btMask)); fresh = false; }   // both children, in flight with the text loads
             const u8* a = ip + ml; const u8* m = base + mi + ml;
-            u32 rem = remTot - ml, ca = 0, cm = 0;
-            bool done;
+            u32 rem = remTot - ml, ca, cm, adv;
             if (rem >= 8) {
                 u32 alo, ahi, mlo, mhi;
                 ld64w(a, alo, ahi); ld64w(m, mlo, mhi);
-                u32 xlo = alo ^ mlo, xhi = ahi ^ mhi, adv;
-                if (xlo) { adv = (ze_ffs(xlo) - 1) >> 3; ca = (alo >> (8 * adv)) & 255u; cm = (mlo >> (8 * adv)) & 255u; }
-                else if (xhi) { u32 t = (ze_ffs(xhi) - 1) >> 3; adv = 4 + t; ca = (ahi >> (8 * t)) & 255u; cm = (mhi >> (8 * t)) & 255u; }
-                else adv = 8;
-                ml += adv;
-                done = adv < 8 || rem == 8;
+                u32 xlo = alo ^ mlo, xhi = ahi ^ mhi;
+                bool inLo = xlo != 0;
+                u32 x = inLo ? xlo : xhi, wa = inLo ? alo : ahi, wm = inLo ? mlo : mhi;
+                u32 t = x ? ((ze_ffs(x) - 1) >> 3) : 0;          // byte of the first difference inside the word
+                adv = x ? (inLo ? t : 4 + t) : 8;
+                ca = (wa >> (8 * t)) & 255u; cm = (wm >> (8 * t)) & 255u;
             } else {
-                u32 adv = 0; while (adv < rem && a[adv] == m[adv]) ++adv;
-                ml += adv; done = true;
+                adv = 0; while (adv < rem && a[adv] == m[adv]) ++adv;
+                ca = cm = 0;
                 if (adv < rem) { ca = a[adv]; cm = m[adv]; }
             }
-            if (done) {                                           // this step's match length is known
-                if (n == PW_CAP) { flags |= 2; act = false; }
+            ml += adv;
+            if (adv < 8 || rem == 8) {                            // this step's match length is known
+                bool atEnd = ml == remTot, ovf = n == PW_CAP;
+                if (ovf) { flags |= 2; act = false; }
                 else {
-                    if (ml > bestI) { bestI = ml; if (ml > endI - mi) endI = mi + ml; }
-                    if (ml == remTot) { st_pair(path + 2 * n, mi, ml); ++n; flags |= 1; act = false; }
-                    else {
-                        bool smaller = cm < ca;
-                        st_pair(path + 2 * n, mi, ml | (smaller ? 0x80000000u : 0u)); ++n;
-                        if (smaller) { clS = ml; mi = nx.y; } else { clL = ml; mi = nx.x; }
-                        fresh = true;
-                        --nb;
-                        if (nb == 0 || mi < windowLow) act = false;
-                        ml = clS < clL ? clS : clL;
-                    }
+                    bool better = ml > bestI;
+                    if (better && ml > endI - mi) endI = mi + ml;
+                    bestI = better ? ml : bestI;
+                    bool smaller = cm < ca;
+                    st_pair(path + 2 * n, mi, atEnd ? ml : (ml | (smaller ? 0x80000000u : 0u))); ++n;
+                    clS = (smaller && !atEnd) ? ml : clS;
+                    clL = (!smaller && !atEnd) ? ml : clL;
+                    mi = smaller ? nx.y : nx.x;
+                    fresh = true;
+                    --nb;
+                    flags |= atEnd ? 1u : 0u;
+                    act = !(atEnd || nb == 0 || mi < windowLow);
+                    ml = clS < clL ? clS : clL;
                 }
             }
         }
@@ -448,10 +452,11 @@ ZE_FN_NOINLINE void pw_commit_insert(Work& w, u32 q)
     if (w.pwFlags & 1u) --n;                                  // the walk stopped on the entry that reached iend
     for (u32 i = 0; i < n; ++i) {
         U2 e = ld_pair(path + 2 * i);
-        u32 mi = e.x, v = e.y;
+        u32 mi = e.x; bool sm = (e.y >> 31) != 0;
         u32* nextPtr = bt + 2 * (mi & btMask);
-        if (v >> 31) { *smallerPtr = mi; smallerPtr = nextPtr + 1; }
-        else { *largerPtr = mi; largerPtr = nextPtr; }
+        *(sm ? smallerPtr : largerPtr) = mi;                      // selects, not branches: lanes replay different walks
+        smallerPtr = sm ? nextPtr + 1 : smallerPtr;
+        largerPtr = sm ? largerPtr : nextPtr;
     }
     *largerPtr = 0;
     *smallerPtr = 0;

@@ -1,6 +1,3 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python tools/zs_prof.py 60000 2 > gpurun_out/zstd_timing.txt 2>&1
-python tools/zs_prof.py 300000 2 raw >> gpurun_out/zstd_timing.txt 2>&1; cat gpurun_out/zstd_timing.txt
 ncu --section SourceCounters --section WarpStateStats --section SchedulerStats --section LaunchStats --section MemoryWorkloadAnalysis --import-source on --clock-control none -k regex:k_zstd -c 1 -f -o gpurun_out/zstd_prof_raw python tools/zs_prof.py 300000 1 raw > gpurun_out/ncu_zstd.log 2>&1; tail -2 gpurun_out/ncu_zstd.log
-ncu --section SourceCounters --section WarpStateStats --section SchedulerStats --section LaunchStats --section MemoryWorkloadAnalysis --import-source on --clock-control none -k regex:k_zstd -c 1 -f -o gpurun_out/zstd_prof_delta python tools/zs_prof.py 60000 1 > gpurun_out/ncu_zstd2.log 2>&1; tail -2 gpurun_out/ncu_zstd2.log
