@@ -31,6 +31,10 @@
 #define ze_match_any(v) __match_any_sync(0xffffffffu, (v))
 #define ze_reduce_or(v) __reduce_or_sync(0xffffffffu, (v))
 #define ze_ctz64(x) ((unsigned)__ffsll((long long)(x)) - 1u)
+#define ze_shfl_up(v, d) __shfl_up_sync(0xffffffffu, (v), (d))
+#define ze_reduce_max(v) __reduce_max_sync(0xffffffffu, (unsigned)(v))
+#define ze_popc(v) ((unsigned)__popc(v))
+#define ze_hibit(v) (31u - (unsigned)__clz((int)(v)))
 #else
 #define ZE_LANE 0u
 #define ZE_LANES 1u
@@ -41,6 +45,10 @@
 #define ze_match_any(v) 1u
 #define ze_reduce_or(v) (v)
 #define ze_ctz64(x) ((unsigned)__builtin_ctzll(x))
+#define ze_shfl_up(v, d) (v)
+#define ze_reduce_max(v) ((unsigned)(v))
+#define ze_popc(v) ((unsigned)__builtin_popcount(v))
+#define ze_hibit(v) (31u - (unsigned)__builtin_clz(v))
 #endif
 
 typedef uint8_t u8; typedef uint16_t u16; typedef uint32_t u32; typedef uint64_t u64; typedef int32_t i32; typedef int16_t i16;
@@ -571,18 +579,46 @@ ZE_FN_NOINLINE u32 get_all_matches(Work& w, Match* matches, u32* nextToUpdate3, 
         bool usable = !((fl & 1u) && (path[2 * (n - 1) + 1] & 0x7fffffffu) <= bestLength);
         if (usable) {
             w.hashTable[h] = curr;
-            for (u32 i = 0; i < n; ++i) {
-                U2 e = ld_pair(path + 2 * i);
-                u32 mi = e.x, v = e.y, ml = v & 0x7fffffffu;
-                if (ml > bestLength) {
-                    if (ml > matchEndIdx - mi) matchEndIdx = mi + ml;
-                    bestLength = ml;
-                    matches[mnum].off = (curr - mi) + 3; matches[mnum].len = ml; ++mnum;
-                    if ((ml > OPT_NUM) | (ip + ml == iLimit)) break;
+            // ZE_LANES recorded steps at a time: which steps set a new best length is a prefix maximum, the slot a step
+            // links into belongs to the previous step on the same side (ballot + highest set bit below the lane)
+            for (u32 c = 0; c < n; c += ZE_LANES) {
+                u32 i = c + ZE_LANE;
+                bool valid = i < n;
+                U2 e; e.x = e.y = 0;
+                if (valid) e = ld_pair(path + 2 * i);
+                u32 mi = e.x, ml = e.y & 0x7fffffffu; bool sm = (e.y >> 31) != 0;
+                u32 incl = valid ? ml : 0;
+                for (u32 d = 1; d < ZE_LANES; d <<= 1) { u32 t = ze_shfl_up(incl, d); if (ZE_LANE >= d && t > incl) incl = t; }
+                u32 excl = ze_shfl_up(incl, 1); if (ZE_LANE == 0) excl = 0;
+                if (excl < bestLength) excl = bestLength;
+                bool rec = valid && ml > excl;
+                u32 brk = ze_ballot(rec && ((ml > OPT_NUM) | (ip + ml == iLimit)));
+                u32 lim = brk ? ze_ffs(brk) - 1 : 32;                               // step that ends the walk (recorded, not linked)
+                u32 upto = lim >= 31 ? 0xffffffffu : ((2u << lim) - 1u);            // lanes <= lim
+                u32 before = lim >= 32 ? 0xffffffffu : ((1u << lim) - 1u);          // lanes <  lim
+                u32 below = (1u << ZE_LANE) - 1u;
+                u32 recmask = ze_ballot(rec) & upto;
+                bool myrec = (recmask >> ZE_LANE) & 1u;
+                if (myrec) { u32 k = mnum + ze_popc(recmask & below); matches[k].off = (curr - mi) + 3; matches[k].len = ml; }
+                u32 mxEnd = ze_reduce_max(myrec ? mi + ml : 0u), mxLen = ze_reduce_max(myrec ? ml : 0u);
+                if (mxEnd > matchEndIdx) matchEndIdx = mxEnd;
+                if (mxLen > bestLength) bestLength = mxLen;
+                mnum += ze_popc(recmask);
+                u32 proc = ze_ballot(valid) & before;
+                u32 S = ze_ballot(valid && sm) & proc, Lm = proc & ~S;
+                u32 mine = sm ? S : Lm;                                           // steps on my side
+                u32 prevm = mine & below;
+                u32 pj = prevm ? ze_hibit(prevm) : ZE_LANE;
+                u32 pmi = ze_shfl(mi, pj);
+                if ((proc >> ZE_LANE) & 1u) {
+                    u32* slot = prevm ? (bt + 2 * (pmi & btMask) + (sm ? 1 : 0)) : (sm ? smallerPtr : largerPtr);
+                    *slot = mi;
                 }
-                u32* nextPtr = bt + 2 * (mi & btMask);
-                if (v >> 31) { *smallerPtr = mi; smallerPtr = nextPtr + 1; }
-                else { *largerPtr = mi; largerPtr = nextPtr; }
+                u32 lastS = ze_shfl(mi, S ? ze_hibit(S) : 0), lastL = ze_shfl(mi, Lm ? ze_hibit(Lm) : 0);
+                if (S) smallerPtr = bt + 2 * (lastS & btMask) + 1;
+                if (Lm) largerPtr = bt + 2 * (lastL & btMask);
+                ze_sync();
+                if (lim < 32) break;
             }
             *largerPtr = 0;
             *smallerPtr = 0;
