@@ -7,6 +7,51 @@
 
 static thread_local std::string g_create_err;
 
+// Device-memory pool shared by all contexts of the process: a context returns its buffers here when it is destroyed and the next
+// one (another `create` in the same process, e.g. a server compressing collection after collection) takes them back instead of
+// paying cudaMalloc / cudaFree -- both synchronise the device and cost tens to hundreds of milliseconds for the large tables.
+#include <mutex>
+namespace {
+struct PoolBlock { void* p; size_t cap; };
+std::mutex g_pool_mu;
+std::vector<PoolBlock> g_pool[32];
+const size_t kPoolMaxBytes = (size_t)64 << 30;
+size_t g_pool_bytes[32];
+std::vector<PoolBlock> g_pin_pool;
+}
+void* agc_dev_alloc(int dev, size_t bytes, size_t* cap_out)
+{
+    {   std::lock_guard<std::mutex> lk(g_pool_mu);
+        auto& v = g_pool[dev & 31];
+        int best = -1;
+        for (int i = 0; i < (int)v.size(); ++i)
+            if (v[i].cap >= bytes && v[i].cap <= 4 * bytes + ((size_t)1 << 20) && (best < 0 || v[i].cap < v[best].cap)) best = i;
+        if (best >= 0) { PoolBlock b = v[best]; v.erase(v.begin() + best); g_pool_bytes[dev & 31] -= b.cap; *cap_out = b.cap; return b.p; }
+    }
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        agc_dev_trim(dev);                                       // give the pooled blocks back to the driver and retry once
+        if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    }
+    *cap_out = bytes;
+    return p;
+}
+void agc_dev_free(int dev, void* p, size_t cap)
+{
+    if (!p) return;
+    {   std::lock_guard<std::mutex> lk(g_pool_mu);
+        if (g_pool_bytes[dev & 31] + cap <= kPoolMaxBytes) { g_pool[dev & 31].push_back(PoolBlock{ p, cap }); g_pool_bytes[dev & 31] += cap; return; }
+    }
+    cudaFree(p);
+}
+void agc_dev_trim(int dev)
+{
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    for (auto& b : g_pool[dev & 31]) cudaFree(b.p);
+    g_pool[dev & 31].clear(); g_pool_bytes[dev & 31] = 0;
+}
+
 int agc_fail(agcgpu_ctx* c, int code, const char* fmt, ...)
 {
     char buf[512];
@@ -20,13 +65,15 @@ int agc_reserve(agcgpu_ctx* ctx, DevBuf& b, size_t bytes, bool keep)
     if (bytes <= b.cap) return 0;
     size_t ncap = std::max(bytes + bytes / 4, (size_t)4096);
     ncap = (ncap + 255) / 256 * 256;
-    void* np = nullptr;
-    if (cudaMalloc(&np, ncap + 64) != cudaSuccess) { cudaGetLastError(); return agc_fail(ctx, AGCGPU_ENOMEM, "cudaMalloc(%zu) failed", ncap); }
+    size_t got = 0;
+    void* np = agc_dev_alloc(ctx->dev, ncap + 64, &got);
+    if (!np) return agc_fail(ctx, AGCGPU_ENOMEM, "cudaMalloc(%zu) failed", ncap);
+    ncap = got - 64;
     if (keep && b.p && b.cap) {
         if (cudaMemcpyAsync(np, b.p, b.cap, cudaMemcpyDeviceToDevice, ctx->st) != cudaSuccess || cudaStreamSynchronize(ctx->st) != cudaSuccess)
             return agc_fail(ctx, AGCGPU_ECUDA, "device realloc copy failed");
     } else if (b.p) cudaStreamSynchronize(ctx->st);
-    if (b.p) { cudaFree(b.p); ctx->device_bytes -= b.cap; }
+    if (b.p) { agc_dev_free(ctx->dev, b.p, b.cap + 64); ctx->device_bytes -= b.cap; }
     b.p = np; b.cap = ncap; ctx->device_bytes += ncap;
     return 0;
 }
@@ -36,9 +83,11 @@ void* agc_arena_alloc(agcgpu_ctx* ctx, size_t bytes)
     bytes = (bytes + 255) / 256 * 256;
     if (bytes > ctx->arena_left) {
         size_t chunk = std::max(bytes, (size_t)256 << 20);
-        void* p = nullptr;
-        if (cudaMalloc(&p, chunk) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-        ctx->arena_chunks.push_back(p);
+        size_t got = 0;
+        void* p = agc_dev_alloc(ctx->dev, chunk, &got);
+        if (!p) return nullptr;
+        chunk = got;
+        ctx->arena_chunks.emplace_back(p, chunk);
         ctx->arena_cur = (uint8_t*)p; ctx->arena_left = chunk; ctx->device_bytes += chunk;
     }
     void* r = ctx->arena_cur;
@@ -51,6 +100,10 @@ int agc_pin_reserve(agcgpu_ctx* ctx, size_t bytes)
     if (bytes <= ctx->pin_cap) return 0;
     if (ctx->pin) cudaFreeHost(ctx->pin);
     ctx->pin = nullptr; ctx->pin_cap = 0;
+    {   std::lock_guard<std::mutex> lk(g_pool_mu);              // pinned staging of a destroyed context
+        for (size_t i = 0; i < g_pin_pool.size(); ++i)
+            if (g_pin_pool[i].cap >= bytes) { ctx->pin = g_pin_pool[i].p; ctx->pin_cap = g_pin_pool[i].cap; g_pin_pool.erase(g_pin_pool.begin() + i); return 0; }
+    }
     size_t ncap = bytes + bytes / 4 + 4096;
     if (cudaMallocHost(&ctx->pin, ncap) != cudaSuccess) { cudaGetLastError(); return agc_fail(ctx, AGCGPU_ENOMEM, "cudaMallocHost(%zu) failed", ncap); }
     ctx->pin_cap = ncap;
@@ -96,8 +149,12 @@ void agcgpu_destroy(agcgpu_ctx* ctx)
                        &ctx->tile_cnt, &ctx->tile_base, &ctx->d_cstart, &ctx->chunk_prefix, &ctx->hits, &ctx->counters, &ctx->map_k1,
                        &ctx->map_k2, &ctx->map_val, &ctx->d_groups, &ctx->scr_req, &ctx->scr_units, &ctx->scr_out, &ctx->scr_sizes,
                        &ctx->scr_offs, &ctx->scr_dense, &ctx->scr_misc, &ctx->scr_bytes };
-    for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
-    for (void* p : ctx->arena_chunks) cudaFree(p);
+    for (DevBuf* b : bufs) if (b->p) agc_dev_free(ctx->dev, b->p, b->cap + 64);
+    for (auto& c : ctx->arena_chunks) agc_dev_free(ctx->dev, c.first, c.second);
+    if (ctx->pin) {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        if (g_pin_pool.size() < 4) { g_pin_pool.push_back(PoolBlock{ ctx->pin, ctx->pin_cap }); ctx->pin = nullptr; }
+    }
     if (ctx->pin) cudaFreeHost(ctx->pin);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
     cudaStreamDestroy(ctx->st);

@@ -1,6 +1,16 @@
 // capi.cpp -- C facade over agc_b200::CAGCCompressor (include/agcgpu.h, "CAGCCompressor facade")
 #include "compressor.h"
 #include <string>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+
+// AGCGPU_TRACE=1: wall time of each facade call on stderr (diagnostics only)
+namespace { struct CallTimer {
+    const char* name; std::chrono::steady_clock::time_point t0; bool on;
+    explicit CallTimer(const char* n) : name(n), t0(std::chrono::steady_clock::now()), on(getenv("AGCGPU_TRACE") != nullptr) {}
+    ~CallTimer() { if (on) fprintf(stderr, "[agcgpu] call  %-22s %8.1f ms\n", name, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count()); }
+}; }
 
 struct agcgpu_compressor { agc_b200::CAGCCompressor impl; std::string err; };
 static thread_local std::string g_err;
@@ -14,6 +24,7 @@ int agcgpu_compressor_create(const char* out_file, uint32_t pack_cardinality, ui
                              const char* dump_parts_path, agcgpu_compressor** out)
 {
     if (!out_file || !reference_file || !out) { g_err = "null argument"; return AGCGPU_EINVAL; }
+    CallTimer ct("compressor_create");
     agcgpu_compressor* c = new agcgpu_compressor();
     c->impl.SetAppMode(false);
     c->impl.SetDevice(device);
@@ -42,6 +53,7 @@ int agcgpu_compressor_add_samples_memory(agcgpu_compressor* c, const char* const
                                          const void* raw, const uint64_t* offsets, int raw_is_device)
 {
     if (!c || !sample_names || !sample_of_contig || !contig_ids || !raw || !offsets) return AGCGPU_EINVAL;
+    CallTimer ct("add_samples_memory");
     std::vector<std::string> sn(sample_names, sample_names + n_samples), ci(contig_ids, contig_ids + n_contigs);
     std::vector<uint32_t> soc(sample_of_contig, sample_of_contig + n_contigs);
     for (auto s : soc) if (s >= n_samples) return AGCGPU_EINVAL;
@@ -65,10 +77,12 @@ int agcgpu_compressor_add_cmd_line(agcgpu_compressor* c, const char* cmd_line)
 int agcgpu_compressor_close(agcgpu_compressor* c, uint32_t no_threads)
 {
     if (!c) return AGCGPU_EINVAL;
+    CallTimer ct("compressor_close");
     bool ok = c->impl.Close(no_threads);
     if (!ok) g_err = c->impl.LastError();
     if (c->impl.Ctx()) agcgpu_get_stats(c->impl.Ctx(), &g_last_stats);
-    delete c;
+    {   CallTimer cd("compressor delete");
+        delete c; }
     return ok ? 0 : AGCGPU_ECUDA;
 }
 

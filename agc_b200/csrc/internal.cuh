@@ -139,7 +139,7 @@ struct agcgpu_ctx {
     // reference store
     std::vector<GroupRefDev> h_groups;
     DevBuf d_groups;
-    std::vector<void*> arena_chunks;
+    std::vector<std::pair<void*, size_t>> arena_chunks;
     uint8_t* arena_cur = nullptr; size_t arena_left = 0;
     size_t device_bytes = 0;
 
@@ -153,6 +153,9 @@ int agc_fail(agcgpu_ctx* c, int code, const char* fmt, ...);
 int agc_reserve(agcgpu_ctx* c, DevBuf& b, size_t bytes, bool keep = false);
 void* agc_arena_alloc(agcgpu_ctx* c, size_t bytes);    // 256-byte aligned, lives until destroy
 int agc_pin_reserve(agcgpu_ctx* c, size_t bytes);
+void* agc_dev_alloc(int dev, size_t bytes, size_t* cap_out);   // process-wide device-memory pool (api.cu)
+void agc_dev_free(int dev, void* p, size_t cap);
+void agc_dev_trim(int dev);
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
     return agc_fail(ctx, AGCGPU_ECUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); } while (0)

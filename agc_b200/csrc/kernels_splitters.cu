@@ -162,7 +162,7 @@ int agc_enumerate_splitters(agcgpu_ctx* ctx, std::vector<uint64_t>& out_sorted)
     CK(cudaMemcpyAsync(ctx->chunk_prefix.p, cp.data(), (n_contigs + 1) * 4, cudaMemcpyHostToDevice, ctx->st));
     DevBuf keys_a, keys_b, flags, tmp, nsel;
     int rc = 0;
-    auto cleanup = [&]() { for (DevBuf* b : { &keys_a, &keys_b, &flags, &tmp, &nsel }) if (b->p) { cudaFree(b->p); ctx->device_bytes -= b->cap; b->p = nullptr; } };
+    auto cleanup = [&]() { for (DevBuf* b : { &keys_a, &keys_b, &flags, &tmp, &nsel }) if (b->p) { agc_dev_free(ctx->dev, b->p, b->cap + 64); ctx->device_bytes -= b->cap; b->p = nullptr; b->cap = 0; } };
     if ((rc = agc_reserve(ctx, keys_a, total * 8)) || (rc = agc_reserve(ctx, keys_b, total * 8)) || (rc = agc_reserve(ctx, flags, total)) ||
         (rc = agc_reserve(ctx, nsel, 64))) { cleanup(); return rc; }
     uint32_t grid = std::min<uint32_t>(total_chunks, (uint32_t)ctx->n_sm * 8);

@@ -18,17 +18,40 @@ struct ZTaskDev {
     uint64_t n, dst_cap;
     int32_t level; int32_t err;
     uint64_t out_size;
+#ifdef ZE_PROF
+    uint64_t prof[24];
+#endif
 };
 
-__global__ void __launch_bounds__(32) k_zstd(ZTaskDev* __restrict__ tasks, uint32_t n_tasks)
+static const uint32_t ZS_THREADS = 256;
+
+__global__ void __launch_bounds__(ZS_THREADS) k_zstd(ZTaskDev* __restrict__ tasks, uint32_t n_tasks, uint32_t smem_bytes)
 {
     uint32_t t = blockIdx.x;
     if (t >= n_tasks) return;
-    // all 32 lanes run the coder with identical scalar state (see zstd_enc.cuh); array-wide steps are split between them
+    extern __shared__ __align__(16) uint8_t zs_smem[];
+    // warp 0 runs the coder: its 32 lanes carry identical scalar state (see zstd_enc.cuh) and split array-wide steps; the other
+    // warps serve the match finder's window jobs (one tree walk per thread) between two named barriers
+    if (threadIdx.x >= 32) {
+        ze::Win& W = *reinterpret_cast<ze::Win*>(zs_smem);
+        for (;;) {
+            ze::ze_bar(1);
+            const uint32_t job = *reinterpret_cast<volatile uint32_t*>(&W.job);
+            if (job == ze::WJ_EXIT) break;
+            ze::win_run(W, job);
+            ze::ze_bar(2);
+        }
+        return;
+    }
     ZTaskDev k = tasks[t];
     int err = 0;
-    uint64_t r = ze::compress_frame(k.src, k.n, k.level, k.dst, k.dst_cap, k.mem, &err);
-    if (threadIdx.x == 0) { tasks[t].err = err; tasks[t].out_size = r; }
+#ifdef ZE_PROF
+    uint64_t r = ze::compress_frame(k.src, k.n, k.level, k.dst, k.dst_cap, k.mem, &err, tasks[t].prof, zs_smem, smem_bytes);
+#else
+    uint64_t r = ze::compress_frame(k.src, k.n, k.level, k.dst, k.dst_cap, k.mem, &err, nullptr, zs_smem, smem_bytes);
+#endif
+    if (threadIdx.x == 0) { tasks[t].err = err; tasks[t].out_size = r; reinterpret_cast<ze::Win*>(zs_smem)->job = ze::WJ_EXIT; }
+    ze::ze_bar(1);
 }
 
 extern "C" int agcgpu_zstd_compress_batch(agcgpu_ctx* ctx, const uint8_t* src, const uint64_t* src_offsets, const int32_t* levels,
@@ -88,7 +111,9 @@ extern "C" int agcgpu_zstd_compress_batch(agcgpu_ctx* ctx, const uint8_t* src, c
         CK(cudaMemcpyAsync(ctx->scr_req.p, tasks.data(), cnt * sizeof(ZTaskDev), cudaMemcpyHostToDevice, ctx->st));
         CK(cudaDeviceSetLimit(cudaLimitStackSize, 16384));
         CK(cudaEventRecord(ctx->ev0, ctx->st));
-        k_zstd<<<cnt, 32, 0, ctx->st>>>((ZTaskDev*)ctx->scr_req.p, cnt);
+        const uint32_t smem_bytes = ze::fast_sizes().total;
+        CK(cudaFuncSetAttribute(k_zstd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        k_zstd<<<cnt, ZS_THREADS, smem_bytes, ctx->st>>>((ZTaskDev*)ctx->scr_req.p, cnt, smem_bytes);
         CKL();
         CK(cudaEventRecord(ctx->ev1, ctx->st));
         CK(cudaMemcpyAsync(tasks.data(), ctx->scr_req.p, cnt * sizeof(ZTaskDev), cudaMemcpyDeviceToHost, ctx->st));
@@ -99,6 +124,16 @@ extern "C" int agcgpu_zstd_compress_batch(agcgpu_ctx* ctx, const uint8_t* src, c
                 uint64_t tot = 0; for (uint32_t j = 0; j < cnt; ++j) tot += tasks[j].n;
                 fprintf(stderr, "[agcgpu] zstd wave: %u inputs, %llu bytes, largest %llu (level %d), kernel %.1f ms\n", cnt,
                         (unsigned long long)tot, (unsigned long long)tasks[0].n, tasks[0].level, ms);
+#ifdef ZE_PROF
+                for (uint32_t j = 0; j < cnt && j < 4; ++j) {
+                    const uint64_t* p = tasks[j].prof; const double us = 1.0 / 1965.0;     // ticks at the max SM clock
+                    fprintf(stderr, "[agcgpu]  frame %u (%llu B, L%d): total %.0f us | parse %.0f  matches %.0f (update_tree %.0f, window build %.0f, commit %.0f, seq query %.0f, replay %.0f)\n"
+                                    "[agcgpu]    counts: get_all_matches %llu, windows %llu, commits %llu, seq inserts %llu, seq queries %llu, replayed queries %llu, window inserts %llu, cuts: unusable slot %llu, skipped positions %llu\n",
+                            j, (unsigned long long)tasks[j].n, tasks[j].level, p[0] * us, p[1] * us, p[2] * us, p[3] * us, p[4] * us, p[5] * us, p[6] * us, p[7] * us,
+                            (unsigned long long)p[12], (unsigned long long)p[8], (unsigned long long)p[14], (unsigned long long)p[9], (unsigned long long)p[10], (unsigned long long)p[11],
+                            (unsigned long long)p[13], (unsigned long long)p[15], (unsigned long long)p[16]);
+                }
+#endif
             } }
         for (uint32_t j = 0; j < cnt; ++j) {
             uint32_t i = order[pos + j];

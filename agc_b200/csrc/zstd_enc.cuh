@@ -55,6 +55,18 @@ typedef uint8_t u8; typedef uint16_t u16; typedef uint32_t u32; typedef uint64_t
 
 namespace ze {
 
+// optional phase profile of the device build (-DZE_PROF): clock64 ticks and event counts per frame, see kernels_zstd.cu
+#if defined(ZE_PROF) && defined(__CUDA_ARCH__)
+#define ZE_PROF_N 24
+#define ZE_T(var) long long var = clock64()
+#define ZE_ACC(w, slot, var) ((w).prof[slot] += (u64)(clock64() - (var)))
+#define ZE_CNT(w, slot, v) ((w).prof[slot] += (u64)(v))
+#else
+#define ZE_T(var) ((void)0)
+#define ZE_ACC(w, slot, var) ((void)0)
+#define ZE_CNT(w, slot, v) ((void)0)
+#endif
+
 // ---------------------------------------------------------------------------------------------------- constants
 enum { ST_BTLAZY2 = 6, ST_BTOPT = 7, ST_BTULTRA = 8, ST_BTULTRA2 = 9 };
 enum { SET_BASIC = 0, SET_RLE = 1, SET_COMPRESSED = 2, SET_REPEAT = 3 };
@@ -155,6 +167,7 @@ struct SeqStore { Seq* seqStart; Seq* seq; u8* litStart; u8* lit; u8* llCode; u8
 struct FseMeta { int llType, ofType, mlType; u32 tablesSize, lastCountSize; u8 buf[133]; };
 struct HufMeta { int hType; u32 desSize; u8 des[128]; };
 
+struct Win;
 struct Work {
     // inputs
     const u8* src; u32 srcSize; Params cp;
@@ -165,6 +178,7 @@ struct Work {
     // optimal parser state (optState_t)
     Opt* opt; Match* matches;
     u32* litFreq; u32* llFreq; u32* mlFreq; u32* ofFreq;
+    u32* priceTab;           // prices of the current statistics: lit[256], ll code[36], ml code[53], off code[32] (refresh_prices)
     u32 litSum, llSum, mlSum, ofSum, litSumBP, llSumBP, mlSumBP, ofSumBP; int pricePredef;
     // sequences
     SeqStore ss; u32 maxNbSeq;
@@ -180,11 +194,11 @@ struct Work {
     FseMeta* fseMeta; HufMeta* hufMeta;
     u32* partitions;         // 196+1
     u32* dummySlot;          // sink for the binary-tree walks (must live in the same address space as the tables)
-    // batched speculative tree walks (pw_*): one recorded read-only walk per lane for positions [pwBase, pwBase + pwCount)
-    u32* pwPath;             // ZE_LANES x PW_CAP x {matchIndex, matchLength | smaller << 31}
-    u32 pwBase, pwCount, pwDirty, pwEnd, pwBaseOff;     // uniform: covered positions, lanes whose bucket changed since, limits the walks assumed
-    u32 pwN, pwFlags, pwSame, pwFwd, pwHash;             // lane-private: entries, 1 = last entry reached iend / 2 = overflow, lanes in the same bucket, insertBt1's advance
+    Win* win;                // window engine of the match finder (below)
     int error;
+#if defined(ZE_PROF) && defined(__CUDA_ARCH__)
+    u64 prof[ZE_PROF_N];
+#endif
 };
 
 ZE_FN void wr16(u8* p, u32 v) { p[0] = (u8)v; p[1] = (u8)(v >> 8); }
@@ -342,176 +356,368 @@ ZE_FN_NOINLINE u32 insert_bt1(Work& w, u32 curr, const u8* iend, u32 target, u32
     return positions > adv ? positions : adv;
 }
 
-// ---- batched speculative walks ----------------------------------------------------------------------------------
-// The tree walk of ZSTD_insertBt1 / ZSTD_insertBtAndGetAllMatches is a chain of dependent steps, but the trees of different
-// hash buckets are disjoint, so walks of nearby positions commute unless they share a bucket.  pw_build lets each lane
-// walk one of the next ZE_LANES positions READ-ONLY on the current tree and record the visited (matchIndex, matchLength,
-// side) sequence; the recorded walk of position q is exactly what the sequential walk would see as long as no position
-// of the same bucket has been inserted in between (pwDirty).  The real operation then replays the record: inserts are
-// committed lane-parallel (pw_commit_insert), a query replays it with its own bestLength / break rules (get_all_matches).
-// Anything the record cannot stand for (bucket conflict, record overflow, positions near the window / tree-buffer edge)
-// takes the sequential walk, so the produced tree and matches are identical to the reference order of operations.
-static const u32 PW_CAP = 256;
+// ---- window engine ----------------------------------------------------------------------------------------------
+// The tree walk of ZSTD_insertBt1 / ZSTD_insertBtAndGetAllMatches is a chain of dependent loads, and one walk per position
+// is the whole cost of the match finder.  The engine takes the next WN_W positions at once:
+//   build  (all threads of the CTA, one position = "slot" per thread, read-only on the tree as it is in memory):
+//     walk    the slot's search path on the snapshot tree, recording (node, match length, side) per step;
+//     pairs   for every earlier slot of the same hash bucket: common prefix length and order of the two positions;
+//     resolve what the walk WOULD be once all earlier slots are inserted.  The binary tree of a bucket is the Cartesian
+//             tree of its nodes (key = suffix order, newest node on top), so the search path of q consists of the nodes
+//             that have no newer node between them and q.  Inserting the earlier slots p (all newer than the snapshot)
+//             therefore (1) puts in front the p's that are not shadowed by a newer p on their side, and (2) removes the
+//             snapshot nodes x that have some p between x and q -- exactly the nodes on the common prefix of the two
+//             recorded paths that lie on p's side.  No tree access is needed for this.
+//   consume (the parser's warp, in position order): inserts only advance a cursor (their tree links are written later),
+//             queries read the slot's resolved path and apply ZSTD_insertBtAndGetAllMatches' rules to it.
+//   commit (all threads): write the links of the consumed slots, bucket by bucket in position order.
+// Whatever breaks the model -- a walk that ran out of compares or reached the end of the block, more than WN_D earlier
+// slots in one bucket, positions the reference skips -- ends the window there (commit, then a fresh build), and a slot that
+// is unusable even as the first of a fresh window takes the sequential walk, so the tree and the matches are always the
+// ones the reference order of operations produces.
+static const u32 WN_W = 256, WN_CAP = 32, WN_D = 12;
+enum { WF_OVF = 1, WF_IEND = 2, WF_BUDGET = 4, WF_BAD = 8, WF_TRUNC = 16 };
+enum { WJ_EXIT = 0, WJ_BUILD = 1, WJ_COMMIT = 2 };
 
-ZE_FN_NOINLINE void pw_build(Work& w, u32 pos, const u8* iend, u32 mls)
+struct Win {
+    u32 job;
+    u32 base, count, next, endIdx, baseOff;        // slots = positions [base, base + count); slots < next are consumed
+    u32 upto;                                       // WJ_COMMIT: slots [0, upto)
+    u32 maxChain;                                   // deepest bucket chain of the window
+    const u8* text;                                 // text[position]
+    u32* hashTable; u32* bt;
+    u32 btMask, hashLog, mls, lowLimit, budget;
+    u32 hash[WN_W];
+    u32 keep[WN_W];                                 // recorded steps that stay on the path
+    u32 adv[WN_W];                                  // ZSTD_insertBt1's return value
+    u8 n[WN_W], flags[WN_W], np[WN_W], tm[WN_W], tn[WN_W], chain[WN_W];   // recorded steps, WF_*, visited earlier slots, path length, linked steps, earlier slots in the bucket
+    // rows are padded to an odd number of words / 8-byte pairs: a warp reads one column (thread = slot) without bank conflicts
+    u8 cs[WN_W][WN_D];                              // earlier slots of the same bucket, newest first
+    u8 pp[WN_W][WN_D];                              // the visited ones (indices into cs), newest first
+    u32 pl[WN_W][WN_D + 1];                           // common prefix with cs[k] | (cs[k] is the smaller one) << 31
+    u32 rec[WN_W][WN_CAP + 1][2];                      // node, match length | (node is smaller) << 31
+};
+
+#if defined(__CUDA_ARCH__)
+#define ZE_TID (threadIdx.x)
+#define ZE_NT (blockDim.x)
+#else
+#define ZE_TID 0u
+#define ZE_NT 1u
+#endif
+ZE_FN void ze_bar(u32 id)                                         // named barrier over the whole CTA
 {
-    const u8* base = w.src - w.baseOff;
-    const u32* bt = w.chainTable;
-    u32 btLog = w.cp.chainLog - 1, btMask = (1u << btLog) - 1;
-    u32 maxDist = 1u << w.cp.windowLog;
-    u32 endIdx = (u32)(iend - base);
-    w.pwBase = pos; w.pwDirty = 0; w.pwCount = 0; w.pwEnd = endIdx; w.pwBaseOff = w.baseOff;
-    w.pwN = 0; w.pwFlags = 0; w.pwSame = 0; w.pwFwd = 1; w.pwHash = 0;
-    // walk limits must not depend on the position: nothing may fall out of the window or of the tree buffer
-    if (endIdx > btMask || endIdx - w.lowLimit > maxDist || w.lowLimit < 1) return;
-    if (pos + 8 > endIdx) return;
-    u32 cnt = endIdx - 8 - pos + 1; if (cnt > ZE_LANES) cnt = ZE_LANES;
-    w.pwCount = cnt;
-    u32 q = pos + ZE_LANE; bool act = ZE_LANE < cnt;
-    const u8* ip = base + q;
-    u32 h = act ? hash_ptr(ip, w.cp.hashLog, mls) : 0xffffffffu - ZE_LANE;
-    w.pwHash = h;
-    w.pwSame = ze_match_any(h);
-    u32* path = w.pwPath + (size_t)ZE_LANE * (2 * PW_CAP);
-    u32 n = 0, flags = 0, nb = 1u << w.cp.searchLog;
-    u32 mi = act ? w.hashTable[h] : 0;
-    u32 clS = 0, clL = 0, ml = 0;
-    u32 bestI = 8, endI = q + 9;
-    const u32 windowLow = w.lowLimit;
-    const u32 remTot = endIdx - q;
-    if (mi < windowLow) act = false;
-    U2 nx; nx.x = nx.y = 0;
-    bool fresh = true;                                            // children of `mi` not loaded yet
-    // lanes diverge only on rare events; the common step is straight-line selects so the warp issues it once for all lanes
-    while (ze_ballot(act)) {
-        if (act) {
-            if (fresh) { nx = ld_pair(bt + 2 * (mi & btMask)); fresh = false; }   // both children, in flight with the text loads
-            const u8* a = ip + ml; const u8* m = base + mi + ml;
-            u32 rem = remTot - ml, ca, cm, adv;
-            if (rem >= 8) {
-                u32 alo, ahi, mlo, mhi;
-                ld64w(a, alo, ahi); ld64w(m, mlo, mhi);
-                u32 xlo = alo ^ mlo, xhi = ahi ^ mhi;
-                bool inLo = xlo != 0;
-                u32 x = inLo ? xlo : xhi, wa = inLo ? alo : ahi, wm = inLo ? mlo : mhi;
-                u32 t = x ? ((ze_ffs(x) - 1) >> 3) : 0;          // byte of the first difference inside the word
-                adv = x ? (inLo ? t : 4 + t) : 8;
-                ca = (wa >> (8 * t)) & 255u; cm = (wm >> (8 * t)) & 255u;
-            } else {
-                adv = 0; while (adv < rem && a[adv] == m[adv]) ++adv;
-                ca = cm = 0;
-                if (adv < rem) { ca = a[adv]; cm = m[adv]; }
-            }
-            ml += adv;
-            if (adv < 8 || rem == 8) {                            // this step's match length is known
-                bool atEnd = ml == remTot, ovf = n == PW_CAP;
-                if (ovf) { flags |= 2; act = false; }
-                else {
-                    bool better = ml > bestI;
-                    if (better && ml > endI - mi) endI = mi + ml;
-                    bestI = better ? ml : bestI;
-                    bool smaller = cm < ca;
-                    st_pair(path + 2 * n, mi, atEnd ? ml : (ml | (smaller ? 0x80000000u : 0u))); ++n;
-                    clS = (smaller && !atEnd) ? ml : clS;
-                    clL = (!smaller && !atEnd) ? ml : clL;
-                    mi = smaller ? nx.y : nx.x;
-                    fresh = true;
-                    --nb;
-                    flags |= atEnd ? 1u : 0u;
-                    act = !(atEnd || nb == 0 || mi < windowLow);
-                    ml = clS < clL ? clS : clL;
-                }
-            }
+#if defined(__CUDA_ARCH__)
+    u32 nt = blockDim.x; asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nt) : "memory");
+#else
+    (void)id;
+#endif
+}
+ZE_FN void ze_cta_sync()
+{
+#if defined(__CUDA_ARCH__)
+    if (blockDim.x > 32) ze_bar(3); else __syncwarp();
+#endif
+}
+
+ZE_FN u32 nth_set_bit(u32 mask, u32 n)                            // position of the n-th (0-based) set bit
+{
+#if defined(__CUDA_ARCH__)
+    return __fns(mask, 0, (int)n + 1);
+#else
+    for (u32 i = 0; i < 32; ++i) if ((mask >> i) & 1u) { if (n == 0) return i; --n; }
+    return 32;
+#endif
+}
+// common prefix of a and b, at most maxlen bytes; ca / cb = the bytes after it (lane-private).  The first 8 bytes decide most
+// comparisons; longer ones continue 32 bytes per round trip (all loads of a step are issued before the first compare).
+ZE_FN u32 lcp_private(const u8* a, const u8* b, u32 maxlen, u32& ca, u32& cb)
+{
+    u32 ml = 0;
+    if (maxlen >= 8) {
+        u32 alo, ahi, blo, bhi;
+        ld64w(a, alo, ahi); ld64w(b, blo, bhi);
+        u32 xlo = alo ^ blo, xhi = ahi ^ bhi;
+        if (xlo | xhi) {
+            bool inLo = xlo != 0;
+            u32 x = inLo ? xlo : xhi, t = (ze_ffs(x) - 1) >> 3;
+            ca = ((inLo ? alo : ahi) >> (8 * t)) & 255u; cb = ((inLo ? blo : bhi) >> (8 * t)) & 255u;
+            return (inLo ? 0 : 4) + t;
+        }
+        ml = 8;
+    }
+#if defined(__CUDA_ARCH__)
+    while (maxlen - ml >= 32) {
+        const u32* qa = (const u32*)((uintptr_t)(a + ml) & ~(uintptr_t)3); const u32 sa = 8u * (u32)((uintptr_t)(a + ml) & 3u);
+        const u32* qb = (const u32*)((uintptr_t)(b + ml) & ~(uintptr_t)3); const u32 sb = 8u * (u32)((uintptr_t)(b + ml) & 3u);
+        u32 wa[9], wb[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) { wa[i] = qa[i]; wb[i] = qb[i]; }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const u32 va = __funnelshift_r(wa[i], wa[i + 1], sa), vb = __funnelshift_r(wb[i], wb[i + 1], sb), x = va ^ vb;
+            if (x) { const u32 t = (ze_ffs(x) - 1) >> 3; ca = (va >> (8 * t)) & 255u; cb = (vb >> (8 * t)) & 255u; return ml + 4 * i + t; }
+        }
+        ml += 32;
+    }
+#endif
+    while (maxlen - ml >= 8) {
+        u32 alo, ahi, blo, bhi;
+        ld64w(a + ml, alo, ahi); ld64w(b + ml, blo, bhi);
+        u32 xlo = alo ^ blo, xhi = ahi ^ bhi;
+        if (xlo | xhi) {
+            bool inLo = xlo != 0;
+            u32 x = inLo ? xlo : xhi, t = (ze_ffs(x) - 1) >> 3;
+            ca = ((inLo ? alo : ahi) >> (8 * t)) & 255u; cb = ((inLo ? blo : bhi) >> (8 * t)) & 255u;
+            return ml + (inLo ? 0 : 4) + t;
+        }
+        ml += 8;
+    }
+    while (ml < maxlen && a[ml] == b[ml]) ++ml;
+    ca = cb = 0;
+    if (ml < maxlen) { ca = a[ml]; cb = b[ml]; }
+    return ml;
+}
+
+ZE_FN void win_walk(Win& W, u32 l)
+{
+    const u8* text = W.text; const u32 q = W.base + l; const u8* ip = text + q;
+    const u32 h = hash_ptr(ip, W.hashLog, W.mls);
+    W.hash[l] = h;
+    u32 mi = W.hashTable[h];
+    u32 n = 0, fl = 0, nb = W.budget, clS = 0, clL = 0;
+    const u32 remTot = W.endIdx - q, low = W.lowLimit, btMask = W.btMask;
+    const u32* bt = W.bt;
+    while (nb && mi >= low) {
+        if (n == WN_CAP) { fl |= WF_OVF; break; }
+        U2 nx = ld_pair(bt + 2 * (mi & btMask));
+        u32 ml = clS < clL ? clS : clL, ca, cm;
+        ml += lcp_private(ip + ml, text + mi + ml, remTot - ml, ca, cm);
+        const bool atEnd = ml == remTot, smaller = cm < ca;
+        W.rec[l][n][0] = mi; W.rec[l][n][1] = atEnd ? ml : (ml | (smaller ? 0x80000000u : 0u)); ++n;
+        if (atEnd) { fl |= WF_IEND; break; }
+        if (smaller) { clS = ml; mi = nx.y; } else { clL = ml; mi = nx.x; }
+        --nb;
+    }
+    if (nb == 0 && mi >= low) fl |= WF_BUDGET;
+    W.n[l] = (u8)n; W.flags[l] = (u8)fl;
+}
+
+ZE_FN void win_pairs(Win& W, u32 l)
+{
+    const u32 h = W.hash[l];
+    u32 c = 0, fl = W.flags[l];
+    for (i32 j = (i32)l - 1; j >= 0 && !(fl & WF_BAD); ) {
+        if ((j & 3) == 3) {                                       // four slots per step
+            const u32 h0 = W.hash[j - 3], h1 = W.hash[j - 2], h2 = W.hash[j - 1], h3 = W.hash[j];
+            if (h3 != h && h2 != h && h1 != h && h0 != h) { j -= 4; continue; }
+        }
+        if (W.hash[j] == h) { if (c == WN_D) fl |= WF_BAD; else W.cs[l][c++] = (u8)j; }
+        --j;
+    }
+    W.chain[l] = (u8)c;
+#if defined(__CUDA_ARCH__)
+    if (c > W.maxChain) atomicMax(&W.maxChain, c);
+#else
+    if (c > W.maxChain) W.maxChain = c;
+#endif
+    const u8* text = W.text; const u32 q = W.base + l, remTot = W.endIdx - q;
+    for (u32 k = 0; k < c; ++k) {
+        u32 ca, cb;
+        u32 ml = lcp_private(text + q, text + W.base + W.cs[l][k], remTot, ca, cb);
+        if (ml == remTot) fl |= WF_BAD;
+        W.pl[l][k] = ml | (cb < ca ? 0x80000000u : 0u);
+    }
+    W.flags[l] = (u8)fl;
+}
+
+ZE_FN void win_resolve(Win& W, u32 l)
+{
+    u32 fl = W.flags[l];
+    const u32 nst = W.n[l], c = W.chain[l], q = W.base + l, B = W.budget;
+    u32 np = 0, bSl = 0, bLl = 0, dropS = 0, dropL = 0;
+    i32 bS = -1, bL = -1;
+    for (u32 k = 0; k < c; ++k) {
+        const u32 v = W.pl[l][k], lcp = v & 0x7fffffffu; const bool sm = (v >> 31) != 0;
+        const i32 b = sm ? bS : bL; const u32 bl = sm ? bSl : bLl;
+        bool vis;
+        if (b < 0) vis = true;
+        else if (lcp != bl) vis = lcp > bl;
+        else { const bool below = (W.pl[W.cs[l][b]][k - (u32)b - 1] >> 31) != 0; vis = sm ? !below : below; }   // order of the two earlier slots
+        if (vis) { W.pp[l][np++] = (u8)k; if (sm) { bS = (i32)k; bSl = lcp; } else { bL = (i32)k; bLl = lcp; } }
+        const u32 p = W.cs[l][k], npz = W.n[p], lim = nst < npz ? nst : npz;
+        u32 cp = 0;
+        while (cp < lim && W.rec[l][cp][0] == W.rec[p][cp][0] && ((W.rec[l][cp][1] ^ W.rec[p][cp][1]) >> 31) == 0) ++cp;
+        if (sm) { if (cp > dropS) dropS = cp; } else if (cp > dropL) dropL = cp;
+    }
+    u32 keep = 0;
+    for (u32 j = 0; j < nst; ++j) { const bool sj = (W.rec[l][j][1] >> 31) != 0; if (j >= (sj ? dropS : dropL)) keep |= 1u << j; }
+    if ((fl & WF_IEND) && c > 0) fl |= WF_BAD;
+    u32 m = np + ze_popc(keep);
+    bool trunc = false;
+    const bool incomplete = (fl & (WF_OVF | WF_BUDGET)) != 0;
+    if (m > B) { m = B; trunc = true; }
+    else if (incomplete) { if (m == B) trunc = true; else fl |= WF_BAD; }
+    u32 tn = m;
+    if ((fl & WF_IEND) && nst <= m) { trunc = true; tn = m - 1; }
+    // ZSTD_insertBt1's bookkeeping over the resolved path
+    u32 best = 8, endI = q + 9, cnt = 0;
+    for (u32 e = 0; e < np && cnt < m; ++e, ++cnt) {
+        const u32 k = W.pp[l][e], mi = W.base + W.cs[l][k], ml = W.pl[l][k] & 0x7fffffffu;
+        if (ml > best) { best = ml; if (ml > endI - mi) endI = mi + ml; }
+    }
+    for (u32 j = 0; j < nst && cnt < m; ++j) if ((keep >> j) & 1u) {
+        const u32 mi = W.rec[l][j][0], ml = W.rec[l][j][1] & 0x7fffffffu;
+        if (ml > best) { best = ml; if (ml > endI - mi) endI = mi + ml; }
+        ++cnt;
+    }
+    u32 positions = 0;
+    if (best > 384) { positions = best - 384; if (positions > 192) positions = 192; }
+    const u32 a2 = endI - (q + 8);
+    if (trunc) fl |= WF_TRUNC;
+    W.keep[l] = keep; W.np[l] = (u8)np; W.tm[l] = (u8)m; W.tn[l] = (u8)tn; W.adv[l] = positions > a2 ? positions : a2; W.flags[l] = (u8)fl;
+}
+
+ZE_FN void win_commit_slot(Win& W, u32 l)
+{
+    const u32 q = W.base + l, btMask = W.btMask; u32* bt = W.bt;
+    u32* sp = bt + 2 * (q & btMask); u32* lp = sp + 1;
+    W.hashTable[W.hash[l]] = q;
+    const u32 np = W.np[l], nst = W.n[l], tn = W.tn[l], keep = W.keep[l];
+    u32 cnt = 0;
+    for (u32 e = 0; e < np && cnt < tn; ++e, ++cnt) {
+        const u32 k = W.pp[l][e], mi = W.base + W.cs[l][k]; u32* nextPtr = bt + 2 * (mi & btMask);
+        if (W.pl[l][k] >> 31) { *sp = mi; sp = nextPtr + 1; } else { *lp = mi; lp = nextPtr; }
+    }
+    for (u32 j = 0; j < nst && cnt < tn; ++j) if ((keep >> j) & 1u) {
+        const u32 mi = W.rec[l][j][0]; u32* nextPtr = bt + 2 * (mi & btMask);
+        if (W.rec[l][j][1] >> 31) { *sp = mi; sp = nextPtr + 1; } else { *lp = mi; lp = nextPtr; }
+        ++cnt;
+    }
+    *lp = 0; *sp = 0;
+}
+
+// executed by every thread of the CTA (device) / by the one host thread
+ZE_FN_NOINLINE void win_run(Win& W, u32 job)
+{
+    const u32 tid = ZE_TID, nt = ZE_NT;
+    if (job == WJ_BUILD) {
+        for (u32 l = tid; l < W.count; l += nt) win_walk(W, l);
+        ze_cta_sync();
+        for (u32 l = tid; l < W.count; l += nt) win_pairs(W, l);
+        ze_cta_sync();
+        for (u32 l = tid; l < W.count; l += nt) win_resolve(W, l);
+        ze_cta_sync();
+        for (u32 l = tid; l < W.count; l += nt) {                    // a truncated walk detaches nodes: later slots of the bucket cannot be resolved
+            u32 fl = W.flags[l];
+            for (u32 k = 0; k < W.chain[l]; ++k) if (W.flags[W.cs[l][k]] & WF_TRUNC) fl |= WF_BAD;
+            W.flags[l] = (u8)fl;
+        }
+    } else if (job == WJ_COMMIT) {
+        const u32 rounds = W.maxChain;
+        for (u32 r = 0; r <= rounds; ++r) {                            // slots of one bucket in position order, buckets side by side
+            for (u32 l = tid; l < W.upto; l += nt) if (W.chain[l] == r) win_commit_slot(W, l);
+            ze_cta_sync();
         }
     }
-    w.pwN = n; w.pwFlags = flags;
-    u32 positions = 0;
-    if (bestI > 384) { positions = bestI - 384; if (positions > 192) positions = 192; }
-    u32 adv2 = endI - (q + 8);
-    w.pwFwd = positions > adv2 ? positions : adv2;
+}
+ZE_FN void win_dispatch(Win& W, u32 job)
+{
+#if defined(__CUDA_ARCH__)
+    if (blockDim.x > 32) {
+        if (ZE_LANE == 0) W.job = job;
+        ze_bar(1); win_run(W, job); ze_bar(2);
+    } else { __syncwarp(); win_run(W, job); __syncwarp(); }
+#else
+    win_run(W, job);
+#endif
+}
+
+// write the links of the consumed slots and close the window
+ZE_FN_NOINLINE void win_flush(Work& w)
+{
+    Win& W = *w.win;
+    if (W.count && W.next > 0 && W.baseOff == w.baseOff) {
+        ZE_T(t_cm); ZE_CNT(w, 14, 1);
+        if (ZE_LANE == 0) W.upto = W.next;
+        ze_sync();
+        win_dispatch(W, WJ_COMMIT);
+        ZE_ACC(w, 5, t_cm);
+    }
+    ze_sync();
+    if (ZE_LANE == 0) { W.count = 0; W.next = 0; }
     ze_sync();
 }
 
-// is the recorded walk of `pos` usable right now?  (re)builds the batch when pos is outside it or its bucket was touched
-ZE_FN_NOINLINE bool pw_ready(Work& w, u32 pos, const u8* iend, u32 mls)
+// is `pos` the next unconsumed slot of the current window?  Otherwise close it and build a new one starting at pos
+// (false when the walk limits would depend on the position: near the window / tree-buffer edge and at the block's tail)
+ZE_FN_NOINLINE bool win_ready(Work& w, u32 pos, const u8* iend, u32 mls)
 {
+    Win& W = *w.win;
     const u8* base = w.src - w.baseOff;
-    u32 endIdx = (u32)(iend - base);
-    if (w.pwCount && pos >= w.pwBase && pos - w.pwBase < w.pwCount && w.pwEnd == endIdx && w.pwBaseOff == w.baseOff) {
-        u32 l = pos - w.pwBase;
-        u32 fl = ze_shfl(w.pwFlags, l);
-        if (!((w.pwDirty >> l) & 1u)) return !(fl & 2u);
+    const u32 endIdx = (u32)(iend - base);
+    if (W.count && W.endIdx == endIdx && W.baseOff == w.baseOff && W.base + W.next == pos && W.next < W.count) return true;
+    win_flush(w);
+    const u32 btMask = (1u << (w.cp.chainLog - 1)) - 1, maxDist = 1u << w.cp.windowLog;
+    if (endIdx > btMask || endIdx - w.lowLimit > maxDist || w.lowLimit < 1) return false;
+    if (pos + 8 > endIdx) return false;
+    ZE_T(t_bd); ZE_CNT(w, 8, 1);
+    u32 cnt = endIdx - 8 - pos + 1; if (cnt > WN_W) cnt = WN_W;
+    if (ZE_LANE == 0) {
+        W.base = pos; W.count = cnt; W.next = 0; W.endIdx = endIdx; W.baseOff = w.baseOff; W.maxChain = 0;
+        W.text = base; W.hashTable = w.hashTable; W.bt = w.chainTable; W.btMask = btMask; W.hashLog = w.cp.hashLog; W.mls = mls;
+        W.lowLimit = w.lowLimit; W.budget = 1u << w.cp.searchLog;
     }
-    pw_build(w, pos, iend, mls);
-    if (!w.pwCount) return false;
-    return !(ze_shfl(w.pwFlags, 0) & 2u);
-}
-
-// replay this lane's recorded walk as ZSTD_insertBt1's tree update (lane-private; no warp-wide operations inside)
-ZE_FN_NOINLINE void pw_commit_insert(Work& w, u32 q)
-{
-    u32* bt = w.chainTable;
-    u32 btLog = w.cp.chainLog - 1, btMask = (1u << btLog) - 1;
-    const u32* path = w.pwPath + (size_t)ZE_LANE * (2 * PW_CAP);
-    u32* smallerPtr = bt + 2 * (q & btMask);
-    u32* largerPtr = smallerPtr + 1;
-    w.hashTable[w.pwHash] = q;
-    u32 n = w.pwN;
-    if (w.pwFlags & 1u) --n;                                  // the walk stopped on the entry that reached iend
-    for (u32 i = 0; i < n; ++i) {
-        U2 e = ld_pair(path + 2 * i);
-        u32 mi = e.x; bool sm = (e.y >> 31) != 0;
-        u32* nextPtr = bt + 2 * (mi & btMask);
-        *(sm ? smallerPtr : largerPtr) = mi;                      // selects, not branches: lanes replay different walks
-        smallerPtr = sm ? nextPtr + 1 : smallerPtr;
-        largerPtr = sm ? largerPtr : nextPtr;
-    }
-    *largerPtr = 0;
-    *smallerPtr = 0;
+    ze_sync();
+    win_dispatch(W, WJ_BUILD);
+    ZE_ACC(w, 4, t_bd);
+    return true;
 }
 
 // ZSTD_updateTree_internal (zstd_opt.c:562-582)
 ZE_FN_NOINLINE void update_tree(Work& w, u32 target, const u8* iend, u32 mls)
 {
     u32 idx = w.nextToUpdate;
+    ZE_T(t_ut);
+    Win& W = *w.win;
     while (idx < target) {
-        if (!pw_ready(w, idx, iend, mls)) {                   // sequential walk
-            bool covered = w.pwCount && idx >= w.pwBase && idx - w.pwBase < w.pwCount;
-            u32 same = covered ? ze_shfl(w.pwSame, idx - w.pwBase) : 0;
-            idx += insert_bt1(w, idx, iend, target, mls);
-            w.pwDirty |= same;
-            continue;
+        if (!win_ready(w, idx, iend, mls)) { ZE_CNT(w, 9, 1); idx += insert_bt1(w, idx, iend, target, mls); continue; }
+        const u32 l = idx - W.base;
+        u32 hi = target - W.base; if (hi > W.count) hi = W.count;
+        u32 s = l;                                            // first slot of [l, hi) that is not a plain insert
+        while (s < hi) {
+            const u32 j = s + ZE_LANE;
+            const bool stop = j < hi && ((W.flags[j] & WF_BAD) || W.adv[j] != 1);
+            const u32 mk = ze_ballot(stop);
+            if (mk) { s += ze_ffs(mk) - 1; break; }
+            s += ZE_LANES;
         }
-        // run of inserts covered by the batch: lanes [l0, hi)
-        u32 l0 = idx - w.pwBase, hi = w.pwCount;
-        if (target - w.pwBase < hi) hi = target - w.pwBase;
-        bool ok = !((w.pwDirty >> ZE_LANE) & 1u) && !(w.pwFlags & 2u);
-        u32 fwd = w.pwFwd;
-        u32 live = 0, cur = l0;
-        while (cur < hi) {                                    // follow insertBt1's skip chain through the lanes
-            u32 m = ze_ballot(ZE_LANE >= cur && ZE_LANE < hi && (fwd != 1 || !ok));
-            if (!m) { live |= (hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u)) & ~((1u << cur) - 1u); cur = hi; break; }
-            u32 f = ze_ffs(m) - 1;
-            live |= ((1u << f) - 1u) & ~((1u << cur) - 1u);
-            if (!ze_shfl((u32)ok, f)) { cur = f; break; }
-            live |= 1u << f;
-            cur = f + ze_shfl(fwd, f);
-        }
-        // a live lane that shares its bucket with an earlier live lane must see that lane's update first: cut there
-        u32 below = (1u << ZE_LANE) - 1u;
-        u32 conf = ze_ballot(((live >> ZE_LANE) & 1u) && (w.pwSame & live & below));
-        if (conf) { u32 c = ze_ffs(conf) - 1; live &= (1u << c) - 1u; cur = c; w.pwDirty |= 1u << c; }
-        bool mine = (live >> ZE_LANE) & 1u;
-        if (mine) pw_commit_insert(w, w.pwBase + ZE_LANE);
-        w.pwDirty |= ze_reduce_or(mine ? w.pwSame : 0u);
+        if (s > hi) s = hi;
+        ZE_CNT(w, 13, s - l);
         ze_sync();
-        idx = w.pwBase + cur;
+        if (ZE_LANE == 0) W.next = s;
+        ze_sync();
+        idx = W.base + s;
+        if (s == hi) continue;
+        if (W.flags[s] & WF_BAD) {
+            ZE_CNT(w, 15, 1);
+            win_flush(w);
+            if (s == 0) { ZE_CNT(w, 9, 1); idx += insert_bt1(w, idx, iend, target, mls); }
+        } else {                                              // the reference skips positions after this insert
+            ZE_CNT(w, 16, 1);
+            idx += W.adv[s];
+            ze_sync();
+            if (ZE_LANE == 0) W.next = s + 1;
+            ze_sync();
+            win_flush(w);
+        }
     }
     w.nextToUpdate = target;
+    ZE_ACC(w, 3, t_ut);
 }
 
 // ZSTD_btGetAllMatches_internal + ZSTD_insertBtAndGetAllMatches (zstd_opt.c:590-820), noDict
-ZE_FN_NOINLINE u32 get_all_matches(Work& w, Match* matches, u32* nextToUpdate3, const u8* ip, const u8* iLimit, const u32* rep, u32 ll0, u32 lengthToBeat)
+ZE_FN_NOINLINE u32 get_all_matches_impl(Work& w, Match* matches, u32* nextToUpdate3, const u8* ip, const u8* iLimit, const u32* rep, u32 ll0, u32 lengthToBeat)
 {
     const u8* base = w.src - w.baseOff;
     u32 curr = (u32)(ip - base);
@@ -521,8 +727,7 @@ ZE_FN_NOINLINE u32 get_all_matches(Work& w, Match* matches, u32* nextToUpdate3, 
 
     u32 sufficient_len = w.cp.targetLength < OPT_NUM - 1 ? w.cp.targetLength : OPT_NUM - 1;
     u32 minMatch = (mls == 3) ? 3 : 4;
-    u32 h = hash_ptr(ip, w.cp.hashLog, mls);
-    u32 matchIndex = w.hashTable[h];
+    u32 h = 0, matchIndex = 0;
     u32* bt = w.chainTable;
     u32 btLog = w.cp.chainLog - 1, btMask = (1u << btLog) - 1;
     u32 clSmaller = 0, clLarger = 0;
@@ -538,14 +743,28 @@ ZE_FN_NOINLINE u32 get_all_matches(Work& w, Match* matches, u32* nextToUpdate3, 
     u32 nbCompares = 1u << w.cp.searchLog;
     u32 bestLength = lengthToBeat - 1;
 
-    // repcodes
-    {   u32 lastR = 3 + ll0;
+    // repcodes: the three candidates are fetched side by side (one per lane), then examined in the reference's order
+    {   const u32 t0 = rd32(ip);
+        u32 repOffsetL = 0; bool eqL = false;
+        if (ZE_LANES > 1) {
+            const u32 rc = ll0 + ZE_LANE;
+            if (ZE_LANE < 3) {
+                repOffsetL = (rc == 3) ? rep[0] - 1 : rep[rc];
+                if (repOffsetL - 1 < curr - dictLimit && curr - repOffsetL >= windowLow) {
+                    const u32 tr = rd32(ip - repOffsetL);
+                    eqL = minMatch == 3 ? ((t0 << 8) == (tr << 8)) : (t0 == tr);
+                }
+            }
+        }
+        const u32 eqMask = ZE_LANES > 1 ? (ze_ballot(eqL) & 7u) : 7u;
+        u32 lastR = 3 + ll0;
         for (u32 rc = ll0; rc < lastR; ++rc) {
-            u32 repOffset = (rc == 3) ? rep[0] - 1 : rep[rc];
+            if (!((eqMask >> (rc - ll0)) & 1u)) continue;
+            u32 repOffset = ZE_LANES > 1 ? ze_shfl(repOffsetL, rc - ll0) : ((rc == 3) ? rep[0] - 1 : rep[rc]);
             u32 repIndex = curr - repOffset;
             u32 repLen = 0;
             if (repOffset - 1 < curr - dictLimit) {
-                bool eq = minMatch == 3 ? ((rd32(ip) << 8) == (rd32(ip - repOffset) << 8)) : (rd32(ip) == rd32(ip - repOffset));
+                bool eq = minMatch == 3 ? ((t0 << 8) == (rd32(ip - repOffset) << 8)) : (t0 == rd32(ip - repOffset));
                 if ((repIndex >= windowLow) & eq) repLen = count_eq(ip + minMatch, ip + minMatch - repOffset, iLimit) + minMatch;
             }
             if (repLen > bestLength) {
@@ -572,63 +791,61 @@ ZE_FN_NOINLINE u32 get_all_matches(Work& w, Match* matches, u32* nextToUpdate3, 
             }
         }
     }
-    if (pw_ready(w, curr, iLimit, mls)) {                     // replay the recorded walk under the query's rules
-        u32 lq = curr - w.pwBase;
-        u32 n = ze_shfl(w.pwN, lq), fl = ze_shfl(w.pwFlags, lq);
-        const u32* path = w.pwPath + (size_t)lq * (2 * PW_CAP);
-        bool usable = !((fl & 1u) && (path[2 * (n - 1) + 1] & 0x7fffffffu) <= bestLength);
+    if (win_ready(w, curr, iLimit, mls) && (w.win->flags[curr - w.win->base] & WF_BAD) && curr != w.win->base) {
+        win_flush(w);                                         // the window ends here: try this position as the first slot of a fresh one
+        win_ready(w, curr, iLimit, mls);
+    }
+    if (win_ready(w, curr, iLimit, mls)) {                     // apply the query's rules to the slot's resolved path
+        ZE_T(t_rp);
+        Win& W = *w.win;
+        const u32 l = curr - W.base;
+        const u32 fl = W.flags[l], nst = W.n[l], np = W.np[l], m = W.tm[l], keep = W.keep[l];
+        bool usable = !(fl & WF_BAD);
+        if (usable && (fl & WF_IEND) && nst <= m && (W.rec[l][nst - 1][1] & 0x7fffffffu) <= bestLength) usable = false;   // the reference compares past iLimit here
         if (usable) {
-            w.hashTable[h] = curr;
-            // ZE_LANES recorded steps at a time: which steps set a new best length is a prefix maximum, the slot a step
-            // links into belongs to the previous step on the same side (ballot + highest set bit below the lane)
-            for (u32 c = 0; c < n; c += ZE_LANES) {
-                u32 i = c + ZE_LANE;
-                bool valid = i < n;
-                U2 e; e.x = e.y = 0;
-                if (valid) e = ld_pair(path + 2 * i);
-                u32 mi = e.x, ml = e.y & 0x7fffffffu; bool sm = (e.y >> 31) != 0;
+            // ZE_LANES steps of the resolved path at a time; which steps set a new best length is a prefix maximum over the lanes
+            u32 linked = m; bool broke = false;
+            for (u32 c = 0; c < m && !broke; c += ZE_LANES) {
+                const u32 e = c + ZE_LANE;
+                const bool valid = e < m;
+                u32 mi = 0, ml = 0;
+                if (valid) {
+                    if (e < np) { const u32 k = W.pp[l][e]; mi = W.base + W.cs[l][k]; ml = W.pl[l][k] & 0x7fffffffu; }
+                    else { const u32 j = nth_set_bit(keep, e - np); mi = W.rec[l][j][0]; ml = W.rec[l][j][1] & 0x7fffffffu; }
+                }
                 u32 incl = valid ? ml : 0;
                 for (u32 d = 1; d < ZE_LANES; d <<= 1) { u32 t = ze_shfl_up(incl, d); if (ZE_LANE >= d && t > incl) incl = t; }
                 u32 excl = ze_shfl_up(incl, 1); if (ZE_LANE == 0) excl = 0;
                 if (excl < bestLength) excl = bestLength;
-                bool rec = valid && ml > excl;
-                u32 brk = ze_ballot(rec && ((ml > OPT_NUM) | (ip + ml == iLimit)));
-                u32 lim = brk ? ze_ffs(brk) - 1 : 32;                               // step that ends the walk (recorded, not linked)
-                u32 upto = lim >= 31 ? 0xffffffffu : ((2u << lim) - 1u);            // lanes <= lim
-                u32 before = lim >= 32 ? 0xffffffffu : ((1u << lim) - 1u);          // lanes <  lim
-                u32 below = (1u << ZE_LANE) - 1u;
-                u32 recmask = ze_ballot(rec) & upto;
-                bool myrec = (recmask >> ZE_LANE) & 1u;
-                if (myrec) { u32 k = mnum + ze_popc(recmask & below); matches[k].off = (curr - mi) + 3; matches[k].len = ml; }
-                u32 mxEnd = ze_reduce_max(myrec ? mi + ml : 0u), mxLen = ze_reduce_max(myrec ? ml : 0u);
+                const bool rec = valid && ml > excl;
+                const u32 brk = ze_ballot(rec && ((ml > OPT_NUM) | (ip + ml == iLimit)));
+                const u32 lim = brk ? ze_ffs(brk) - 1 : 32;                          // step that ends the walk (reported, not linked)
+                const u32 uptoM = lim >= 31 ? 0xffffffffu : ((2u << lim) - 1u);
+                const u32 below = (1u << ZE_LANE) - 1u;
+                const u32 recmask = ze_ballot(rec) & uptoM;
+                const bool myrec = (recmask >> ZE_LANE) & 1u;
+                if (myrec) { const u32 k = mnum + ze_popc(recmask & below); matches[k].off = (curr - mi) + 3; matches[k].len = ml; }
+                const u32 mxEnd = ze_reduce_max(myrec ? mi + ml : 0u), mxLen = ze_reduce_max(myrec ? ml : 0u);
                 if (mxEnd > matchEndIdx) matchEndIdx = mxEnd;
                 if (mxLen > bestLength) bestLength = mxLen;
                 mnum += ze_popc(recmask);
-                u32 proc = ze_ballot(valid) & before;
-                u32 S = ze_ballot(valid && sm) & proc, Lm = proc & ~S;
-                u32 mine = sm ? S : Lm;                                           // steps on my side
-                u32 prevm = mine & below;
-                u32 pj = prevm ? ze_hibit(prevm) : ZE_LANE;
-                u32 pmi = ze_shfl(mi, pj);
-                if ((proc >> ZE_LANE) & 1u) {
-                    u32* slot = prevm ? (bt + 2 * (pmi & btMask) + (sm ? 1 : 0)) : (sm ? smallerPtr : largerPtr);
-                    *slot = mi;
-                }
-                u32 lastS = ze_shfl(mi, S ? ze_hibit(S) : 0), lastL = ze_shfl(mi, Lm ? ze_hibit(Lm) : 0);
-                if (S) smallerPtr = bt + 2 * (lastS & btMask) + 1;
-                if (Lm) largerPtr = bt + 2 * (lastL & btMask);
-                ze_sync();
-                if (lim < 32) break;
+                if (brk) { broke = true; linked = c + lim; }
             }
-            *largerPtr = 0;
-            *smallerPtr = 0;
-            w.nextToUpdate = matchEndIdx - 8;
-            w.pwDirty |= ze_shfl(w.pwSame, lq);
+            ze_sync();
+            const u32 ntu = matchEndIdx - 8;
+            if (ZE_LANE == 0) { W.next = l + 1; if (broke && linked < W.tn[l]) W.tn[l] = (u8)linked; }
+            ze_sync();
+            if (broke || ntu != curr + 1) { ZE_CNT(w, 16, 1); win_flush(w); }
+            w.nextToUpdate = ntu;
+            ZE_ACC(w, 7, t_rp); ZE_CNT(w, 11, 1);
             return mnum;
         }
     }
-    if (w.pwCount && curr >= w.pwBase && curr - w.pwBase < w.pwCount) w.pwDirty |= ze_shfl(w.pwSame, curr - w.pwBase);
+    win_flush(w);                                             // sequential walk on the tree in memory
+    h = hash_ptr(ip, w.cp.hashLog, mls);
+    matchIndex = w.hashTable[h];
     w.hashTable[h] = curr;
+    ZE_T(t_sq); ZE_CNT(w, 10, 1);
     for (; nbCompares && matchIndex >= matchLow; --nbCompares) {
         u32* nextPtr = bt + 2 * (matchIndex & btMask);
         u32 ml = clSmaller < clLarger ? clSmaller : clLarger;
@@ -653,7 +870,15 @@ ZE_FN_NOINLINE u32 get_all_matches(Work& w, Match* matches, u32* nextToUpdate3, 
     *largerPtr = 0;
     *smallerPtr = 0;
     w.nextToUpdate = matchEndIdx - 8;
+    ZE_ACC(w, 6, t_sq);
     return mnum;
+}
+ZE_FN u32 get_all_matches(Work& w, Match* matches, u32* nextToUpdate3, const u8* ip, const u8* iLimit, const u32* rep, u32 ll0, u32 lengthToBeat)
+{
+    ZE_T(t_gm); ZE_CNT(w, 12, 1);
+    u32 r = get_all_matches_impl(w, matches, nextToUpdate3, ip, iLimit, rep, ll0, lengthToBeat);
+    ZE_ACC(w, 2, t_gm);
+    return r;
 }
 
 // ---------------------------------------------------------------------------------------------------- price model (zstd_opt.c:30-380)
@@ -729,6 +954,35 @@ ZE_FN u32 match_price(const Work& w, u32 offBase, u32 ml, int optLevel)   // ZST
     price += BITCOST_MULT / 5;
     return price;
 }
+// The statistics only change when sequences are stored, so between two stores every price is a table lookup.
+ZE_FN_NOINLINE void refresh_prices(Work& w, int optLevel)
+{
+    if (w.pricePredef) return;
+    u32* T = w.priceTab;
+    const u32 maxLit = w.litSumBP - BITCOST_MULT;
+    for (u32 i = ZE_LANE; i < 256 + 36 + 53 + 32; i += ZE_LANES) {
+        u32 v;
+        if (i < 256) { u32 lp = weight(w.litFreq[i], optLevel); if (lp > maxLit) lp = maxLit; v = w.litSumBP - lp; }
+        else if (i < 256 + 36) { const u32 c = i - 256; v = kLLbits[c] * BITCOST_MULT + w.llSumBP - weight(w.llFreq[c], optLevel); }
+        else if (i < 256 + 36 + 53) { const u32 c = i - 292; v = kMLbits[c] * BITCOST_MULT + (w.mlSumBP - weight(w.mlFreq[c], optLevel)); }
+        else { const u32 c = i - 345; v = c * BITCOST_MULT + (w.ofSumBP - weight(w.ofFreq[c], optLevel)); if (optLevel < 2 && c >= 20) v += (c - 19) * 2 * BITCOST_MULT; }
+        T[i] = v;
+    }
+    ze_sync();
+}
+ZE_FN u32 lit_cost1_t(const Work& w, u8 lit) { return w.pricePredef ? 6 * BITCOST_MULT : w.priceTab[lit]; }
+ZE_FN u32 ll_price_t(const Work& w, u32 ll, int optLevel)
+{
+    if (w.pricePredef) return weight(ll, optLevel);
+    u32 extra = 0;
+    if (ll == BLOCK_MAX) { extra = BITCOST_MULT; ll = BLOCK_MAX - 1; }
+    return extra + w.priceTab[256 + LLcode(ll)];
+}
+ZE_FN u32 match_price_t(const Work& w, u32 offBase, u32 ml, int optLevel)
+{
+    if (w.pricePredef) return match_price(w, offBase, ml, optLevel);
+    return w.priceTab[345 + highbit(offBase)] + w.priceTab[292 + MLcode(ml - 3)] + BITCOST_MULT / 5;
+}
 ZE_FN_NOINLINE void update_stats(Work& w, u32 ll, const u8* lits, u32 offBase, u32 ml)
 {
     for (u32 u = 0; u < ll; ++u) w.litFreq[lits[u]] += 2;
@@ -755,7 +1009,7 @@ ZE_FN_NOINLINE void store_seq(SeqStore& ss, u32 ll, const u8* lits, u32 offBase,
 
 // ---------------------------------------------------------------------------------------------------- optimal parser
 // ZSTD_compressBlock_opt_generic (zstd_opt.c:1075-1437), noDict, no LDM.  Returns the size of the last literals run.
-ZE_FN_NOINLINE u32 compress_block_opt(Work& w, u32* rep, const u8* src, u32 srcSize, int optLevel)
+ZE_FN_NOINLINE u32 compress_block_opt_impl(Work& w, u32* rep, const u8* src, u32 srcSize, int optLevel)
 {
     const u8* istart = src; const u8* ip = istart; const u8* anchor = istart;
     const u8* iend = istart + srcSize; const u8* ilimit = iend - 8;
@@ -767,6 +1021,7 @@ ZE_FN_NOINLINE u32 compress_block_opt(Work& w, u32* rep, const u8* src, u32 srcS
     Opt lastStretch; lastStretch.price = 0; lastStretch.off = lastStretch.mlen = lastStretch.litlen = 0; lastStretch.rep[0] = lastStretch.rep[1] = lastStretch.rep[2] = 0;
 
     rescale_freqs(w, src, srcSize, optLevel);
+    refresh_prices(w, optLevel);
     ip += (ip == prefixStart);
 
     while (ip < ilimit) {
@@ -775,7 +1030,7 @@ ZE_FN_NOINLINE u32 compress_block_opt(Work& w, u32* rep, const u8* src, u32 srcS
         {   u32 litlen = (u32)(ip - anchor), ll0 = !litlen;
             u32 nbMatches = get_all_matches(w, matches, &nextToUpdate3, ip, iend, rep, ll0, minMatch);
             if (!nbMatches) { ip++; continue; }
-            opt[0].mlen = 0; opt[0].litlen = litlen; opt[0].price = (i32)ll_price(w, litlen, optLevel);
+            opt[0].mlen = 0; opt[0].litlen = litlen; opt[0].price = (i32)ll_price_t(w, litlen, optLevel);
             opt[0].rep[0] = rep[0]; opt[0].rep[1] = rep[1]; opt[0].rep[2] = rep[2];
             {   u32 maxML = matches[nbMatches - 1].len, maxOff = matches[nbMatches - 1].off;
                 if (maxML > sufficient_len) {
@@ -786,11 +1041,11 @@ ZE_FN_NOINLINE u32 compress_block_opt(Work& w, u32* rep, const u8* src, u32 srcS
             if (!shortest) {
                 u32 pos;
                 for (pos = 1; pos < minMatch; pos++) { opt[pos].price = MAX_PRICE; opt[pos].mlen = 0; opt[pos].litlen = litlen + pos; }
-                {   const i32 ll0p = (i32)ll_price(w, 0, optLevel), p0 = opt[0].price;
+                {   const i32 ll0p = (i32)ll_price_t(w, 0, optLevel), p0 = opt[0].price;
                     for (u32 m = 0; m < nbMatches; m++) {
                         u32 offBase = matches[m].off, end = matches[m].len;
                         for (u32 q = pos + ZE_LANE; q <= end; q += ZE_LANES) {          // lanes take different lengths
-                            i32 mp = (i32)match_price(w, offBase, q, optLevel);
+                            i32 mp = (i32)match_price_t(w, offBase, q, optLevel);
                             opt[q].mlen = q; opt[q].off = offBase; opt[q].litlen = 0;
                             opt[q].price = p0 + mp + ll0p;
                         }
@@ -806,19 +1061,19 @@ ZE_FN_NOINLINE u32 compress_block_opt(Work& w, u32* rep, const u8* src, u32 srcS
             for (cur = 1; cur <= last_pos; cur++) {
                 const u8* inr = ip + cur;
                 {   u32 litlen = opt[cur - 1].litlen + 1;
-                    i32 price = opt[cur - 1].price + (i32)lit_cost1(w, ip[cur - 1], optLevel)
-                              + ((i32)ll_price(w, litlen, optLevel) - (i32)ll_price(w, litlen - 1, optLevel));
+                    i32 price = opt[cur - 1].price + (i32)lit_cost1_t(w, ip[cur - 1])
+                              + ((i32)ll_price_t(w, litlen, optLevel) - (i32)ll_price_t(w, litlen - 1, optLevel));
                     if (price <= opt[cur].price) {
                         Opt prevMatch = opt[cur];
                         opt[cur] = opt[cur - 1];
                         opt[cur].litlen = litlen; opt[cur].price = price;
                         if (optLevel >= 1 && prevMatch.litlen == 0
-                            && ((i32)ll_price(w, 1, optLevel) - (i32)ll_price(w, 0, optLevel)) < 0
+                            && ((i32)ll_price_t(w, 1, optLevel) - (i32)ll_price_t(w, 0, optLevel)) < 0
                             && ip + cur < iend) {
-                            i32 with1 = prevMatch.price + (i32)lit_cost1(w, ip[cur], optLevel)
-                                      + ((i32)ll_price(w, 1, optLevel) - (i32)ll_price(w, 0, optLevel));
-                            i32 withMore = price + (i32)lit_cost1(w, ip[cur], optLevel)
-                                         + ((i32)ll_price(w, litlen + 1, optLevel) - (i32)ll_price(w, litlen, optLevel));
+                            i32 with1 = prevMatch.price + (i32)lit_cost1_t(w, ip[cur])
+                                      + ((i32)ll_price_t(w, 1, optLevel) - (i32)ll_price_t(w, 0, optLevel));
+                            i32 withMore = price + (i32)lit_cost1_t(w, ip[cur])
+                                         + ((i32)ll_price_t(w, litlen + 1, optLevel) - (i32)ll_price_t(w, litlen, optLevel));
                             if (with1 < withMore && with1 < opt[cur + 1].price) {
                                 u32 prev = cur - prevMatch.mlen;
                                 u32 nr[3] = { opt[prev].rep[0], opt[prev].rep[1], opt[prev].rep[2] };
@@ -841,7 +1096,7 @@ ZE_FN_NOINLINE u32 compress_block_opt(Work& w, u32* rep, const u8* src, u32 srcS
                 if (cur == last_pos) break;
                 if (optLevel == 0 && opt[cur + 1].price <= opt[cur].price + (i32)(BITCOST_MULT / 2)) continue;
                 {   u32 ll0 = (opt[cur].litlen == 0);
-                    i32 basePrice = opt[cur].price + (i32)ll_price(w, 0, optLevel);
+                    i32 basePrice = opt[cur].price + (i32)ll_price_t(w, 0, optLevel);
                     u32 nbMatches = get_all_matches(w, matches, &nextToUpdate3, inr, iend, opt[cur].rep, ll0, minMatch);
                     if (!nbMatches) continue;
                     {   u32 longestML = matches[nbMatches - 1].len;
@@ -857,7 +1112,7 @@ ZE_FN_NOINLINE u32 compress_block_opt(Work& w, u32* rep, const u8* src, u32 srcS
                         if (optLevel == 0) {                       // btopt: the early abort makes the scan order-dependent
                             for (u32 mlen = lastML; mlen >= startML; mlen--) {
                                 u32 pos = cur + mlen;
-                                i32 price = basePrice + (i32)match_price(w, offset, mlen, optLevel);
+                                i32 price = basePrice + (i32)match_price_t(w, offset, mlen, optLevel);
                                 if (pos > last_pos || price < opt[pos].price) {
                                     while (last_pos < pos) { last_pos++; opt[last_pos].price = MAX_PRICE; opt[last_pos].litlen = 1; }
                                     opt[pos].mlen = mlen; opt[pos].off = offset; opt[pos].litlen = 0; opt[pos].price = price;
@@ -872,7 +1127,7 @@ ZE_FN_NOINLINE u32 compress_block_opt(Work& w, u32* rep, const u8* src, u32 srcS
                             }
                             for (u32 mlen = startML + ZE_LANE; mlen <= lastML; mlen += ZE_LANES) {
                                 u32 pos = cur + mlen;
-                                i32 price = basePrice + (i32)match_price(w, offset, mlen, optLevel);
+                                i32 price = basePrice + (i32)match_price_t(w, offset, mlen, optLevel);
                                 if (price < opt[pos].price) { opt[pos].mlen = mlen; opt[pos].off = offset; opt[pos].litlen = 0; opt[pos].price = price; }
                             }
                             ze_sync();
@@ -915,9 +1170,17 @@ ZE_FN_NOINLINE u32 compress_block_opt(Work& w, u32* rep, const u8* src, u32 srcS
                 anchor += advance; ip = anchor;
             }
             set_base_prices(w, optLevel);
+            refresh_prices(w, optLevel);
         }
     }
     return (u32)(iend - anchor);
+}
+ZE_FN u32 compress_block_opt(Work& w, u32* rep, const u8* src, u32 srcSize, int optLevel)
+{
+    ZE_T(t_bo);
+    u32 r = compress_block_opt_impl(w, rep, src, srcSize, optLevel);
+    ZE_ACC(w, 1, t_bo);
+    return r;
 }
 
 
@@ -1947,18 +2210,37 @@ ZE_FN WorkSizes work_sizes(const Params& cp)
     z.lits = align_up((u64)cp.blockSize + 64, 256);
     z.codes = align_up((u64)3 * (maxNbSeq + 2), 256);
     z.bstates = align_up(2 * sizeof(BlockState), 256);
-    z.misc = align_up(4 * 256 + sizeof(HufNode) * 520 + 4 * 192 * 2 + 1024 + sizeof(FseCT) + sizeof(HufCT) + sizeof(FseMeta) + sizeof(HufMeta) + 4 * 200 + 256 + 16, 256)
-           + align_up((u64)4 * 32 * 2 * PW_CAP, 256);
+    z.misc = align_up(4 * 256 + sizeof(HufNode) * 520 + 4 * 192 * 2 + 1024 + sizeof(FseCT) + sizeof(HufCT) + sizeof(FseMeta) + sizeof(HufMeta) + 4 * 200 + 256 + 16 + 4 * 384, 256)
+           + align_up((u64)sizeof(Win), 256);
     z.total = z.hash + z.chain + z.hash3 + z.opt + z.matches + z.freqs + z.seqs + z.lits + z.codes + z.bstates + z.misc;
     return z;
+}
+// low-latency scratch layout: opt table, match list (<= 3 repcodes + 1 hash3 + 2^searchLog tree matches), frequency tables
+struct FastSizes { u32 win, opt, matches, freqs, prices, total; };
+ZE_FN FastSizes fast_sizes()
+{
+    FastSizes f;
+    f.win = (u32)align_up((u64)sizeof(Win), 16);                  // first: the helper threads of the CTA find it at offset 0
+    f.opt = (u32)align_up((u64)sizeof(Opt) * OPT_SIZE, 16);
+    f.matches = (u32)align_up((u64)sizeof(Match) * (256 + 8), 16);
+    f.freqs = (u32)align_up(4 * (256 + 36 + 53 + 32 + 16), 16);
+    f.prices = 4 * 384;
+    f.total = f.win + f.opt + f.matches + f.freqs + f.prices;
+    return f;
 }
 ZE_FN u64 compress_bound(u64 n) { return n + (n >> 8) + (n < (128u << 10) ? (((128u << 10) - n) >> 11) : 0); }    // ZSTD_COMPRESSBOUND
 
 // ZSTD_compressCCtx (:5317) for one input.  `mem` = zero-initialised workspace of work_sizes(cp).total bytes.
 // returns the frame size, 0 on failure (w.error says why)
-ZE_FN_NOINLINE u64 compress_frame(const u8* src, u64 srcSize64, int level, u8* dst, u64 dstCap, u8* mem, int* err)
+// `fast` / `fastBytes`: optional low-latency scratch (shared memory on the device) for the parser's hot state, see fast_sizes()
+ZE_FN_NOINLINE u64 compress_frame(const u8* src, u64 srcSize64, int level, u8* dst, u64 dstCap, u8* mem, int* err, u64* prof_out = nullptr,
+                                  u8* fast = nullptr, u32 fastBytes = 0)
 {
     Work w; *err = 0;
+#if defined(ZE_PROF) && defined(__CUDA_ARCH__)
+    for (int i = 0; i < ZE_PROF_N; ++i) w.prof[i] = 0;
+    long long t_frame = clock64();
+#endif
     Params cp = get_params(level, srcSize64);
     if (!cp.supported) { *err = 1; return 0; }
     u32 srcSize = (u32)srcSize64;
@@ -1968,6 +2250,13 @@ ZE_FN_NOINLINE u64 compress_frame(const u8* src, u64 srcSize64, int level, u8* d
     w.hashTable = (u32*)p; p += z.hash; w.chainTable = (u32*)p; p += z.chain; w.hashTable3 = (u32*)p; p += z.hash3;
     w.opt = (Opt*)p; p += z.opt; w.matches = (Match*)p; p += z.matches;
     w.litFreq = (u32*)p; w.llFreq = w.litFreq + 256; w.mlFreq = w.llFreq + 36; w.ofFreq = w.mlFreq + 53; p += z.freqs;
+    if (fast && fastBytes >= fast_sizes().total) {               // parser tables in the low-latency scratch
+        FastSizes fz = fast_sizes(); u8* f = fast;
+        w.win = (Win*)f; f += fz.win;
+        w.opt = (Opt*)f; f += fz.opt; w.matches = (Match*)f; f += fz.matches;
+        w.litFreq = (u32*)f; w.llFreq = w.litFreq + 256; w.mlFreq = w.llFreq + 36; w.ofFreq = w.mlFreq + 53; f += fz.freqs;
+        w.priceTab = (u32*)f;
+    }
     w.ss.seqStart = (Seq*)p; p += z.seqs; w.ss.litStart = p; p += z.lits;
     w.maxNbSeq = cp.blockSize / (cp.minMatch == 3 ? 3 : 4);
     w.ss.llCode = p; w.ss.mlCode = p + (w.maxNbSeq + 2); w.ss.ofCode = p + 2 * (w.maxNbSeq + 2); p += z.codes;
@@ -1984,9 +2273,12 @@ ZE_FN_NOINLINE u64 compress_frame(const u8* src, u64 srcSize64, int level, u8* d
     p = (u8*)align_up((u64)p, 8);
     w.partitions = (u32*)p; p += 4 * 200;
     w.dummySlot = (u32*)p; p += 256;
+    if (!(fast && fastBytes >= fast_sizes().total)) w.priceTab = (u32*)p;
+    p += 4 * 384;
     p = (u8*)align_up((u64)p, 8);
-    w.pwPath = (u32*)p;
-    w.pwBase = w.pwCount = w.pwDirty = w.pwEnd = w.pwBaseOff = 0; w.pwN = w.pwFlags = w.pwSame = w.pwHash = 0; w.pwFwd = 1;
+    if (!(fast && fastBytes >= fast_sizes().total)) w.win = (Win*)p;
+    if (ZE_LANE == 0) { w.win->count = 0; w.win->next = 0; w.win->baseOff = 0; }
+    ze_sync();
     reset_seqstore(w);
     w.hashLog3 = cp.minMatch == 3 ? (cp.windowLog < 17 ? cp.windowLog : 17) : 0;
     w.baseOff = 2; w.lowLimit = 2; w.dictLimit = 2; w.nextToUpdate = 2;
@@ -2025,6 +2317,10 @@ ZE_FN_NOINLINE u64 compress_frame(const u8* src, u64 srcSize64, int level, u8* d
         w.isFirstBlock = 0;
     }
     if (srcSize == 0) { wr24(op, 1); op += 3; }                     // ZSTD_writeEpilogue: empty last raw block
+#if defined(ZE_PROF) && defined(__CUDA_ARCH__)
+    w.prof[0] = (u64)(clock64() - t_frame);
+    if (prof_out && ZE_LANE == 0) for (int i = 0; i < ZE_PROF_N; ++i) prof_out[i] = w.prof[i];
+#endif
     return (u64)(op - dst);
 }
 
