@@ -23,9 +23,9 @@ struct ZTaskDev {
 #endif
 };
 
-static const uint32_t ZS_THREADS = 256;
+static const uint32_t ZS_THREADS = 512;
 
-__global__ void __launch_bounds__(ZS_THREADS) k_zstd(ZTaskDev* __restrict__ tasks, uint32_t n_tasks, uint32_t smem_bytes)
+__global__ void __launch_bounds__(ZS_THREADS, 1) k_zstd(ZTaskDev* __restrict__ tasks, uint32_t n_tasks, uint32_t smem_bytes)
 {
     uint32_t t = blockIdx.x;
     if (t >= n_tasks) return;
@@ -128,10 +128,10 @@ extern "C" int agcgpu_zstd_compress_batch(agcgpu_ctx* ctx, const uint8_t* src, c
                 for (uint32_t j = 0; j < cnt && j < 4; ++j) {
                     const uint64_t* p = tasks[j].prof; const double us = 1.0 / 1965.0;     // ticks at the max SM clock
                     fprintf(stderr, "[agcgpu]  frame %u (%llu B, L%d): total %.0f us | parse %.0f  matches %.0f (update_tree %.0f, window build %.0f, commit %.0f, seq query %.0f, replay %.0f)\n"
-                                    "[agcgpu]    counts: get_all_matches %llu, windows %llu, commits %llu, seq inserts %llu, seq queries %llu, replayed queries %llu, window inserts %llu, cuts: unusable slot %llu, skipped positions %llu\n",
+                                    "[agcgpu]    counts: get_all_matches %llu, windows %llu, commits %llu, seq inserts %llu, seq queries %llu, replayed queries %llu, window inserts %llu, cuts: unusable slot %llu, skipped positions %llu, re-resolves %llu (%.0f us)\n",
                             j, (unsigned long long)tasks[j].n, tasks[j].level, p[0] * us, p[1] * us, p[2] * us, p[3] * us, p[4] * us, p[5] * us, p[6] * us, p[7] * us,
                             (unsigned long long)p[12], (unsigned long long)p[8], (unsigned long long)p[14], (unsigned long long)p[9], (unsigned long long)p[10], (unsigned long long)p[11],
-                            (unsigned long long)p[13], (unsigned long long)p[15], (unsigned long long)p[16]);
+                            (unsigned long long)p[13], (unsigned long long)p[15], (unsigned long long)p[16], (unsigned long long)p[17], p[18] * us);
                 }
 #endif
             } }

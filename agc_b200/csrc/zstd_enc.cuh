@@ -375,9 +375,9 @@ ZE_FN_NOINLINE u32 insert_bt1(Work& w, u32 curr, const u8* iend, u32 target, u32
 // slots in one bucket, positions the reference skips -- ends the window there (commit, then a fresh build), and a slot that
 // is unusable even as the first of a fresh window takes the sequential walk, so the tree and the matches are always the
 // ones the reference order of operations produces.
-static const u32 WN_W = 256, WN_CAP = 32, WN_D = 12;
+static const u32 WN_W = 512, WN_CAP = 32, WN_D = 12, WN_Q = 6;
 enum { WF_OVF = 1, WF_IEND = 2, WF_BUDGET = 4, WF_BAD = 8, WF_TRUNC = 16 };
-enum { WJ_EXIT = 0, WJ_BUILD = 1, WJ_COMMIT = 2 };
+enum { WJ_EXIT = 0, WJ_BUILD = 1, WJ_COMMIT = 2, WJ_RESOLVE = 3 };
 
 struct Win {
     u32 job;
@@ -387,12 +387,16 @@ struct Win {
     const u8* text;                                 // text[position]
     u32* hashTable; u32* bt;
     u32 btMask, hashLog, mls, lowLimit, budget;
+    u32 qbase;                                      // a query's initial best length (minimum match - 1)
     u32 hash[WN_W];
     u32 keep[WN_W];                                 // recorded steps that stay on the path
     u32 adv[WN_W];                                  // ZSTD_insertBt1's return value
-    u8 n[WN_W], flags[WN_W], np[WN_W], tm[WN_W], tn[WN_W], chain[WN_W];   // recorded steps, WF_*, visited earlier slots, path length, linked steps, earlier slots in the bucket
+    u8 wflags[WN_W], sflags[WN_W];                  // flags after the walk / after walk + pairs (resolve starts from the latter)
+    u8 nq[WN_W];                                    // matches a query at this slot reports when no repcode beats them; 0xff = take the general path
+    u32 qm[WN_W][WN_Q + 1][2];                      // their (offBase, length), lengths increasing
+    u8 n[WN_W], flags[WN_W], np[WN_W], tm[WN_W], tn[WN_W], chain[WN_W], dead[WN_W];   // dead: a position the reference skips (never inserted)   // recorded steps, WF_*, visited earlier slots, path length, linked steps, earlier slots in the bucket
     // rows are padded to an odd number of words / 8-byte pairs: a warp reads one column (thread = slot) without bank conflicts
-    u8 cs[WN_W][WN_D];                              // earlier slots of the same bucket, newest first
+    u16 cs[WN_W][WN_D + 1];                            // earlier slots of the same bucket, newest first
     u8 pp[WN_W][WN_D];                              // the visited ones (indices into cs), newest first
     u32 pl[WN_W][WN_D + 1];                           // common prefix with cs[k] | (cs[k] is the smaller one) << 31
     u32 rec[WN_W][WN_CAP + 1][2];                      // node, match length | (node is smaller) << 31
@@ -500,19 +504,19 @@ ZE_FN void win_walk(Win& W, u32 l)
         --nb;
     }
     if (nb == 0 && mi >= low) fl |= WF_BUDGET;
-    W.n[l] = (u8)n; W.flags[l] = (u8)fl;
+    W.n[l] = (u8)n; W.wflags[l] = (u8)fl; W.dead[l] = 0;
 }
 
 ZE_FN void win_pairs(Win& W, u32 l)
 {
     const u32 h = W.hash[l];
-    u32 c = 0, fl = W.flags[l];
+    u32 c = 0, fl = W.wflags[l];
     for (i32 j = (i32)l - 1; j >= 0 && !(fl & WF_BAD); ) {
         if ((j & 3) == 3) {                                       // four slots per step
             const u32 h0 = W.hash[j - 3], h1 = W.hash[j - 2], h2 = W.hash[j - 1], h3 = W.hash[j];
             if (h3 != h && h2 != h && h1 != h && h0 != h) { j -= 4; continue; }
         }
-        if (W.hash[j] == h) { if (c == WN_D) fl |= WF_BAD; else W.cs[l][c++] = (u8)j; }
+        if (W.hash[j] == h && !W.dead[j]) { if (c == WN_D) fl |= WF_BAD; else W.cs[l][c++] = (u16)j; }
         --j;
     }
     W.chain[l] = (u8)c;
@@ -528,16 +532,19 @@ ZE_FN void win_pairs(Win& W, u32 l)
         if (ml == remTot) fl |= WF_BAD;
         W.pl[l][k] = ml | (cb < ca ? 0x80000000u : 0u);
     }
-    W.flags[l] = (u8)fl;
+    W.sflags[l] = (u8)fl;
 }
 
 ZE_FN void win_resolve(Win& W, u32 l)
 {
-    u32 fl = W.flags[l];
+    u32 fl = W.sflags[l];
     const u32 nst = W.n[l], c = W.chain[l], q = W.base + l, B = W.budget;
+    u32 live = 0;
     u32 np = 0, bSl = 0, bLl = 0, dropS = 0, dropL = 0;
     i32 bS = -1, bL = -1;
     for (u32 k = 0; k < c; ++k) {
+        if (W.dead[W.cs[l][k]]) continue;
+        ++live;
         const u32 v = W.pl[l][k], lcp = v & 0x7fffffffu; const bool sm = (v >> 31) != 0;
         const i32 b = sm ? bS : bL; const u32 bl = sm ? bSl : bLl;
         bool vis;
@@ -552,7 +559,7 @@ ZE_FN void win_resolve(Win& W, u32 l)
     }
     u32 keep = 0;
     for (u32 j = 0; j < nst; ++j) { const bool sj = (W.rec[l][j][1] >> 31) != 0; if (j >= (sj ? dropS : dropL)) keep |= 1u << j; }
-    if ((fl & WF_IEND) && c > 0) fl |= WF_BAD;
+    if ((fl & WF_IEND) && live > 0) fl |= WF_BAD;
     u32 m = np + ze_popc(keep);
     bool trunc = false;
     const bool incomplete = (fl & (WF_OVF | WF_BUDGET)) != 0;
@@ -562,20 +569,24 @@ ZE_FN void win_resolve(Win& W, u32 l)
     if ((fl & WF_IEND) && nst <= m) { trunc = true; tn = m - 1; }
     // ZSTD_insertBt1's bookkeeping over the resolved path
     u32 best = 8, endI = q + 9, cnt = 0;
+    u32 qb = W.qbase, nq = 0; const u32 remTot = W.endIdx - q;       // ... and ZSTD_insertBtAndGetAllMatches' list for a query without repcode matches
     for (u32 e = 0; e < np && cnt < m; ++e, ++cnt) {
         const u32 k = W.pp[l][e], mi = W.base + W.cs[l][k], ml = W.pl[l][k] & 0x7fffffffu;
         if (ml > best) { best = ml; if (ml > endI - mi) endI = mi + ml; }
+        if (ml > qb) { qb = ml; if (nq < WN_Q && ml <= OPT_NUM && ml != remTot) { W.qm[l][nq][0] = q - mi + 3; W.qm[l][nq][1] = ml; ++nq; } else nq = 0xff; }
     }
     for (u32 j = 0; j < nst && cnt < m; ++j) if ((keep >> j) & 1u) {
         const u32 mi = W.rec[l][j][0], ml = W.rec[l][j][1] & 0x7fffffffu;
         if (ml > best) { best = ml; if (ml > endI - mi) endI = mi + ml; }
+        if (ml > qb) { qb = ml; if (nq < WN_Q && ml <= OPT_NUM && ml != remTot) { W.qm[l][nq][0] = q - mi + 3; W.qm[l][nq][1] = ml; ++nq; } else nq = 0xff; }
         ++cnt;
     }
+    if ((fl & WF_IEND) && nst <= m) nq = 0xff;
     u32 positions = 0;
     if (best > 384) { positions = best - 384; if (positions > 192) positions = 192; }
     const u32 a2 = endI - (q + 8);
     if (trunc) fl |= WF_TRUNC;
-    W.keep[l] = keep; W.np[l] = (u8)np; W.tm[l] = (u8)m; W.tn[l] = (u8)tn; W.adv[l] = positions > a2 ? positions : a2; W.flags[l] = (u8)fl;
+    W.nq[l] = (u8)(nq > WN_Q ? 0xff : nq); W.keep[l] = keep; W.np[l] = (u8)np; W.tm[l] = (u8)m; W.tn[l] = (u8)tn; W.adv[l] = positions > a2 ? positions : a2; W.flags[l] = (u8)fl;
 }
 
 ZE_FN void win_commit_slot(Win& W, u32 l)
@@ -610,13 +621,23 @@ ZE_FN_NOINLINE void win_run(Win& W, u32 job)
         ze_cta_sync();
         for (u32 l = tid; l < W.count; l += nt) {                    // a truncated walk detaches nodes: later slots of the bucket cannot be resolved
             u32 fl = W.flags[l];
-            for (u32 k = 0; k < W.chain[l]; ++k) if (W.flags[W.cs[l][k]] & WF_TRUNC) fl |= WF_BAD;
+            for (u32 k = 0; k < W.chain[l]; ++k) if (!W.dead[W.cs[l][k]] && (W.flags[W.cs[l][k]] & WF_TRUNC)) fl |= WF_BAD;
+            W.flags[l] = (u8)fl;
+        }
+    } else if (job == WJ_RESOLVE) {                                  // some slots died: the later ones are resolved again without them
+        for (u32 l = W.next + tid; l < W.count; l += nt) win_pairs(W, l);     // bucket chains without the dead slots (they may now reach further back)
+        ze_cta_sync();
+        for (u32 l = W.next + tid; l < W.count; l += nt) win_resolve(W, l);
+        ze_cta_sync();
+        for (u32 l = W.next + tid; l < W.count; l += nt) {
+            u32 fl = W.flags[l];
+            for (u32 k = 0; k < W.chain[l]; ++k) if (!W.dead[W.cs[l][k]] && (W.flags[W.cs[l][k]] & WF_TRUNC)) fl |= WF_BAD;
             W.flags[l] = (u8)fl;
         }
     } else if (job == WJ_COMMIT) {
         const u32 rounds = W.maxChain;
         for (u32 r = 0; r <= rounds; ++r) {                            // slots of one bucket in position order, buckets side by side
-            for (u32 l = tid; l < W.upto; l += nt) if (W.chain[l] == r) win_commit_slot(W, l);
+            for (u32 l = tid; l < W.upto; l += nt) if (W.chain[l] == r && !W.dead[l]) win_commit_slot(W, l);
             ze_cta_sync();
         }
     }
@@ -649,6 +670,21 @@ ZE_FN_NOINLINE void win_flush(Work& w)
     ze_sync();
 }
 
+// the reference skips the positions [first unconsumed slot, newpos): they never enter the tree
+ZE_FN_NOINLINE void win_skip_to(Work& w, u32 newpos)
+{
+    Win& W = *w.win;
+    const u32 t = newpos - W.base;
+    if (!W.count || newpos < W.base + W.next || t + 8 >= W.count) { win_flush(w); return; }
+    ZE_T(t_rs); ZE_CNT(w, 17, 1);
+    for (u32 j = W.next + ZE_LANE; j < t; j += ZE_LANES) W.dead[j] = 1;
+    ze_sync();
+    if (ZE_LANE == 0) W.next = t;
+    ze_sync();
+    win_dispatch(W, WJ_RESOLVE);
+    ZE_ACC(w, 18, t_rs);
+}
+
 // is `pos` the next unconsumed slot of the current window?  Otherwise close it and build a new one starting at pos
 // (false when the walk limits would depend on the position: near the window / tree-buffer edge and at the block's tail)
 ZE_FN_NOINLINE bool win_ready(Work& w, u32 pos, const u8* iend, u32 mls)
@@ -662,11 +698,14 @@ ZE_FN_NOINLINE bool win_ready(Work& w, u32 pos, const u8* iend, u32 mls)
     if (endIdx > btMask || endIdx - w.lowLimit > maxDist || w.lowLimit < 1) return false;
     if (pos + 8 > endIdx) return false;
     ZE_T(t_bd); ZE_CNT(w, 8, 1);
-    u32 cnt = endIdx - 8 - pos + 1; if (cnt > WN_W) cnt = WN_W;
+    // insert-heavy parses (btopt: long skips) fill a large window; where nearly every position is a query and long repeats cut
+    // windows short (btultra*), a smaller one costs less to build
+    const u32 cap = w.cp.strategy == ST_BTOPT ? WN_W : WN_W / 2;
+    u32 cnt = endIdx - 8 - pos + 1; if (cnt > cap) cnt = cap;
     if (ZE_LANE == 0) {
         W.base = pos; W.count = cnt; W.next = 0; W.endIdx = endIdx; W.baseOff = w.baseOff; W.maxChain = 0;
         W.text = base; W.hashTable = w.hashTable; W.bt = w.chainTable; W.btMask = btMask; W.hashLog = w.cp.hashLog; W.mls = mls;
-        W.lowLimit = w.lowLimit; W.budget = 1u << w.cp.searchLog;
+        W.lowLimit = w.lowLimit; W.budget = 1u << w.cp.searchLog; W.qbase = (mls == 3 ? 3u : 4u) - 1u;
     }
     ze_sync();
     win_dispatch(W, WJ_BUILD);
@@ -709,7 +748,7 @@ ZE_FN_NOINLINE void update_tree(Work& w, u32 target, const u8* iend, u32 mls)
             ze_sync();
             if (ZE_LANE == 0) W.next = s + 1;
             ze_sync();
-            win_flush(w);
+            win_skip_to(w, idx);
         }
     }
     w.nextToUpdate = target;
@@ -717,13 +756,13 @@ ZE_FN_NOINLINE void update_tree(Work& w, u32 target, const u8* iend, u32 mls)
 }
 
 // ZSTD_btGetAllMatches_internal + ZSTD_insertBtAndGetAllMatches (zstd_opt.c:590-820), noDict
-ZE_FN_NOINLINE u32 get_all_matches_impl(Work& w, Match* matches, u32* nextToUpdate3, const u8* ip, const u8* iLimit, const u32* rep, u32 ll0, u32 lengthToBeat)
+ZE_FN u32 get_all_matches_impl(Work& w, Match* matches, u32* nextToUpdate3, const u8* ip, const u8* iLimit, const u32* rep, u32 ll0, u32 lengthToBeat)
 {
     const u8* base = w.src - w.baseOff;
     u32 curr = (u32)(ip - base);
     u32 mls = w.cp.minMatch < 3 ? 3 : (w.cp.minMatch > 6 ? 6 : w.cp.minMatch);
     if (curr < w.nextToUpdate) return 0;                 // skipped area
-    update_tree(w, curr, iLimit, mls);
+    if (curr != w.nextToUpdate) update_tree(w, curr, iLimit, mls);
 
     u32 sufficient_len = w.cp.targetLength < OPT_NUM - 1 ? w.cp.targetLength : OPT_NUM - 1;
     u32 minMatch = (mls == 3) ? 3 : 4;
@@ -791,6 +830,35 @@ ZE_FN_NOINLINE u32 get_all_matches_impl(Work& w, Match* matches, u32* nextToUpda
             }
         }
     }
+    {   // common case: the position is the next slot of the current window and its match list was resolved with the window
+        Win& W = *w.win;
+        const u32 l = curr - W.base;
+        if (W.count && l == W.next && l < W.count && !(W.flags[l] & WF_BAD) && W.nq[l] != 0xff && lengthToBeat - 1 == W.qbase) {
+            ZE_T(t_rp);
+            const u32 nq = W.nq[l];
+            u32 endMax = 0;
+            for (u32 c = 0; c < nq; c += ZE_LANES) {
+                const u32 i = c + ZE_LANE;
+                u32 off = 0, len = 0;
+                if (i < nq) { off = W.qm[l][i][0]; len = W.qm[l][i][1]; }
+                const bool take = i < nq && len > bestLength;
+                const u32 tk = ze_ballot(take);
+                if (take) { const u32 k = mnum + ze_popc(tk & ((1u << ZE_LANE) - 1u)); matches[k].off = off; matches[k].len = len; }
+                const u32 e = ze_reduce_max(take ? curr + 3 - off + len : 0u);
+                if (e > endMax) endMax = e;
+                mnum += ze_popc(tk);
+            }
+            if (endMax > matchEndIdx) matchEndIdx = endMax;
+            const u32 ntu = matchEndIdx - 8;
+            ze_sync();
+            if (ZE_LANE == 0) W.next = l + 1;
+            ze_sync();
+            if (ntu != curr + 1) { ZE_CNT(w, 16, 1); win_skip_to(w, ntu); }
+            w.nextToUpdate = ntu;
+            ZE_ACC(w, 7, t_rp); ZE_CNT(w, 11, 1);
+            return mnum;
+        }
+    }
     if (win_ready(w, curr, iLimit, mls) && (w.win->flags[curr - w.win->base] & WF_BAD) && curr != w.win->base) {
         win_flush(w);                                         // the window ends here: try this position as the first slot of a fresh one
         win_ready(w, curr, iLimit, mls);
@@ -835,7 +903,7 @@ ZE_FN_NOINLINE u32 get_all_matches_impl(Work& w, Match* matches, u32* nextToUpda
             const u32 ntu = matchEndIdx - 8;
             if (ZE_LANE == 0) { W.next = l + 1; if (broke && linked < W.tn[l]) W.tn[l] = (u8)linked; }
             ze_sync();
-            if (broke || ntu != curr + 1) { ZE_CNT(w, 16, 1); win_flush(w); }
+            if (broke) win_flush(w); else if (ntu != curr + 1) { ZE_CNT(w, 16, 1); win_skip_to(w, ntu); }
             w.nextToUpdate = ntu;
             ZE_ACC(w, 7, t_rp); ZE_CNT(w, 11, 1);
             return mnum;
@@ -1173,6 +1241,7 @@ ZE_FN_NOINLINE u32 compress_block_opt_impl(Work& w, u32* rep, const u8* src, u32
             refresh_prices(w, optLevel);
         }
     }
+    win_flush(w);                                             // the next block (other limits, maybe another index base) starts a fresh window
     return (u32)(iend - anchor);
 }
 ZE_FN u32 compress_block_opt(Work& w, u32* rep, const u8* src, u32 srcSize, int optLevel)
@@ -2215,17 +2284,16 @@ ZE_FN WorkSizes work_sizes(const Params& cp)
     z.total = z.hash + z.chain + z.hash3 + z.opt + z.matches + z.freqs + z.seqs + z.lits + z.codes + z.bstates + z.misc;
     return z;
 }
-// low-latency scratch layout: opt table, match list (<= 3 repcodes + 1 hash3 + 2^searchLog tree matches), frequency tables
-struct FastSizes { u32 win, opt, matches, freqs, prices, total; };
+// low-latency scratch layout: match-finder window, match list (<= 3 repcodes + 1 hash3 + 2^searchLog tree matches), frequency tables
+struct FastSizes { u32 win, matches, freqs, prices, total; };
 ZE_FN FastSizes fast_sizes()
 {
     FastSizes f;
     f.win = (u32)align_up((u64)sizeof(Win), 16);                  // first: the helper threads of the CTA find it at offset 0
-    f.opt = (u32)align_up((u64)sizeof(Opt) * OPT_SIZE, 16);
     f.matches = (u32)align_up((u64)sizeof(Match) * (256 + 8), 16);
     f.freqs = (u32)align_up(4 * (256 + 36 + 53 + 32 + 16), 16);
     f.prices = 4 * 384;
-    f.total = f.win + f.opt + f.matches + f.freqs + f.prices;
+    f.total = f.win + f.matches + f.freqs + f.prices;
     return f;
 }
 ZE_FN u64 compress_bound(u64 n) { return n + (n >> 8) + (n < (128u << 10) ? (((128u << 10) - n) >> 11) : 0); }    // ZSTD_COMPRESSBOUND
@@ -2253,7 +2321,7 @@ ZE_FN_NOINLINE u64 compress_frame(const u8* src, u64 srcSize64, int level, u8* d
     if (fast && fastBytes >= fast_sizes().total) {               // parser tables in the low-latency scratch
         FastSizes fz = fast_sizes(); u8* f = fast;
         w.win = (Win*)f; f += fz.win;
-        w.opt = (Opt*)f; f += fz.opt; w.matches = (Match*)f; f += fz.matches;
+        w.matches = (Match*)f; f += fz.matches;
         w.litFreq = (u32*)f; w.llFreq = w.litFreq + 256; w.mlFreq = w.llFreq + 36; w.ofFreq = w.mlFreq + 53; f += fz.freqs;
         w.priceTab = (u32*)f;
     }
