@@ -19,7 +19,7 @@ struct ZTaskDev {
     int32_t level; int32_t err;
     uint64_t out_size;
 #ifdef ZE_PROF
-    uint64_t prof[24];
+    uint64_t prof[32];
 #endif
 };
 
@@ -35,11 +35,11 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) k_zstd(ZTaskDev* __restrict__ t
     if (threadIdx.x >= 32) {
         ze::Win& W = *reinterpret_cast<ze::Win*>(zs_smem);
         for (;;) {
-            ze::ze_bar(1);
+            ze::ze_bar_sync(1, ZS_THREADS);                      // a job was posted
             const uint32_t job = *reinterpret_cast<volatile uint32_t*>(&W.job);
             if (job == ze::WJ_EXIT) break;
             ze::win_run(W, job);
-            ze::ze_bar(2);
+            ze::ze_bar_arrive(2, ZS_THREADS);                    // done (the parser waits on barrier 2 when it needs the result)
         }
         return;
     }
@@ -51,7 +51,8 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) k_zstd(ZTaskDev* __restrict__ t
     uint64_t r = ze::compress_frame(k.src, k.n, k.level, k.dst, k.dst_cap, k.mem, &err, nullptr, zs_smem, smem_bytes);
 #endif
     if (threadIdx.x == 0) { tasks[t].err = err; tasks[t].out_size = r; reinterpret_cast<ze::Win*>(zs_smem)->job = ze::WJ_EXIT; }
-    ze::ze_bar(1);
+    __syncwarp();
+    ze::ze_bar_arrive(1, ZS_THREADS);
 }
 
 extern "C" int agcgpu_zstd_compress_batch(agcgpu_ctx* ctx, const uint8_t* src, const uint64_t* src_offsets, const int32_t* levels,
@@ -128,10 +129,10 @@ extern "C" int agcgpu_zstd_compress_batch(agcgpu_ctx* ctx, const uint8_t* src, c
                 for (uint32_t j = 0; j < cnt && j < 4; ++j) {
                     const uint64_t* p = tasks[j].prof; const double us = 1.0 / 1965.0;     // ticks at the max SM clock
                     fprintf(stderr, "[agcgpu]  frame %u (%llu B, L%d): total %.0f us | parse %.0f  matches %.0f (update_tree %.0f, window build %.0f, commit %.0f, seq query %.0f, replay %.0f)\n"
-                                    "[agcgpu]    counts: get_all_matches %llu, windows %llu, commits %llu, seq inserts %llu, seq queries %llu, replayed queries %llu, window inserts %llu, cuts: unusable slot %llu, skipped positions %llu, re-resolves %llu (%.0f us)\n",
+                                    "[agcgpu]    counts: get_all_matches %llu, windows %llu, commits %llu, seq inserts %llu, seq queries %llu, replayed queries %llu, window inserts %llu, cuts: unusable slot %llu, skipped positions %llu, re-resolves %llu (%.0f us)\n[agcgpu]    build phases (thread 0): walk %.0f +wait %.0f, pairs %.0f +wait %.0f, resolve %.0f +wait %.0f us\n",
                             j, (unsigned long long)tasks[j].n, tasks[j].level, p[0] * us, p[1] * us, p[2] * us, p[3] * us, p[4] * us, p[5] * us, p[6] * us, p[7] * us,
                             (unsigned long long)p[12], (unsigned long long)p[8], (unsigned long long)p[14], (unsigned long long)p[9], (unsigned long long)p[10], (unsigned long long)p[11],
-                            (unsigned long long)p[13], (unsigned long long)p[15], (unsigned long long)p[16], (unsigned long long)p[17], p[18] * us);
+                            (unsigned long long)p[13], (unsigned long long)p[15], (unsigned long long)p[16], (unsigned long long)p[17], p[18] * us, p[19] * us, p[20] * us, p[21] * us, p[22] * us, p[23] * us, p[24] * us);
                 }
 #endif
             } }

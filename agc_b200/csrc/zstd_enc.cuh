@@ -57,7 +57,7 @@ namespace ze {
 
 // optional phase profile of the device build (-DZE_PROF): clock64 ticks and event counts per frame, see kernels_zstd.cu
 #if defined(ZE_PROF) && defined(__CUDA_ARCH__)
-#define ZE_PROF_N 24
+#define ZE_PROF_N 32
 #define ZE_T(var) long long var = clock64()
 #define ZE_ACC(w, slot, var) ((w).prof[slot] += (u64)(clock64() - (var)))
 #define ZE_CNT(w, slot, v) ((w).prof[slot] += (u64)(v))
@@ -239,6 +239,18 @@ ZE_FN void ld64w(const u8* p, u32& lo, u32& hi)                   // unaligned 8
     hi = (u32)p[4] | ((u32)p[5] << 8) | ((u32)p[6] << 16) | ((u32)p[7] << 24);
 #endif
 }
+ZE_FN void ld64w2(const u8* p, u32& lo, u32& hi)                  // same bytes through two aligned 8-byte loads (may touch 15 bytes past p)
+{
+#if defined(__CUDA_ARCH__)
+    const uint2* q = (const uint2*)((uintptr_t)p & ~(uintptr_t)7);
+    const u32 o = (u32)((uintptr_t)p & 7u), sh = 8u * (o & 3u);
+    const uint2 v0 = q[0], v1 = q[1];
+    const u32 w0 = o < 4 ? v0.x : v0.y, w1 = o < 4 ? v0.y : v1.x, w2 = o < 4 ? v1.x : v1.y;
+    lo = __funnelshift_r(w0, w1, sh); hi = __funnelshift_r(w1, w2, sh);
+#else
+    ld64w(p, lo, hi);
+#endif
+}
 struct U2 { u32 x, y; };
 ZE_FN U2 ld_pair(const u32* p)                                    // 8-byte aligned pair
 {
@@ -383,12 +395,15 @@ struct Win {
     u32 job;
     u32 base, count, next, endIdx, baseOff;        // slots = positions [base, base + count); slots < next are consumed
     u32 upto;                                       // WJ_COMMIT: slots [0, upto)
+    u32 jfrom, jto;                                 // WJ_BUILD: slots [jfrom, jto)
+    u32 built, pending;                             // slots < built are resolved; pending: a posted job has not been waited for yet
     u32 maxChain;                                   // deepest bucket chain of the window
     const u8* text;                                 // text[position]
     u32* hashTable; u32* bt;
     u32 btMask, hashLog, mls, lowLimit, budget;
     u32 qbase;                                      // a query's initial best length (minimum match - 1)
-    u32 hash[WN_W];
+    u64 phase[8];                                   // -DZE_PROF: ticks per build phase as thread 0 sees them
+    u32 hash[WN_W + 4];
     u32 keep[WN_W];                                 // recorded steps that stay on the path
     u32 adv[WN_W];                                  // ZSTD_insertBt1's return value
     u8 wflags[WN_W], sflags[WN_W];                  // flags after the walk / after walk + pairs (resolve starts from the latter)
@@ -402,25 +417,37 @@ struct Win {
     u32 rec[WN_W][WN_CAP + 1][2];                      // node, match length | (node is smaller) << 31
 };
 
+// Who runs the window jobs.  Device, wide CTA: the helper warps (threads 32..) only -- the parser's warp posts a job with
+// bar.arrive on barrier 1 and, when it needs the result, waits on barrier 2, so a job can run while the parser goes on; the
+// helpers separate the phases of a job among themselves on barrier 3.  Device, one-warp CTA and host: the caller runs the job.
 #if defined(__CUDA_ARCH__)
-#define ZE_TID (threadIdx.x)
-#define ZE_NT (blockDim.x)
+#define ZE_JOB_TID (blockDim.x > 32 ? threadIdx.x - 32u : threadIdx.x)
+#define ZE_JOB_NT (blockDim.x > 32 ? blockDim.x - 32u : 32u)
 #else
-#define ZE_TID 0u
-#define ZE_NT 1u
+#define ZE_JOB_TID 0u
+#define ZE_JOB_NT 1u
 #endif
-ZE_FN void ze_bar(u32 id)                                         // named barrier over the whole CTA
+ZE_FN void ze_bar_sync(u32 id, u32 nt)
 {
 #if defined(__CUDA_ARCH__)
-    u32 nt = blockDim.x; asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nt) : "memory");
+    asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nt) : "memory");
 #else
-    (void)id;
+    (void)id; (void)nt;
 #endif
 }
-ZE_FN void ze_cta_sync()
+ZE_FN void ze_bar_arrive(u32 id, u32 nt)
 {
 #if defined(__CUDA_ARCH__)
-    if (blockDim.x > 32) ze_bar(3); else __syncwarp();
+    __threadfence_block();
+    asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(nt) : "memory");
+#else
+    (void)id; (void)nt;
+#endif
+}
+ZE_FN void ze_job_sync()                                          // between the phases of a job
+{
+#if defined(__CUDA_ARCH__)
+    if (blockDim.x > 32) ze_bar_sync(3, blockDim.x - 32u); else __syncwarp();
 #endif
 }
 
@@ -440,7 +467,7 @@ ZE_FN u32 lcp_private(const u8* a, const u8* b, u32 maxlen, u32& ca, u32& cb)
     u32 ml = 0;
     if (maxlen >= 8) {
         u32 alo, ahi, blo, bhi;
-        ld64w(a, alo, ahi); ld64w(b, blo, bhi);
+        ld64w(a, alo, ahi); ld64w2(b, blo, bhi);
         u32 xlo = alo ^ blo, xhi = ahi ^ bhi;
         if (xlo | xhi) {
             bool inLo = xlo != 0;
@@ -467,7 +494,7 @@ ZE_FN u32 lcp_private(const u8* a, const u8* b, u32 maxlen, u32& ca, u32& cb)
 #endif
     while (maxlen - ml >= 8) {
         u32 alo, ahi, blo, bhi;
-        ld64w(a + ml, alo, ahi); ld64w(b + ml, blo, bhi);
+        ld64w(a + ml, alo, ahi); ld64w2(b + ml, blo, bhi);
         u32 xlo = alo ^ blo, xhi = ahi ^ bhi;
         if (xlo | xhi) {
             bool inLo = xlo != 0;
@@ -511,13 +538,16 @@ ZE_FN void win_pairs(Win& W, u32 l)
 {
     const u32 h = W.hash[l];
     u32 c = 0, fl = W.wflags[l];
-    for (i32 j = (i32)l - 1; j >= 0 && !(fl & WF_BAD); ) {
-        if ((j & 3) == 3) {                                       // four slots per step
-            const u32 h0 = W.hash[j - 3], h1 = W.hash[j - 2], h2 = W.hash[j - 1], h3 = W.hash[j];
-            if (h3 != h && h2 != h && h1 != h && h0 != h) { j -= 4; continue; }
+    // the lanes of a warp hold consecutive slots: all of them step through the same groups of four earlier slots, newest first
+    // (uniform loop, broadcast loads); a lane only looks at slots before its own
+    for (i32 g = (i32)((l | (ZE_LANES - 1)) >> 2); g >= 0; --g) {
+        const u32 j0 = 4u * (u32)g;
+        const u32 h0 = W.hash[j0], h1 = W.hash[j0 + 1], h2 = W.hash[j0 + 2], h3 = W.hash[j0 + 3];
+        if (h3 != h && h2 != h && h1 != h && h0 != h) continue;
+        for (i32 t = 3; t >= 0; --t) {
+            const u32 j = j0 + (u32)t;
+            if (j < l && W.hash[j] == h && !W.dead[j]) { if (c == WN_D) fl |= WF_BAD; else W.cs[l][c++] = (u16)j; }
         }
-        if (W.hash[j] == h && !W.dead[j]) { if (c == WN_D) fl |= WF_BAD; else W.cs[l][c++] = (u16)j; }
-        --j;
     }
     W.chain[l] = (u8)c;
 #if defined(__CUDA_ARCH__)
@@ -608,28 +638,34 @@ ZE_FN void win_commit_slot(Win& W, u32 l)
     *lp = 0; *sp = 0;
 }
 
-// executed by every thread of the CTA (device) / by the one host thread
+// one job, executed by the job threads (see above)
 ZE_FN_NOINLINE void win_run(Win& W, u32 job)
 {
-    const u32 tid = ZE_TID, nt = ZE_NT;
-    if (job == WJ_BUILD) {
-        for (u32 l = tid; l < W.count; l += nt) win_walk(W, l);
-        ze_cta_sync();
-        for (u32 l = tid; l < W.count; l += nt) win_pairs(W, l);
-        ze_cta_sync();
-        for (u32 l = tid; l < W.count; l += nt) win_resolve(W, l);
-        ze_cta_sync();
-        for (u32 l = tid; l < W.count; l += nt) {                    // a truncated walk detaches nodes: later slots of the bucket cannot be resolved
-            u32 fl = W.flags[l];
-            for (u32 k = 0; k < W.chain[l]; ++k) if (!W.dead[W.cs[l][k]] && (W.flags[W.cs[l][k]] & WF_TRUNC)) fl |= WF_BAD;
-            W.flags[l] = (u8)fl;
+    const u32 tid = ZE_JOB_TID, nt = ZE_JOB_NT;
+    if (job == WJ_BUILD || job == WJ_RESOLVE) {
+#if defined(ZE_PROF) && defined(__CUDA_ARCH__)
+#define ZE_PH(i) do { if (tid == 0) { long long t_ = clock64(); W.phase[i] += (u64)(t_ - t_ph); t_ph = t_; } } while (0)
+        long long t_ph = clock64();
+#else
+#define ZE_PH(i) ((void)0)
+#endif
+        // WJ_RESOLVE: some slots died, the later ones get their bucket chains (which may now reach further back) and paths again
+        const u32 from = job == WJ_BUILD ? W.jfrom : W.next, to = job == WJ_BUILD ? W.jto : W.count;
+        if (job == WJ_BUILD) {
+            for (u32 l = from + tid; l < to; l += nt) win_walk(W, l);
+            ZE_PH(0);
+            ze_job_sync();
+            ZE_PH(1);
         }
-    } else if (job == WJ_RESOLVE) {                                  // some slots died: the later ones are resolved again without them
-        for (u32 l = W.next + tid; l < W.count; l += nt) win_pairs(W, l);     // bucket chains without the dead slots (they may now reach further back)
-        ze_cta_sync();
-        for (u32 l = W.next + tid; l < W.count; l += nt) win_resolve(W, l);
-        ze_cta_sync();
-        for (u32 l = W.next + tid; l < W.count; l += nt) {
+        for (u32 l = from + tid; l < to; l += nt) win_pairs(W, l);
+        ZE_PH(2);
+        ze_job_sync();
+        ZE_PH(3);
+        for (u32 l = from + tid; l < to; l += nt) win_resolve(W, l);
+        ZE_PH(4);
+        ze_job_sync();
+        ZE_PH(5);
+        for (u32 l = from + tid; l < to; l += nt) {                  // a truncated walk detaches nodes: later slots of the bucket cannot be resolved
             u32 fl = W.flags[l];
             for (u32 k = 0; k < W.chain[l]; ++k) if (!W.dead[W.cs[l][k]] && (W.flags[W.cs[l][k]] & WF_TRUNC)) fl |= WF_BAD;
             W.flags[l] = (u8)fl;
@@ -638,26 +674,42 @@ ZE_FN_NOINLINE void win_run(Win& W, u32 job)
         const u32 rounds = W.maxChain;
         for (u32 r = 0; r <= rounds; ++r) {                            // slots of one bucket in position order, buckets side by side
             for (u32 l = tid; l < W.upto; l += nt) if (W.chain[l] == r && !W.dead[l]) win_commit_slot(W, l);
-            ze_cta_sync();
+            ze_job_sync();
         }
     }
 }
-ZE_FN void win_dispatch(Win& W, u32 job)
+// wait for the posted job
+ZE_FN void win_wait(Win& W)
 {
+    if (!W.pending) return;
 #if defined(__CUDA_ARCH__)
-    if (blockDim.x > 32) {
-        if (ZE_LANE == 0) W.job = job;
-        ze_bar(1); win_run(W, job); ze_bar(2);
-    } else { __syncwarp(); win_run(W, job); __syncwarp(); }
+    if (blockDim.x > 32) ze_bar_sync(2, blockDim.x);
+#endif
+    ze_sync();
+    if (ZE_LANE == 0) { if (W.job == WJ_BUILD) W.built = W.jto; W.pending = 0; }
+    ze_sync();
+}
+// hand a job to the job threads; the caller's parameters in W must be written (by lane 0) before
+ZE_FN void win_post(Win& W, u32 job)
+{
+    win_wait(W);
+    ze_sync();
+    if (ZE_LANE == 0) { W.job = job; W.pending = 1; }
+    ze_sync();
+#if defined(__CUDA_ARCH__)
+    if (blockDim.x > 32) ze_bar_arrive(1, blockDim.x);
+    else { win_run(W, job); __syncwarp(); }
 #else
     win_run(W, job);
 #endif
 }
+ZE_FN void win_dispatch(Win& W, u32 job) { win_post(W, job); win_wait(W); }
 
 // write the links of the consumed slots and close the window
 ZE_FN_NOINLINE void win_flush(Work& w)
 {
     Win& W = *w.win;
+    win_wait(W);
     if (W.count && W.next > 0 && W.baseOff == w.baseOff) {
         ZE_T(t_cm); ZE_CNT(w, 14, 1);
         if (ZE_LANE == 0) W.upto = W.next;
@@ -700,15 +752,20 @@ ZE_FN_NOINLINE bool win_ready(Work& w, u32 pos, const u8* iend, u32 mls)
     ZE_T(t_bd); ZE_CNT(w, 8, 1);
     // insert-heavy parses (btopt: long skips) fill a large window; where nearly every position is a query and long repeats cut
     // windows short (btultra*), a smaller one costs less to build
-    const u32 cap = w.cp.strategy == ST_BTOPT ? WN_W : WN_W / 2;
+    u32 cap = w.cp.strategy == ST_BTOPT ? WN_W : WN_W / 2;
+    if (cap > ZE_JOB_NT && ZE_JOB_NT >= 32) cap = ZE_JOB_NT;          // one slot per job thread
     u32 cnt = endIdx - 8 - pos + 1; if (cnt > cap) cnt = cap;
+    // (Building a window in stages while the parser consumes the earlier ones was measured and lost: the stages are latency
+    // bound, so k stages cost k times the walk latency, and the job warps slow the parser's warp on the same SM.)
+    win_wait(W);
     if (ZE_LANE == 0) {
-        W.base = pos; W.count = cnt; W.next = 0; W.endIdx = endIdx; W.baseOff = w.baseOff; W.maxChain = 0;
+        W.base = pos; W.count = cnt; W.next = 0; W.endIdx = endIdx; W.baseOff = w.baseOff; W.maxChain = 0; W.jfrom = 0; W.jto = cnt;
         W.text = base; W.hashTable = w.hashTable; W.bt = w.chainTable; W.btMask = btMask; W.hashLog = w.cp.hashLog; W.mls = mls;
         W.lowLimit = w.lowLimit; W.budget = 1u << w.cp.searchLog; W.qbase = (mls == 3 ? 3u : 4u) - 1u;
     }
     ze_sync();
     win_dispatch(W, WJ_BUILD);
+    ze_sync();
     ZE_ACC(w, 4, t_bd);
     return true;
 }
@@ -720,7 +777,7 @@ ZE_FN_NOINLINE void update_tree(Work& w, u32 target, const u8* iend, u32 mls)
     ZE_T(t_ut);
     Win& W = *w.win;
     while (idx < target) {
-        if (!win_ready(w, idx, iend, mls)) { ZE_CNT(w, 9, 1); idx += insert_bt1(w, idx, iend, target, mls); continue; }
+        if (!(W.count && idx - W.base == W.next && W.next < W.count) && !win_ready(w, idx, iend, mls)) { ZE_CNT(w, 9, 1); idx += insert_bt1(w, idx, iend, target, mls); continue; }
         const u32 l = idx - W.base;
         u32 hi = target - W.base; if (hi > W.count) hi = W.count;
         u32 s = l;                                            // first slot of [l, hi) that is not a plain insert
@@ -1022,34 +1079,63 @@ ZE_FN u32 match_price(const Work& w, u32 offBase, u32 ml, int optLevel)   // ZST
     price += BITCOST_MULT / 5;
     return price;
 }
-// The statistics only change when sequences are stored, so between two stores every price is a table lookup.
+// Price tables.  The statistics only change when sequences are stored, so a price is a table lookup plus the base price of
+// its category: priceTab = lit[256] weight(litFreq), then per code extraBits * 256 - weight(freq) for ll[36], ml[53], off[32]
+// (offset codes >= 20 carry btopt's handicap).  refresh_prices rebuilds everything (block start); update_stats_t patches the
+// entries one stored sequence touches.  Same unsigned arithmetic as ZSTD_litLengthPrice / ZSTD_getMatchPrice, regrouped.
+struct BP { u32 lit, ll, ml, of; };
+ZE_FN BP base_prices(const Work& w) { BP b; b.lit = w.litSumBP; b.ll = w.llSumBP; b.ml = w.mlSumBP; b.of = w.ofSumBP; return b; }
+ZE_FN u32 of_entry(const Work& w, u32 c, int optLevel) { u32 v = c * BITCOST_MULT - weight(w.ofFreq[c], optLevel); if (optLevel < 2 && c >= 20) v += (c - 19) * 2 * BITCOST_MULT; return v; }
 ZE_FN_NOINLINE void refresh_prices(Work& w, int optLevel)
 {
     if (w.pricePredef) return;
     u32* T = w.priceTab;
-    const u32 maxLit = w.litSumBP - BITCOST_MULT;
     for (u32 i = ZE_LANE; i < 256 + 36 + 53 + 32; i += ZE_LANES) {
         u32 v;
-        if (i < 256) { u32 lp = weight(w.litFreq[i], optLevel); if (lp > maxLit) lp = maxLit; v = w.litSumBP - lp; }
-        else if (i < 256 + 36) { const u32 c = i - 256; v = kLLbits[c] * BITCOST_MULT + w.llSumBP - weight(w.llFreq[c], optLevel); }
-        else if (i < 256 + 36 + 53) { const u32 c = i - 292; v = kMLbits[c] * BITCOST_MULT + (w.mlSumBP - weight(w.mlFreq[c], optLevel)); }
-        else { const u32 c = i - 345; v = c * BITCOST_MULT + (w.ofSumBP - weight(w.ofFreq[c], optLevel)); if (optLevel < 2 && c >= 20) v += (c - 19) * 2 * BITCOST_MULT; }
+        if (i < 256) v = weight(w.litFreq[i], optLevel);
+        else if (i < 256 + 36) { const u32 c = i - 256; v = kLLbits[c] * BITCOST_MULT - weight(w.llFreq[c], optLevel); }
+        else if (i < 256 + 36 + 53) { const u32 c = i - 292; v = kMLbits[c] * BITCOST_MULT - weight(w.mlFreq[c], optLevel); }
+        else v = of_entry(w, i - 345, optLevel);
         T[i] = v;
     }
     ze_sync();
 }
-ZE_FN u32 lit_cost1_t(const Work& w, u8 lit) { return w.pricePredef ? 6 * BITCOST_MULT : w.priceTab[lit]; }
-ZE_FN u32 ll_price_t(const Work& w, u32 ll, int optLevel)
+ZE_FN u32 lit_cost1_t(const Work& w, const BP& bp, u8 lit)
+{
+    if (w.pricePredef) return 6 * BITCOST_MULT;
+    u32 lp = w.priceTab[lit]; const u32 maxp = bp.lit - BITCOST_MULT;
+    if (lp > maxp) lp = maxp;
+    return bp.lit - lp;
+}
+ZE_FN u32 ll_price_t(const Work& w, const BP& bp, u32 ll, int optLevel)
 {
     if (w.pricePredef) return weight(ll, optLevel);
     u32 extra = 0;
     if (ll == BLOCK_MAX) { extra = BITCOST_MULT; ll = BLOCK_MAX - 1; }
-    return extra + w.priceTab[256 + LLcode(ll)];
+    return extra + w.priceTab[256 + LLcode(ll)] + bp.ll;
 }
-ZE_FN u32 match_price_t(const Work& w, u32 offBase, u32 ml, int optLevel)
+ZE_FN u32 match_price_t(const Work& w, const BP& bp, u32 offBase, u32 ml, int optLevel)
 {
     if (w.pricePredef) return match_price(w, offBase, ml, optLevel);
-    return w.priceTab[345 + highbit(offBase)] + w.priceTab[292 + MLcode(ml - 3)] + BITCOST_MULT / 5;
+    return w.priceTab[345 + highbit(offBase)] + bp.of + w.priceTab[292 + MLcode(ml - 3)] + bp.ml + BITCOST_MULT / 5;
+}
+// ZSTD_updateStats (zstd_opt.c:356) + the table entries it invalidates
+ZE_FN_NOINLINE void update_stats_t(Work& w, u32 ll, const u8* lits, u32 offBase, u32 ml, int optLevel)
+{
+    for (u32 u = 0; u < ll; ++u) w.litFreq[lits[u]] += 2;
+    w.litSum += ll * 2;
+    const u32 lc = LLcode(ll), oc = highbit(offBase), mc = MLcode(ml - 3);
+    w.llFreq[lc]++; w.llSum++;
+    w.ofFreq[oc]++; w.ofSum++;
+    w.mlFreq[mc]++; w.mlSum++;
+    if (w.pricePredef) return;
+    u32* T = w.priceTab;
+    ze_sync();
+    for (u32 u = ZE_LANE; u < ll; u += ZE_LANES) T[lits[u]] = weight(w.litFreq[lits[u]], optLevel);
+    T[256 + lc] = kLLbits[lc] * BITCOST_MULT - weight(w.llFreq[lc], optLevel);
+    T[292 + mc] = kMLbits[mc] * BITCOST_MULT - weight(w.mlFreq[mc], optLevel);
+    T[345 + oc] = of_entry(w, oc, optLevel);
+    ze_sync();
 }
 ZE_FN_NOINLINE void update_stats(Work& w, u32 ll, const u8* lits, u32 offBase, u32 ml)
 {
@@ -1090,6 +1176,7 @@ ZE_FN_NOINLINE u32 compress_block_opt_impl(Work& w, u32* rep, const u8* src, u32
 
     rescale_freqs(w, src, srcSize, optLevel);
     refresh_prices(w, optLevel);
+    BP bp = base_prices(w);
     ip += (ip == prefixStart);
 
     while (ip < ilimit) {
@@ -1098,7 +1185,7 @@ ZE_FN_NOINLINE u32 compress_block_opt_impl(Work& w, u32* rep, const u8* src, u32
         {   u32 litlen = (u32)(ip - anchor), ll0 = !litlen;
             u32 nbMatches = get_all_matches(w, matches, &nextToUpdate3, ip, iend, rep, ll0, minMatch);
             if (!nbMatches) { ip++; continue; }
-            opt[0].mlen = 0; opt[0].litlen = litlen; opt[0].price = (i32)ll_price_t(w, litlen, optLevel);
+            opt[0].mlen = 0; opt[0].litlen = litlen; opt[0].price = (i32)ll_price_t(w, bp, litlen, optLevel);
             opt[0].rep[0] = rep[0]; opt[0].rep[1] = rep[1]; opt[0].rep[2] = rep[2];
             {   u32 maxML = matches[nbMatches - 1].len, maxOff = matches[nbMatches - 1].off;
                 if (maxML > sufficient_len) {
@@ -1109,11 +1196,11 @@ ZE_FN_NOINLINE u32 compress_block_opt_impl(Work& w, u32* rep, const u8* src, u32
             if (!shortest) {
                 u32 pos;
                 for (pos = 1; pos < minMatch; pos++) { opt[pos].price = MAX_PRICE; opt[pos].mlen = 0; opt[pos].litlen = litlen + pos; }
-                {   const i32 ll0p = (i32)ll_price_t(w, 0, optLevel), p0 = opt[0].price;
+                {   const i32 ll0p = (i32)ll_price_t(w, bp, 0, optLevel), p0 = opt[0].price;
                     for (u32 m = 0; m < nbMatches; m++) {
                         u32 offBase = matches[m].off, end = matches[m].len;
                         for (u32 q = pos + ZE_LANE; q <= end; q += ZE_LANES) {          // lanes take different lengths
-                            i32 mp = (i32)match_price_t(w, offBase, q, optLevel);
+                            i32 mp = (i32)match_price_t(w, bp, offBase, q, optLevel);
                             opt[q].mlen = q; opt[q].off = offBase; opt[q].litlen = 0;
                             opt[q].price = p0 + mp + ll0p;
                         }
@@ -1129,19 +1216,19 @@ ZE_FN_NOINLINE u32 compress_block_opt_impl(Work& w, u32* rep, const u8* src, u32
             for (cur = 1; cur <= last_pos; cur++) {
                 const u8* inr = ip + cur;
                 {   u32 litlen = opt[cur - 1].litlen + 1;
-                    i32 price = opt[cur - 1].price + (i32)lit_cost1_t(w, ip[cur - 1])
-                              + ((i32)ll_price_t(w, litlen, optLevel) - (i32)ll_price_t(w, litlen - 1, optLevel));
+                    i32 price = opt[cur - 1].price + (i32)lit_cost1_t(w, bp, ip[cur - 1])
+                              + ((i32)ll_price_t(w, bp, litlen, optLevel) - (i32)ll_price_t(w, bp, litlen - 1, optLevel));
                     if (price <= opt[cur].price) {
                         Opt prevMatch = opt[cur];
                         opt[cur] = opt[cur - 1];
                         opt[cur].litlen = litlen; opt[cur].price = price;
                         if (optLevel >= 1 && prevMatch.litlen == 0
-                            && ((i32)ll_price_t(w, 1, optLevel) - (i32)ll_price_t(w, 0, optLevel)) < 0
+                            && ((i32)ll_price_t(w, bp, 1, optLevel) - (i32)ll_price_t(w, bp, 0, optLevel)) < 0
                             && ip + cur < iend) {
-                            i32 with1 = prevMatch.price + (i32)lit_cost1_t(w, ip[cur])
-                                      + ((i32)ll_price_t(w, 1, optLevel) - (i32)ll_price_t(w, 0, optLevel));
-                            i32 withMore = price + (i32)lit_cost1_t(w, ip[cur])
-                                         + ((i32)ll_price_t(w, litlen + 1, optLevel) - (i32)ll_price_t(w, litlen, optLevel));
+                            i32 with1 = prevMatch.price + (i32)lit_cost1_t(w, bp, ip[cur])
+                                      + ((i32)ll_price_t(w, bp, 1, optLevel) - (i32)ll_price_t(w, bp, 0, optLevel));
+                            i32 withMore = price + (i32)lit_cost1_t(w, bp, ip[cur])
+                                         + ((i32)ll_price_t(w, bp, litlen + 1, optLevel) - (i32)ll_price_t(w, bp, litlen, optLevel));
                             if (with1 < withMore && with1 < opt[cur + 1].price) {
                                 u32 prev = cur - prevMatch.mlen;
                                 u32 nr[3] = { opt[prev].rep[0], opt[prev].rep[1], opt[prev].rep[2] };
@@ -1164,7 +1251,7 @@ ZE_FN_NOINLINE u32 compress_block_opt_impl(Work& w, u32* rep, const u8* src, u32
                 if (cur == last_pos) break;
                 if (optLevel == 0 && opt[cur + 1].price <= opt[cur].price + (i32)(BITCOST_MULT / 2)) continue;
                 {   u32 ll0 = (opt[cur].litlen == 0);
-                    i32 basePrice = opt[cur].price + (i32)ll_price_t(w, 0, optLevel);
+                    i32 basePrice = opt[cur].price + (i32)ll_price_t(w, bp, 0, optLevel);
                     u32 nbMatches = get_all_matches(w, matches, &nextToUpdate3, inr, iend, opt[cur].rep, ll0, minMatch);
                     if (!nbMatches) continue;
                     {   u32 longestML = matches[nbMatches - 1].len;
@@ -1177,14 +1264,28 @@ ZE_FN_NOINLINE u32 compress_block_opt_impl(Work& w, u32* rep, const u8* src, u32
                     for (u32 m = 0; m < nbMatches; m++) {
                         u32 offset = matches[m].off, lastML = matches[m].len;
                         u32 startML = m > 0 ? matches[m - 1].len + 1 : minMatch;
-                        if (optLevel == 0) {                       // btopt: the early abort makes the scan order-dependent
-                            for (u32 mlen = lastML; mlen >= startML; mlen--) {
-                                u32 pos = cur + mlen;
-                                i32 price = basePrice + (i32)match_price_t(w, offset, mlen, optLevel);
-                                if (pos > last_pos || price < opt[pos].price) {
-                                    while (last_pos < pos) { last_pos++; opt[last_pos].price = MAX_PRICE; opt[last_pos].litlen = 1; }
-                                    opt[pos].mlen = mlen; opt[pos].off = offset; opt[pos].litlen = 0; opt[pos].price = price;
-                                } else break;
+                        if (optLevel == 0) {
+                            // btopt scans the lengths downwards and stops at the first one that does not improve its position.
+                            // Every length has its own position, so the tests are independent: lanes take ZE_LANES lengths at a
+                            // time and the first failing one (ballot) ends the scan exactly where the sequential loop would.
+                            if (lastML >= startML) {
+                                const u32 top = cur + lastML;
+                                if (top > last_pos) {
+                                    for (u32 q = last_pos + 1 + ZE_LANE; q <= top; q += ZE_LANES) { opt[q].price = MAX_PRICE; opt[q].litlen = 1; }
+                                    ze_sync();
+                                    last_pos = top;
+                                }
+                                for (u32 c = 0; c <= lastML - startML; c += ZE_LANES) {
+                                    const u32 d = c + ZE_LANE; const bool in = d <= lastML - startML;
+                                    const u32 mlen = lastML - d, pos = cur + mlen;
+                                    i32 price = 0; bool ok = false;
+                                    if (in) { price = basePrice + (i32)match_price_t(w, bp, offset, mlen, optLevel); ok = price < opt[pos].price; }
+                                    const u32 fail = ze_ballot(in && !ok);
+                                    const u32 upto = fail ? ze_ffs(fail) - 1 : 32;
+                                    if (in && ZE_LANE < upto) { opt[pos].mlen = mlen; opt[pos].off = offset; opt[pos].litlen = 0; opt[pos].price = price; }
+                                    if (fail) break;
+                                }
+                                ze_sync();
                             }
                         } else if (lastML >= startML) {            // btultra(2): every length is tried -> lanes take different lengths
                             u32 top = cur + lastML;
@@ -1195,7 +1296,7 @@ ZE_FN_NOINLINE u32 compress_block_opt_impl(Work& w, u32* rep, const u8* src, u32
                             }
                             for (u32 mlen = startML + ZE_LANE; mlen <= lastML; mlen += ZE_LANES) {
                                 u32 pos = cur + mlen;
-                                i32 price = basePrice + (i32)match_price_t(w, offset, mlen, optLevel);
+                                i32 price = basePrice + (i32)match_price_t(w, bp, offset, mlen, optLevel);
                                 if (price < opt[pos].price) { opt[pos].mlen = mlen; opt[pos].off = offset; opt[pos].litlen = 0; opt[pos].price = price; }
                             }
                             ze_sync();
@@ -1233,12 +1334,12 @@ ZE_FN_NOINLINE u32 compress_block_opt_impl(Work& w, u32* rep, const u8* src, u32
             for (u32 sp = storeStart; sp <= storeEnd; sp++) {
                 u32 llen = opt[sp].litlen, mlen = opt[sp].mlen, offBase = opt[sp].off, advance = llen + mlen;
                 if (mlen == 0) { ip = anchor + llen; continue; }
-                update_stats(w, llen, anchor, offBase, mlen);
+                update_stats_t(w, llen, anchor, offBase, mlen, optLevel);
                 store_seq(w.ss, llen, anchor, offBase, mlen);
                 anchor += advance; ip = anchor;
             }
             set_base_prices(w, optLevel);
-            refresh_prices(w, optLevel);
+            bp = base_prices(w);
         }
     }
     win_flush(w);                                             // the next block (other limits, maybe another index base) starts a fresh window
@@ -2345,7 +2446,7 @@ ZE_FN_NOINLINE u64 compress_frame(const u8* src, u64 srcSize64, int level, u8* d
     p += 4 * 384;
     p = (u8*)align_up((u64)p, 8);
     if (!(fast && fastBytes >= fast_sizes().total)) w.win = (Win*)p;
-    if (ZE_LANE == 0) { w.win->count = 0; w.win->next = 0; w.win->baseOff = 0; }
+    if (ZE_LANE == 0) { w.win->count = 0; w.win->next = 0; w.win->baseOff = 0; w.win->pending = 0; w.win->built = 0; for (int i = 0; i < 8; ++i) w.win->phase[i] = 0; }
     ze_sync();
     reset_seqstore(w);
     w.hashLog3 = cp.minMatch == 3 ? (cp.windowLog < 17 ? cp.windowLog : 17) : 0;
@@ -2387,6 +2488,7 @@ ZE_FN_NOINLINE u64 compress_frame(const u8* src, u64 srcSize64, int level, u8* d
     if (srcSize == 0) { wr24(op, 1); op += 3; }                     // ZSTD_writeEpilogue: empty last raw block
 #if defined(ZE_PROF) && defined(__CUDA_ARCH__)
     w.prof[0] = (u64)(clock64() - t_frame);
+    for (int i = 0; i < 6; ++i) w.prof[19 + i] = w.win->phase[i];
     if (prof_out && ZE_LANE == 0) for (int i = 0; i < ZE_PROF_N; ++i) prof_out[i] = w.prof[i];
 #endif
     return (u64)(op - dst);
