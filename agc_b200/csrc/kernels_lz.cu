@@ -48,6 +48,18 @@ struct PackedAcc {
     __device__ __forceinline__ uint64_t rwin(int64_t pos) const { return agc_win_s(R, pos); }
     __device__ __forceinline__ bool tcode(uint32_t p, uint32_t kl, uint64_t& x) const { x = twin(p) >> (64 - 2 * kl); return true; }
     __device__ __forceinline__ bool rcode_eq(uint32_t rp, uint64_t x, uint32_t kl) const { return (rwin(rp) >> (64 - 2 * kl)) == x; }
+    // cheap reject for the probe loops: indexed reference positions are multiples of 4 bases = whole bytes, so the first
+    // min(kl, 16) bases of the key at slot value v are the (unaligned, big-endian) 32 bits at byte v: two word loads + one
+    // PRMT.  xq = the same bits of the text key (key_quick).  true = "may be equal" (rcode_eq decides).
+    __device__ __forceinline__ uint32_t key_quick(uint64_t x, uint32_t kl) const { return kl >= 16 ? (uint32_t)(x >> (2 * kl - 32)) : (uint32_t)(x << (32 - 2 * kl)); }
+    __device__ __forceinline__ bool rcode_quick(uint32_t v, uint32_t xq, uint32_t kl) const
+    {
+        const uint32_t* w = (const uint32_t*)R + (v >> 2);
+        const uint32_t o = v & 3u;
+        const uint32_t r = __byte_perm(w[0], w[1], 0x0123u + o * 0x1111u);
+        const uint32_t d = r ^ xq;
+        return kl >= 16 ? d == 0 : (d >> (32 - 2 * kl)) == 0;
+    }
     __device__ __forceinline__ uint32_t tsym(uint32_t q) const { return (uint32_t)(twin(q) >> 62); }
     __device__ __forceinline__ uint32_t rsym(uint32_t q) const { return (uint32_t)(rwin(q) >> 62); }
     __device__ __forceinline__ uint32_t nrun(uint32_t, uint32_t, uint32_t) const { return 0; }
@@ -106,6 +118,8 @@ struct ByteAcc {
         for (uint32_t i = 0; i < kl; ++i) { uint32_t s = R[rp + i]; if (s > 3) return false; y = (y << 2) + s; }
         return y == x;
     }
+    __device__ __forceinline__ uint32_t key_quick(uint64_t, uint32_t) const { return 0; }
+    __device__ __forceinline__ bool rcode_quick(uint32_t, uint32_t, uint32_t) const { return true; }
     __device__ __forceinline__ uint32_t tsym(uint32_t q) const { return T[q]; }
     __device__ __forceinline__ uint32_t rsym(uint32_t q) const { return R[q]; }
     // get_Nrun_len (lz_diff.h:122-132)
@@ -248,11 +262,12 @@ __device__ bool eval_chain(const A& a, const HT& ht, uint32_t hpos, uint64_t x, 
                            uint32_t mml, uint32_t lane, uint32_t& o_rp, uint32_t& o_b, uint32_t& o_f)
 {
     uint32_t best_b = 0, best_f = 0, best_rp = 0, mtu = mml;
+    const uint32_t xq = a.key_quick(x, kl);
     for (uint32_t t0 = 0; t0 < 64; t0 += 32) {
         uint32_t v = ht.get((hpos + t0 + lane) & ht.mask);
         uint32_t em = __ballot_sync(FULL, v == AGC_EMPTY32);
         uint32_t cnt = em ? (uint32_t)__ffs(em) - 1 : 32u;
-        bool cand = lane < cnt && a.rcode_eq(v * 4u, x, kl);
+        bool cand = lane < cnt && a.rcode_quick(v, xq, kl) && a.rcode_eq(v * 4u, x, kl);
         uint32_t cm = __ballot_sync(FULL, cand);
         while (cm) {
             uint32_t l = __ffs(cm) - 1; cm &= cm - 1;
@@ -282,21 +297,26 @@ __device__ void lz_parse(const A& a, const HT& ht, uint32_t mml, uint32_t lane, 
         uint32_t p = i + lane;
         bool active = p + kl < n;
         uint32_t ev = 0; uint64_t x = 0;
-        if (active) {
-            if (!a.tcode(p, kl, x)) ev = 1;
-            else {
-                uint32_t hp = (uint32_t)agc_murmur64(x) & ht.mask;
-                for (uint32_t t = 0; t < 64; ++t) {
-                    uint32_t v = ht.get((hp + t) & ht.mask);
-                    if (v == AGC_EMPTY32) break;
-                    if (a.rcode_eq(v * 4u, x, kl)) { ev = 2; break; }
-                }
-            }
-        }
+        if (active && !a.tcode(p, kl, x)) ev = 1;
         uint32_t nact = __popc(__ballot_sync(FULL, active));
-        uint32_t evmask = __ballot_sync(FULL, ev != 0);
         uint32_t c = 0;                              // lanes [0,c) of this round are already committed as literals
         bool restart = false;
+        // The probe walk of a round costs as many steps as the longest chain among the probing lanes, and after a mismatch the
+        // next match starts within a few positions (the first one that is a multiple of 4 on the reference): the first 8
+        // positions are probed on their own, the other 24 only if none of them ends the round.
+        for (uint32_t grp = 0; grp < 2 && !restart; ++grp) {
+        const bool mine = grp == 0 ? lane < 8 : lane >= 8;
+        if (grp == 1 && nact <= 8) break;
+        if (active && mine && ev == 0) {
+            uint32_t hp = (uint32_t)agc_murmur64(x) & ht.mask;
+            const uint32_t xq = a.key_quick(x, kl);
+            for (uint32_t t = 0; t < 64; ++t) {
+                uint32_t v = ht.get((hp + t) & ht.mask);
+                if (v == AGC_EMPTY32) break;
+                if (a.rcode_quick(v, xq, kl) && a.rcode_eq(v * 4u, x, kl)) { ev = 2; break; }
+            }
+        }
+        uint32_t evmask = __ballot_sync(FULL, mine && ev != 0);
         while (evmask) {
             uint32_t L = __ffs(evmask) - 1; evmask &= evmask - 1;
             uint32_t evL = __shfl_sync(FULL, ev, L);
@@ -351,6 +371,7 @@ __device__ void lz_parse(const A& a, const HT& ht, uint32_t mml, uint32_t lane, 
             }
             pred = mp + len; i = ts + len; np = 0; restart = true;
             break;
+        }
         }
         if (!restart) {
             uint32_t r = nact - c;
@@ -430,6 +451,11 @@ __global__ void __launch_bounds__(LZ_THREADS, 2) k_lz_packed(
         r = __shfl_sync(FULL, r, 0);
         if (r >= u.count) break;
         const LzReqDev q = reqs[u.first + r];
+        if (lane == 0) {                                 // pull the whole packed segment into L2 while the parse works on its head
+            const uint64_t b0 = (q.gstart >> 2) & ~(uint64_t)15;
+            const uint32_t nb = (uint32_t)(((q.gstart + q.n + 3) >> 2) - b0 + 15) & ~15u;
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"((const uint8_t*)P + b0), "r"(nb) : "memory");
+        }
         PackedAcc a; a.T = P; a.gs = (int64_t)q.gstart; a.n = q.n; a.rc = q.is_rc; a.R = (const uint64_t*)refp; a.m = g.m;
         Sink s; s.out = slab + q.out_off; s.olen = 0; s.cap = q.out_cap; s.ovf = 0; s.est = 0; s.bound = q.bound;
         s.v = costv + q.out_off; s.prefix = prefix;
@@ -859,8 +885,10 @@ int agc_lz_run(agcgpu_ctx* ctx, int mode, const agcgpu_seg_req* reqs, uint32_t n
     }
     std::stable_sort(packed_reqs.begin(), packed_reqs.end(), [](const LzReqDev& a, const LzReqDev& b) { return a.group < b.group; });
     // units: requests of one group, at most UNIT_MAX per CTA; longest-first inside a group helps the tail
-    // unit size: enough CTAs to cover every SM twice, at most one request per warp of a CTA
-    const uint32_t UNIT_MAX = (uint32_t)std::min<size_t>(16, std::max<size_t>(1, (packed_reqs.size() + 2 * (size_t)ctx->n_sm - 1) / (2 * (size_t)ctx->n_sm)));
+    // A CTA has 16 warps and two CTAs fit on an SM: give every warp a request while the batch fits in one wave of CTAs, and make
+    // the warps loop over several requests (instead of launching a second, mostly empty wave) when it does not.
+    const size_t resident = 2 * (size_t)ctx->n_sm;
+    const uint32_t UNIT_MAX = (uint32_t)std::max<size_t>(16, ((packed_reqs.size() + resident - 1) / resident + 15) / 16 * 16);
     std::vector<LzUnit> units;
     size_t smem_need = 0;
     for (size_t a = 0; a < packed_reqs.size();) {

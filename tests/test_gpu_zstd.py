@@ -30,6 +30,53 @@ def _gen(rng, kind, n):
     return bytes(np.concatenate([a, a, a])[:n])
 
 
+def _gen_adv(rng, kind, n):
+    """inputs aimed at the match finder's window engine: deep bucket chains, positions the reference skips, walks that run
+    out of compares or reach the end of a block, near-copies across block boundaries"""
+    if kind == 0:                                            # long runs of few symbols (period 1, very deep chains)
+        out = bytearray()
+        while len(out) < n:
+            out += bytes([int(rng.integers(33, 36))]) * int(rng.integers(1, 400))
+        return bytes(out[:n])
+    if kind == 1:                                            # short periods 2..9 with sparse errors
+        out = bytearray()
+        while len(out) < n:
+            per = bytes(rng.integers(48, 58, int(rng.integers(2, 10)), dtype=np.uint8))
+            seg = bytearray(per * int(rng.integers(3, 120)))
+            for _ in range(len(seg) // 200):
+                seg[int(rng.integers(0, len(seg)))] = 65
+            out += seg
+        return bytes(out[:n])
+    if kind == 2:                                            # near-copies of one 20 kb sequence over 4 symbols (raw-group packs)
+        ref = rng.integers(0, 4, 20000).astype(np.uint8); parts = []
+        while sum(map(len, parts)) < n:
+            t = ref.copy(); m = rng.random(len(t)) < 0.02; t[m] = (t[m] + rng.integers(1, 4, int(m.sum()))) % 4
+            parts.append(bytes(t) + b"\xff")
+        return b"".join(parts)[:n]
+    if kind == 3:                                            # exact repeats of a block much longer than ZSTD_OPT_NUM
+        blk = bytes(rng.integers(0, 256, 9000, dtype=np.uint8))
+        return (blk * (n // 9000 + 1))[:n]
+    if kind == 4:                                            # two-symbol text: every bucket is deep, walks hit the compare limit
+        return bytes(rng.integers(0, 2, n, dtype=np.uint8) + 97)
+    # delta-pack-like text with long '!' runs
+    out = bytearray()
+    while len(out) < n:
+        out += b"!" * int(rng.integers(0, 60)) + str(int(rng.integers(0, 3000))).encode() + b"," + str(int(rng.integers(0, 900))).encode() + b"." + bytes([int(rng.integers(65, 69))])
+    return bytes(out[:n])
+
+
+def test_zstd_window_engine_cases(dev_factory):
+    rng = np.random.default_rng(8)
+    dev = dev_factory(k=21, min_match_len=20)
+    inputs, levels = [], []
+    for kind in range(6):
+        for n, level in ((3000, 17), (16000, 13), (16384, 19), (40000, 17), (100000, 17), (131080, 19), (200000, 18), (300000, 17)):
+            inputs.append(_gen_adv(rng, kind, n)); levels.append(level)
+    got = dev.zstd_compress(inputs, levels)
+    for i, (raw, lv) in enumerate(zip(inputs, levels)):
+        assert got[i] == agc_parts.zstd_compress(raw, lv), f"frame {i}: kind {i // 8}, {len(raw)} bytes, level {lv}"
+
+
 def test_zstd_frames_match_reference(dev_factory):
     rng = np.random.default_rng(5)
     dev = dev_factory(k=21, min_match_len=20)

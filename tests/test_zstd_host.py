@@ -10,7 +10,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 import agc_parts
-from test_gpu_zstd import _gen
+from test_gpu_zstd import _gen, _gen_adv
 
 pytestmark = pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libzstd_ref.so")), reason="libzstd_ref.so not built")
 
@@ -67,3 +67,12 @@ def test_host_near_duplicate_text(ze):
     raw = b"".join(parts)
     for level in (17, 19):
         assert ze(raw, level) == agc_parts.zstd_compress(raw, level)
+
+
+def test_host_window_engine_cases(ze):
+    """deep bucket chains, skipped positions, compare-limit and end-of-block walks, copies across block boundaries"""
+    rng = np.random.default_rng(8)
+    for kind in range(6):
+        for n, level in ((3000, 17), (16000, 13), (16384, 19), (40000, 17), (100000, 17), (131080, 19), (200000, 18), (300000, 17)):
+            raw = _gen_adv(rng, kind, n)
+            assert ze(raw, level) == agc_parts.zstd_compress(raw, level), f"kind {kind}, {n} bytes, level {level}"
