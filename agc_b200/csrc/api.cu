@@ -157,6 +157,7 @@ void agcgpu_destroy(agcgpu_ctx* ctx)
     }
     if (ctx->pin) cudaFreeHost(ctx->pin);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
+    if (ctx->st2) { cudaStreamSynchronize(ctx->st2); cudaStreamDestroy(ctx->st2); cudaEventDestroy(ctx->ev2); }
     cudaStreamDestroy(ctx->st);
     delete ctx;
 }

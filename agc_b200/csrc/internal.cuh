@@ -107,6 +107,7 @@ struct agcgpu_ctx {
     int n_sm = 0;
     cudaStream_t st = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t st2 = nullptr; cudaEvent_t ev2 = nullptr;      // second stream (residual coder: narrow kernel beside the wide one)
     std::string err;
     agcgpu_stats stats;
 

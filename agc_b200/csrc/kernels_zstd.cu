@@ -7,7 +7,16 @@
 // pointer chasing -- so each warp runs it with warp-uniform control flow; tables live in a per-input workspace in HBM
 // (hash / chain tables are L2 resident for the <= 128 KB classes).  Largest inputs are scheduled first.
 #include "internal.cuh"
+#define ZE_NS ze                 // wide coder: 512-slot match-finder window, parser warp + 15 warps of tree walks
+#define ZE_WN_W 512
 #include "zstd_enc.cuh"
+#undef ZE_NS
+#undef ZE_WN_W
+#define ZE_NS zen                // narrow coder: 32-slot window, one warp and ~20 KB of shared memory per frame
+#define ZE_WN_W 32
+#include "zstd_enc.cuh"
+#undef ZE_NS
+#undef ZE_WN_W
 #include <algorithm>
 #include <numeric>
 #include <cstdio>
@@ -53,6 +62,28 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) k_zstd(ZTaskDev* __restrict__ t
     if (threadIdx.x == 0) { tasks[t].err = err; tasks[t].out_size = r; reinterpret_cast<ze::Win*>(zs_smem)->job = ze::WJ_EXIT; }
     __syncwarp();
     ze::ze_bar_arrive(1, ZS_THREADS);
+}
+
+// small inputs: one warp per frame, many frames per SM
+__global__ void __launch_bounds__(32) k_zstd_narrow(ZTaskDev* __restrict__ tasks, uint32_t n_tasks, uint32_t smem_bytes)
+{
+    uint32_t t = blockIdx.x;
+    if (t >= n_tasks) return;
+    extern __shared__ __align__(16) uint8_t zs_smem[];
+    ZTaskDev k = tasks[t];
+    int err = 0;
+#ifdef ZE_PROF
+    uint64_t r = zen::compress_frame(k.src, k.n, k.level, k.dst, k.dst_cap, k.mem, &err, tasks[t].prof, zs_smem, smem_bytes);
+#else
+    uint64_t r = zen::compress_frame(k.src, k.n, k.level, k.dst, k.dst_cap, k.mem, &err, nullptr, zs_smem, smem_bytes);
+#endif
+    if (threadIdx.x == 0) { tasks[t].err = err; tasks[t].out_size = r; }
+}
+// inputs up to this size take the narrow coder (AGCGPU_ZSTD_NARROW_MAX overrides it: diagnostics)
+static uint64_t zs_narrow_max()
+{
+    static const uint64_t v = getenv("AGCGPU_ZSTD_NARROW_MAX") ? strtoull(getenv("AGCGPU_ZSTD_NARROW_MAX"), nullptr, 10) : (32u << 10);
+    return v;
 }
 
 extern "C" int agcgpu_zstd_compress_batch(agcgpu_ctx* ctx, const uint8_t* src, const uint64_t* src_offsets, const int32_t* levels,
@@ -112,10 +143,25 @@ extern "C" int agcgpu_zstd_compress_batch(agcgpu_ctx* ctx, const uint8_t* src, c
         CK(cudaMemcpyAsync(ctx->scr_req.p, tasks.data(), cnt * sizeof(ZTaskDev), cudaMemcpyHostToDevice, ctx->st));
         CK(cudaDeviceSetLimit(cudaLimitStackSize, 16384));
         CK(cudaEventRecord(ctx->ev0, ctx->st));
-        const uint32_t smem_bytes = ze::fast_sizes().total;
-        CK(cudaFuncSetAttribute(k_zstd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-        k_zstd<<<cnt, ZS_THREADS, smem_bytes, ctx->st>>>((ZTaskDev*)ctx->scr_req.p, cnt, smem_bytes);
-        CKL();
+        // inputs are sorted by size: the first n_wide take the wide coder, the rest the narrow one on a second stream so that
+        // the two kernels share the device
+        uint32_t n_wide = 0;
+        while (n_wide < cnt && tasks[n_wide].n > zs_narrow_max()) ++n_wide;
+        if (n_wide) {
+            const uint32_t smem_bytes = ze::fast_sizes().total;
+            CK(cudaFuncSetAttribute(k_zstd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+            k_zstd<<<n_wide, ZS_THREADS, smem_bytes, ctx->st>>>((ZTaskDev*)ctx->scr_req.p, n_wide, smem_bytes);
+            CKL();
+        }
+        if (cnt > n_wide) {
+            if (!ctx->st2) { CK(cudaStreamCreateWithFlags(&ctx->st2, cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&ctx->ev2, cudaEventDisableTiming)); }
+            const uint32_t smem_n = zen::fast_sizes().total;
+            CK(cudaStreamWaitEvent(ctx->st2, ctx->ev0, 0));
+            k_zstd_narrow<<<cnt - n_wide, 32, smem_n, ctx->st2>>>((ZTaskDev*)ctx->scr_req.p + n_wide, cnt - n_wide, smem_n);
+            CKL();
+            CK(cudaEventRecord(ctx->ev2, ctx->st2));
+            CK(cudaStreamWaitEvent(ctx->st, ctx->ev2, 0));
+        }
         CK(cudaEventRecord(ctx->ev1, ctx->st));
         CK(cudaMemcpyAsync(tasks.data(), ctx->scr_req.p, cnt * sizeof(ZTaskDev), cudaMemcpyDeviceToHost, ctx->st));
         CK(cudaStreamSynchronize(ctx->st));
@@ -136,15 +182,32 @@ extern "C" int agcgpu_zstd_compress_batch(agcgpu_ctx* ctx, const uint8_t* src, c
                 }
 #endif
             } }
+        // frames back: one copy when the batch is small or mostly incompressible, one copy per frame otherwise
+        uint64_t out_total = 0;
         for (uint32_t j = 0; j < cnt; ++j) {
             uint32_t i = order[pos + j];
             if (tasks[j].err) return agc_fail(ctx, AGCGPU_EUNSUPPORTED, "zstd: device coder failed on input %u (code %d)", i, tasks[j].err);
-            out_size[i] = tasks[j].out_size;
-            frames[i].resize(out_size[i]);
-            CK(cudaMemcpyAsync(frames[i].data(), tasks[j].dst, out_size[i], cudaMemcpyDeviceToHost, ctx->st));
-            ctx->stats.d2h_bytes += out_size[i];
+            out_size[i] = tasks[j].out_size; out_total += out_size[i];
         }
-        CK(cudaStreamSynchronize(ctx->st));
+        if (osum <= (64ull << 20) || out_total * 2 >= osum) {
+            std::vector<uint8_t> host(osum);
+            CK(cudaMemcpyAsync(host.data(), ctx->scr_dense.p, osum, cudaMemcpyDeviceToHost, ctx->st));
+            CK(cudaStreamSynchronize(ctx->st));
+            ctx->stats.d2h_bytes += osum;
+            for (uint32_t j = 0; j < cnt; ++j) {
+                uint32_t i = order[pos + j];
+                const uint8_t* p = host.data() + (tasks[j].dst - (uint8_t*)ctx->scr_dense.p);
+                frames[i].assign(p, p + out_size[i]);
+            }
+        } else {
+            for (uint32_t j = 0; j < cnt; ++j) {
+                uint32_t i = order[pos + j];
+                frames[i].resize(out_size[i]);
+                CK(cudaMemcpyAsync(frames[i].data(), tasks[j].dst, out_size[i], cudaMemcpyDeviceToHost, ctx->st));
+                ctx->stats.d2h_bytes += out_size[i];
+            }
+            CK(cudaStreamSynchronize(ctx->st));
+        }
         pos = end;
     }
     for (uint32_t i = 0; i < n; ++i) dst_offsets[i + 1] = dst_offsets[i] + out_size[i];

@@ -7,7 +7,18 @@
 // The code is written once for host and device (ZE_FN): the device build is what libagcgpu ships (kernels_zstd.cu);
 // the host build exists only so tests/ can diff it against the reference's libzstd on a CPU box.  One *warp* works on one input:
 // scalar control flow is warp-uniform (every lane computes the same value), array-wide steps are lane-strided.
-#pragma once
+//
+// The header can be included more than once with different ZE_NS (namespace) / ZE_WN_W (slots of the match-finder window):
+// kernels_zstd.cu instantiates a wide coder (512-slot window, 16 warps per frame) for large inputs and a narrow one (32-slot
+// window, one warp and ~20 KB of shared memory per frame) for the small frames that dominate at scale.
+#ifndef ZE_NS
+#define ZE_NS ze
+#endif
+#ifndef ZE_WN_W
+#define ZE_WN_W 512
+#endif
+#ifndef ZE_COMMON_DEFS
+#define ZE_COMMON_DEFS
 #include <stdint.h>
 #include <stddef.h>
 
@@ -52,8 +63,9 @@
 #endif
 
 typedef uint8_t u8; typedef uint16_t u16; typedef uint32_t u32; typedef uint64_t u64; typedef int32_t i32; typedef int16_t i16;
+#endif  // ZE_COMMON_DEFS
 
-namespace ze {
+namespace ZE_NS {
 
 // optional phase profile of the device build (-DZE_PROF): clock64 ticks and event counts per frame, see kernels_zstd.cu
 #if defined(ZE_PROF) && defined(__CUDA_ARCH__)
@@ -387,7 +399,7 @@ ZE_FN_NOINLINE u32 insert_bt1(Work& w, u32 curr, const u8* iend, u32 target, u32
 // slots in one bucket, positions the reference skips -- ends the window there (commit, then a fresh build), and a slot that
 // is unusable even as the first of a fresh window takes the sequential walk, so the tree and the matches are always the
 // ones the reference order of operations produces.
-static const u32 WN_W = 512, WN_CAP = 32, WN_D = 12, WN_Q = 6;
+static const u32 WN_W = ZE_WN_W, WN_CAP = 32, WN_D = 12, WN_Q = 6;
 enum { WF_OVF = 1, WF_IEND = 2, WF_BUDGET = 4, WF_BAD = 8, WF_TRUNC = 16 };
 enum { WJ_EXIT = 0, WJ_BUILD = 1, WJ_COMMIT = 2, WJ_RESOLVE = 3 };
 
@@ -752,7 +764,7 @@ ZE_FN_NOINLINE bool win_ready(Work& w, u32 pos, const u8* iend, u32 mls)
     ZE_T(t_bd); ZE_CNT(w, 8, 1);
     // insert-heavy parses (btopt: long skips) fill a large window; where nearly every position is a query and long repeats cut
     // windows short (btultra*), a smaller one costs less to build
-    u32 cap = w.cp.strategy == ST_BTOPT ? WN_W : WN_W / 2;
+    u32 cap = (WN_W >= 512 && w.cp.strategy != ST_BTOPT) ? WN_W / 2 : WN_W;
     if (cap > ZE_JOB_NT && ZE_JOB_NT >= 32) cap = ZE_JOB_NT;          // one slot per job thread
     u32 cnt = endIdx - 8 - pos + 1; if (cnt > cap) cnt = cap;
     // (Building a window in stages while the parser consumes the earlier ones was measured and lost: the stages are latency
@@ -2494,4 +2506,4 @@ ZE_FN_NOINLINE u64 compress_frame(const u8* src, u64 srcSize64, int level, u8* d
     return (u64)(op - dst);
 }
 
-}  // namespace ze
+}  // namespace ZE_NS

@@ -23,16 +23,17 @@ def ze():
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src):
         subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-o", so, src[0]])
     L = C.CDLL(so)
-    L.ze_host_compress.restype = C.c_long
-    L.ze_host_compress.argtypes = [C.c_char_p, C.c_ulong, C.c_int, C.c_char_p, C.c_ulong]
+    for f in (L.ze_host_compress, L.ze_host_compress_narrow):
+        f.restype = C.c_long
+        f.argtypes = [C.c_char_p, C.c_ulong, C.c_int, C.c_char_p, C.c_ulong]
     L.ze_host_bound.restype = C.c_ulong
     L.ze_host_bound.argtypes = [C.c_ulong]
 
-    def compress(raw, level):
+    def compress(raw, level, narrow=False):
         cap = L.ze_host_bound(len(raw)) + 64
         out = C.create_string_buffer(cap)
         buf = raw + b"\0" * 64                       # the coder may read (never use) a few bytes past the input
-        r = L.ze_host_compress(buf, len(raw), level, out, cap)
+        r = (L.ze_host_compress_narrow if narrow else L.ze_host_compress)(buf, len(raw), level, out, cap)
         assert r >= 0, f"ze_host_compress failed: {r}"
         return out.raw[:r]
     return compress
@@ -76,3 +77,17 @@ def test_host_window_engine_cases(ze):
         for n, level in ((3000, 17), (16000, 13), (16384, 19), (40000, 17), (100000, 17), (131080, 19), (200000, 18), (300000, 17)):
             raw = _gen_adv(rng, kind, n)
             assert ze(raw, level) == agc_parts.zstd_compress(raw, level), f"kind {kind}, {n} bytes, level {level}"
+
+
+def test_host_narrow_coder(ze):
+    """the 32-slot-window instantiation (device: one warp per frame, inputs <= 32 KB) produces the same frames"""
+    rng = np.random.default_rng(14)
+    for n in (0, 1, 9, 300, 4000, 16384, 16385, 32768):
+        for kind in range(7):
+            for level in (13, 17, 19):
+                raw = _gen(rng, kind, n)
+                assert ze(raw, level, narrow=True) == agc_parts.zstd_compress(raw, level), f"{n} bytes kind {kind} level {level}"
+    for kind in range(6):
+        for n, level in ((3000, 17), (16000, 13), (30000, 19)):
+            raw = _gen_adv(rng, kind, n)
+            assert ze(raw, level, narrow=True) == agc_parts.zstd_compress(raw, level), f"adv kind {kind}, {n} bytes, level {level}"
