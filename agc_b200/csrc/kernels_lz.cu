@@ -176,15 +176,18 @@ __device__ __forceinline__ uint32_t int_len_base(uint32_t x)    // lz_diff.h:179
          : x < 100000000 ? 8 : x < 1000000000 ? 9 : 10;
 }
 // append_int (lz_diff.h:229-262)
-__device__ __forceinline__ uint32_t put_int(uint8_t* dst, int64_t x)
+// (32-bit arithmetic: every value AGC prints here is a position difference or a length below 2^32; a 64-bit divide costs
+// ~10x more instructions on the device)
+__device__ __forceinline__ uint32_t put_int(uint8_t* dst, int64_t xs)
 {
     uint32_t n = 0;
-    if (x == 0) { dst[0] = '0'; return 1; }
-    if (x < 0) { dst[n++] = '-'; x = -x; }
-    char tmp[12]; int k = 0;
-    while (x) { tmp[k++] = (char)('0' + (int)(x % 10)); x /= 10; }
-    while (k) dst[n++] = (uint8_t)tmp[--k];
-    return n;
+    if (xs == 0) { dst[0] = '0'; return 1; }
+    if (xs < 0) { dst[n++] = '-'; xs = -xs; }
+    uint32_t x = (uint32_t)xs;
+    const uint32_t nd = x < 10 ? 1 : x < 100 ? 2 : x < 1000 ? 3 : x < 10000 ? 4 : x < 100000 ? 5 : x < 1000000 ? 6 : x < 10000000 ? 7
+                      : x < 100000000 ? 8 : x < 1000000000 ? 9 : 10;
+    for (uint32_t k = nd; k-- > 0;) { const uint32_t q = x / 10u; dst[n + k] = (uint8_t)('0' + (x - q * 10u)); x = q; }
+    return n + nd;
 }
 
 struct Sink {

@@ -399,7 +399,7 @@ ZE_FN_NOINLINE u32 insert_bt1(Work& w, u32 curr, const u8* iend, u32 target, u32
 // slots in one bucket, positions the reference skips -- ends the window there (commit, then a fresh build), and a slot that
 // is unusable even as the first of a fresh window takes the sequential walk, so the tree and the matches are always the
 // ones the reference order of operations produces.
-static const u32 WN_W = ZE_WN_W, WN_CAP = 32, WN_D = 12, WN_Q = 6;
+static const u32 WN_W = ZE_WN_W, WN_CAP = 32, WN_D = 12, WN_Q = 6, WN_KEYS = 2 * ZE_WN_W, WN_HOPS = 64;
 enum { WF_OVF = 1, WF_IEND = 2, WF_BUDGET = 4, WF_BAD = 8, WF_TRUNC = 16 };
 enum { WJ_EXIT = 0, WJ_BUILD = 1, WJ_COMMIT = 2, WJ_RESOLVE = 3 };
 
@@ -416,6 +416,7 @@ struct Win {
     u32 qbase;                                      // a query's initial best length (minimum match - 1)
     u64 phase[8];                                   // -DZE_PROF: ticks per build phase as thread 0 sees them
     u32 hash[WN_W + 4];
+    u16 ktab[WN_KEYS], prevKey[WN_W];               // bucket links: latest slot per key (hash & (WN_KEYS-1)) / the previous slot of the same key, +1, 0 = none
     u32 keep[WN_W];                                 // recorded steps that stay on the path
     u32 adv[WN_W];                                  // ZSTD_insertBt1's return value
     u8 wflags[WN_W], sflags[WN_W];                  // flags after the walk / after walk + pairs (resolve starts from the latter)
@@ -546,19 +547,43 @@ ZE_FN void win_walk(Win& W, u32 l)
     W.n[l] = (u8)n; W.wflags[l] = (u8)fl; W.dead[l] = 0;
 }
 
+// bucket links of a window: prevKey[l] = the nearest earlier slot with the same key.  Slots are taken 32 at a time in position
+// order (one warp per group, __match_any inside the group, a table of the latest slot per key across groups), so the links
+// cost one pass instead of a scan over all earlier slots per slot.
+ZE_FN void win_links(Win& W)
+{
+    const u32 tid = ZE_JOB_TID, nt = ZE_JOB_NT;
+    for (u32 i = tid; i < WN_KEYS; i += nt) W.ktab[i] = 0;
+    ze_job_sync();
+#if defined(__CUDA_ARCH__)
+    const u32 nwarps = nt >> 5, wj = tid >> 5, lane = tid & 31u;
+    for (u32 g = 0; 32u * g < W.count; ++g) {
+        if (wj == g % nwarps) {
+            const u32 l = 32u * g + lane; const bool act = l < W.count;
+            const u32 key = act ? (W.hash[l] & (WN_KEYS - 1u)) : (0x80000000u | lane);
+            u32 pk = act ? W.ktab[key] : 0u;
+            const u32 mk = __match_any_sync(0xffffffffu, key), lower = mk & ((1u << lane) - 1u);
+            if (lower) pk = 32u * g + (31u - (u32)__clz((int)lower)) + 1u;
+            if (act) { W.prevKey[l] = (u16)pk; if ((mk >> lane) == 1u) W.ktab[key] = (u16)(l + 1u); }
+        }
+        ze_job_sync();
+    }
+#else
+    for (u32 l = 0; l < W.count; ++l) { const u32 key = W.hash[l] & (WN_KEYS - 1u); W.prevKey[l] = W.ktab[key]; W.ktab[key] = (u16)(l + 1u); }
+#endif
+}
+
 ZE_FN void win_pairs(Win& W, u32 l)
 {
     const u32 h = W.hash[l];
     u32 c = 0, fl = W.wflags[l];
-    // the lanes of a warp hold consecutive slots: all of them step through the same groups of four earlier slots, newest first
-    // (uniform loop, broadcast loads); a lane only looks at slots before its own
-    for (i32 g = (i32)((l | (ZE_LANES - 1)) >> 2); g >= 0; --g) {
-        const u32 j0 = 4u * (u32)g;
-        const u32 h0 = W.hash[j0], h1 = W.hash[j0 + 1], h2 = W.hash[j0 + 2], h3 = W.hash[j0 + 3];
-        if (h3 != h && h2 != h && h1 != h && h0 != h) continue;
-        for (i32 t = 3; t >= 0; --t) {
-            const u32 j = j0 + (u32)t;
-            if (j < l && W.hash[j] == h && !W.dead[j]) { if (c == WN_D) fl |= WF_BAD; else W.cs[l][c++] = (u16)j; }
+    // earlier slots of the bucket, newest first: follow the links of the key, keep the live slots with the same hash
+    {   u32 j = W.prevKey[l], hops = 0;
+        while (j) {
+            const u32 sidx = j - 1;
+            if (W.hash[sidx] == h && !W.dead[sidx]) { if (c == WN_D) { fl |= WF_BAD; break; } W.cs[l][c++] = (u16)sidx; }
+            j = W.prevKey[sidx];
+            if (++hops == WN_HOPS && j) { fl |= WF_BAD; break; }      // too many dead / foreign slots on the way: give up on this slot
         }
     }
     W.chain[l] = (u8)c;
@@ -668,6 +693,7 @@ ZE_FN_NOINLINE void win_run(Win& W, u32 job)
             ZE_PH(0);
             ze_job_sync();
             ZE_PH(1);
+            win_links(W);
         }
         for (u32 l = from + tid; l < to; l += nt) win_pairs(W, l);
         ZE_PH(2);
@@ -851,30 +877,72 @@ ZE_FN u32 get_all_matches_impl(Work& w, Match* matches, u32* nextToUpdate3, cons
     u32 nbCompares = 1u << w.cp.searchLog;
     u32 bestLength = lengthToBeat - 1;
 
-    // repcodes: the three candidates are fetched side by side (one per lane), then examined in the reference's order
-    {   const u32 t0 = rd32(ip);
-        u32 repOffsetL = 0; bool eqL = false;
-        if (ZE_LANES > 1) {
-            const u32 rc = ll0 + ZE_LANE;
+    // repcodes.  Device: the first 40 bytes of all three candidates are compared in one round trip (lanes 0-9 / 10-19 / 20-29 take
+    // 4 bytes each of candidate 0 / 1 / 2), which settles most of them; a longer one continues with count_eq.  (The narrow coder
+    // only fetches the first word of each candidate that way: its inputs rarely have repcode matches, and the check is cheaper.)
+    // Then they are examined in the reference's order.
+    {   u32 repLenAll[3] = { 0, 0, 0 };
+#if defined(__CUDA_ARCH__)
+        if (WN_W < 512) {
+            const u32 t0 = rd32(ip);
+            u32 off = 0; bool eqL = false;
             if (ZE_LANE < 3) {
-                repOffsetL = (rc == 3) ? rep[0] - 1 : rep[rc];
-                if (repOffsetL - 1 < curr - dictLimit && curr - repOffsetL >= windowLow) {
-                    const u32 tr = rd32(ip - repOffsetL);
+                const u32 rc = ll0 + ZE_LANE;
+                off = (rc == 3) ? rep[0] - 1 : rep[rc];
+                if (off - 1 < curr - dictLimit && curr - off >= windowLow) {
+                    const u32 tr = rd32(ip - off);
                     eqL = minMatch == 3 ? ((t0 << 8) == (tr << 8)) : (t0 == tr);
                 }
             }
+            const u32 eqMask = ze_ballot(eqL) & 7u;
+            for (u32 g = 0; g < 3; ++g) if ((eqMask >> g) & 1u) {
+                const u32 o = ze_shfl(off, g);
+                repLenAll[g] = count_eq(ip + minMatch, ip + minMatch - o, iLimit) + minMatch;
+            }
+        } else
+        {   const u32 grp = ZE_LANE / 10u, k = ZE_LANE - grp * 10u;
+            const u32 rem = (u32)(iLimit - ip);
+            u32 off = 0; bool ok = false;
+            if (grp < 3) {
+                const u32 rc = ll0 + grp;
+                off = (rc == 3) ? rep[0] - 1 : rep[rc];
+                ok = off - 1 < curr - dictLimit && curr - off >= windowLow;
+            }
+            u32 nb = 0;                                        // equal bytes among this lane's four
+            if (ok && 4 * k < rem) {
+                const u32 x = rd32(ip + 4 * k) ^ rd32(ip + 4 * k - off);
+                nb = x ? ((ze_ffs(x) - 1) >> 3) : 4;
+                if (4 * k + nb > rem) nb = rem - 4 * k;
+            }
+            const u32 stopMask = ze_ballot(grp < 3 && nb < 4);
+            const u32 okMask = ze_ballot(ok);
+            for (u32 g = 0; g < 3; ++g) {
+                if (!((okMask >> (10 * g)) & 1u)) continue;
+                const u32 sm = (stopMask >> (10 * g)) & 0x3ffu;
+                u32 len;
+                if (sm) { const u32 f = ze_ffs(sm) - 1; len = 4 * f + ze_shfl(nb, 10 * g + f); }
+                else {
+                    const u32 o = ze_shfl(off, 10 * g);
+                    len = 40 + count_eq(ip + 40, ip + 40 - o, iLimit);
+                }
+                repLenAll[g] = len >= minMatch ? len : 0;
+            }
         }
-        const u32 eqMask = ZE_LANES > 1 ? (ze_ballot(eqL) & 7u) : 7u;
+#endif
         u32 lastR = 3 + ll0;
         for (u32 rc = ll0; rc < lastR; ++rc) {
-            if (!((eqMask >> (rc - ll0)) & 1u)) continue;
-            u32 repOffset = ZE_LANES > 1 ? ze_shfl(repOffsetL, rc - ll0) : ((rc == 3) ? rep[0] - 1 : rep[rc]);
-            u32 repIndex = curr - repOffset;
             u32 repLen = 0;
+#if defined(__CUDA_ARCH__)
+            repLen = repLenAll[rc - ll0];
+#else
+            u32 repOffset = (rc == 3) ? rep[0] - 1 : rep[rc];
+            u32 repIndex = curr - repOffset;
             if (repOffset - 1 < curr - dictLimit) {
-                bool eq = minMatch == 3 ? ((t0 << 8) == (rd32(ip - repOffset) << 8)) : (t0 == rd32(ip - repOffset));
+                bool eq = minMatch == 3 ? ((rd32(ip) << 8) == (rd32(ip - repOffset) << 8)) : (rd32(ip) == rd32(ip - repOffset));
                 if ((repIndex >= windowLow) & eq) repLen = count_eq(ip + minMatch, ip + minMatch - repOffset, iLimit) + minMatch;
             }
+            (void)repLenAll;
+#endif
             if (repLen > bestLength) {
                 bestLength = repLen;
                 matches[mnum].off = rc - ll0 + 1; matches[mnum].len = repLen; ++mnum;
