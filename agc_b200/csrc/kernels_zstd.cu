@@ -2,10 +2,12 @@
 // independent inputs.  The frame producer itself is zstd_enc.cuh (bit-identical to the reference's
 // vendored libzstd; see the header for the function-by-function citations).
 //
-// Mapping: one warp per input; inputs are independent so the batch is the parallel dimension (HPP scale: ~10^5 frames
-// per batch).  The optimal parser is a sequential dynamic program over a binary-tree match finder -- latency bound
-// pointer chasing -- so each warp runs it with warp-uniform control flow; tables live in a per-input workspace in HBM
-// (hash / chain tables are L2 resident for the <= 128 KB classes).  Largest inputs are scheduled first.
+// Mapping: one CTA per input; inputs are independent so the batch is the parallel dimension (HPP scale: ~10^5 frames per
+// batch).  The optimal parser is a sequential dynamic program -- one warp runs it with warp-uniform control flow -- over a
+// binary-tree match finder, whose dependent tree walks are taken out of the parser's critical path by the window engine of
+// zstd_enc.cuh: the wide kernel (inputs > 32 KB) gives the engine 15 more warps and 221 KB of shared memory, the narrow one
+// (one warp, 19 KB) keeps ~1600 small frames resident.  zstd's tables live in a per-input workspace in HBM (L2 resident).
+// Largest inputs are scheduled first.
 #include "internal.cuh"
 #define ZE_NS ze                 // wide coder: 512-slot match-finder window, parser warp + 15 warps of tree walks
 #define ZE_WN_W 512

@@ -5,8 +5,9 @@
 // function it restates (paths relative to 3rd_party/zstd/lib/compress unless noted).
 //
 // The code is written once for host and device (ZE_FN): the device build is what libagcgpu ships (kernels_zstd.cu);
-// the host build exists only so tests/ can diff it against the reference's libzstd on a CPU box.  One *warp* works on one input:
-// scalar control flow is warp-uniform (every lane computes the same value), array-wide steps are lane-strided.
+// the host build exists only so tests/ can diff it against the reference's libzstd on a CPU box.  One *warp* parses one input:
+// scalar control flow is warp-uniform (every lane computes the same value), array-wide steps are lane-strided; the match
+// finder's tree walks run one per thread on all threads of the CTA ("window engine" below).
 //
 // The header can be included more than once with different ZE_NS (namespace) / ZE_WN_W (slots of the match-finder window):
 // kernels_zstd.cu instantiates a wide coder (512-slot window, 16 warps per frame) for large inputs and a narrow one (32-slot

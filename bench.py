@@ -308,8 +308,11 @@ def lz_hpp_batch(device, peak):
             ms.append(st.last_lz_kernel_ms)
         ms = sorted(ms[2:])[len(ms[2:]) // 2]
         gbs = st.lz_alg_bytes / (ms * 1e-3) / 1e9
+        tp = os.path.join(ROOT, "profiles", "r01_lz_traffic_hpp.json")
+        traffic = json.load(open(tp)).get("traffic_bytes_per_launch") if os.path.exists(tp) else None
         return {"workload": f"{n_seg} segments x {seg_len} bases, 0.1% SNP, {n_groups} reference segments (working set 125 MB ~ L2 size, 2 warm-up launches)",
-                "kernel_ms": ms, "algorithmic_bytes_per_launch": int(st.lz_alg_bytes), "achieved": gbs, "unit": "GB/s", "frac": gbs / peak}
+                "kernel_ms": ms, "algorithmic_bytes_per_launch": int(st.lz_alg_bytes), "achieved": gbs, "unit": "GB/s", "frac": gbs / peak,
+                "traffic": traffic}
     finally:
         dev.close()
 
