@@ -103,7 +103,7 @@ extern "C" int agcgpu_zstd_compress_batch(agcgpu_ctx* ctx, const uint8_t* src, c
         ze::Params cp = ze::get_params(levels[i], len);
         if (!cp.supported)
             return agc_fail(ctx, AGCGPU_EUNSUPPORTED, "zstd: input %u (level %d, %llu bytes) is outside the implemented envelope "
-                            "(levels 13/17/18/19; level 13 above 256 KB uses btlazy2)", i, levels[i], (unsigned long long)len);
+                            "(levels 13/17/18/19, inputs below 1 GiB)", i, levels[i], (unsigned long long)len);
         ws[i] = (ze::work_sizes(cp).total + 255) / 256 * 256;
         ob[i] = (ze::compress_bound(len) + 64 + 255) / 256 * 256;
     }

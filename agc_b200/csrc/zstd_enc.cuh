@@ -150,7 +150,6 @@ ZE_FN Params get_params(int level, u64 n)
     u32 tid = (n <= (256u << 10)) + (n <= (128u << 10)) + (n <= (16u << 10));
     p.windowLog = kLevels[li][tid][0]; p.chainLog = kLevels[li][tid][1]; p.hashLog = kLevels[li][tid][2];
     p.searchLog = kLevels[li][tid][3]; p.minMatch = kLevels[li][tid][4]; p.targetLength = kLevelsT[li][tid]; p.strategy = kLevels[li][tid][6];
-    if (p.strategy < ST_BTOPT) p.supported = 0;                 // level 13 on > 256 KB inputs is btlazy2: not implemented
     if (n >= (1ull << 30)) p.supported = 0;
     {   u32 t = (u32)n;
         u32 srcLog = t < 64 ? 6 : highbit(t - 1) + 1;
@@ -161,7 +160,7 @@ ZE_FN Params get_params(int level, u64 n)
         if (cycleLog > dw) p.chainLog -= (cycleLog - dw);
         if (p.windowLog < 10) p.windowLog = 10;
     }
-    p.splitter = p.windowLog >= 17;
+    p.splitter = p.strategy >= ST_BTOPT && p.windowLog >= 17;         // ZSTD_resolveBlockSplitterMode (:255)
     u64 ws = 1ull << p.windowLog; if (ws > n) ws = n; if (ws < 1) ws = 1;
     p.blockSize = (u32)(ws < BLOCK_MAX ? ws : BLOCK_MAX);
     return p;
@@ -1435,6 +1434,215 @@ ZE_FN u32 compress_block_opt(Work& w, u32* rep, const u8* src, u32 srcSize, int 
 }
 
 
+// ---------------------------------------------------------------------------------------------------- btlazy2 (zstd_lazy.c)
+// Level 13 on inputs above 256 KB (tuple-packed references of very long segments) selects ZSTD_btlazy2: the lazy parser at
+// depth 2 over the "delayed update" binary tree.  Rare in AGC's call population, so it is restated as it is -- sequential,
+// every lane of the parser's warp executes the same scalar steps -- without a window engine.
+// ZSTD_updateDUBT (zstd_lazy.c:29-65): positions enter the tree as an unsorted chain through the hash bucket
+ZE_FN_NOINLINE void update_dubt(Work& w, u32 target, u32 mls)
+{
+    const u8* base = w.src - w.baseOff;
+    u32* bt = w.chainTable; const u32 btMask = (1u << (w.cp.chainLog - 1)) - 1;
+    for (u32 idx = w.nextToUpdate; idx < target; ++idx) {
+        const u32 h = hash_ptr(base + idx, w.cp.hashLog, mls);
+        const u32 matchIndex = w.hashTable[h];
+        ze_sync();
+        w.hashTable[h] = idx;
+        bt[2 * (idx & btMask)] = matchIndex;                 // next candidate
+        bt[2 * (idx & btMask) + 1] = 1;                       // ZSTD_DUBT_UNSORTED_MARK
+        ze_sync();
+    }
+    w.nextToUpdate = target;
+}
+// ZSTD_insertDUBT1 (zstd_lazy.c:68-164), noDict: sort one already chained position into the tree
+ZE_FN_NOINLINE void insert_dubt1(Work& w, u32 curr, const u8* iend, u32 nbCompares, u32 btLow)
+{
+    const u8* base = w.src - w.baseOff;
+    u32* bt = w.chainTable; const u32 btMask = (1u << (w.cp.chainLog - 1)) - 1;
+    const u8* ip = base + curr;
+    u32 clSmaller = 0, clLarger = 0;
+    u32* smallerPtr = bt + 2 * (curr & btMask);
+    u32* largerPtr = smallerPtr + 1;
+    u32 matchIndex = *smallerPtr;
+    u32* const dummyPtr = w.dummySlot;
+    const u32 maxDist = 1u << w.cp.windowLog;
+    const u32 windowLow = (curr - w.lowLimit > maxDist) ? curr - maxDist : w.lowLimit;
+    ze_sync();
+    for (; nbCompares && matchIndex > windowLow; --nbCompares) {
+        u32* nextPtr = bt + 2 * (matchIndex & btMask);
+        u32 ml = clSmaller < clLarger ? clSmaller : clLarger;
+        const u8* match = base + matchIndex;
+        ml += count_eq(ip + ml, match + ml, iend);
+        if (ip + ml == iend) break;
+        const u32 n0 = nextPtr[0], n1 = nextPtr[1];
+        ze_sync();
+        if (match[ml] < ip[ml]) {
+            *smallerPtr = matchIndex; clSmaller = ml;
+            if (matchIndex <= btLow) { smallerPtr = dummyPtr; break; }
+            smallerPtr = nextPtr + 1; matchIndex = n1;
+        } else {
+            *largerPtr = matchIndex; clLarger = ml;
+            if (matchIndex <= btLow) { largerPtr = dummyPtr + 1; break; }
+            largerPtr = nextPtr; matchIndex = n0;
+        }
+        ze_sync();
+    }
+    ze_sync();
+    *smallerPtr = 0; *largerPtr = 0;
+    ze_sync();
+}
+// ZSTD_BtFindBestMatch + ZSTD_DUBT_findBestMatch (zstd_lazy.c:243-404), noDict.  *offBase must hold the caller's current value
+ZE_FN_NOINLINE u32 dubt_find_best(Work& w, const u8* ip, const u8* iend, u32* offBasePtr, u32 mls)
+{
+    const u8* base = w.src - w.baseOff;
+    const u32 curr = (u32)(ip - base);
+    if (curr < w.nextToUpdate) return 0;                     // skipped area
+    update_dubt(w, curr, mls);
+    u32* bt = w.chainTable; const u32 btMask = (1u << (w.cp.chainLog - 1)) - 1;
+    const u32 h = hash_ptr(ip, w.cp.hashLog, mls);
+    u32 matchIndex = w.hashTable[h];
+    const u32 windowLow = lowest_match_index(w, curr);
+    const u32 btLow = btMask >= curr ? 0 : curr - btMask;
+    const u32 unsortLimit = btLow > windowLow ? btLow : windowLow;
+    u32* nextCandidate = bt + 2 * (matchIndex & btMask);
+    u32* unsortedMark = nextCandidate + 1;
+    u32 nbCompares = 1u << w.cp.searchLog, nbCandidates = nbCompares, previousCandidate = 0;
+    ze_sync();
+    // reach the end of the unsorted candidates, turning their marks into a reversed chain
+    while (matchIndex > unsortLimit && *unsortedMark == 1 && nbCandidates > 1) {
+        const u32 nxt = *nextCandidate;
+        ze_sync();
+        *unsortedMark = previousCandidate;
+        previousCandidate = matchIndex;
+        matchIndex = nxt;
+        nextCandidate = bt + 2 * (matchIndex & btMask);
+        unsortedMark = nextCandidate + 1;
+        nbCandidates--;
+        ze_sync();
+    }
+    if (matchIndex > unsortLimit && *unsortedMark == 1) { ze_sync(); *nextCandidate = 0; *unsortedMark = 0; }
+    ze_sync();
+    // batch sort the stacked candidates
+    matchIndex = previousCandidate;
+    while (matchIndex) {
+        const u32 nextIdx = bt[2 * (matchIndex & btMask) + 1];
+        ze_sync();
+        insert_dubt1(w, matchIndex, iend, nbCandidates, unsortLimit);
+        matchIndex = nextIdx;
+        nbCandidates++;
+    }
+    // find the longest match (and insert curr)
+    u32 clSmaller = 0, clLarger = 0;
+    u32* smallerPtr = bt + 2 * (curr & btMask);
+    u32* largerPtr = smallerPtr + 1;
+    u32* const dummyPtr = w.dummySlot;
+    u32 matchEndIdx = curr + 8 + 1, bestLength = 0;
+    matchIndex = w.hashTable[h];
+    ze_sync();
+    w.hashTable[h] = curr;
+    for (; nbCompares && matchIndex > windowLow; --nbCompares) {
+        u32* nextPtr = bt + 2 * (matchIndex & btMask);
+        u32 ml = clSmaller < clLarger ? clSmaller : clLarger;
+        const u8* match = base + matchIndex;
+        ml += count_eq(ip + ml, match + ml, iend);
+        if (ml > bestLength) {
+            if (ml > matchEndIdx - matchIndex) matchEndIdx = matchIndex + ml;
+            if ((i32)(4 * (ml - bestLength)) > (i32)(highbit(curr - matchIndex + 1) - highbit(*offBasePtr))) { bestLength = ml; *offBasePtr = (curr - matchIndex) + 3; }
+            if (ip + ml == iend) break;
+        }
+        const u32 n0 = nextPtr[0], n1 = nextPtr[1];
+        ze_sync();
+        if (match[ml] < ip[ml]) {
+            *smallerPtr = matchIndex; clSmaller = ml;
+            if (matchIndex <= btLow) { smallerPtr = dummyPtr; break; }
+            smallerPtr = nextPtr + 1; matchIndex = n1;
+        } else {
+            *largerPtr = matchIndex; clLarger = ml;
+            if (matchIndex <= btLow) { largerPtr = dummyPtr + 1; break; }
+            largerPtr = nextPtr; matchIndex = n0;
+        }
+        ze_sync();
+    }
+    ze_sync();
+    *smallerPtr = 0; *largerPtr = 0;
+    ze_sync();
+    w.nextToUpdate = matchEndIdx - 8;
+    return bestLength;
+}
+// ZSTD_compressBlock_btlazy2 = ZSTD_compressBlock_lazy_generic(search_binaryTree, depth 2, noDict) (zstd_lazy.c:1516-1777)
+ZE_FN_NOINLINE u32 compress_block_btlazy2(Work& w, u32* rep, const u8* src, u32 srcSize)
+{
+    const u8* istart = src; const u8* ip = istart; const u8* anchor = istart;
+    const u8* iend = istart + srcSize; const u8* ilimit = iend - 8;
+    const u8* base = w.src - w.baseOff;
+    const u8* prefixLowest = base + w.dictLimit;
+    const u32 mls = w.cp.minMatch < 4 ? 4 : (w.cp.minMatch > 6 ? 6 : w.cp.minMatch);
+    u32 offset_1 = rep[0], offset_2 = rep[1], offsetSaved1 = 0, offsetSaved2 = 0;
+    ip += (ip == prefixLowest);
+    {   const u32 curr = (u32)(ip - base), maxDist = 1u << w.cp.windowLog;
+        const u32 windowLow = (curr - w.dictLimit > maxDist) ? curr - maxDist : w.dictLimit;     // ZSTD_getLowestPrefixIndex
+        const u32 maxRep = curr - windowLow;
+        if (offset_2 > maxRep) { offsetSaved2 = offset_2; offset_2 = 0; }
+        if (offset_1 > maxRep) { offsetSaved1 = offset_1; offset_1 = 0; }
+    }
+    while (ip < ilimit) {
+        u32 matchLength = 0, offBase = 1;                     // REPCODE1_TO_OFFBASE
+        const u8* start = ip + 1;
+        if ((offset_1 > 0) & (rd32(ip + 1 - offset_1) == rd32(ip + 1))) matchLength = count_eq(ip + 1 + 4, ip + 1 + 4 - offset_1, iend) + 4;
+        {   u32 offFound = 999999999u;
+            const u32 ml2 = dubt_find_best(w, ip, iend, &offFound, mls);
+            if (ml2 > matchLength) { matchLength = ml2; start = ip; offBase = offFound; }
+        }
+        if (matchLength < 4) { ip += ((u32)(ip - anchor) >> 8) + 1; continue; }       // kSearchStrength
+        while (ip < ilimit) {                                 // depth 1 and 2
+            ip++;
+            if (offBase && ((offset_1 > 0) & (rd32(ip) == rd32(ip - offset_1)))) {
+                const u32 mlRep = count_eq(ip + 4, ip + 4 - offset_1, iend) + 4;
+                const i32 gain2 = (i32)(mlRep * 3), gain1 = (i32)(matchLength * 3 - highbit(offBase) + 1);
+                if (mlRep >= 4 && gain2 > gain1) { matchLength = mlRep; offBase = 1; start = ip; }
+            }
+            {   u32 ofb = 999999999u;
+                const u32 ml2 = dubt_find_best(w, ip, iend, &ofb, mls);
+                const i32 gain2 = (i32)(ml2 * 4 - highbit(ofb)), gain1 = (i32)(matchLength * 4 - highbit(offBase) + 4);
+                if (ml2 >= 4 && gain2 > gain1) { matchLength = ml2; offBase = ofb; start = ip; continue; }
+            }
+            if (ip < ilimit) {
+                ip++;
+                if (offBase && ((offset_1 > 0) & (rd32(ip) == rd32(ip - offset_1)))) {
+                    const u32 mlRep = count_eq(ip + 4, ip + 4 - offset_1, iend) + 4;
+                    const i32 gain2 = (i32)(mlRep * 4), gain1 = (i32)(matchLength * 4 - highbit(offBase) + 1);
+                    if (mlRep >= 4 && gain2 > gain1) { matchLength = mlRep; offBase = 1; start = ip; }
+                }
+                {   u32 ofb = 999999999u;
+                    const u32 ml2 = dubt_find_best(w, ip, iend, &ofb, mls);
+                    const i32 gain2 = (i32)(ml2 * 4 - highbit(ofb)), gain1 = (i32)(matchLength * 4 - highbit(offBase) + 7);
+                    if (ml2 >= 4 && gain2 > gain1) { matchLength = ml2; offBase = ofb; start = ip; continue; }
+                }
+            }
+            break;
+        }
+        if (offBase > 3) {                                    // catch up
+            const u32 off = offBase - 3;
+            while (((start > anchor) & (start - off > prefixLowest)) && start[-1] == (start - off)[-1]) { start--; matchLength++; }
+            offset_2 = offset_1; offset_1 = off;
+        }
+        {   const u32 litLength = (u32)(start - anchor);
+            store_seq(w.ss, litLength, anchor, offBase, matchLength);
+            anchor = ip = start + matchLength;
+        }
+        while (((ip <= ilimit) & (offset_2 > 0)) && rd32(ip) == rd32(ip - offset_2)) {      // immediate repcode
+            matchLength = count_eq(ip + 4, ip + 4 - offset_2, iend) + 4;
+            { const u32 t = offset_2; offset_2 = offset_1; offset_1 = t; }
+            store_seq(w.ss, 0, anchor, 1, matchLength);
+            ip += matchLength; anchor = ip;
+        }
+    }
+    offsetSaved2 = (offsetSaved1 != 0 && offset_1 != 0) ? offsetSaved1 : offsetSaved2;
+    rep[0] = offset_1 ? offset_1 : offsetSaved1;
+    rep[1] = offset_2 ? offset_2 : offsetSaved2;
+    return (u32)(iend - anchor);
+}
+
 // ---------------------------------------------------------------------------------------------------- bit stream (common/bitstream.h)
 struct BitW { u64 cont; u32 pos; u8* start; u8* ptr; u8* end; };
 ZE_FN bool bit_init(BitW& b, u8* dst, u64 cap) { b.cont = 0; b.pos = 0; b.start = b.ptr = dst; b.end = dst + cap - 8; return cap > 8; }
@@ -2328,7 +2536,8 @@ ZE_FN_NOINLINE bool build_seqstore(Work& w, const u8* src, u32 srcSize)
     BlockState& prev = *w.bs[w.prevIdx]; BlockState& next = *w.bs[w.prevIdx ^ 1];
     next.rep[0] = prev.rep[0]; next.rep[1] = prev.rep[1]; next.rep[2] = prev.rep[2];
     u32 lastLL;
-    if (w.cp.strategy == ST_BTOPT) lastLL = compress_block_opt(w, next.rep, src, srcSize, 0);
+    if (w.cp.strategy == ST_BTLAZY2) lastLL = compress_block_btlazy2(w, next.rep, src, srcSize);
+    else if (w.cp.strategy == ST_BTOPT) lastLL = compress_block_opt(w, next.rep, src, srcSize, 0);
     else if (w.cp.strategy == ST_BTULTRA) lastLL = compress_block_opt(w, next.rep, src, srcSize, 2);
     else {
         // ZSTD_compressBlock_btultra2 (zstd_opt.c:1513): first block is parsed twice, the first pass only seeds the statistics

@@ -91,3 +91,14 @@ def test_host_narrow_coder(ze):
         for n, level in ((3000, 17), (16000, 13), (30000, 19)):
             raw = _gen_adv(rng, kind, n)
             assert ze(raw, level, narrow=True) == agc_parts.zstd_compress(raw, level), f"adv kind {kind}, {n} bytes, level {level}"
+
+
+def test_host_btlazy2_class(ze):
+    """level 13 above 256 KB = ZSTD_btlazy2 (lazy parser at depth 2 over the delayed-update binary tree)"""
+    rng = np.random.default_rng(21)
+    for kind, n in ((0, 262145), (1, 300000), (2, 262145), (2, 700000), (6, 300000)):
+        raw = _gen(rng, kind, n)
+        assert ze(raw, 13) == agc_parts.zstd_compress(raw, 13), f"kind {kind}, {n} bytes"
+    for kind, n in ((2, 270000), (5, 1200000), (0, 270000)):
+        raw = _gen_adv(rng, kind, n)
+        assert ze(raw, 13) == agc_parts.zstd_compress(raw, 13), f"adv kind {kind}, {n} bytes"
