@@ -45,6 +45,7 @@
 #define ze_ctz64(x) ((unsigned)__ffsll((long long)(x)) - 1u)
 #define ze_shfl_up(v, d) __shfl_up_sync(0xffffffffu, (v), (d))
 #define ze_reduce_max(v) __reduce_max_sync(0xffffffffu, (unsigned)(v))
+#define ze_reduce_add(v) __reduce_add_sync(0xffffffffu, (unsigned)(v))
 #define ze_popc(v) ((unsigned)__popc(v))
 #define ze_hibit(v) (31u - (unsigned)__clz((int)(v)))
 #else
@@ -59,6 +60,7 @@
 #define ze_ctz64(x) ((unsigned)__builtin_ctzll(x))
 #define ze_shfl_up(v, d) (v)
 #define ze_reduce_max(v) ((unsigned)(v))
+#define ze_reduce_add(v) ((unsigned)(v))
 #define ze_popc(v) ((unsigned)__builtin_popcount(v))
 #define ze_hibit(v) (31u - (unsigned)__builtin_clz(v))
 #endif
@@ -190,6 +192,7 @@ struct Work {
     // optimal parser state (optState_t)
     Opt* opt; Match* matches;
     u32* litFreq; u32* llFreq; u32* mlFreq; u32* ofFreq;
+    u32* histTab;            // 256 counters in the low-latency scratch (device: lane-parallel histograms), may be null
     u32* priceTab;           // prices of the current statistics: lit[256], ll code[36], ml code[53], off code[32] (refresh_prices)
     u32 litSum, llSum, mlSum, ofSum, litSumBP, llSumBP, mlSumBP, ofSumBP; int pricePredef;
     // sequences
@@ -1851,6 +1854,27 @@ ZE_FN_NOINLINE u32 hist(u32* count, u32* maxSymPtr, const u8* src, u32 n)    // 
     return largest;
 }
 
+// the same over a warp: lanes count into the shared-memory table with atomics, the counters are then copied to `count`
+ZE_FN_NOINLINE u32 hist_w(Work& w, u32* count, u32* maxSymPtr, const u8* src, u32 n)
+{
+#if defined(__CUDA_ARCH__)
+    if (w.histTab && n >= 64) {
+        u32 ms = *maxSymPtr;
+        u32* T = w.histTab;
+        for (u32 i = ZE_LANE; i < 256; i += ZE_LANES) T[i] = 0;
+        ze_sync();
+        for (u32 i = ZE_LANE; i < n; i += ZE_LANES) atomicAdd(&T[src[i]], 1u);
+        ze_sync();
+        u32 top = 0, largest = 0;
+        for (u32 i = ZE_LANE; i <= ms; i += ZE_LANES) { const u32 c = T[i]; count[i] = c; if (c) top = i; if (c > largest) largest = c; }
+        ze_sync();
+        *maxSymPtr = ze_reduce_max(top);
+        return ze_reduce_max(largest);
+    }
+#endif
+    return hist(count, maxSymPtr, src, n);
+}
+
 // ---------------------------------------------------------------------------------------------------- Huffman (huf_compress.c)
 ZE_FN u32 huf_get_index(u32 c) { return c < 166 ? c : highbit(c) + 158; }       // HUF_getIndex (:497)
 ZE_FN_NOINLINE void huf_insertion_sort(HufNode* a, i32 low, i32 high)
@@ -2131,11 +2155,11 @@ ZE_FN_NOINLINE u32 huf_compress(Work& w, u8* dst, u32 dstSize, const u8* src, u3
     if (!srcSize || !dstSize) return 0;
     if (suspectUncompressible && srcSize >= 4096 * 10) {
         u32 lt = 0, m1 = 255, m2 = 255;
-        lt += hist(w.count, &m1, src, 4096);
-        lt += hist(w.count, &m2, src + srcSize - 4096, 4096);
+        lt += hist_w(w, w.count, &m1, src, 4096);
+        lt += hist_w(w, w.count, &m2, src + srcSize - 4096, 4096);
         if (lt <= ((2 * 4096) >> 7) + 4) return 0;
     }
-    {   u32 largest = hist(w.count, &maxSym, src, srcSize);
+    {   u32 largest = hist_w(w, w.count, &maxSym, src, srcSize);
         if (largest == srcSize) { *ostart = src[0]; return 1; }
         if (largest <= (srcSize >> 7) + 4) return 0; }
     if (*repeat == REP_CHECK && !huf_validate(oldTable, w.count, maxSym)) *repeat = REP_NONE;
@@ -2293,11 +2317,12 @@ ZE_FN_NOINLINE u32 build_ctable(Work& w, u8* op, FseCT& next, u32 FSELog, int ty
 ZE_FN_NOINLINE void seq_to_codes(const SeqStore& ss)
 {
     u32 nbSeq = (u32)(ss.seq - ss.seqStart);
-    for (u32 u = 0; u < nbSeq; u++) {
+    for (u32 u = ZE_LANE; u < nbSeq; u += ZE_LANES) {
         ss.llCode[u] = (u8)LLcode(ss.seqStart[u].litLength);
         ss.ofCode[u] = (u8)highbit(ss.seqStart[u].offBase);
         ss.mlCode[u] = (u8)MLcode(ss.seqStart[u].mlBase);
     }
+    ze_sync();
     if (ss.longType == 1) ss.llCode[ss.longPos] = MaxLL;
     if (ss.longType == 2) ss.mlCode[ss.longPos] = MaxML;
 }
@@ -2308,14 +2333,14 @@ ZE_FN_NOINLINE SeqStats build_seq_stats(Work& w, const SeqStore& ss, u32 nbSeq, 
     SeqStats st; st.lastCountSize = 0; st.err = 0; st.size = 0;
     u8* op = dst; u32* count = w.count;
     seq_to_codes(ss);
-    {   u32 max = MaxLL; u32 mf = hist(count, &max, ss.llCode, nbSeq);
+    {   u32 max = MaxLL; u32 mf = hist_w(w, count, &max, ss.llCode, nbSeq);
         next.llRep = prev.llRep;
         st.LLtype = select_encoding_type(w, &next.llRep, count, max, mf, nbSeq, 9, prev.ll, kLLnorm, 6, 1);
         u32 cs = build_ctable(w, op, next.ll, 9, st.LLtype, count, max, ss.llCode, nbSeq, kLLnorm, 6, MaxLL, prev.ll);
         if (cs == ~0u) { st.err = 1; return st; }
         if (st.LLtype == SET_COMPRESSED) st.lastCountSize = cs;
         op += cs; }
-    {   u32 max = MaxOff; u32 mf = hist(count, &max, ss.ofCode, nbSeq);
+    {   u32 max = MaxOff; u32 mf = hist_w(w, count, &max, ss.ofCode, nbSeq);
         int defaultAllowed = max <= DefaultMaxOff;
         next.ofRep = prev.ofRep;
         st.Offtype = select_encoding_type(w, &next.ofRep, count, max, mf, nbSeq, 8, prev.of, kOFnorm, 5, defaultAllowed);
@@ -2323,7 +2348,7 @@ ZE_FN_NOINLINE SeqStats build_seq_stats(Work& w, const SeqStore& ss, u32 nbSeq, 
         if (cs == ~0u) { st.err = 1; return st; }
         if (st.Offtype == SET_COMPRESSED) st.lastCountSize = cs;
         op += cs; }
-    {   u32 max = MaxML; u32 mf = hist(count, &max, ss.mlCode, nbSeq);
+    {   u32 max = MaxML; u32 mf = hist_w(w, count, &max, ss.mlCode, nbSeq);
         next.mlRep = prev.mlRep;
         st.MLtype = select_encoding_type(w, &next.mlRep, count, max, mf, nbSeq, 9, prev.ml, kMLnorm, 6, 1);
         u32 cs = build_ctable(w, op, next.ml, 9, st.MLtype, count, max, ss.mlCode, nbSeq, kMLnorm, 6, MaxML, prev.ml);
@@ -2404,7 +2429,7 @@ ZE_FN_NOINLINE u32 block_stats_literals(Work& w, const u8* src, u32 srcSize, con
     next.huf = prev.huf; next.hufRepeat = prev.hufRepeat;
     {   u32 minLit = (prev.hufRepeat == REP_VALID) ? 6 : 63;
         if (srcSize <= minLit) { hm.hType = SET_BASIC; return 0; } }
-    {   u32 largest = hist(w.count, &maxSym, src, srcSize);
+    {   u32 largest = hist_w(w, w.count, &maxSym, src, srcSize);
         if (largest == srcSize) { hm.hType = SET_RLE; return 0; }
         if (largest <= (srcSize >> 7) + 4) { hm.hType = SET_BASIC; return 0; } }
     if (repeat == REP_CHECK && !huf_validate(prev.huf, w.count, maxSym)) repeat = REP_NONE;
@@ -2428,7 +2453,7 @@ ZE_FN_NOINLINE u32 estimate_literal(Work& w, const u8* lits, u32 litSize, const 
     u32 maxSym = 255, hdr = 3 + (litSize >= 1024) + (litSize >= 16384), single = litSize < 256;
     if (hm.hType == SET_BASIC) return litSize;
     if (hm.hType == SET_RLE) return 1;
-    hist(w.count, &maxSym, lits, litSize);
+    hist_w(w, w.count, &maxSym, lits, litSize);
     u32 est = huf_estimate_size(huf, w.count, maxSym);
     if (writeEntropy) est += hm.desSize;
     if (!single) est += 6;
@@ -2438,12 +2463,14 @@ ZE_FN_NOINLINE u64 estimate_symbol_type(Work& w, int type, const u8* codeTable, 
                                const i16* defaultNorm, u32 defaultNormLog)
 {
     u32 max = maxCode; u64 bits = 0;
-    hist(w.count, &max, codeTable, nbSeq);
+    hist_w(w, w.count, &max, codeTable, nbSeq);
     if (type == SET_BASIC) bits = cross_entropy_cost(defaultNorm, defaultNormLog, w.count, max);
     else if (type == SET_RLE) bits = 0;
     else bits = fse_bit_cost_total(ct, w.count, max);
     if (bits == ~0ull) return (u64)nbSeq * 10;
-    for (u32 i = 0; i < nbSeq; ++i) bits += addBits ? addBits[codeTable[i]] : codeTable[i];
+    {   u32 part = 0;                                         // nbSeq <= 128 K/3 sequences x <= 31 bits: fits 32 bits per lane
+        for (u32 i = ZE_LANE; i < nbSeq; i += ZE_LANES) part += addBits ? addBits[codeTable[i]] : codeTable[i];
+        bits += ze_reduce_add(part); }
     return bits >> 3;
 }
 // ZSTD_buildEntropyStatisticsAndEstimateSubBlockSize (:3845). ~0 = error
@@ -2676,7 +2703,7 @@ ZE_FN WorkSizes work_sizes(const Params& cp)
     return z;
 }
 // low-latency scratch layout: match-finder window, match list (<= 3 repcodes + 1 hash3 + 2^searchLog tree matches), frequency tables
-struct FastSizes { u32 win, matches, freqs, prices, total; };
+struct FastSizes { u32 win, matches, freqs, prices, hist, total; };
 ZE_FN FastSizes fast_sizes()
 {
     FastSizes f;
@@ -2684,7 +2711,8 @@ ZE_FN FastSizes fast_sizes()
     f.matches = (u32)align_up((u64)sizeof(Match) * (256 + 8), 16);
     f.freqs = (u32)align_up(4 * (256 + 36 + 53 + 32 + 16), 16);
     f.prices = 4 * 384;
-    f.total = f.win + f.matches + f.freqs + f.prices;
+    f.hist = 4 * 256;
+    f.total = f.win + f.matches + f.freqs + f.prices + f.hist;
     return f;
 }
 ZE_FN u64 compress_bound(u64 n) { return n + (n >> 8) + (n < (128u << 10) ? (((128u << 10) - n) >> 11) : 0); }    // ZSTD_COMPRESSBOUND
@@ -2696,6 +2724,7 @@ ZE_FN_NOINLINE u64 compress_frame(const u8* src, u64 srcSize64, int level, u8* d
                                   u8* fast = nullptr, u32 fastBytes = 0)
 {
     Work w; *err = 0;
+    w.histTab = nullptr;
 #if defined(ZE_PROF) && defined(__CUDA_ARCH__)
     for (int i = 0; i < ZE_PROF_N; ++i) w.prof[i] = 0;
     long long t_frame = clock64();
@@ -2714,7 +2743,8 @@ ZE_FN_NOINLINE u64 compress_frame(const u8* src, u64 srcSize64, int level, u8* d
         w.win = (Win*)f; f += fz.win;
         w.matches = (Match*)f; f += fz.matches;
         w.litFreq = (u32*)f; w.llFreq = w.litFreq + 256; w.mlFreq = w.llFreq + 36; w.ofFreq = w.mlFreq + 53; f += fz.freqs;
-        w.priceTab = (u32*)f;
+        w.priceTab = (u32*)f; f += fz.prices;
+        w.histTab = (u32*)f;
     }
     w.ss.seqStart = (Seq*)p; p += z.seqs; w.ss.litStart = p; p += z.lits;
     w.maxNbSeq = cp.blockSize / (cp.minMatch == 3 ? 3 : 4);
