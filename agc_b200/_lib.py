@@ -18,7 +18,7 @@ class AgcGpuError(RuntimeError):
 
 class Params(C.Structure):
     _fields_ = [("kmer_length", C.c_uint32), ("min_match_len", C.c_uint32), ("segment_size", C.c_uint32),
-                ("pack_cardinality", C.c_uint32), ("device", C.c_int32), ("reserved", C.c_uint32)]
+                ("pack_cardinality", C.c_uint32), ("device", C.c_int32), ("flags", C.c_uint32)]
 
 
 class Cut(C.Structure):

@@ -351,11 +351,12 @@ bool CAGCCompressor::Create(const std::string& file_name, uint32_t _pack_cardina
     pack_cardinality = _pack_cardinality; kmer_length = _kmer_length; min_match_len = _min_match_len;
     segment_size = _segment_size; verbosity = _verbosity;
     concatenated_genomes = _concatenated_genomes; adaptive_compression = _adaptive_compression;
-    if (concatenated_genomes || adaptive_compression || fallback_frac != 0.0)
-        return fail("agc-b200: -c / -a / -f are not implemented on the GPU path yet (refusing rather than falling back)");
+    if (concatenated_genomes || fallback_frac != 0.0)
+        return fail("agc-b200: -c / -f are not implemented on the GPU path yet (refusing rather than falling back)");
     agcgpu_params prm; memset(&prm, 0, sizeof prm);
     prm.kmer_length = kmer_length; prm.min_match_len = min_match_len; prm.segment_size = segment_size;
     prm.pack_cardinality = pack_cardinality; prm.device = device;
+    prm.flags = adaptive_compression ? AGCGPU_F_ADAPTIVE : 0;      // keeps v_candidate_kmers / v_duplicated_kmers on the device (493-494)
     PhaseTimer pt_create("create+splitters");
     int rc = agcgpu_create(&prm, &ctx);
     if (rc) return fail(std::string("agcgpu_create: ") + agcgpu_last_error(nullptr));
@@ -533,7 +534,12 @@ bool CAGCCompressor::AddSampleFiles(std::vector<std::pair<std::string, std::stri
         }
         if (!any_read) std::cerr << "Warning: Pair sample_name:file_path " << sf.first << ":" << sf.second << " contains no contigs and will not be included in the archive!\n";
         if (!any_added) std::cerr << "Warning: Pair sample_name:file_path " << sf.first << ":" << sf.second << " contains only contigs already present in the archive!\n";
-        if (raw_in_batch >= batch_bases) { if (!process_batch(raws, owners)) return false; raws.clear(); owners.clear(); raw_in_batch = 0; }
+        // -a: the splitter set may grow at every sample's synchronisation point (new_splitters stage, 1187-1229), so a
+        // device batch is one sample
+        if (raw_in_batch >= batch_bases || (adaptive_compression && !raws.empty())) {
+            if (!process_batch(raws, owners)) return false;
+            raws.clear(); owners.clear(); raw_in_batch = 0;
+        }
     }
     if (!raws.empty()) if (!process_batch(raws, owners)) return false;
     if (processed_samples % pack_cardinality != 0)                                     // agc_compressor.cpp:2258-2259
@@ -569,7 +575,19 @@ bool CAGCCompressor::AddSamplesFromMemory(const std::vector<std::string>& sample
         owners.push_back(BatchContig{ sid, (uint32_t)collection.sample_desc[sid].contigs.size() - 1 });
     }
     std::vector<uint64_t> offs(offsets, offsets + contig_ids.size() + 1);
-    if (!process_batch_raw(raw, raw_is_device, offs, owners)) return false;
+    if (!adaptive_compression) { if (!process_batch_raw(raw, raw_is_device, offs, owners)) return false; }
+    else {                                                           // one device batch per sample (see AddSampleFiles)
+        for (size_t a = 0; a < owners.size();) {
+            size_t b = a;
+            while (b < owners.size() && owners[b].sample_id == owners[a].sample_id) ++b;
+            std::vector<BatchContig> ow(owners.begin() + a, owners.begin() + b);
+            std::vector<uint64_t> of(offs.begin() + a, offs.begin() + b + 1);
+            const uint8_t* base = raw;
+            if (!raw_is_device) { base = raw + of[0]; const uint64_t o0 = of[0]; for (auto& x : of) x -= o0; }   // device pointers keep their alignment
+            if (!process_batch_raw(base, raw_is_device, of, ow)) return false;
+            a = b;
+        }
+    }
     if (processed_samples % pack_cardinality != 0)
         store_contig_batch((processed_samples / pack_cardinality) * pack_cardinality, processed_samples, epoch);
     ++epoch;
@@ -590,6 +608,52 @@ bool CAGCCompressor::process_batch_raw(const uint8_t* cat, bool is_device, const
     if (!gpu_ok(rc, "scan_contigs")) return false;
     cuts.resize(n_cuts);
     for (uint32_t i = 0; i < nc; ++i) total_bases += clen[i];
+
+    // -a mode.  compress_contig (agc_compressor.cpp:2038-2044) sets aside every contig in which the scan met no splitter
+    // (a contig with a hit always yields >= 2 cuts) and, if it is at least segment_size long, looks for new splitters in it
+    // (find_new_splitters, 2054-2082).  At the sample's new_splitters token (1187-1229) they join the splitter set and
+    // the contigs set aside are compressed again (hard_contigs stage); the other contigs keep their first segmentation.
+    if (adaptive_compression) {
+        std::vector<uint32_t> n_cuts_of(nc, 0);
+        for (auto& c : cuts) ++n_cuts_of[c.contig];
+        std::vector<uint32_t> hard, searched;
+        uint64_t cap_new = 16;
+        for (uint32_t c = 0; c < nc; ++c) if (n_cuts_of[c] <= 1) {
+            hard.push_back(c);
+            if (clen[c] >= segment_size) { searched.push_back(c); cap_new += clen[c] / std::max<uint32_t>(segment_size, 1) + 2; }
+        }
+        bool grown = false;
+        if (!searched.empty()) {
+            PhaseTimer pt("find_new_splitters");
+            std::vector<uint64_t> fresh_spl(cap_new); uint64_t n_new = 0;
+            if (!gpu_ok(agcgpu_find_new_splitters(ctx, searched.data(), (uint32_t)searched.size(), fresh_spl.data(), cap_new, &n_new), "find_new_splitters")) return false;
+            fresh_spl.resize(n_new);
+            std::vector<uint64_t> merged; merged.reserve(splitters.size() + n_new);
+            std::set_union(splitters.begin(), splitters.end(), fresh_spl.begin(), fresh_spl.end(), std::back_inserter(merged));
+            if (merged.size() != splitters.size()) {
+                grown = true; splitters.swap(merged);
+                if (!gpu_ok(agcgpu_set_splitters(ctx, splitters.data(), splitters.size()), "set_splitters")) return false;
+                if (verbosity > 1 && is_app_mode) std::cerr << "No. of splitters: " << splitters.size() << std::endl;
+            }
+        }
+        if (grown) {
+            uint64_t cap2 = cap_cuts, n2 = 0;
+            std::vector<agcgpu_cut> again(cap2);
+            int rc2 = agcgpu_rescan_contigs(ctx, again.data(), cap2, &n2);
+            if (rc2 == AGCGPU_EOVERFLOW && n2 > cap2) { cap2 = n2 + 16; again.resize(cap2); rc2 = agcgpu_rescan_contigs(ctx, again.data(), cap2, &n2); }
+            if (!gpu_ok(rc2, "rescan_contigs")) return false;
+            again.resize(n2);
+            std::vector<uint8_t> is_hard(nc, 0);
+            for (auto c : hard) is_hard[c] = 1;
+            std::vector<agcgpu_cut> mixed; mixed.reserve(cuts.size() + again.size());
+            size_t a = 0, b = 0;
+            for (uint32_t c = 0; c < nc; ++c) {
+                for (; a < cuts.size() && cuts[a].contig == c; ++a) if (!is_hard[c]) mixed.push_back(cuts[a]);
+                for (; b < again.size() && again[b].contig == c; ++b) if (is_hard[c]) mixed.push_back(again[b]);
+            }
+            cuts.swap(mixed); n_cuts = cuts.size();
+        }
+    }
 
     // cut ranges per contig
     std::vector<uint64_t> cut_first(nc + 1, 0);

@@ -45,8 +45,11 @@ typedef struct {
     uint32_t segment_size;       /* -s */
     uint32_t pack_cardinality;   /* -b */
     int32_t  device;             /* CUDA device ordinal */
-    uint32_t reserved;
+    uint32_t flags;              /* AGCGPU_F_* */
 } agcgpu_params;
+/* -a (adaptive_compression, agc_compressor.cpp:493-494,536-541): agcgpu_determine_splitters keeps the sorted k-mer
+ * list of the reference sample on the device (v_candidate_kmers + v_duplicated_kmers) for agcgpu_find_new_splitters */
+#define AGCGPU_F_ADAPTIVE 1u
 
 /* One segment cut out of a contig: what compress_contig hands to add_segment
  * (src/core/agc_compressor.cpp:2019-2048).  front/back are the CKmer words (src/core/kmer.h:21-31) of the
@@ -113,6 +116,15 @@ int agcgpu_determine_splitters(agcgpu_ctx* ctx, const uint8_t* raw, const uint64
 /* hs_splitters / bloom_splitters fill (agc_compressor.cpp:543-555; append: 339-351; -a: 1191-1209) */
 int agcgpu_set_splitters(agcgpu_ctx* ctx, const uint64_t* splitters, uint64_t n);
 
+/* -a mode, CAGCCompressor::find_new_splitters (agc_compressor.cpp:2054-2082) for resident contigs that the scan left
+ * without a single splitter (compress_contig 2038-2044): per contig, its singleton k-mers that do not occur in the
+ * reference sample (neither as singletons nor duplicated) are the candidates of find_splitters_in_contig (762-825).
+ * Needs AGCGPU_F_ADAPTIVE.  out = the new splitters of all listed contigs, sorted, de-duplicated (the reference
+ * inserts them into a hash set, 1191-1209).  The splitter set itself is NOT changed: the caller merges and calls
+ * agcgpu_set_splitters. */
+int agcgpu_find_new_splitters(agcgpu_ctx* ctx, const uint32_t* contigs, uint32_t n, uint64_t* out_splitters, uint64_t cap,
+                              uint64_t* out_n);
+
 /* ---- contig batch: preprocess + scan ---------------------------------------------------------------------------- */
 /* preprocess_raw_contig (agc_compressor.cpp:907-951) + compress_contig's scan loop (1997-2051) for a batch of
  * contigs.  raw = concatenated raw bodies, contig i = raw[raw_offsets[i] .. raw_offsets[i+1]).  The preprocessed
@@ -125,6 +137,10 @@ int agcgpu_scan_contigs(agcgpu_ctx* ctx, const uint8_t* raw, const uint64_t* raw
 int agcgpu_scan_contigs_dev(agcgpu_ctx* ctx, const void* raw_dev, uint64_t raw_bytes, const uint64_t* raw_offsets,
                             uint32_t n_contigs, uint64_t* out_contig_len, agcgpu_cut* out_cuts, uint64_t cap_cuts,
                             uint64_t* out_n_cuts);
+/* compress_contig's scan loop again over the RESIDENT batch under the current splitter set: the hard_contigs stage of
+ * -a mode (agc_compressor.cpp:1211-1227), after agcgpu_set_splitters added the new splitters.  Cuts of every resident
+ * contig come out ordered by (contig, start); the caller keeps those of the contigs it re-queued. */
+int agcgpu_rescan_contigs(agcgpu_ctx* ctx, agcgpu_cut* out_cuts, uint64_t cap_cuts, uint64_t* out_n_cuts);
 /* get_part (agc_compressor.cpp:2085-2091) / reverse_complement_copy: download symbols (1 byte each) of a segment */
 int agcgpu_get_segment(agcgpu_ctx* ctx, uint32_t contig, uint64_t start, uint32_t len, uint32_t is_rc, uint8_t* out);
 

@@ -1,0 +1,390 @@
+// agcgpu_mock.cpp -- TEST INFRASTRUCTURE ONLY (never built by agc_b200/csrc/Makefile, never shipped, never loaded by agc_b200/).
+//
+// The device-level entry points of include/agcgpu.h restated over the C oracle (oracle/agc_oracle.c) and the host build of
+// the residual coder (agc_b200/csrc/zstd_enc.cuh, as tests/zstd_host builds it), so that the HOST side of the path --
+// agc_b200/csrc/host/compressor.cpp: add_segment's rare branches, registration order, pack bookkeeping, CCollection_V3,
+// CArchive -- can be run end to end in the CPU test-suite and its archives compared byte for byte with the reference
+// binary's.  tests/test_host_pipeline.py links this file with the product's host objects into tests/mock/libagcgpu_mock.so.
+// The product library has no such path: without an sm_100 device agcgpu_create fails there.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+#include "../../include/agcgpu.h"
+
+#define ZE_NS ze
+#define ZE_WN_W 512
+#include "../../agc_b200/csrc/zstd_enc.cuh"
+#undef ZE_NS
+#undef ZE_WN_W
+#define ZE_NS zen
+#define ZE_WN_W 32
+#include "../../agc_b200/csrc/zstd_enc.cuh"
+#undef ZE_NS
+#undef ZE_WN_W
+
+extern "C" {
+typedef struct olz olz_t;
+typedef struct { uint64_t start, len, front_dir, front_rc, back_dir, back_rc; uint32_t has_front, has_back; } orc_cut_t;
+uint64_t orc_preprocess(const uint8_t* raw, uint64_t len, uint8_t* out);
+void orc_reverse_complement(const uint8_t* src, uint64_t n, uint8_t* dst);
+uint64_t orc_scan_contig(const uint8_t* ctg, uint64_t n, uint32_t k, const uint64_t* spl, uint64_t n_spl, orc_cut_t* cuts);
+uint64_t orc_enumerate_kmers(const uint8_t* ctg, uint64_t n, uint32_t k, uint64_t* out);
+uint64_t orc_determine_splitters(const uint8_t* ctgs, const uint64_t* offs, uint32_t n_ctg, uint32_t k, uint64_t segment_size,
+                                 uint64_t* out, uint64_t* singletons_out, uint64_t* n_singletons);
+uint64_t orc_find_new_splitters(const uint8_t* ctg, uint64_t n, uint32_t k, uint64_t segment_size, const uint64_t* ref_kmers,
+                                uint64_t n_ref, uint64_t* out);
+olz_t* orc_lz_prepare(const uint8_t* ref, uint32_t m, uint32_t min_match_len);
+void orc_lz_free(olz_t* z);
+uint64_t orc_lz_ht_size(const olz_t* z);
+void orc_lz_get_ht(const olz_t* z, uint32_t* out);
+uint64_t orc_lz_encode(const olz_t* z, const uint8_t* text, uint32_t n, uint8_t** out);
+void orc_free(void* p);
+uint64_t orc_lz_estimate(const olz_t* z, const uint8_t* text, uint32_t n, uint32_t bound);
+uint64_t orc_lz_cost_vector(const olz_t* z, const uint8_t* text, uint32_t n, int prefix_costs, uint32_t* v);
+uint64_t orc_bytes2tuples(const uint8_t* b, uint64_t n, uint8_t* out);
+int orc_ref_use_tuples(const uint8_t* d, uint64_t n);
+}
+
+struct agcgpu_ctx {
+    agcgpu_params prm;
+    std::string err;
+    agcgpu_stats stats;
+    std::vector<uint64_t> splitters;                          // sorted
+    std::vector<std::vector<uint8_t>> contigs;                // resident batch, preprocessed symbols
+    std::map<std::pair<uint64_t, uint64_t>, int32_t> map;
+    struct Group { std::vector<uint8_t> ref; olz_t* lz = nullptr; };
+    std::map<uint32_t, Group> groups;
+    std::vector<uint64_t> ref_kmers;                          // AGCGPU_F_ADAPTIVE: sorted k-mers of the reference sample
+};
+
+static thread_local std::string g_create_err;
+
+static int fail(agcgpu_ctx* c, int code, const char* fmt, ...)
+{
+    char b[512]; va_list ap; va_start(ap, fmt); vsnprintf(b, sizeof b, fmt, ap); va_end(ap);
+    if (c) c->err = b; else g_create_err = b;
+    return code;
+}
+
+static void preprocess_all(agcgpu_ctx* ctx, const uint8_t* raw, const uint64_t* offs, uint32_t n)
+{
+    ctx->contigs.assign(n, {});
+    for (uint32_t c = 0; c < n; ++c) {
+        uint64_t len = offs[c + 1] - offs[c];
+        ctx->contigs[c].resize(len + 1);
+        uint64_t m = orc_preprocess(raw + offs[c], len, ctx->contigs[c].data());
+        ctx->contigs[c].resize(m);
+    }
+}
+
+// symbols of a request, padded so that the oracle's key reads stay inside the buffer
+static int fetch(agcgpu_ctx* ctx, uint32_t contig, uint64_t start, uint32_t len, uint32_t is_rc, std::vector<uint8_t>& out)
+{
+    if (contig >= ctx->contigs.size() || start + len > ctx->contigs[contig].size())
+        return fail(ctx, AGCGPU_EINVAL, "segment outside the resident batch (contig %u, start %llu, len %u)", contig, (unsigned long long)start, len);
+    out.assign(len + 64, 0);
+    const uint8_t* p = ctx->contigs[contig].data() + start;
+    if (is_rc) orc_reverse_complement(p, len, out.data()); else if (len) memcpy(out.data(), p, len);
+    return 0;
+}
+
+static void scan_all(agcgpu_ctx* ctx, std::vector<agcgpu_cut>& cuts)
+{
+    for (uint32_t c = 0; c < ctx->contigs.size(); ++c) {
+        auto& s = ctx->contigs[c];
+        uint64_t n = orc_scan_contig(s.data(), s.size(), ctx->prm.kmer_length, ctx->splitters.data(), ctx->splitters.size(), nullptr);
+        std::vector<orc_cut_t> oc(n + 1);
+        orc_scan_contig(s.data(), s.size(), ctx->prm.kmer_length, ctx->splitters.data(), ctx->splitters.size(), oc.data());
+        for (uint64_t i = 0; i < n; ++i) {
+            agcgpu_cut q; memset(&q, 0, sizeof q);
+            q.contig = c; q.has_front = oc[i].has_front; q.has_back = oc[i].has_back; q.start = oc[i].start; q.len = oc[i].len;
+            if (q.has_front) { q.front_dir = oc[i].front_dir; q.front_rc = oc[i].front_rc; }
+            if (q.has_back) { q.back_dir = oc[i].back_dir; q.back_rc = oc[i].back_rc; }
+            cuts.push_back(q);
+        }
+    }
+}
+
+static int emit_cuts(agcgpu_ctx* ctx, std::vector<agcgpu_cut>& cuts, agcgpu_cut* out, uint64_t cap, uint64_t* out_n)
+{
+    if (out_n) *out_n = cuts.size();
+    if (cuts.size() > cap) return fail(ctx, AGCGPU_EOVERFLOW, "scan: %zu cuts, caller buffer holds %llu", cuts.size(), (unsigned long long)cap);
+    if (!cuts.empty()) memcpy(out, cuts.data(), cuts.size() * sizeof(agcgpu_cut));
+    return 0;
+}
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+int agcgpu_create(const agcgpu_params* p, agcgpu_ctx** out)
+{
+    if (!p || !out) return AGCGPU_EINVAL;
+    if (p->kmer_length < 1 || p->kmer_length > 32) return fail(nullptr, AGCGPU_EINVAL, "kmer_length out of range");
+    agcgpu_ctx* c = new agcgpu_ctx();
+    c->prm = *p; memset(&c->stats, 0, sizeof c->stats);
+    c->map[std::make_pair(~0ULL, ~0ULL)] = 0;                  // raw groups (agc_compressor.cpp:2307), as api.cu seeds it
+    *out = c;
+    return 0;
+}
+void agcgpu_destroy(agcgpu_ctx* ctx)
+{
+    if (!ctx) return;
+    for (auto& g : ctx->groups) orc_lz_free(g.second.lz);
+    delete ctx;
+}
+const char* agcgpu_last_error(const agcgpu_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+int agcgpu_sync(agcgpu_ctx*) { return 0; }
+void* agcgpu_stream(agcgpu_ctx*) { return nullptr; }
+int agcgpu_get_stats(agcgpu_ctx* ctx, agcgpu_stats* out) { if (!ctx || !out) return AGCGPU_EINVAL; *out = ctx->stats; return 0; }
+
+int agcgpu_set_splitters(agcgpu_ctx* ctx, const uint64_t* s, uint64_t n)
+{
+    if (!ctx || (n && !s)) return AGCGPU_EINVAL;
+    ctx->splitters.assign(s, s + n);
+    std::sort(ctx->splitters.begin(), ctx->splitters.end());
+    return 0;
+}
+
+int agcgpu_determine_splitters(agcgpu_ctx* ctx, const uint8_t* raw, const uint64_t* offs, uint32_t n, uint64_t* out, uint64_t cap, uint64_t* out_n)
+{
+    if (!ctx || !offs || !out_n) return AGCGPU_EINVAL;
+    preprocess_all(ctx, raw, offs, n);
+    std::vector<uint8_t> cat; std::vector<uint64_t> co(n + 1, 0);
+    for (uint32_t c = 0; c < n; ++c) { cat.insert(cat.end(), ctx->contigs[c].begin(), ctx->contigs[c].end()); co[c + 1] = cat.size(); }
+    cat.push_back(0);
+    std::vector<uint64_t> spl(cat.size() + 2 * n + 16);
+    uint64_t ns = orc_determine_splitters(cat.data(), co.data(), n, ctx->prm.kmer_length, ctx->prm.segment_size, spl.data(), nullptr, nullptr);
+    if (ctx->prm.flags & AGCGPU_F_ADAPTIVE) {
+        ctx->ref_kmers.assign(cat.size() + 1, 0);
+        uint64_t nk = 0;
+        for (uint32_t c = 0; c < n; ++c) nk += orc_enumerate_kmers(cat.data() + co[c], co[c + 1] - co[c], ctx->prm.kmer_length, ctx->ref_kmers.data() + nk);
+        ctx->ref_kmers.resize(nk);
+        std::sort(ctx->ref_kmers.begin(), ctx->ref_kmers.end());
+    }
+    ctx->contigs.clear();
+    *out_n = ns;
+    if (ns > cap) return fail(ctx, AGCGPU_EOVERFLOW, "determine_splitters: %llu splitters, buffer holds %llu", (unsigned long long)ns, (unsigned long long)cap);
+    if (ns) memcpy(out, spl.data(), ns * 8);
+    ctx->splitters.assign(spl.begin(), spl.begin() + ns);
+    return 0;
+}
+
+int agcgpu_find_new_splitters(agcgpu_ctx* ctx, const uint32_t* contigs, uint32_t n, uint64_t* out, uint64_t cap, uint64_t* out_n)
+{
+    if (!ctx || !out_n || (n && !contigs)) return AGCGPU_EINVAL;
+    if (!(ctx->prm.flags & AGCGPU_F_ADAPTIVE)) return fail(ctx, AGCGPU_EINVAL, "find_new_splitters needs AGCGPU_F_ADAPTIVE");
+    std::vector<uint64_t> all;
+    for (uint32_t i = 0; i < n; ++i) {
+        if (contigs[i] >= ctx->contigs.size()) return fail(ctx, AGCGPU_EINVAL, "find_new_splitters: contig %u is not resident", contigs[i]);
+        auto& s = ctx->contigs[contigs[i]];
+        std::vector<uint64_t> o(s.size() + 2);
+        std::vector<uint8_t> padded(s); padded.push_back(0);
+        uint64_t no = orc_find_new_splitters(padded.data(), s.size(), ctx->prm.kmer_length, ctx->prm.segment_size, ctx->ref_kmers.data(), ctx->ref_kmers.size(), o.data());
+        all.insert(all.end(), o.begin(), o.begin() + no);
+    }
+    std::sort(all.begin(), all.end());
+    all.erase(std::unique(all.begin(), all.end()), all.end());
+    *out_n = all.size();
+    if (all.size() > cap) return fail(ctx, AGCGPU_EOVERFLOW, "find_new_splitters: %zu splitters, buffer holds %llu", all.size(), (unsigned long long)cap);
+    if (!all.empty()) memcpy(out, all.data(), all.size() * 8);
+    return 0;
+}
+
+int agcgpu_scan_contigs(agcgpu_ctx* ctx, const uint8_t* raw, const uint64_t* offs, uint32_t n, uint64_t* out_len, agcgpu_cut* out_cuts,
+                        uint64_t cap, uint64_t* out_n)
+{
+    if (!ctx || !offs || (n && !raw && offs[n])) return AGCGPU_EINVAL;
+    preprocess_all(ctx, raw, offs, n);
+    if (out_len) for (uint32_t c = 0; c < n; ++c) out_len[c] = ctx->contigs[c].size();
+    std::vector<agcgpu_cut> cuts;
+    scan_all(ctx, cuts);
+    return emit_cuts(ctx, cuts, out_cuts, cap, out_n);
+}
+int agcgpu_scan_contigs_dev(agcgpu_ctx* ctx, const void* raw_dev, uint64_t, const uint64_t* offs, uint32_t n, uint64_t* out_len,
+                            agcgpu_cut* out_cuts, uint64_t cap, uint64_t* out_n)
+{
+    return agcgpu_scan_contigs(ctx, (const uint8_t*)raw_dev, offs, n, out_len, out_cuts, cap, out_n);   // "device" memory is host memory here
+}
+int agcgpu_rescan_contigs(agcgpu_ctx* ctx, agcgpu_cut* out_cuts, uint64_t cap, uint64_t* out_n)
+{
+    if (!ctx) return AGCGPU_EINVAL;
+    std::vector<agcgpu_cut> cuts;
+    scan_all(ctx, cuts);
+    return emit_cuts(ctx, cuts, out_cuts, cap, out_n);
+}
+
+int agcgpu_get_segment(agcgpu_ctx* ctx, uint32_t contig, uint64_t start, uint32_t len, uint32_t is_rc, uint8_t* out)
+{
+    if (!ctx || (len && !out)) return AGCGPU_EINVAL;
+    std::vector<uint8_t> s;
+    if (int r = fetch(ctx, contig, start, len, is_rc, s)) return r;
+    if (len) memcpy(out, s.data(), len);
+    return 0;
+}
+
+int agcgpu_map_insert(agcgpu_ctx* ctx, const uint64_t* k1, const uint64_t* k2, const int32_t* gid, uint64_t n)
+{
+    if (!ctx || (n && (!k1 || !k2 || !gid))) return AGCGPU_EINVAL;
+    for (uint64_t i = 0; i < n; ++i) {
+        if (gid[i] < 0) return fail(ctx, AGCGPU_EINVAL, "map_insert: negative group id");
+        auto key = std::make_pair(k1[i], k2[i]);
+        auto p = ctx->map.find(key);
+        if (p == ctx->map.end()) ctx->map[key] = gid[i]; else if (p->second > gid[i]) p->second = gid[i];
+    }
+    return 0;
+}
+
+int agcgpu_assign_cuts(agcgpu_ctx* ctx, const agcgpu_cut* cuts, uint64_t n, agcgpu_assign* out)
+{
+    if (!ctx || (n && (!cuts || !out))) return AGCGPU_EINVAL;
+    for (uint64_t i = 0; i < n; ++i) {                          // add_segment key construction (agc_compressor.cpp:1287-1313)
+        const agcgpu_cut& c = cuts[i];
+        agcgpu_assign a; memset(&a, 0, sizeof a);
+        uint64_t fc = std::min(c.front_dir, c.front_rc), bc = std::min(c.back_dir, c.back_rc);
+        a.group_id = -1;
+        if (c.has_front && c.has_back) { a.klass = 0; if (fc < bc) { a.key1 = fc; a.key2 = bc; } else { a.key1 = bc; a.key2 = fc; a.is_rc = 1; } }
+        else if (c.has_front) { a.klass = 1; a.key1 = fc; a.key2 = ~0ULL; }
+        else if (c.has_back) { a.klass = 2; a.key1 = ~0ULL; a.key2 = bc; }
+        else { a.klass = 3; a.key1 = a.key2 = ~0ULL; }
+        if (a.klass == 0 || a.klass == 3) { auto p = ctx->map.find(std::make_pair(a.key1, a.key2)); if (p != ctx->map.end()) a.group_id = p->second; }
+        out[i] = a;
+    }
+    return 0;
+}
+
+int agcgpu_group_put_reference(agcgpu_ctx* ctx, uint32_t group_id, const uint8_t* symbols, uint32_t len)
+{
+    if (!ctx || (len && !symbols)) return AGCGPU_EINVAL;
+    agcgpu_ctx::Group& g = ctx->groups[group_id];
+    if (g.lz) { orc_lz_free(g.lz); g.lz = nullptr; }
+    g.ref.assign(symbols, symbols + len);
+    std::vector<uint8_t> padded(g.ref); padded.resize(len + 64, 0);
+    g.lz = orc_lz_prepare(padded.data(), len, ctx->prm.min_match_len);
+    return 0;
+}
+int agcgpu_group_put_reference_batch(agcgpu_ctx* ctx, const agcgpu_seg_req* reqs, uint32_t n)
+{
+    if (!ctx || (n && !reqs)) return AGCGPU_EINVAL;
+    for (uint32_t i = 0; i < n; ++i) {
+        std::vector<uint8_t> s;
+        if (int r = fetch(ctx, reqs[i].contig, reqs[i].start, reqs[i].len, reqs[i].is_rc, s)) return r;
+        if (int r = agcgpu_group_put_reference(ctx, reqs[i].group_id, s.data(), reqs[i].len)) return r;
+    }
+    return 0;
+}
+int agcgpu_group_get_index(agcgpu_ctx* ctx, uint32_t group_id, uint32_t* out_slots, uint64_t cap, uint64_t* out_ht_size)
+{
+    if (!ctx || !out_ht_size) return AGCGPU_EINVAL;
+    auto p = ctx->groups.find(group_id);
+    if (p == ctx->groups.end()) return fail(ctx, AGCGPU_EINVAL, "group %u has no reference", group_id);
+    *out_ht_size = orc_lz_ht_size(p->second.lz);
+    if (*out_ht_size > cap) return fail(ctx, AGCGPU_EOVERFLOW, "index larger than the caller's buffer");
+    orc_lz_get_ht(p->second.lz, out_slots);
+    return 0;
+}
+
+static int lz_prep(agcgpu_ctx* ctx, const agcgpu_seg_req& q, std::vector<uint8_t>& text, olz_t** z)
+{
+    auto p = ctx->groups.find(q.group_id);
+    if (p == ctx->groups.end()) return fail(ctx, AGCGPU_EINVAL, "group %u has no reference", q.group_id);
+    *z = p->second.lz;
+    return fetch(ctx, q.contig, q.start, q.len, q.is_rc, text);
+}
+
+int agcgpu_lz_encode_batch(agcgpu_ctx* ctx, const agcgpu_seg_req* reqs, uint32_t n, uint8_t* out, uint64_t out_cap, uint64_t* out_offsets)
+{
+    if (!ctx || !out_offsets || (n && (!reqs || !out))) return AGCGPU_EINVAL;
+    uint64_t o = 0; out_offsets[0] = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        std::vector<uint8_t> t; olz_t* z;
+        if (int r = lz_prep(ctx, reqs[i], t, &z)) return r;
+        uint8_t* e = nullptr;
+        uint64_t en = orc_lz_encode(z, t.data(), reqs[i].len, &e);
+        if (o + en > out_cap) { orc_free(e); return fail(ctx, AGCGPU_EOVERFLOW, "lz_encode: output buffer too small"); }
+        if (en) memcpy(out + o, e, en);
+        orc_free(e);
+        o += en; out_offsets[i + 1] = o;
+    }
+    return 0;
+}
+int agcgpu_lz_estimate_batch(agcgpu_ctx* ctx, const agcgpu_seg_req* reqs, uint32_t n, uint32_t* out)
+{
+    if (!ctx || (n && (!reqs || !out))) return AGCGPU_EINVAL;
+    for (uint32_t i = 0; i < n; ++i) {
+        std::vector<uint8_t> t; olz_t* z;
+        if (int r = lz_prep(ctx, reqs[i], t, &z)) return r;
+        out[i] = (uint32_t)orc_lz_estimate(z, t.data(), reqs[i].len, reqs[i].bound);
+    }
+    return 0;
+}
+int agcgpu_lz_cost_vector(agcgpu_ctx* ctx, const agcgpu_seg_req* req, int prefix_costs, uint32_t* out)
+{
+    if (!ctx || !req || (req->len && !out)) return AGCGPU_EINVAL;
+    std::vector<uint8_t> t; olz_t* z;
+    if (int r = lz_prep(ctx, *req, t, &z)) return r;
+    std::vector<uint32_t> v(req->len + 64, 0);
+    uint64_t vn = orc_lz_cost_vector(z, t.data(), req->len, prefix_costs, v.data());
+    if (vn != req->len) return fail(ctx, AGCGPU_EINVAL, "cost vector has %llu entries for %u symbols", (unsigned long long)vn, req->len);
+    if (req->len) memcpy(out, v.data(), (size_t)req->len * 4);
+    return 0;
+}
+
+int agcgpu_pack_ref_batch(agcgpu_ctx* ctx, const uint32_t* group_ids, uint32_t n, uint8_t* out, uint64_t out_cap, uint64_t* out_offsets,
+                          uint8_t* out_use_tuples)
+{
+    if (!ctx || !out_offsets || (n && (!group_ids || !out || !out_use_tuples))) return AGCGPU_EINVAL;
+    uint64_t o = 0; out_offsets[0] = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        auto p = ctx->groups.find(group_ids[i]);
+        if (p == ctx->groups.end()) return fail(ctx, AGCGPU_EINVAL, "group %u has no reference", group_ids[i]);
+        const std::vector<uint8_t>& r = p->second.ref;
+        std::vector<uint8_t> pay(r.size() + 8);
+        uint64_t pn;
+        out_use_tuples[i] = (uint8_t)orc_ref_use_tuples(r.data(), r.size());
+        if (out_use_tuples[i]) pn = orc_bytes2tuples(r.data(), r.size(), pay.data());
+        else { pn = r.size(); if (pn) memcpy(pay.data(), r.data(), pn); }
+        if (o + pn > out_cap) return fail(ctx, AGCGPU_EOVERFLOW, "pack_ref: output buffer too small");
+        if (pn) memcpy(out + o, pay.data(), pn);
+        o += pn; out_offsets[i + 1] = o;
+    }
+    return 0;
+}
+
+int agcgpu_zstd_compress_batch(agcgpu_ctx* ctx, const uint8_t* src, const uint64_t* so, const int32_t* levels, uint32_t n, uint8_t* dst,
+                               uint64_t dst_cap, uint64_t* dof)
+{
+    if (!ctx || !so || !dof || (n && (!src || !levels || !dst))) return AGCGPU_EINVAL;
+    uint64_t o = 0; dof[0] = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        uint64_t len = so[i + 1] - so[i];
+        ze::Params cp = ze::get_params(levels[i], len);
+        if (!cp.supported) return fail(ctx, AGCGPU_EUNSUPPORTED, "zstd: input %u (level %d, %llu bytes) is outside the implemented envelope", i, levels[i], (unsigned long long)len);
+        std::vector<uint8_t> in(len + 64, 0), fr(ze::compress_bound(len) + 64);
+        if (len) memcpy(in.data(), src + so[i], len);
+        int err = 0; uint64_t r;
+        if (len > 32768) {                                      // same routing as kernels_zstd.cu: wide coder above 32 KB
+            ze::WorkSizes z = ze::work_sizes(cp);
+            std::vector<uint8_t> mem(z.total + 64, 0);
+            r = ze::compress_frame(in.data(), len, levels[i], fr.data(), fr.size(), mem.data(), &err);
+        } else {
+            zen::Params cpn = zen::get_params(levels[i], len);
+            zen::WorkSizes z = zen::work_sizes(cpn);
+            std::vector<uint8_t> mem(z.total + 64, 0);
+            r = zen::compress_frame(in.data(), len, levels[i], fr.data(), fr.size(), mem.data(), &err);
+        }
+        if (err) return fail(ctx, AGCGPU_EUNSUPPORTED, "zstd: coder error %d on input %u", err, i);
+        if (o + r > dst_cap) return fail(ctx, AGCGPU_EOVERFLOW, "zstd: output buffer too small");
+        memcpy(dst + o, fr.data(), r);
+        o += r; dof[i + 1] = o;
+        ctx->stats.zstd_input_mb += (float)len / 1e6f;
+    }
+    return 0;
+}
+
+#pragma GCC visibility pop
+}

@@ -103,3 +103,35 @@ def total_bases(files):
                 if not line.startswith(b">"):
                     n += len(line.rstrip(b"\r\n"))
     return n
+
+
+def adaptive_collection(out_dir, seed=2, n_samples=8, ref_len=60000, n_ctg=2, novel_len=9000, p=0.01):
+    """config C3 in small: every sample = mutated reference contigs + 20 random 1-50 b indels + one NOVEL random contig
+    (>= segment_size, so `-a` looks for new splitters in it, agc_compressor.cpp:2038-2044).  Later samples also carry a
+    mutated copy of an earlier sample's novel contig (cut by the splitters that sample added), a short novel contig
+    (< segment_size: set aside but not searched) and, once, a contig that only occurs reverse-complemented."""
+    os.makedirs(out_dir, exist_ok=True)
+    rng = np.random.default_rng(seed)
+    ref = [rng.integers(0, 4, ref_len // n_ctg + 777 * i, dtype=np.uint8) for i in range(n_ctg)]
+    files = [os.path.join(out_dir, "ref.fa")]
+    write_fasta(files[0], [(f"chr{i + 1}", c) for i, c in enumerate(ref)])
+    novel = []
+    for s in range(n_samples):
+        ctgs = [(f"a{s}_chr{i + 1}", indels(rng, substitute(rng, c, p), 20 // n_ctg)) for i, c in enumerate(ref)]
+        nv = rng.integers(0, 4, novel_len + 531 * s, dtype=np.uint8)
+        ctgs.append((f"a{s}_novel", nv))
+        if novel:
+            old = novel[int(rng.integers(0, len(novel)))]
+            t = indels(rng, substitute(rng, old, p), 3)
+            if s % 3 == 2:
+                t = (3 - t[::-1]).astype(np.uint8)
+            ctgs.append((f"a{s}_seen_before", t))
+        if s % 2 == 1:
+            ctgs.append((f"a{s}_short_novel", rng.integers(0, 4, 700, dtype=np.uint8)))
+        if s == 4:
+            ctgs.append((f"a{s}_twice", nv[::-1].copy()))     # shares no canonical k-mer with nv: a second searched contig
+        novel.append(nv)
+        fn = os.path.join(out_dir, f"a{s:02d}.fa")
+        write_fasta(fn, ctgs)
+        files.append(fn)
+    return files
