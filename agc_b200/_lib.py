@@ -50,6 +50,7 @@ EXPORTED_SYMBOLS = [
     "agcgpu_get_segment", "agcgpu_map_insert", "agcgpu_assign_cuts", "agcgpu_group_put_reference_batch",
     "agcgpu_group_put_reference", "agcgpu_group_get_index", "agcgpu_lz_encode_batch", "agcgpu_lz_estimate_batch",
     "agcgpu_lz_cost_vector", "agcgpu_pack_ref_batch", "agcgpu_zstd_compress_batch",
+    "agcgpu_find_new_splitters", "agcgpu_rescan_contigs",
 ]
 
 
@@ -79,6 +80,9 @@ def lib():
     L.agcgpu_set_splitters.restype = C.c_int; L.agcgpu_set_splitters.argtypes = [vp, u64p, C.c_uint64]
     L.agcgpu_scan_contigs.restype = C.c_int
     L.agcgpu_scan_contigs.argtypes = [vp, u8p, u64p, C.c_uint32, u64p, C.POINTER(Cut), C.c_uint64, u64p]
+    L.agcgpu_find_new_splitters.restype = C.c_int
+    L.agcgpu_find_new_splitters.argtypes = [vp, u32p, C.c_uint32, u64p, C.c_uint64, u64p]
+    L.agcgpu_rescan_contigs.restype = C.c_int; L.agcgpu_rescan_contigs.argtypes = [vp, C.POINTER(Cut), C.c_uint64, u64p]
     L.agcgpu_scan_contigs_dev.restype = C.c_int
     L.agcgpu_scan_contigs_dev.argtypes = [vp, vp, C.c_uint64, u64p, C.c_uint32, u64p, C.POINTER(Cut), C.c_uint64, u64p]
     L.agcgpu_get_segment.restype = C.c_int
@@ -108,9 +112,9 @@ def _p(a, t):
 class Device:
     """One context = the device side of one CAGCCompressor (src/core/agc_compressor.h:540-764)."""
 
-    def __init__(self, k=31, min_match_len=20, segment_size=60000, pack_cardinality=50, device=0):
+    def __init__(self, k=31, min_match_len=20, segment_size=60000, pack_cardinality=50, device=0, adaptive=False):
         self.L = lib()
-        self.params = Params(k, min_match_len, segment_size, pack_cardinality, device, 0)
+        self.params = Params(k, min_match_len, segment_size, pack_cardinality, device, 1 if adaptive else 0)
         h = C.c_void_p()
         rc = self.L.agcgpu_create(C.byref(self.params), C.byref(h))
         if rc != 0:
@@ -194,6 +198,23 @@ class Device:
             self._ck(rc)
             break
         self.contig_len = lens[:n].copy()
+        return [cuts[i] for i in range(nc.value)]
+
+    def find_new_splitters(self, contigs):
+        """-a mode: new splitters of the listed resident contigs (CAGCCompressor::find_new_splitters); sorted, unique"""
+        c = np.ascontiguousarray(contigs, np.uint32)
+        cap = int(sum(int(self.contig_len[i]) for i in c)) // max(1, self.params.segment_size) + 2 * len(c) + 16
+        out = np.zeros(cap, np.uint64)
+        n = C.c_uint64(0)
+        self._ck(self.L.agcgpu_find_new_splitters(self.h, _p(c, u32p), len(c), _p(out, u64p), cap, C.byref(n)))
+        return out[:n.value].copy()
+
+    def rescan_contigs(self):
+        """scan of the resident batch again under the current splitter set (-a mode, hard_contigs stage)"""
+        cap = int(self.contig_len.sum()) // 16 + 4 * len(self.contig_len) + 64
+        cuts = (Cut * cap)()
+        nc = C.c_uint64(0)
+        self._ck(self.L.agcgpu_rescan_contigs(self.h, cuts, cap, C.byref(nc)))
         return [cuts[i] for i in range(nc.value)]
 
     def scan_contigs_dev(self, dev_ptr, offs):

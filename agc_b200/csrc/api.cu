@@ -148,7 +148,7 @@ void agcgpu_destroy(agcgpu_ctx* ctx)
     DevBuf* bufs[] = { &ctx->spl_keys, &ctx->spl_filter, &ctx->raw, &ctx->packed, &ctx->exc_pos, &ctx->exc_code, &ctx->tile_desc,
                        &ctx->tile_cnt, &ctx->tile_base, &ctx->d_cstart, &ctx->chunk_prefix, &ctx->hits, &ctx->counters, &ctx->map_k1,
                        &ctx->map_k2, &ctx->map_val, &ctx->d_groups, &ctx->scr_req, &ctx->scr_units, &ctx->scr_out, &ctx->scr_sizes,
-                       &ctx->scr_offs, &ctx->scr_dense, &ctx->scr_misc, &ctx->scr_bytes };
+                       &ctx->scr_offs, &ctx->scr_dense, &ctx->scr_misc, &ctx->scr_bytes, &ctx->ref_kmers };
     for (DevBuf* b : bufs) if (b->p) agc_dev_free(ctx->dev, b->p, b->cap + 64);
     for (auto& c : ctx->arena_chunks) agc_dev_free(ctx->dev, c.first, c.second);
     if (ctx->pin) {
@@ -268,11 +268,44 @@ int agcgpu_determine_splitters(agcgpu_ctx* ctx, const uint8_t* raw, const uint64
     if (int r = upload_raw(ctx, raw, raw_bytes)) return r;
     if (int r = agc_prep_and_scan(ctx, (const uint8_t*)ctx->raw.p, raw_bytes, raw_offsets, n_contigs, false, nullptr)) return r;
     std::vector<uint64_t> spl;
-    if (int r = agc_enumerate_splitters(ctx, spl)) return r;
+    if (int r = agc_enumerate_splitters(ctx, 0, ctx->n_contigs, false, (ctx->prm.flags & AGCGPU_F_ADAPTIVE) != 0, spl)) return r;
     *out_n = spl.size();
     if (spl.size() > cap) return agc_fail(ctx, AGCGPU_EOVERFLOW, "determine_splitters: %zu splitters, buffer holds %llu", spl.size(), (unsigned long long)cap);
     if (!spl.empty()) memcpy(out_splitters, spl.data(), spl.size() * 8);
     return agc_upload_splitters(ctx, spl.data(), spl.size());
+}
+
+int agcgpu_find_new_splitters(agcgpu_ctx* ctx, const uint32_t* contigs, uint32_t n, uint64_t* out_splitters, uint64_t cap, uint64_t* out_n)
+{
+    if (!ctx || !out_n || (n && !contigs)) return AGCGPU_EINVAL;
+    cudaSetDevice(ctx->dev);
+    if (!(ctx->prm.flags & AGCGPU_F_ADAPTIVE)) return agc_fail(ctx, AGCGPU_EINVAL, "find_new_splitters needs AGCGPU_F_ADAPTIVE");
+    std::vector<uint64_t> all, one;
+    for (uint32_t i = 0; i < n; ++i) {                   // candidates are per contig (its own singletons), so one pass each
+        if (contigs[i] >= ctx->n_contigs) return agc_fail(ctx, AGCGPU_EINVAL, "find_new_splitters: contig %u is not resident", contigs[i]);
+        if (int r = agc_enumerate_splitters(ctx, contigs[i], 1, true, false, one)) return r;
+        all.insert(all.end(), one.begin(), one.end());
+    }
+    std::sort(all.begin(), all.end());
+    all.erase(std::unique(all.begin(), all.end()), all.end());
+    *out_n = all.size();
+    if (all.size() > cap) return agc_fail(ctx, AGCGPU_EOVERFLOW, "find_new_splitters: %zu splitters, buffer holds %llu", all.size(), (unsigned long long)cap);
+    if (!all.empty()) memcpy(out_splitters, all.data(), all.size() * 8);
+    return 0;
+}
+
+int agcgpu_rescan_contigs(agcgpu_ctx* ctx, agcgpu_cut* out_cuts, uint64_t cap_cuts, uint64_t* out_n_cuts)
+{
+    if (!ctx || (cap_cuts && !out_cuts)) return AGCGPU_EINVAL;
+    cudaSetDevice(ctx->dev);
+    std::vector<ScanHit> hits;
+    if (ctx->total_bases) { if (int r = agc_scan_resident(ctx, &hits)) return r; }
+    std::vector<agcgpu_cut> cuts;
+    resolve_cuts(ctx, hits, cuts);
+    if (out_n_cuts) *out_n_cuts = cuts.size();
+    if (cuts.size() > cap_cuts) return agc_fail(ctx, AGCGPU_EOVERFLOW, "rescan: %zu cuts, caller buffer holds %llu", cuts.size(), (unsigned long long)cap_cuts);
+    if (!cuts.empty()) memcpy(out_cuts, cuts.data(), cuts.size() * sizeof(agcgpu_cut));
+    return 0;
 }
 
 int agcgpu_get_segment(agcgpu_ctx* ctx, uint32_t contig, uint64_t start, uint32_t len, uint32_t is_rc, uint8_t* out)

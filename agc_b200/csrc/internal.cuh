@@ -117,6 +117,10 @@ struct agcgpu_ctx {
     DevBuf spl_filter;         // 2^filter_log2 bits, one hash: first-level reject in shared memory
     uint32_t filter_log2 = 10;
     uint64_t n_spl = 0;
+    // -a mode (AGCGPU_F_ADAPTIVE): every k-mer of the reference sample, sorted (invalid positions = ~0 at the end) --
+    // v_candidate_kmers and v_duplicated_kmers of the reference in one list (agc_compressor.cpp:493-494, 2066-2076)
+    DevBuf ref_kmers;
+    uint64_t n_ref_kmers = 0;
 
     // resident contig batch
     DevBuf raw;                // raw FASTA bytes (only when uploaded through agcgpu_scan_contigs)
@@ -167,7 +171,10 @@ void agc_dev_trim(int dev);
 // kernels_prep.cu
 int agc_prep_and_scan(agcgpu_ctx* ctx, const uint8_t* raw_dev, uint64_t raw_bytes, const uint64_t* raw_offsets,
                       uint32_t n_contigs, bool do_scan, std::vector<ScanHit>* hits_out);
-int agc_enumerate_splitters(agcgpu_ctx* ctx, std::vector<uint64_t>& out_sorted);
+int agc_scan_resident(agcgpu_ctx* ctx, std::vector<ScanHit>* hits_out);
+// splitters of resident contigs [c0, c0+nc): candidates = singletons among the k-mers of those contigs, minus (exclude_ref)
+// the k-mers of the reference sample; keep_kmers moves the sorted k-mer list into ctx->ref_kmers
+int agc_enumerate_splitters(agcgpu_ctx* ctx, uint32_t c0, uint32_t nc, bool exclude_ref, bool keep_kmers, std::vector<uint64_t>& out_sorted);
 int agc_expand_segment(agcgpu_ctx* ctx, uint64_t gstart, uint32_t n, uint32_t is_rc, uint8_t* dst_dev, uint32_t pad_bytes);
 int agc_upload_splitters(agcgpu_ctx* ctx, const uint64_t* s, uint64_t n);
 int agc_map_rebuild(agcgpu_ctx* ctx);

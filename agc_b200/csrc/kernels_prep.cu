@@ -382,8 +382,15 @@ int agc_prep_and_scan(agcgpu_ctx* ctx, const uint8_t* raw_dev, uint64_t raw_byte
         ctx->stats.d2h_bytes += totals[1] * 8;
     }
     if (!do_scan) { CK(cudaStreamSynchronize(ctx->st)); return 0; }
+    return agc_scan_resident(ctx, hits_out);
+}
 
-    // ---- scan
+// compress_contig's scan loop over the resident batch under the current splitter set (also the hard_contigs stage of -a mode)
+int agc_scan_resident(agcgpu_ctx* ctx, std::vector<ScanHit>* hits_out)
+{
+    const uint32_t n_contigs = ctx->n_contigs;
+    const uint64_t totals[1] = { ctx->total_bases };
+    hits_out->clear();
     if (ctx->spl_keys.p == nullptr) return agc_fail(ctx, AGCGPU_EINVAL, "scan requested before agcgpu_set_splitters");
     std::vector<uint32_t> cp(n_contigs + 1);
     uint32_t total_chunks = 0;

@@ -33,8 +33,9 @@ __device__ __forceinline__ uint64_t last_exc_in(const uint64_t* __restrict__ exc
 __global__ void __launch_bounds__(256) k_enum_kmers(const uint64_t* __restrict__ P, const uint64_t* __restrict__ cstart,
                                                     uint32_t n_contigs, const uint32_t* __restrict__ chunk_prefix, uint32_t total_chunks,
                                                     uint32_t k, const uint64_t* __restrict__ exc_pos, uint64_t n_exc,
-                                                    uint64_t* __restrict__ out)
+                                                    uint64_t* __restrict__ out, uint64_t out_base)
 {
+    out -= out_base;                                 // out[0] belongs to the first base of the first listed contig
     const uint32_t shift = 64 - 2 * k;
     const uint64_t kmask = (~0ULL) << shift;
     for (uint32_t u = blockIdx.x; u < total_chunks; u += gridDim.x) {
@@ -76,6 +77,15 @@ __device__ __forceinline__ bool in_sorted(const uint64_t* __restrict__ v, uint64
     uint64_t a = 0, b = n;
     while (a < b) { uint64_t mid = (a + b) >> 1; if (v[mid] < x) a = mid + 1; else b = mid; }
     return a < n && v[a] == x;
+}
+
+// find_new_splitters' two set_difference passes (agc_compressor.cpp:2066-2076) as one membership test per candidate
+__global__ void k_absent_flags(const uint64_t* __restrict__ cand, uint64_t n, const uint64_t* __restrict__ ref, uint64_t n_ref,
+                               uint8_t* __restrict__ flags)
+{
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    flags[i] = !in_sorted(ref, n_ref, cand[i]);
 }
 
 // one warp per contig
@@ -145,29 +155,37 @@ __global__ void __launch_bounds__(128) k_find_splitters(const uint64_t* __restri
     }
 }
 
-int agc_enumerate_splitters(agcgpu_ctx* ctx, std::vector<uint64_t>& out_sorted)
+int agc_enumerate_splitters(agcgpu_ctx* ctx, uint32_t c0, uint32_t n_contigs, bool exclude_ref, bool keep_kmers, std::vector<uint64_t>& out_sorted)
 {
     out_sorted.clear();
-    const uint32_t k = ctx->prm.kmer_length, n_contigs = ctx->n_contigs;
-    const uint64_t total = ctx->total_bases;
+    const uint32_t k = ctx->prm.kmer_length;
+    if (c0 + n_contigs > ctx->n_contigs) return agc_fail(ctx, AGCGPU_EINVAL, "splitters: contig range outside the resident batch");
+    const uint64_t base0 = n_contigs ? ctx->h_cstart[c0] : 0;
+    const uint64_t total = n_contigs ? ctx->h_cstart[c0 + n_contigs] - base0 : 0;
+    if (keep_kmers && exclude_ref) return agc_fail(ctx, AGCGPU_EINVAL, "splitters: keep_kmers and exclude_ref are exclusive");
+    if (keep_kmers) ctx->n_ref_kmers = 0;
     if (total == 0 || n_contigs == 0) return 0;
+    if (exclude_ref && ctx->n_ref_kmers == 0 && !(ctx->prm.flags & AGCGPU_F_ADAPTIVE))
+        return agc_fail(ctx, AGCGPU_EINVAL, "find_new_splitters needs AGCGPU_F_ADAPTIVE and a reference sample (agcgpu_determine_splitters)");
     std::vector<uint32_t> cp(n_contigs + 1);
     uint32_t total_chunks = 0;
     for (uint32_t c = 0; c < n_contigs; ++c) {
         cp[c] = total_chunks;
-        total_chunks += (uint32_t)((ctx->h_cstart[c + 1] - ctx->h_cstart[c] + AGC_SCAN_CHUNK - 1) / AGC_SCAN_CHUNK);
+        total_chunks += (uint32_t)((ctx->h_cstart[c0 + c + 1] - ctx->h_cstart[c0 + c] + AGC_SCAN_CHUNK - 1) / AGC_SCAN_CHUNK);
     }
     cp[n_contigs] = total_chunks;
     if (int r = agc_reserve(ctx, ctx->chunk_prefix, (n_contigs + 1) * 4)) return r;
     CK(cudaMemcpyAsync(ctx->chunk_prefix.p, cp.data(), (n_contigs + 1) * 4, cudaMemcpyHostToDevice, ctx->st));
-    DevBuf keys_a, keys_b, flags, tmp, nsel;
+    const uint64_t* d_cstart = (const uint64_t*)ctx->d_cstart.p + c0;
+    DevBuf keys_a, keys_b, flags, tmp, nsel, outb;
     int rc = 0;
-    auto cleanup = [&]() { for (DevBuf* b : { &keys_a, &keys_b, &flags, &tmp, &nsel }) if (b->p) { agc_dev_free(ctx->dev, b->p, b->cap + 64); ctx->device_bytes -= b->cap; b->p = nullptr; b->cap = 0; } };
+    auto cleanup = [&]() { for (DevBuf* b : { &keys_a, &keys_b, &flags, &tmp, &nsel, &outb }) if (b->p) { agc_dev_free(ctx->dev, b->p, b->cap + 64); ctx->device_bytes -= b->cap; b->p = nullptr; b->cap = 0; } };
+    uint32_t out_cap = (uint32_t)std::min<uint64_t>(0x7fffffff, total / std::max<uint32_t>(ctx->prm.segment_size, 1) + 2ull * n_contigs + 16);
     if ((rc = agc_reserve(ctx, keys_a, total * 8)) || (rc = agc_reserve(ctx, keys_b, total * 8)) || (rc = agc_reserve(ctx, flags, total)) ||
-        (rc = agc_reserve(ctx, nsel, 64))) { cleanup(); return rc; }
+        (rc = agc_reserve(ctx, nsel, 64)) || (rc = agc_reserve(ctx, outb, (size_t)out_cap * 8))) { cleanup(); return rc; }
     uint32_t grid = std::min<uint32_t>(total_chunks, (uint32_t)ctx->n_sm * 8);
-    k_enum_kmers<<<grid, 256, 0, ctx->st>>>((const uint64_t*)ctx->packed.p, (const uint64_t*)ctx->d_cstart.p, n_contigs,
-        (const uint32_t*)ctx->chunk_prefix.p, total_chunks, k, (const uint64_t*)ctx->exc_pos.p, ctx->n_exc, (uint64_t*)keys_a.p);
+    k_enum_kmers<<<grid, 256, 0, ctx->st>>>((const uint64_t*)ctx->packed.p, d_cstart, n_contigs,
+        (const uint32_t*)ctx->chunk_prefix.p, total_chunks, k, (const uint64_t*)ctx->exc_pos.p, ctx->n_exc, (uint64_t*)keys_a.p, base0);
     ctx->stats.kernel_launches++;
     size_t tb = 0;
     cub::DeviceRadixSort::SortKeys(nullptr, tb, (const uint64_t*)keys_a.p, (uint64_t*)keys_b.p, (uint64_t)total, 0, 64, ctx->st);
@@ -185,17 +203,37 @@ int agc_enumerate_splitters(agcgpu_ctx* ctx, std::vector<uint64_t>& out_sorted)
     cudaError_t e = cudaMemcpyAsync(&n_singles, nsel.p, 8, cudaMemcpyDeviceToHost, ctx->st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->st);
     if (e != cudaSuccess) { cleanup(); return agc_fail(ctx, AGCGPU_ECUDA, "determine_splitters: %s", cudaGetErrorString(e)); }
-    uint32_t out_cap = (uint32_t)std::min<uint64_t>(0x7fffffff, total / std::max<uint32_t>(ctx->prm.segment_size, 1) + 2ull * n_contigs + 16);
-    uint64_t* d_out = (uint64_t*)keys_b.p;           // sorted input no longer needed
+    const uint64_t* d_cand = (const uint64_t*)keys_a.p;
+    if (exclude_ref && n_singles) {
+        // candidates := singletons of these contigs that are not k-mers of the reference sample (sorted order is kept)
+        k_absent_flags<<<(uint32_t)((n_singles + 255) / 256), 256, 0, ctx->st>>>((const uint64_t*)keys_a.p, n_singles,
+            (const uint64_t*)ctx->ref_kmers.p, ctx->n_ref_kmers, (uint8_t*)flags.p);
+        ctx->stats.kernel_launches++;
+        size_t tb3 = 0;
+        cub::DeviceSelect::Flagged(nullptr, tb3, (const uint64_t*)keys_a.p, (const uint8_t*)flags.p, (uint64_t*)keys_b.p, (uint64_t*)nsel.p, (int64_t)n_singles, ctx->st);
+        if ((rc = agc_reserve(ctx, tmp, tb3 + 256))) { cleanup(); return rc; }
+        cub::DeviceSelect::Flagged(tmp.p, tb3, (const uint64_t*)keys_a.p, (const uint8_t*)flags.p, (uint64_t*)keys_b.p, (uint64_t*)nsel.p, (int64_t)n_singles, ctx->st);
+        ctx->stats.kernel_launches++;
+        e = cudaMemcpyAsync(&n_singles, nsel.p, 8, cudaMemcpyDeviceToHost, ctx->st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->st);
+        if (e != cudaSuccess) { cleanup(); return agc_fail(ctx, AGCGPU_ECUDA, "find_new_splitters: %s", cudaGetErrorString(e)); }
+        d_cand = (const uint64_t*)keys_b.p;
+    }
+    uint64_t* d_out = (uint64_t*)outb.p;
     uint32_t* d_cnt = (uint32_t*)nsel.p + 4;
     cudaMemsetAsync(nsel.p, 0, 64, ctx->st);
-    k_find_splitters<<<(n_contigs + 3) / 4, 128, 0, ctx->st>>>((const uint64_t*)ctx->packed.p, (const uint64_t*)ctx->d_cstart.p, n_contigs, k,
-        ctx->prm.segment_size, (const uint64_t*)keys_a.p, n_singles, (const uint64_t*)ctx->exc_pos.p, ctx->n_exc, d_out, d_cnt, out_cap);
+    k_find_splitters<<<(n_contigs + 3) / 4, 128, 0, ctx->st>>>((const uint64_t*)ctx->packed.p, d_cstart, n_contigs, k,
+        ctx->prm.segment_size, d_cand, n_singles, (const uint64_t*)ctx->exc_pos.p, ctx->n_exc, d_out, d_cnt, out_cap);
     ctx->stats.kernel_launches++;
     uint32_t cnt = 0;
     e = cudaMemcpyAsync(&cnt, d_cnt, 4, cudaMemcpyDeviceToHost, ctx->st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->st);
     if (e == cudaSuccess && cnt <= out_cap && cnt) { out_sorted.resize(cnt); e = cudaMemcpy(out_sorted.data(), d_out, (size_t)cnt * 8, cudaMemcpyDeviceToHost); }
+    if (keep_kmers && e == cudaSuccess) {                  // the sorted k-mer list of the reference sample stays on the device
+        if (ctx->ref_kmers.p) { agc_dev_free(ctx->dev, ctx->ref_kmers.p, ctx->ref_kmers.cap + 64); ctx->device_bytes -= ctx->ref_kmers.cap; }
+        ctx->ref_kmers = keys_b; keys_b.p = nullptr; keys_b.cap = 0;
+        ctx->n_ref_kmers = total;
+    }
     cleanup();
     if (e != cudaSuccess) return agc_fail(ctx, AGCGPU_ECUDA, "determine_splitters: %s", cudaGetErrorString(e));
     if (cnt > out_cap) return agc_fail(ctx, AGCGPU_EUNSUPPORTED, "determine_splitters: too many splitters");

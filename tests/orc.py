@@ -188,3 +188,19 @@ def ref_cost_vector(refcodes, text, mml, prefix) -> np.ndarray:
     out = np.empty(len(t) + 1, np.uint32)
     n = ref().ref_lz_cost_vector(_p8(r), len(r), _p8(t), len(t), mml, int(prefix), out.ctypes.data_as(u32p))
     return out[:n].copy()
+
+
+def enumerate_kmers(codes, k):
+    codes = np.ascontiguousarray(codes, np.uint8)
+    out = np.empty(len(codes) + 1, np.uint64)
+    n = oracle().orc_enumerate_kmers(_p8(codes), len(codes), k, out.ctypes.data_as(u64p))
+    return out[:n].copy()
+
+
+def find_new_splitters(codes, k, segment_size, ref_kmers_sorted):
+    """-a mode: CAGCCompressor::find_new_splitters for one contig; ref_kmers_sorted = every k-mer of the reference sample"""
+    codes = np.ascontiguousarray(codes, np.uint8)
+    rk = np.ascontiguousarray(ref_kmers_sorted, np.uint64)
+    out = np.empty(len(codes) + 2, np.uint64)
+    n = oracle().orc_find_new_splitters(_p8(codes), len(codes), k, segment_size, rk.ctypes.data_as(u64p), len(rk), out.ctypes.data_as(u64p))
+    return out[:n].copy()

@@ -216,6 +216,42 @@ def test_determine_splitters(dev_factory):
         assert np.array_equal(got, exp), (k, seg, len(got), len(exp))
 
 
+def test_find_new_splitters_and_rescan(dev_factory):
+    """-a mode entry points: new splitters of resident contigs that share no splitter with the reference, then the scan
+    of the resident batch again under the grown set (agc_compressor.cpp:2054-2082, 1187-1229)"""
+    rng = np.random.default_rng(21)
+    for k, seg in ((21, 700), (31, 4000)):
+        dev = dev_factory(k=k, min_match_len=20, segment_size=seg, adaptive=True)
+        ref = [rng.integers(0, 4, n).astype(np.uint8) for n in (30000, 9000)]
+        ref[0][3000:3600] = ref[0][12000:12600]                     # duplicated reference k-mers (v_duplicated_kmers)
+        spl, _ = orc.determine_splitters(ref, k, seg)
+        got = dev.determine_splitters([to_fasta_body(c, 70) for c in ref])
+        assert np.array_equal(got, spl)
+        ref_kmers = np.sort(np.concatenate([orc.enumerate_kmers(c, k) for c in ref]))
+        novel = rng.integers(0, 4, 5 * seg + 123).astype(np.uint8)
+        half = novel.copy(); half[:2 * seg] = ref[0][3000:3000 + 2 * seg]      # starts with reference sequence (incl. the duplicated part)
+        withn = mutate(rng, rng.integers(0, 4, 3 * seg).astype(np.uint8), 0, 0, 4)
+        rep = np.tile(rng.integers(0, 4, seg // 2).astype(np.uint8), 5)         # every k-mer occurs 5 times: no singleton
+        batch = [mutate(rng, ref[0], 0.01, 2), novel, half, withn, rep, rng.integers(0, 4, k - 1).astype(np.uint8), mutate(rng, ref[1], 0.002, 0)]
+        cuts0 = dev.scan_contigs([to_fasta_body(c, 60) for c in batch])
+        for c, codes in enumerate(batch):
+            assert [(x.start, x.len) for x in cuts0 if x.contig == c] == [(x.start, x.len) for x in orc.scan_contig(codes, k, spl)]
+        per = [orc.find_new_splitters(codes, k, seg, ref_kmers) for codes in batch]
+        for c in (1, 2, 3, 4, 5):
+            assert np.array_equal(dev.find_new_splitters([c]), np.unique(per[c])), (k, seg, c)
+        assert len(per[1]) >= 4 and len(per[4]) == 0
+        new = dev.find_new_splitters([1, 2, 3, 4])
+        assert np.array_equal(new, np.unique(np.concatenate([per[c] for c in (1, 2, 3, 4)])))
+        grown = np.union1d(spl, new)
+        dev.set_splitters(grown)
+        cuts1 = dev.rescan_contigs()
+        for c, codes in enumerate(batch):
+            exp = orc.scan_contig(codes, k, grown)
+            gotc = [x for x in cuts1 if x.contig == c]
+            assert [(x.start, x.len, x.has_front, x.has_back, x.front_dir, x.back_dir, x.back_rc) for x in gotc] == \
+                   [(x.start, x.len, x.has_front, x.has_back, x.front_dir if x.has_front else 0, x.back_dir if x.has_back else 0, x.back_rc if x.has_back else 0) for x in exp], (k, seg, c)
+
+
 def test_assign(dev_factory):
     rng = np.random.default_rng(15)
     k = 25

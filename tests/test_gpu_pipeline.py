@@ -12,6 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 import gen_data
 import agc_parts
+from test_host_pipeline import collection, ALL_CASES
 
 pytestmark = pytest.mark.gpu
 
@@ -27,30 +28,10 @@ def _run_both(tmp, files, flags):
 
 
 @pytest.mark.skipif(not os.path.exists(REF_AGC), reason="reference binary not built (make -f oracle/Makefile.ref)")
-@pytest.mark.parametrize("case", ["viral", "complex", "complex_n", "tiny", "smallpacks"])
+@pytest.mark.parametrize("case", ALL_CASES)
 def test_parts_match_reference(tmp_path, case):
     tmp = str(tmp_path)
-    if case == "viral":
-        files, _ = gen_data.viral(os.path.join(tmp, "d"), n_samples=40, ref_len=30000, p=0.01, seed=1)
-        flags = ["-k", "25"]
-    elif case == "complex":
-        files = gen_data.complex_collection(os.path.join(tmp, "d"), seed=5)
-        flags = ["-k", "21", "-s", "2000", "-b", "5"]
-    elif case == "complex_n":
-        files = gen_data.complex_collection(os.path.join(tmp, "d"), seed=6, with_n=True)
-        flags = ["-k", "31", "-s", "3000", "-l", "18", "-b", "4"]
-    elif case == "tiny":
-        rng = np.random.default_rng(3)
-        d = os.path.join(tmp, "d"); os.makedirs(d)
-        files = []
-        for i, nm in enumerate(["ref", "a", "b", "c"]):
-            fn = os.path.join(d, nm + ".fa")
-            gen_data.write_fasta(fn, [(f"{nm}{j}", rng.integers(0, 4, int(rng.integers(5, 28)), dtype=np.uint8)) for j in range(1 + i)])
-            files.append(fn)
-        flags = ["-k", "29", "-l", "22"]
-    else:
-        files, _ = gen_data.viral(os.path.join(tmp, "d"), n_samples=25, ref_len=9000, p=0.02, seed=9)
-        flags = ["-k", "17", "-s", "1000", "-b", "3", "-l", "15"]
+    files, flags = collection(case, tmp)          # the same collections the CPU suite runs through the mocked device ABI
     bad = _run_both(tmp, files, flags)
     assert not bad, "\n".join(bad[:10])
     # and the real thing: the archive written through the device residual coder is byte-identical to the reference's
