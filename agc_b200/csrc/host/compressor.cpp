@@ -351,8 +351,8 @@ bool CAGCCompressor::Create(const std::string& file_name, uint32_t _pack_cardina
     pack_cardinality = _pack_cardinality; kmer_length = _kmer_length; min_match_len = _min_match_len;
     segment_size = _segment_size; verbosity = _verbosity;
     concatenated_genomes = _concatenated_genomes; adaptive_compression = _adaptive_compression;
-    if (concatenated_genomes || fallback_frac != 0.0)
-        return fail("agc-b200: -c / -f are not implemented on the GPU path yet (refusing rather than falling back)");
+    if (fallback_frac != 0.0)
+        return fail("agc-b200: -f is not implemented on the GPU path yet (refusing rather than falling back)");
     agcgpu_params prm; memset(&prm, 0, sizeof prm);
     prm.kmer_length = kmer_length; prm.min_match_len = min_match_len; prm.segment_size = segment_size;
     prm.pack_cardinality = pack_cardinality; prm.device = device;
@@ -515,6 +515,9 @@ bool CAGCCompressor::AddSampleFiles(std::vector<std::pair<std::string, std::stri
     std::vector<std::vector<uint8_t>> raws;
     std::vector<BatchContig> owners;
     uint64_t raw_in_batch = 0;
+    // -c: every contig is its own sample (named after the contig) and the synchronisation tokens come every
+    // pack_cardinality contigs, across files (agc_compressor.cpp:2148-2156, 2180-2199)
+    uint32_t cnt_contigs_in_sample = concatenated_genomes ? processed_samples % pack_cardinality : 0, unit = 0;
     for (auto& sf : files) {
         collection.reset_prev_sample_name();
         CGenomeIO gio;
@@ -523,9 +526,21 @@ bool CAGCCompressor::AddSampleFiles(std::vector<std::pair<std::string, std::stri
         bool any_read = false, any_added = false;
         while (gio.ReadContigRaw(id, contig)) {
             any_read = true;
-            if (collection.register_sample_contig(sf.first, id)) {
+            if (concatenated_genomes) {
+                if (!collection.register_sample_contig("", id)) { std::cerr << "Error: Pair sample_name:contig_name " << id << ":" << id << " is already in the archive!\n"; continue; }
                 uint32_t sid = (uint32_t)collection.sample_desc.size() - 1;
-                owners.push_back(BatchContig{ sid, (uint32_t)collection.sample_desc[sid].contigs.size() - 1 });
+                owners.push_back(BatchContig{ sid, (uint32_t)collection.sample_desc[sid].contigs.size() - 1, unit });
+                raw_in_batch += contig.size();
+                raws.emplace_back(std::move(contig));
+                contig.clear();
+                any_added = true;
+                if (++cnt_contigs_in_sample >= pack_cardinality) {
+                    cnt_contigs_in_sample = 0; ++unit;
+                    if (raw_in_batch >= batch_bases || adaptive_compression) { if (!process_batch(raws, owners)) return false; raws.clear(); owners.clear(); raw_in_batch = 0; }
+                }
+            } else if (collection.register_sample_contig(sf.first, id)) {
+                uint32_t sid = (uint32_t)collection.sample_desc.size() - 1;
+                owners.push_back(BatchContig{ sid, (uint32_t)collection.sample_desc[sid].contigs.size() - 1, sid });
                 raw_in_batch += contig.size();
                 raws.emplace_back(std::move(contig));
                 contig.clear();
@@ -536,12 +551,17 @@ bool CAGCCompressor::AddSampleFiles(std::vector<std::pair<std::string, std::stri
         if (!any_added) std::cerr << "Warning: Pair sample_name:file_path " << sf.first << ":" << sf.second << " contains only contigs already present in the archive!\n";
         // -a: the splitter set may grow at every sample's synchronisation point (new_splitters stage, 1187-1229), so a
         // device batch is one sample
-        if (raw_in_batch >= batch_bases || (adaptive_compression && !raws.empty())) {
+        if (!concatenated_genomes && (raw_in_batch >= batch_bases || (adaptive_compression && !raws.empty()))) {
             if (!process_batch(raws, owners)) return false;
             raws.clear(); owners.clear(); raw_in_batch = 0;
         }
     }
+    // -c: one more token after the last file (2241-2249), sent even when the last unit is complete -- the registration it
+    // triggers is then empty but still runs the processed_samples bookkeeping (1142-1156)
+    const bool trailing_empty_unit = concatenated_genomes && (owners.empty() || owners.back().unit != unit);
     if (!raws.empty()) if (!process_batch(raws, owners)) return false;
+    if (trailing_empty_unit) { account_registration(); if (!flush_jobs(false)) return false; }
+    if (concatenated_genomes) processed_samples = (uint32_t)collection.get_no_samples();        // 2255-2256
     if (processed_samples % pack_cardinality != 0)                                     // agc_compressor.cpp:2258-2259
         store_contig_batch((processed_samples / pack_cardinality) * pack_cardinality, processed_samples, epoch);
     ++epoch;
@@ -561,10 +581,24 @@ bool CAGCCompressor::process_batch(std::vector<std::vector<uint8_t>>& raws, std:
     return process_batch_raw(cat.data(), false, offs, owners);
 }
 
+// what the registration token does once the segments are stored (agc_compressor.cpp:1136-1179)
+void CAGCCompressor::account_registration()
+{
+    if (!concatenated_genomes) ++processed_samples;
+    else {
+        processed_samples = processed_samples / pack_cardinality * pack_cardinality + pack_cardinality;
+        const uint32_t max_ps = (uint32_t)collection.get_no_samples();
+        if (max_ps < processed_samples) processed_samples = max_ps;
+    }
+    if (processed_samples % pack_cardinality == 0) store_contig_batch(processed_samples - pack_cardinality, processed_samples, epoch);
+    ++epoch;
+}
+
 bool CAGCCompressor::AddSamplesFromMemory(const std::vector<std::string>& sample_names, const std::vector<uint32_t>& sample_of_contig,
                                           const std::vector<std::string>& contig_ids, const uint8_t* raw, const uint64_t* offsets, bool raw_is_device)
 {
     if (!working) return false;
+    if (concatenated_genomes) return fail("agc-b200: -c is only implemented for AddSampleFiles");
     std::vector<BatchContig> owners;
     uint32_t prev = ~0u;
     for (size_t i = 0; i < contig_ids.size(); ++i) {
@@ -572,7 +606,7 @@ bool CAGCCompressor::AddSamplesFromMemory(const std::vector<std::string>& sample
         if (!collection.register_sample_contig(sample_names[sample_of_contig[i]], contig_ids[i]))
             return fail("Error: Pair sample_name:contig_name " + sample_names[sample_of_contig[i]] + ":" + contig_ids[i] + " is already in the archive!");
         uint32_t sid = (uint32_t)collection.sample_desc.size() - 1;
-        owners.push_back(BatchContig{ sid, (uint32_t)collection.sample_desc[sid].contigs.size() - 1 });
+        owners.push_back(BatchContig{ sid, (uint32_t)collection.sample_desc[sid].contigs.size() - 1, sid });
     }
     std::vector<uint64_t> offs(offsets, offsets + contig_ids.size() + 1);
     if (!adaptive_compression) { if (!process_batch_raw(raw, raw_is_device, offs, owners)) return false; }
@@ -784,13 +818,14 @@ bool CAGCCompressor::process_batch_raw(const uint8_t* cat, bool is_device, const
 
     uint32_t ci = 0;
     while (ci < nc) {
-        const uint32_t sid = owners[ci].sample_id;
+        const uint32_t unit = owners[ci].unit;           // contigs registered together: one sample, or (-c) pack_cardinality contigs
         uint32_t cj = ci;
-        while (cj < nc && owners[cj].sample_id == sid) ++cj;
+        while (cj < nc && owners[cj].unit == unit) ++cj;
         std::vector<Item> known, fresh;
         // ---- add_segment for every cut of the sample (agc_compressor.cpp:1275-1499)
         for (uint32_t bc = ci; bc < cj; ++bc) {
             uint32_t part_no = 0;
+            const uint32_t sid = owners[bc].sample_id;
             const std::string* cname = &collection.sample_desc[sid].contigs[owners[bc].contig_idx].name;
             for (uint64_t x = cut_first[bc]; x < cut_first[bc + 1]; ++x) {
                 const agcgpu_cut& cut = cuts[x];
@@ -817,7 +852,7 @@ bool CAGCCompressor::process_batch_raw(const uint8_t* cat, bool is_device, const
                 else { p = map_segments.find(pk); found = p != map_segments.end(); }
                 if (found && p == map_segments.end()) return fail("internal: device and host segment maps disagree");
                 int32_t segment_id = -1, segment_id2 = -1;
-                if (p == map_segments.end() && pk.first != EMPTY && pk.second != EMPTY &&
+                if (!concatenated_genomes && p == map_segments.end() && pk.first != EMPTY && pk.second != EMPTY &&
                     map_segments_terminators.count(pk.first) && map_segments_terminators.count(pk.second)) {
                     if (fc == bcn) { if (!(cut.front_dir <= cut.front_rc)) store_rc = true; }
                     else {
@@ -859,7 +894,7 @@ bool CAGCCompressor::process_batch_raw(const uint8_t* cat, bool is_device, const
         std::stable_sort(fresh.begin(), fresh.end(), item_less);
         fresh.erase(std::unique(fresh.begin(), fresh.end(), [](const Item& a, const Item& b) {
             return *a.contig_name == *b.contig_name && a.seg_part_no == b.seg_part_no; }), fresh.end());    // std::set semantics
-        SampleReg reg; reg.sample_id = sid;
+        SampleReg reg; reg.sample_id = unit;
         std::map<uint32_t, std::vector<Item>> by_group;
         for (auto& it : known) by_group[(uint32_t)it.group].push_back(it);
         for (auto& kv : by_group) std::sort(kv.second.begin(), kv.second.end(), item_less);            // sort_known
@@ -997,9 +1032,7 @@ bool CAGCCompressor::process_batch_raw(const uint8_t* cat, bool is_device, const
                 collection.add_segment_placed(it.sample_id, it.contig_idx, it.seg_part_no, d);
             }
         }
-        ++processed_samples;                                                       // agc_compressor.cpp:1162-1179
-        if (processed_samples % pack_cardinality == 0) store_contig_batch(processed_samples - pack_cardinality, processed_samples, epoch);
-        ++epoch;
+        account_registration();
     }
     return flush_jobs(false);
 }

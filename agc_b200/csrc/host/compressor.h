@@ -143,7 +143,8 @@ private:
         bool exists = false;
         uint32_t ref_size = 0;                       // symbols + 1 (segment.cpp:47)
     };
-    struct BatchContig { uint32_t sample_id, contig_idx; };
+    struct BatchContig { uint32_t sample_id, contig_idx; uint32_t unit = 0; };   // unit: contigs registered at the same synchronisation token
+    void account_registration();
 
     bool fail(const std::string& msg);
     bool gpu_ok(int rc, const char* what);

@@ -47,10 +47,17 @@ def collection(case, tmp):
         return gen_data.adaptive_collection(d, seed=7, n_samples=6, ref_len=120000, n_ctg=3, novel_len=30000), ["-a", "-k", "29", "-s", "10000"]
     if case == "adaptive_complex":  # -a on a collection whose novel contigs are mostly shorter than segment_size
         return gen_data.complex_collection(d, seed=5), ["-a", "-k", "21", "-s", "2000", "-b", "5"]
+    if case == "concatenated":      # -c: 3 + 23 contigs, units of 5, a partial last unit
+        return gen_data.concatenated_collection(d, seed=1, n_ctg=23, per_file=9), ["-c", "-k", "21", "-s", "2000", "-b", "5"]
+    if case == "concatenated_full_units":   # 3 + 17 = 20 contigs = 5 complete units: the trailing token registers nothing (1142-1156)
+        return gen_data.concatenated_collection(d, seed=2, n_ctg=17, per_file=6), ["-c", "-k", "21", "-s", "2000", "-b", "4"]
+    if case == "concatenated_adaptive":
+        return gen_data.concatenated_collection(d, seed=3, n_ctg=22, per_file=8), ["-c", "-a", "-k", "21", "-s", "2000", "-b", "6"]
     raise KeyError(case)
 
 
-ALL_CASES = ["viral", "complex", "complex_n", "tiny", "smallpacks", "adaptive", "adaptive_big_segments", "adaptive_complex"]
+ALL_CASES = ["viral", "complex", "complex_n", "tiny", "smallpacks", "adaptive", "adaptive_big_segments", "adaptive_complex",
+             "concatenated", "concatenated_full_units", "concatenated_adaptive"]
 
 
 @pytest.fixture(scope="module")
@@ -76,6 +83,6 @@ def test_host_pipeline_archives_match_reference(tmp_path, mock_agc, case):
 
 def test_refused_modes_fail_loudly(tmp_path, mock_agc):
     files, flags = collection("tiny", str(tmp_path))
-    for extra in (["-c"], ["-f", "0.1"]):
+    for extra in (["-f", "0.1"],):
         r = subprocess.run([mock_agc, "create", "-o", os.path.join(str(tmp_path), "x.agc")] + extra + flags + files, capture_output=True)
         assert r.returncode != 0 and b"not implemented" in r.stderr

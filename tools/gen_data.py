@@ -95,6 +95,31 @@ def complex_collection(out_dir, seed=5, n_samples=12, ctg_len=40000, n_ctg=3, wi
     return files
 
 
+def concatenated_collection(out_dir, seed=1, n_ctg=23, per_file=9):
+    """-c mode: multi-genome FASTA files; every contig becomes a sample of its own (named after the contig) and the
+    registration points come every pack_cardinality contigs, across file boundaries (agc_compressor.cpp:2180-2199)."""
+    os.makedirs(out_dir, exist_ok=True)
+    rng = np.random.default_rng(seed)
+    ref = [rng.integers(0, 4, 20000 + 500 * i, dtype=np.uint8) for i in range(3)]
+    files = [os.path.join(out_dir, "ref.fa")]
+    write_fasta(files[0], [(f"chr{i + 1} desc", c) for i, c in enumerate(ref)])
+    ctgs = []
+    for j in range(n_ctg):
+        t = indels(rng, substitute(rng, ref[j % 3], [0, 0.001, 0.02][j % 3]), j % 4)
+        if j % 5 == 1:
+            t = (3 - t[::-1]).astype(np.uint8)
+        if j % 7 == 3:
+            t = np.concatenate([t[:3000], t[9000:]])          # deleted splitters: no missing-middle split in -c mode (1366)
+        if j % 11 == 4:
+            t = rng.integers(0, 4, 3000, dtype=np.uint8)
+        ctgs.append((f"g{j:03d} genome {j}", t))
+    for f in range(0, n_ctg, per_file):
+        fn = os.path.join(out_dir, f"part{f:03d}.fa")
+        write_fasta(fn, ctgs[f:f + per_file])
+        files.append(fn)
+    return files
+
+
 def total_bases(files):
     n = 0
     for fn in files:
