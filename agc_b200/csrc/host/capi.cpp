@@ -15,8 +15,16 @@ namespace { struct CallTimer {
 struct agcgpu_compressor { agc_b200::CAGCCompressor impl; std::string err; };
 static thread_local std::string g_err;
 static agcgpu_stats g_last_stats = {};
+static struct { uint32_t rank = 0, world = 1; agcgpu_allgather_fn fn = nullptr; void* user = nullptr; } g_exchange;
 
 extern "C" {
+
+int agcgpu_set_exchange(uint32_t rank, uint32_t world, agcgpu_allgather_fn allgather, void* user)
+{
+    if (allgather && world > 1 && rank >= world) return AGCGPU_EINVAL;
+    g_exchange.rank = rank; g_exchange.world = world; g_exchange.fn = allgather; g_exchange.user = user;
+    return 0;
+}
 
 int agcgpu_compressor_create(const char* out_file, uint32_t pack_cardinality, uint32_t kmer_length, const char* reference_file,
                              uint32_t segment_size, uint32_t min_match_len, int concatenated_genomes, int adaptive_compression,
@@ -28,6 +36,7 @@ int agcgpu_compressor_create(const char* out_file, uint32_t pack_cardinality, ui
     agcgpu_compressor* c = new agcgpu_compressor();
     c->impl.SetAppMode(false);
     c->impl.SetDevice(device);
+    c->impl.SetExchange(g_exchange.rank, g_exchange.world, g_exchange.fn, g_exchange.user);
     if (dump_parts_path && *dump_parts_path) c->impl.SetDumpParts(dump_parts_path);
     if (!c->impl.Create(out_file, pack_cardinality, kmer_length, reference_file, segment_size, min_match_len,
                         concatenated_genomes != 0, adaptive_compression != 0, verbosity, no_threads, fallback_frac)) {

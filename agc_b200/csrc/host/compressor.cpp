@@ -381,7 +381,8 @@ bool CAGCCompressor::Create(const std::string& file_name, uint32_t _pack_cardina
         dump_f = fopen(dump_path.c_str(), "wb");
         if (!dump_f) return fail("cannot open dump file " + dump_path);
     }
-    if (!out_archive.Open(file_name)) return fail("Cannot create archive " + file_name);
+    // multi-GPU: every rank keeps the identical bookkeeping, rank 0 alone owns the output file
+    if (!out_archive.Open(xrank == 0 ? file_name : std::string("/dev/null"))) return fail("Cannot create archive " + file_name);
     working = true;
     collection.set_params(pack_cardinality, segment_size, kmer_length);
     collection_samples_id = out_archive.RegisterStream("collection-samples");      // collection_v3.cpp:38-45
@@ -435,7 +436,100 @@ void CAGCCompressor::store_contig_batch(uint32_t id_from, uint32_t id_to, uint64
     collection.clear_batch(id_from, id_to);
 }
 
+// variable-size all-gather over the fixed-size primitive: sizes first, then blocks padded to the largest
+bool CAGCCompressor::exchange(const std::vector<uint8_t>& mine, std::vector<std::vector<uint8_t>>& all)
+{
+    all.assign(xworld, {});
+    uint64_t sz = mine.size();
+    std::vector<uint64_t> sizes(xworld, 0);
+    if (xfn(xuser, &sz, sizes.data(), 8)) return fail("exchange: all-gather of the block sizes failed");
+    if (sizes[xrank] != sz) return fail("exchange: all-gather returned a wrong block for this rank");
+    uint64_t mx = *std::max_element(sizes.begin(), sizes.end());
+    if (mx == 0) return true;
+    std::vector<uint8_t> send(mx, 0), recv(mx * xworld);
+    if (sz) memcpy(send.data(), mine.data(), sz);
+    if (xfn(xuser, send.data(), recv.data(), mx)) return fail("exchange: all-gather failed");
+    for (uint32_t r = 0; r < xworld; ++r) all[r].assign(recv.begin() + r * mx, recv.begin() + r * mx + sizes[r]);
+    return true;
+}
+
+// residual coder over all ranks: the frames of a drain are dealt out by size (largest first, round-robin), coded where
+// they land and all-gathered; every rank ends up with every frame (only rank 0 writes them)
 bool CAGCCompressor::compress_tasks(std::vector<ZTask*>& tasks)
+{
+    if (xworld <= 1 || tasks.empty()) return compress_tasks_local(tasks);
+    std::vector<size_t> order(tasks.size());
+    std::iota(order.begin(), order.end(), (size_t)0);
+    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return tasks[a]->raw.size() > tasks[b]->raw.size(); });
+    std::vector<ZTask*> mine;
+    for (size_t i = xrank; i < order.size(); i += xworld) mine.push_back(tasks[order[i]]);
+    if (!compress_tasks_local(mine)) return false;
+    std::vector<uint8_t> blob;
+    for (auto* t : mine) { uint64_t n = t->packed.size(); const uint8_t* p = (const uint8_t*)&n; blob.insert(blob.end(), p, p + 8); blob.insert(blob.end(), t->packed.begin(), t->packed.end()); }
+    std::vector<std::vector<uint8_t>> all;
+    if (!exchange(blob, all)) return false;
+    for (uint32_t r = 0; r < xworld; ++r) {
+        size_t o = 0;
+        for (size_t i = r; i < order.size(); i += xworld) {
+            uint64_t n;
+            if (o + 8 > all[r].size()) return fail("exchange: truncated frame block");
+            memcpy(&n, all[r].data() + o, 8); o += 8;
+            if (o + n > all[r].size()) return fail("exchange: truncated frame block");
+            if (r != xrank) tasks[order[i]]->packed.assign(all[r].begin() + o, all[r].begin() + o + n);
+            o += n;
+        }
+    }
+    return true;
+}
+
+bool CAGCCompressor::lz_encode_local(const agcgpu_seg_req* lz, size_t n, std::vector<uint8_t>& deltas, std::vector<uint64_t>& doffs)
+{
+    doffs.assign(n + 1, 0);
+    deltas.clear();
+    if (!n) return true;
+    uint64_t cap = 64; for (size_t i = 0; i < n; ++i) cap += (uint64_t)lz[i].len * 3 / 2 + 32;
+    // the ABI wants a buffer large enough for the worst case; typical deltas are ~1% of that, so try small first
+    uint64_t try_cap = std::max<uint64_t>(cap / 16, 1 << 20);
+    deltas.resize(try_cap);
+    int rc2 = agcgpu_lz_encode_batch(ctx, lz, (uint32_t)n, deltas.data(), try_cap, doffs.data());
+    if (rc2 == AGCGPU_EOVERFLOW) { deltas.resize(cap); rc2 = agcgpu_lz_encode_batch(ctx, lz, (uint32_t)n, deltas.data(), cap, doffs.data()); }
+    return gpu_ok(rc2, "lz_encode_batch");
+}
+
+// LZ-diff encoding over all ranks: contiguous runs of requests (they are grouped by reference), balanced by bases
+bool CAGCCompressor::lz_encode(std::vector<agcgpu_seg_req>& lz, std::vector<uint8_t>& deltas, std::vector<uint64_t>& doffs)
+{
+    if (xworld <= 1 || lz.empty()) return lz_encode_local(lz.data(), lz.size(), deltas, doffs);
+    std::vector<uint64_t> cum(lz.size() + 1, 0);
+    for (size_t i = 0; i < lz.size(); ++i) cum[i + 1] = cum[i] + lz[i].len + 64;
+    std::vector<size_t> cutp(xworld + 1, lz.size());
+    cutp[0] = 0;
+    for (uint32_t r = 1; r < xworld; ++r)
+        cutp[r] = std::lower_bound(cum.begin(), cum.end(), cum.back() / xworld * r) - cum.begin();
+    for (uint32_t r = 1; r <= xworld; ++r) if (cutp[r] < cutp[r - 1]) cutp[r] = cutp[r - 1];
+    cutp[xworld] = lz.size();
+    const size_t lo = cutp[xrank], hi = cutp[xrank + 1];
+    std::vector<uint8_t> my_d; std::vector<uint64_t> my_o;
+    if (!lz_encode_local(lz.data() + lo, hi - lo, my_d, my_o)) return false;
+    std::vector<uint8_t> blob((hi - lo + 1) * 8 + my_o.back());
+    memcpy(blob.data(), my_o.data(), (hi - lo + 1) * 8);
+    if (my_o.back()) memcpy(blob.data() + (hi - lo + 1) * 8, my_d.data(), my_o.back());
+    std::vector<std::vector<uint8_t>> all;
+    if (!exchange(blob, all)) return false;
+    doffs.assign(lz.size() + 1, 0); deltas.clear();
+    for (uint32_t r = 0; r < xworld; ++r) {
+        const size_t n = cutp[r + 1] - cutp[r];
+        if (all[r].size() < (n + 1) * 8) return fail("exchange: truncated delta block");
+        const uint64_t* o = (const uint64_t*)all[r].data();
+        if (all[r].size() != (n + 1) * 8 + o[n]) return fail("exchange: delta block has the wrong size");
+        const uint64_t base = deltas.size();
+        for (size_t i = 0; i < n; ++i) doffs[cutp[r] + i + 1] = base + o[i + 1];
+        deltas.insert(deltas.end(), all[r].begin() + (n + 1) * 8, all[r].end());
+    }
+    return true;
+}
+
+bool CAGCCompressor::compress_tasks_local(std::vector<ZTask*>& tasks)
 {
     PhaseTimer pt("residual coder batch");
     if (tasks.empty()) return true;
@@ -971,16 +1065,8 @@ bool CAGCCompressor::process_batch_raw(const uint8_t* cat, bool is_device, const
             }
         }
     }
-    std::vector<uint8_t> deltas; std::vector<uint64_t> doffs(lz.size() + 1, 0);
-    if (!lz.empty()) {
-        uint64_t cap = 64; for (auto& q : lz) cap += (uint64_t)q.len * 3 / 2 + 32;
-        // the ABI wants a buffer large enough for the worst case; typical deltas are ~1% of that, so try small first
-        uint64_t try_cap = std::max<uint64_t>(cap / 16, 1 << 20);
-        deltas.resize(try_cap);
-        int rc2 = agcgpu_lz_encode_batch(ctx, lz.data(), (uint32_t)lz.size(), deltas.data(), try_cap, doffs.data());
-        if (rc2 == AGCGPU_EOVERFLOW) { deltas.resize(cap); rc2 = agcgpu_lz_encode_batch(ctx, lz.data(), (uint32_t)lz.size(), deltas.data(), cap, doffs.data()); }
-        if (!gpu_ok(rc2, "lz_encode_batch")) return false;
-    }
+    std::vector<uint8_t> deltas; std::vector<uint64_t> doffs;
+    if (!lz_encode(lz, deltas, doffs)) return false;
     // reference payloads (tuples or raw symbols) of the groups created in this batch
     std::vector<uint8_t> refpay; std::vector<uint64_t> roffs(ref_groups.size() + 1, 0); std::vector<uint8_t> ruse(ref_groups.size() + 1, 0);
     if (!ref_groups.empty()) {

@@ -124,6 +124,8 @@ public:
     void SetAppMode(bool m) { is_app_mode = m; }
     void SetDumpParts(const std::string& path) { dump_path = path; }   // test hook: write every part's pre-zstd content
     void SetBatchBases(uint64_t b) { batch_bases = b; }
+    // multi-GPU (include/agcgpu.h, agcgpu_set_exchange): this object is rank `rank` of `world` identical ones
+    void SetExchange(uint32_t rank, uint32_t world, agcgpu_allgather_fn fn, void* user) { xrank = rank; xworld = fn && world > 1 ? world : 1; xfn = fn; xuser = user; }
     const std::string& LastError() const { return last_error; }
     uint64_t TotalBases() const { return total_bases; }
     agcgpu_ctx* Ctx() { return ctx; }
@@ -152,6 +154,10 @@ private:
     bool process_batch_raw(const uint8_t* cat, bool is_device, const std::vector<uint64_t>& offs, std::vector<BatchContig>& owners);
     bool flush_jobs(bool final_flush);
     bool compress_tasks(std::vector<ZTask*>& tasks);
+    bool compress_tasks_local(std::vector<ZTask*>& tasks);
+    bool exchange(const std::vector<uint8_t>& mine, std::vector<std::vector<uint8_t>>& all);
+    bool lz_encode(std::vector<agcgpu_seg_req>& lz, std::vector<uint8_t>& deltas, std::vector<uint64_t>& doffs);
+    bool lz_encode_local(const agcgpu_seg_req* lz, size_t n, std::vector<uint8_t>& deltas, std::vector<uint64_t>& doffs);
     void add_job(PartJob&& j);
     void store_pack(uint32_t group_id, GroupState& g, uint64_t epoch);
     void store_contig_batch(uint32_t id_from, uint32_t id_to, uint64_t epoch);
@@ -161,6 +167,7 @@ private:
     uint32_t pack_cardinality = 50, kmer_length = 31, min_match_len = 20, segment_size = 60000, verbosity = 0;
     bool concatenated_genomes = false, adaptive_compression = false, is_app_mode = true;
     int device = 0;
+    uint32_t xrank = 0, xworld = 1; agcgpu_allgather_fn xfn = nullptr; void* xuser = nullptr;
     uint64_t batch_bases = 1ull << 30;
     std::string dump_path, last_error;
     bool discard_parts = false;

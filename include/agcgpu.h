@@ -202,6 +202,19 @@ int agcgpu_compressor_add_sample_files(agcgpu_compressor* c, const char* const* 
 int agcgpu_compressor_add_samples_memory(agcgpu_compressor* c, const char* const* sample_names, uint32_t n_samples,
                                          const uint32_t* sample_of_contig, const char* const* contig_ids, uint32_t n_contigs,
                                          const void* raw, const uint64_t* offsets, int raw_is_device);
+/* ---- multi-GPU: one process per GPU -----------------------------------------------------------------------
+ * Every rank makes the same Create / AddSampleFiles / Close calls on the same inputs.  The host bookkeeping (O(#segments))
+ * and the cheap device passes (ingest, scan, hash-assign, reference indexes) are replicated, so every rank holds the same
+ * splitter set, segment map and reference store without an exchange; the per-base work whose results do not depend on where
+ * they are computed -- LZ-diff encoding of the segments (CSegment::add -> CLZDiff_V2::Encode) and the residual coding of the
+ * parts (ZSTD_compressCCtx) -- is split across the ranks and the results are all-gathered, the one exchange step of the path.
+ * Rank 0 writes the archive (byte-identical to the single-GPU one); the other ranks write nothing.
+ * `allgather` must gather `bytes` bytes from every rank into recv (rank r's block at recv + r*bytes) on all ranks -- e.g.
+ * ncclAllGather / torch.distributed.all_gather_into_tensor (agc_b200/dist.py).  Process-wide; applies to compressors created
+ * afterwards; world <= 1 or allgather == NULL switches it off. */
+typedef int (*agcgpu_allgather_fn)(void* user, const void* send, void* recv, uint64_t bytes);
+int agcgpu_set_exchange(uint32_t rank, uint32_t world, agcgpu_allgather_fn allgather, void* user);
+
 /* measurement hook: build every archive part but skip the residual coder and the file writes */
 int agcgpu_compressor_set_discard_parts(agcgpu_compressor* c, int discard);
 /* CAGCCompressor::AddCmdLine */

@@ -40,3 +40,39 @@ def test_gloo_world2(tmp_path):
                           "--master-port", "29533", str(script)], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "ok0" in out.stdout and "ok1" in out.stdout
+
+
+def _sharded_create(tmp, case, world, port, so, device):
+    """one archive from `world` ranks (agcgpu_set_exchange + torch.distributed all-gather over gloo); returns (archive bytes,
+    reference archive bytes, per-rank residual-coder input in MB)"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_host_pipeline import collection, REF_AGC
+    files, flags = collection(case, tmp)
+    ref = os.path.join(tmp, "ref.agc"); out = os.path.join(tmp, "our.agc")
+    subprocess.check_call([REF_AGC, "create", "-t", "4", "-o", ref] + flags + files, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), os.path.join(ROOT, "tests", "sharded_create_worker.py"), so, out, str(device)] + flags + ["--"] + files,
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-3000:]
+    import re
+    mb = {int(m.group(1)): float(m.group(2)) for m in re.finditer(r"rank(\d+)/\d+ zstd_input_mb=([0-9.]+)", r.stdout)}
+    assert sorted(mb) == list(range(world)), r.stdout
+    return open(out, "rb").read(), open(ref, "rb").read(), mb
+
+
+def test_sharded_create_gloo(tmp_path):
+    """SURVEY 8e on the CPU: 2 and 3 ranks (host objects + the oracle-backed stand-in of the device ABI, tests/mock) write ONE
+    archive, byte-identical to the reference's, and the residual-coder work is really split between the ranks."""
+    import pytest
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_host_pipeline import REF_AGC, MOCK_DIR
+    if not os.path.exists(REF_AGC):
+        pytest.skip("reference binary not built")
+    subprocess.check_call(["make", "-C", MOCK_DIR, "-j4"], stdout=subprocess.DEVNULL)
+    so = os.path.join(MOCK_DIR, "libagcgpu_mock.so")
+    for case, world, port in (("complex", 2, 29541), ("adaptive", 3, 29542)):
+        tmp = os.path.join(str(tmp_path), case); os.makedirs(tmp)
+        a, b, mb = _sharded_create(tmp, case, world, port, so, -1)
+        assert a == b, f"{case}: archive of {world} ranks differs from the reference's ({len(a)} vs {len(b)} bytes)"
+        total = sum(mb.values())
+        assert total > 0 and all(v > 0.5 * total / world for v in mb.values()), mb     # every rank coded its share of the parts

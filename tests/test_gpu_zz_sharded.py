@@ -1,0 +1,23 @@
+"""SURVEY 8e on the device: two ranks (two processes, two contexts -- both on cuda:0, so the test also runs on a one-GPU box;
+the exchange step goes over gloo) write ONE archive through libagcgpu.so, byte-identical to the reference's.  On a multi-GPU
+box the same calls run with one GPU per rank and agc_b200.dist.install_exchange(L, device="cuda:<local rank>") (NCCL)."""
+import os
+import sys
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from test_dist_gloo import _sharded_create
+from test_host_pipeline import REF_AGC
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.skipif(not os.path.exists(REF_AGC), reason="reference binary not built (make -f oracle/Makefile.ref)")
+@pytest.mark.parametrize("case", ["complex", "adaptive"])
+def test_two_ranks_one_archive(tmp_path, case):
+    import agc_b200
+    a, b, mb = _sharded_create(str(tmp_path), case, 2, 29551 if case == "complex" else 29552, agc_b200.lib_path(), 0)
+    assert a == b, f"{case}: archive of 2 ranks differs from the reference's ({len(a)} vs {len(b)} bytes)"
+    total = sum(mb.values())
+    assert total > 0 and all(v > 0.25 * total for v in mb.values()), mb
