@@ -1,0 +1,102 @@
+"""Differential fuzzing of the host side of the path (TEST TOOL): random small collections and random `create` flags through
+tests/mock/agc-mock (product host objects + oracle-backed device ABI) and through the reference binary; archives must be
+byte-identical.  usage: python tools/fuzz_host_pipeline.py [n_cases] [first_seed] [agc binary]"""
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import gen_data
+
+REF = os.path.join(ROOT, "oracle", "_ref", "agc")
+OUR = sys.argv[3] if len(sys.argv) > 3 else os.path.join(ROOT, "tests", "mock", "agc-mock")
+
+
+def make_case(d, seed):
+    rng = np.random.default_rng(seed)
+    k = int(rng.choice([17, 21, 25, 31, 32]))
+    l = int(rng.choice([15, 18, 20, 24]))
+    s = int(rng.choice([300, 1000, 2500, 8000]))
+    b = int(rng.choice([1, 2, 3, 7, 50]))
+    flags = ["-k", str(k), "-l", str(l), "-s", str(s), "-b", str(b)]
+    if rng.random() < 0.45:
+        flags.append("-a")
+    conc = rng.random() < 0.3
+    if conc:
+        flags.append("-c")
+    n_ref = int(rng.integers(1, 4))
+    ref = [rng.integers(0, 4, int(rng.integers(s // 2, 12 * s)), dtype=np.uint8) for _ in range(n_ref)]
+    if rng.random() < 0.3 and len(ref[0]) > 4 * s:
+        ref[0][s:2 * s] = ref[0][3 * s:4 * s]                         # repeat inside the reference
+    os.makedirs(d, exist_ok=True)
+    files = [os.path.join(d, "ref.fa")]
+    gen_data.write_fasta(files[0], [(f"r{i} x", c) for i, c in enumerate(ref)])
+    pool = list(ref)
+    n_samples = int(rng.integers(1, 7))
+    uid = 0
+    for si in range(n_samples):
+        ctgs = []
+        for _ in range(int(rng.integers(1, 5))):
+            kind = rng.integers(0, 9)
+            src = pool[int(rng.integers(0, len(pool)))]
+            if kind == 0:
+                t = rng.integers(0, 4, int(rng.integers(0, 6 * s)), dtype=np.uint8)           # novel (maybe >= segment_size, maybe empty)
+                if len(t) > 100:
+                    pool.append(t)
+            elif kind == 1:
+                t = src.copy()
+            elif kind == 2:
+                t = (3 - src[::-1]).astype(np.uint8)
+            elif kind == 3 and len(src) > 4 * k:
+                a = int(rng.integers(0, len(src) // 2)); t = src[a:a + int(rng.integers(1, len(src) - a))]
+            elif kind == 4 and len(src) > 3000:
+                a = int(rng.integers(100, len(src) - 2000)); t = np.concatenate([src[:a], src[a + int(rng.integers(200, 1900)):]])
+            elif kind == 5:
+                t = rng.integers(0, 4, int(rng.integers(1, k + 3)), dtype=np.uint8)           # around k
+            elif kind == 6 and len(pool) > 1:
+                o = pool[int(rng.integers(0, len(pool)))]; t = np.concatenate([src[:len(src) // 2], o[len(o) // 2:]])   # chimera
+            else:
+                t = src.copy()
+            t = gen_data.substitute(rng, np.asarray(t, np.uint8), float(rng.choice([0, 0.001, 0.01, 0.08])))
+            t = gen_data.indels(rng, t, int(rng.integers(0, 4)))
+            if rng.random() < 0.2 and len(t) > 50:
+                a = int(rng.integers(0, len(t) - 20)); t = np.array(t, np.uint8); t[a:a + int(rng.integers(1, 40))] = 4       # N run
+            # contig names are unique: with a repeated (sample, contig name) the reference's own result depends on how its
+            # std::sort orders equal keys (agc_compressor.h:112-119)
+            name = f"c{uid} d"
+            uid += 1
+            ctgs.append((name, np.asarray(t, np.uint8)))
+        fn = os.path.join(d, f"s{si}.fa")
+        gen_data.write_fasta(fn, ctgs, width=int(rng.choice([60, 80, 10000])))
+        files.append(fn)
+    return files, flags
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 50
+    seed0 = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
+    bad = 0
+    for seed in range(seed0, seed0 + n):
+        tmp = tempfile.mkdtemp(prefix="agcfuzz")
+        files, flags = make_case(os.path.join(tmp, "d"), seed)
+        r = os.path.join(tmp, "ref.agc"); o = os.path.join(tmp, "our.agc")
+        rr = subprocess.run([REF, "create", "-t", "3", "-o", r] + flags + files, capture_output=True)
+        ro = subprocess.run([OUR, "create", "-o", o] + flags + files, capture_output=True)
+        same = rr.returncode == 0 and ro.returncode == 0 and open(r, "rb").read() == open(o, "rb").read()
+        if not same:
+            bad += 1
+            print(f"seed {seed}: MISMATCH rc_ref={rr.returncode} rc_our={ro.returncode} flags={' '.join(flags)} dir={tmp}", flush=True)
+            if ro.returncode:
+                print("   our stderr:", ro.stderr.decode()[-300:], flush=True)
+        else:
+            shutil.rmtree(tmp)
+    print(f"{n - bad}/{n} identical")
+    return 1 if bad else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
