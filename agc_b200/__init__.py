@@ -5,6 +5,6 @@ pipeline that mirrors CAGCCompressor lives in agc_b200/csrc/host (C++), as the r
 There is no CPU fallback: importing works everywhere (so the symbol table can be checked on a CPU box), creating a
 context without an sm_100 GPU raises.
 """
-from ._lib import (Device, AgcGpuError, lib, lib_path, Cut, SegReq, Assign, Stats, Params, EXPORTED_SYMBOLS)
+from ._lib import (Device, AgcGpuError, lib, lib_path, Cut, SegReq, Assign, Stats, Params, FKmer, EXPORTED_SYMBOLS)
 
-__all__ = ["Device", "AgcGpuError", "lib", "lib_path", "Cut", "SegReq", "Assign", "Stats", "Params", "EXPORTED_SYMBOLS"]
+__all__ = ["Device", "AgcGpuError", "lib", "lib_path", "Cut", "SegReq", "Assign", "Stats", "Params", "FKmer", "EXPORTED_SYMBOLS"]

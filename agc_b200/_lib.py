@@ -37,6 +37,10 @@ class Assign(C.Structure):
                 ("klass", C.c_uint32), ("reserved", C.c_uint32)]
 
 
+class FKmer(C.Structure):
+    _fields_ = [("pos", C.c_uint64), ("kmer", C.c_uint64), ("is_dir_oriented", C.c_uint32), ("is_symmetric", C.c_uint32)]
+
+
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("device_bytes_in_use", C.c_uint64), ("lz_alg_bytes", C.c_uint64), ("last_lz_kernel_ms", C.c_float),
@@ -50,7 +54,7 @@ EXPORTED_SYMBOLS = [
     "agcgpu_get_segment", "agcgpu_map_insert", "agcgpu_assign_cuts", "agcgpu_group_put_reference_batch",
     "agcgpu_group_put_reference", "agcgpu_group_get_index", "agcgpu_lz_encode_batch", "agcgpu_lz_estimate_batch",
     "agcgpu_lz_cost_vector", "agcgpu_pack_ref_batch", "agcgpu_zstd_compress_batch",
-    "agcgpu_find_new_splitters", "agcgpu_rescan_contigs",
+    "agcgpu_find_new_splitters", "agcgpu_rescan_contigs", "agcgpu_filtered_kmers", "agcgpu_last_splitter_positions",
 ]
 
 
@@ -82,6 +86,10 @@ def lib():
     L.agcgpu_scan_contigs.argtypes = [vp, u8p, u64p, C.c_uint32, u64p, C.POINTER(Cut), C.c_uint64, u64p]
     L.agcgpu_find_new_splitters.restype = C.c_int
     L.agcgpu_find_new_splitters.argtypes = [vp, u32p, C.c_uint32, u64p, C.c_uint64, u64p]
+    L.agcgpu_filtered_kmers.restype = C.c_int
+    L.agcgpu_filtered_kmers.argtypes = [vp, C.POINTER(SegReq), C.c_uint32, C.c_uint64, C.POINTER(FKmer), C.c_uint64, u64p]
+    L.agcgpu_last_splitter_positions.restype = C.c_int
+    L.agcgpu_last_splitter_positions.argtypes = [vp, u32p, u64p, u64p, u8p, C.c_uint64, u64p]
     L.agcgpu_rescan_contigs.restype = C.c_int; L.agcgpu_rescan_contigs.argtypes = [vp, C.POINTER(Cut), C.c_uint64, u64p]
     L.agcgpu_scan_contigs_dev.restype = C.c_int
     L.agcgpu_scan_contigs_dev.argtypes = [vp, vp, C.c_uint64, u64p, C.c_uint32, u64p, C.POINTER(Cut), C.c_uint64, u64p]
@@ -208,6 +216,29 @@ class Device:
         n = C.c_uint64(0)
         self._ck(self.L.agcgpu_find_new_splitters(self.h, _p(c, u32p), len(c), _p(out, u64p), cap, C.byref(n)))
         return out[:n.value].copy()
+
+    def filtered_kmers(self, ranges, threshold):
+        """-f mode: k-mers of resident ranges [(contig, start, len)] that pass kmer_filter_t; list of lists of FKmer"""
+        reqs = self._reqs([(c, s, l, False, 0) for c, s, l in ranges])
+        offs = np.zeros(len(ranges) + 1, np.uint64)
+        cap = 1 << 12
+        while True:
+            out = (FKmer * cap)()
+            rc = self.L.agcgpu_filtered_kmers(self.h, reqs, len(ranges), int(threshold), out, cap, _p(offs, u64p))
+            if rc == -4 and int(offs[-1]) > cap:
+                cap = int(offs[-1]) + 16
+                continue
+            self._ck(rc)
+            break
+        return [[out[j] for j in range(int(offs[i]), int(offs[i + 1]))] for i in range(len(ranges))]
+
+    def last_splitter_positions(self):
+        """(contig, pos, kmer, is_last) of the splitters the last determine_splitters / find_new_splitters call found"""
+        cap = 1 << 16
+        c = np.zeros(cap, np.uint32); p = np.zeros(cap, np.uint64); k = np.zeros(cap, np.uint64); l = np.zeros(cap, np.uint8)
+        n = C.c_uint64(0)
+        self._ck(self.L.agcgpu_last_splitter_positions(self.h, _p(c, u32p), _p(p, u64p), _p(k, u64p), _p(l, u8p), cap, C.byref(n)))
+        return [(int(c[i]), int(p[i]), int(k[i]), int(l[i])) for i in range(n.value)]
 
     def rescan_contigs(self):
         """scan of the resident batch again under the current splitter set (-a mode, hard_contigs stage)"""

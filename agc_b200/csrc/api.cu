@@ -268,6 +268,7 @@ int agcgpu_determine_splitters(agcgpu_ctx* ctx, const uint8_t* raw, const uint64
     if (int r = upload_raw(ctx, raw, raw_bytes)) return r;
     if (int r = agc_prep_and_scan(ctx, (const uint8_t*)ctx->raw.p, raw_bytes, raw_offsets, n_contigs, false, nullptr)) return r;
     std::vector<uint64_t> spl;
+    ctx->h_last_spl.clear();
     if (int r = agc_enumerate_splitters(ctx, 0, ctx->n_contigs, false, (ctx->prm.flags & AGCGPU_F_ADAPTIVE) != 0, spl)) return r;
     *out_n = spl.size();
     if (spl.size() > cap) return agc_fail(ctx, AGCGPU_EOVERFLOW, "determine_splitters: %zu splitters, buffer holds %llu", spl.size(), (unsigned long long)cap);
@@ -281,6 +282,7 @@ int agcgpu_find_new_splitters(agcgpu_ctx* ctx, const uint32_t* contigs, uint32_t
     cudaSetDevice(ctx->dev);
     if (!(ctx->prm.flags & AGCGPU_F_ADAPTIVE)) return agc_fail(ctx, AGCGPU_EINVAL, "find_new_splitters needs AGCGPU_F_ADAPTIVE");
     std::vector<uint64_t> all, one;
+    ctx->h_last_spl.clear();
     for (uint32_t i = 0; i < n; ++i) {                   // candidates are per contig (its own singletons), so one pass each
         if (contigs[i] >= ctx->n_contigs) return agc_fail(ctx, AGCGPU_EINVAL, "find_new_splitters: contig %u is not resident", contigs[i]);
         if (int r = agc_enumerate_splitters(ctx, contigs[i], 1, true, false, one)) return r;
@@ -291,6 +293,41 @@ int agcgpu_find_new_splitters(agcgpu_ctx* ctx, const uint32_t* contigs, uint32_t
     *out_n = all.size();
     if (all.size() > cap) return agc_fail(ctx, AGCGPU_EOVERFLOW, "find_new_splitters: %zu splitters, buffer holds %llu", all.size(), (unsigned long long)cap);
     if (!all.empty()) memcpy(out_splitters, all.data(), all.size() * 8);
+    return 0;
+}
+
+int agcgpu_filtered_kmers(agcgpu_ctx* ctx, const agcgpu_seg_req* reqs, uint32_t n, uint64_t threshold, agcgpu_fkmer* out, uint64_t cap,
+                          uint64_t* out_offsets)
+{
+    if (!ctx || !out_offsets || (n && !reqs) || (cap && !out)) return AGCGPU_EINVAL;
+    cudaSetDevice(ctx->dev);
+    out_offsets[0] = 0;
+    std::vector<agcgpu_fkmer> one;
+    bool overflow = false;
+    for (uint32_t i = 0; i < n; ++i) {
+        const agcgpu_seg_req& q = reqs[i];
+        if (q.contig >= ctx->n_contigs || q.start > ctx->h_cstart[q.contig + 1] - ctx->h_cstart[q.contig])
+            return agc_fail(ctx, AGCGPU_EINVAL, "filtered_kmers: range %u is outside the resident batch", i);
+        const uint64_t len = std::min<uint64_t>(q.len, ctx->h_cstart[q.contig + 1] - ctx->h_cstart[q.contig] - q.start);   // clipped like get_part
+        if (int r = agc_filtered_kmers(ctx, ctx->h_cstart[q.contig] + q.start, len, threshold, one)) return r;
+        uint64_t o = out_offsets[i];
+        out_offsets[i + 1] = o + one.size();
+        if (out_offsets[i + 1] > cap) overflow = true;
+        else if (!one.empty()) memcpy(out + o, one.data(), one.size() * sizeof(agcgpu_fkmer));
+    }
+    if (overflow) return agc_fail(ctx, AGCGPU_EOVERFLOW, "filtered_kmers: %llu k-mers, buffer holds %llu", (unsigned long long)out_offsets[n], (unsigned long long)cap);
+    return 0;
+}
+
+int agcgpu_last_splitter_positions(agcgpu_ctx* ctx, uint32_t* out_contig, uint64_t* out_pos, uint64_t* out_kmer, uint8_t* out_is_last,
+                                   uint64_t cap, uint64_t* out_n)
+{
+    if (!ctx || !out_n) return AGCGPU_EINVAL;
+    auto v = ctx->h_last_spl;
+    std::sort(v.begin(), v.end(), [](const agcgpu_ctx::SplFound& a, const agcgpu_ctx::SplFound& b) { return a.contig != b.contig ? a.contig < b.contig : a.pos < b.pos; });
+    *out_n = v.size();
+    if (v.size() > cap) return agc_fail(ctx, AGCGPU_EOVERFLOW, "last_splitter_positions: %zu entries, buffer holds %llu", v.size(), (unsigned long long)cap);
+    for (size_t i = 0; i < v.size(); ++i) { out_contig[i] = v[i].contig; out_pos[i] = v[i].pos; out_kmer[i] = v[i].kmer; out_is_last[i] = v[i].is_last; }
     return 0;
 }
 

@@ -351,8 +351,8 @@ bool CAGCCompressor::Create(const std::string& file_name, uint32_t _pack_cardina
     pack_cardinality = _pack_cardinality; kmer_length = _kmer_length; min_match_len = _min_match_len;
     segment_size = _segment_size; verbosity = _verbosity;
     concatenated_genomes = _concatenated_genomes; adaptive_compression = _adaptive_compression;
-    if (fallback_frac != 0.0)
-        return fail("agc-b200: -f is not implemented on the GPU path yet (refusing rather than falling back)");
+    fallback_thr = fallback_frac == 0.0 ? 0ull : (uint64_t)(((double)~0ull) * fallback_frac);       // kmer_filter_t::reset
+    map_fallback_minimizers.clear(); pending_fallbacks.clear();
     agcgpu_params prm; memset(&prm, 0, sizeof prm);
     prm.kmer_length = kmer_length; prm.min_match_len = min_match_len; prm.segment_size = segment_size;
     prm.pack_cardinality = pack_cardinality; prm.device = device;
@@ -376,6 +376,11 @@ bool CAGCCompressor::Create(const std::string& file_name, uint32_t _pack_cardina
             return false;
         splitters.resize(n);
         if (verbosity > 1 && is_app_mode) std::cerr << "No. of splitters: " << n << std::endl;
+        if (fallback_thr) {                                  // v_fallbacks of find_splitters_in_contig for the reference contigs (797-802, 821-822)
+            std::vector<uint32_t> all_ctg(offs.size() - 1);
+            std::iota(all_ctg.begin(), all_ctg.end(), 0u);
+            if (!collect_fallbacks(all_ctg)) return false;
+        }
     }
     if (!dump_path.empty()) {
         dump_f = fopen(dump_path.c_str(), "wb");
@@ -675,9 +680,124 @@ bool CAGCCompressor::process_batch(std::vector<std::vector<uint8_t>>& raws, std:
     return process_batch_raw(cat.data(), false, offs, owners);
 }
 
+// -f mode.  find_splitters_in_contig (agc_compressor.cpp:762-825) remembers, for every splitter it finds, the k-mers that pass
+// the fallback filter (and are not their own reverse complement) seen since the previous splitter: v_fallbacks entries
+// (previous splitter, this splitter, k-mer, orientation).  The device reports where the splitters of its last
+// determine / find_new call were found and the filtered k-mers of the contigs; the intervals are put together here.
+bool CAGCCompressor::collect_fallbacks(const std::vector<uint32_t>& contigs)
+{
+    if (contigs.empty()) return true;
+    uint64_t cap = 1024, n = 0;
+    std::vector<uint32_t> sc; std::vector<uint64_t> sp, sk; std::vector<uint8_t> sl;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        sc.resize(cap); sp.resize(cap); sk.resize(cap); sl.resize(cap);
+        int rc = agcgpu_last_splitter_positions(ctx, sc.data(), sp.data(), sk.data(), sl.data(), cap, &n);
+        if (rc == AGCGPU_EOVERFLOW && attempt == 0) { cap = n + 16; continue; }
+        if (!gpu_ok(rc, "last_splitter_positions")) return false;
+        break;
+    }
+    std::vector<agcgpu_seg_req> rq;
+    for (auto c : contigs) { agcgpu_seg_req q; memset(&q, 0, sizeof q); q.contig = c; q.start = 0; q.len = 0xffffffffu; rq.push_back(q); }   // whole contigs
+    std::vector<uint64_t> offs(rq.size() + 1, 0);
+    std::vector<agcgpu_fkmer> fk(1 << 16);
+    int rc = agcgpu_filtered_kmers(ctx, rq.data(), (uint32_t)rq.size(), fallback_thr, fk.data(), fk.size(), offs.data());
+    if (rc == AGCGPU_EOVERFLOW) { fk.resize(offs.back() + 16); rc = agcgpu_filtered_kmers(ctx, rq.data(), (uint32_t)rq.size(), fallback_thr, fk.data(), fk.size(), offs.data()); }
+    if (!gpu_ok(rc, "filtered_kmers")) return false;
+    for (size_t ci = 0; ci < contigs.size(); ++ci) {
+        const agcgpu_fkmer* f = fk.data() + offs[ci]; const size_t nf = offs[ci + 1] - offs[ci];
+        size_t fi = 0;
+        uint64_t prev_splitter = EMPTY, lo = 0;                 // k-mers ending before `lo` were cut off by the reset after a splitter
+        bool have_last = false; uint64_t last_kmer = 0;
+        for (uint64_t i = 0; i < n; ++i) {
+            if (sc[i] != contigs[ci]) continue;
+            if (sl[i]) { have_last = true; last_kmer = sk[i]; continue; }
+            for (; fi < nf && f[fi].pos <= sp[i]; ++fi)
+                if (f[fi].pos >= lo && !f[fi].is_symmetric) pending_fallbacks.push_back({ prev_splitter, sk[i], f[fi].kmer, (uint64_t)f[fi].is_dir_oriented });
+            prev_splitter = sk[i]; lo = sp[i] + kmer_length;
+        }
+        if (have_last)
+            for (; fi < nf; ++fi)
+                if (f[fi].pos >= lo && !f[fi].is_symmetric) pending_fallbacks.push_back({ prev_splitter, last_kmer, f[fi].kmer, (uint64_t)f[fi].is_dir_oriented });
+    }
+    return true;
+}
+
+// the registration token's add_fallback_mapping pass (agc_compressor.cpp:1121-1128, 413-427)
+void CAGCCompressor::apply_pending_fallbacks()
+{
+    for (auto& x : pending_fallbacks) {
+        auto& v = map_fallback_minimizers[x[2]];
+        auto to_add = x[3] ? std::make_pair(x[0], x[1]) : std::make_pair(x[1], x[0]);
+        if (std::count(v.begin(), v.end(), to_add) == 0) v.push_back(to_add);
+    }
+    pending_fallbacks.clear();
+}
+
+// find_cand_segment_using_fallback_minimizers (agc_compressor.cpp:1812-1963).  The segment is the resident range
+// (bc, start, len); rc_view: the caller's "segment" is its reverse complement (call site 1352).
+bool CAGCCompressor::find_cand_segment_using_fallback_minimizers(uint32_t bc, uint64_t start, uint32_t len, bool rc_view, uint64_t max_val,
+                                                                 std::pair<uint64_t, uint64_t>& pk, bool& store_rc)
+{
+    const auto pk_empty = std::make_pair(EMPTY, EMPTY);
+    pk = pk_empty; store_rc = false;
+    const size_t max_num_to_estimate = 10;
+    const bool short_segments = segment_size <= 10000;
+    agcgpu_seg_req q; memset(&q, 0, sizeof q); q.contig = bc; q.start = start; q.len = len;
+    uint64_t offs[2] = { 0, 0 };
+    std::vector<agcgpu_fkmer> fk((size_t)((double)len * ((double)fallback_thr / 18446744073709551616.0) * 2.0) + 256);
+    int rc = agcgpu_filtered_kmers(ctx, &q, 1, fallback_thr, fk.data(), fk.size(), offs);
+    if (rc == AGCGPU_EOVERFLOW) { fk.resize(offs[1] + 16); rc = agcgpu_filtered_kmers(ctx, &q, 1, fallback_thr, fk.data(), fk.size(), offs); }
+    if (!gpu_ok(rc, "filtered_kmers")) return false;
+    std::map<std::pair<uint64_t, uint64_t>, std::vector<uint64_t>> cand_seg_counts;
+    for (uint64_t i = 0; i < offs[1]; ++i) {
+        auto p = map_fallback_minimizers.find(fk[i].kmer);
+        if (p == map_fallback_minimizers.end()) continue;
+        const bool dir_oriented = rc_view ? (fk[i].is_symmetric ? true : !fk[i].is_dir_oriented) : (fk[i].is_dir_oriented != 0);
+        for (auto y : p->second)
+            if (y.first != EMPTY && y.second != EMPTY) {
+                if (!dir_oriented) std::swap(y.first, y.second);
+                cand_seg_counts[y].push_back(fk[i].kmer);
+            }
+    }
+    std::vector<std::pair<uint64_t, std::pair<uint64_t, uint64_t>>> pruned;
+    for (auto& x : cand_seg_counts) {
+        std::sort(x.second.begin(), x.second.end());
+        size_t x_size = std::unique(x.second.begin(), x.second.end()) - x.second.begin();
+        if (x_size >= max_val) pruned.emplace_back((uint64_t)x_size, x.first);
+    }
+    if (pruned.empty()) return true;
+    std::sort(pruned.begin(), pruned.end(), std::greater<std::pair<uint64_t, std::pair<uint64_t, uint64_t>>>());
+    if (pruned.size() > max_num_to_estimate) pruned.resize(max_num_to_estimate);
+    while (pruned.back().first * 2 < pruned.front().first) pruned.pop_back();
+    auto best_pair = pk_empty;
+    uint64_t best_es = len;
+    for (auto& x : pruned) {
+        const bool is_seg_rc = x.second.first > x.second.second;
+        auto p = map_segments.find(is_seg_rc ? std::make_pair(x.second.second, x.second.first) : x.second);
+        uint64_t es = 0;
+        if (p != map_segments.end()) {                      // can fail if the mappings are to a segment of the same sample
+            if (short_segments) { best_pair = x.second; best_es = 0; break; }
+            agcgpu_seg_req e; memset(&e, 0, sizeof e);
+            e.contig = bc; e.start = start; e.len = len; e.is_rc = is_seg_rc != rc_view; e.group_id = (uint32_t)p->second; e.bound = (uint32_t)best_es;
+            uint32_t est = 0;
+            if (!gpu_ok(agcgpu_lz_estimate_batch(ctx, &e, 1, &est), "lz_estimate")) return false;
+            es = est;
+        }
+        if (es && es < best_es) { best_es = es; best_pair = x.second; }
+    }
+    if (adaptive_compression) {                             // better left as a new reference (1944-1957)
+        if (short_segments) { if ((double)best_es >= len * 0.9) return true; }
+        else if ((double)best_es >= len * 0.2) return true;
+    }
+    if (best_pair.first <= best_pair.second) { pk = best_pair; store_rc = false; }
+    else { pk = std::make_pair(best_pair.second, best_pair.first); store_rc = true; }
+    return true;
+}
+
 // what the registration token does once the segments are stored (agc_compressor.cpp:1136-1179)
 void CAGCCompressor::account_registration()
 {
+    apply_pending_fallbacks();
     if (!concatenated_genomes) ++processed_samples;
     else {
         processed_samples = processed_samples / pack_cardinality * pack_cardinality + pack_cardinality;
@@ -756,6 +876,7 @@ bool CAGCCompressor::process_batch_raw(const uint8_t* cat, bool is_device, const
             std::vector<uint64_t> fresh_spl(cap_new); uint64_t n_new = 0;
             if (!gpu_ok(agcgpu_find_new_splitters(ctx, searched.data(), (uint32_t)searched.size(), fresh_spl.data(), cap_new, &n_new), "find_new_splitters")) return false;
             fresh_spl.resize(n_new);
+            if (fallback_thr && !collect_fallbacks(searched)) return false;
             std::vector<uint64_t> merged; merged.reserve(splitters.size() + n_new);
             std::set_union(splitters.begin(), splitters.end(), fresh_spl.begin(), fresh_spl.end(), std::back_inserter(merged));
             if (merged.size() != splitters.size()) {
@@ -930,19 +1051,33 @@ bool CAGCCompressor::process_batch_raw(const uint8_t* cat, bool is_device, const
                 bool store_rc = false, have_second = false;
                 Item it2 = it;
                 const uint64_t fc = canon(cut.front_dir, cut.front_rc), bcn = canon(cut.back_dir, cut.back_rc);
-                if (!cut.has_front && !cut.has_back) pk = std::make_pair(EMPTY, EMPTY);
+                const auto pk_empty = std::make_pair(EMPTY, EMPTY);
+                if (!cut.has_front && !cut.has_back) {
+                    pk = pk_empty;
+                    if (fallback_thr && !find_cand_segment_using_fallback_minimizers(bc, it.start, it.len, false, 1, pk, store_rc)) return false;   // 1290-1298
+                }
                 else if (cut.has_front && cut.has_back) { pk = std::make_pair(as.key1, as.key2); store_rc = as.is_rc; }
                 else if (cut.has_front) {
                     if (!one_splitter(x, cut.front_dir, cut.front_rc, it.len, pk, store_rc)) return false;
+                    if (fallback_thr && (pk.first == EMPTY || pk.second == EMPTY)) {                  // 1322-1336
+                        std::pair<uint64_t, uint64_t> pk_alt; bool rc_alt = false;
+                        if (!find_cand_segment_using_fallback_minimizers(bc, it.start, it.len, false, 5, pk_alt, rc_alt)) return false;
+                        if (pk_alt != pk_empty) { pk = pk_alt; store_rc = rc_alt; }
+                    }
                 } else {
                     bool store_dir = false;      // kmer = kmer_back with swap_dir_rc; "segment_dir" is the reverse complement
                     if (!one_splitter(x, cut.back_rc, cut.back_dir, it.len, pk, store_dir)) return false;
                     store_rc = !store_dir;
+                    if (fallback_thr && (pk.first == EMPTY || pk.second == EMPTY)) {                  // 1347-1361
+                        std::pair<uint64_t, uint64_t> pk_alt; bool dir_alt = false;
+                        if (!find_cand_segment_using_fallback_minimizers(bc, it.start, it.len, true, 5, pk_alt, dir_alt)) return false;
+                        if (pk_alt != pk_empty) { pk = pk_alt; store_rc = !dir_alt; }
+                    }
                 }
                 // map_segments.find(pk): the device hash-assign already answered it for the two-splitter / no-splitter classes
                 auto p = map_segments.end();
                 bool found = false;
-                if (as.klass == 0 || as.klass == 3) { found = as.group_id >= 0; if (found) p = map_segments.find(pk); }
+                if (as.klass == 0 || (as.klass == 3 && !fallback_thr)) { found = as.group_id >= 0; if (found) p = map_segments.find(pk); }
                 else { p = map_segments.find(pk); found = p != map_segments.end(); }
                 if (found && p == map_segments.end()) return fail("internal: device and host segment maps disagree");
                 int32_t segment_id = -1, segment_id2 = -1;
@@ -974,6 +1109,11 @@ bool CAGCCompressor::process_batch_raw(const uint8_t* cat, bool is_device, const
                         }
                     }
                     p = map_segments.find(pk);
+                }
+                if (p == map_segments.end() && fallback_thr) {                                       // 1461-1477
+                    std::pair<uint64_t, uint64_t> pk_fb; bool rc_fb = false;
+                    if (!find_cand_segment_using_fallback_minimizers(bc, it.start, it.len, false, 2, pk_fb, rc_fb)) return false;
+                    if (pk_fb != pk_empty) { pk = pk_fb; store_rc = rc_fb; p = map_segments.find(pk); }
                 }
                 it.is_rc = store_rc; it.k1 = pk.first; it.k2 = pk.second;
                 if (p == map_segments.end()) { it.group = -1; fresh.push_back(it); }
@@ -1048,6 +1188,7 @@ bool CAGCCompressor::process_batch_raw(const uint8_t* cat, bool is_device, const
             if (!prefetch_estimates(cut_first[cj])) return false;
         }
         regs.push_back(std::move(reg));
+        apply_pending_fallbacks();                 // the token's add_fallback_mapping pass: visible to the next unit's add_segment calls
         ci = cj;
     }
 

@@ -15,6 +15,7 @@
 #include <map>
 #include <memory>
 #include <string>
+#include <array>
 #include <unordered_map>
 #include <vector>
 #include "../../../include/agcgpu.h"
@@ -155,6 +156,11 @@ private:
     bool flush_jobs(bool final_flush);
     bool compress_tasks(std::vector<ZTask*>& tasks);
     bool compress_tasks_local(std::vector<ZTask*>& tasks);
+    // -f mode (fallback minimizers)
+    bool collect_fallbacks(const std::vector<uint32_t>& contigs);
+    void apply_pending_fallbacks();
+    bool find_cand_segment_using_fallback_minimizers(uint32_t bc, uint64_t start, uint32_t len, bool rc_view, uint64_t max_val,
+                                                     std::pair<uint64_t, uint64_t>& pk, bool& store_rc);
     bool exchange(const std::vector<uint8_t>& mine, std::vector<std::vector<uint8_t>>& all);
     bool lz_encode(std::vector<agcgpu_seg_req>& lz, std::vector<uint8_t>& deltas, std::vector<uint64_t>& doffs);
     bool lz_encode_local(const agcgpu_seg_req* lz, size_t n, std::vector<uint8_t>& deltas, std::vector<uint64_t>& doffs);
@@ -181,6 +187,9 @@ private:
     std::vector<uint64_t> splitters;                          // sorted
     std::map<std::pair<uint64_t, uint64_t>, int32_t> map_segments;            // agc_compressor.h:628
     std::unordered_map<uint64_t, std::vector<uint64_t>> map_segments_terminators;   // 629
+    uint64_t fallback_thr = 0;                                                // kmer_filter_t::thr (agc_compressor.h:570-599); 0 = off
+    std::unordered_map<uint64_t, std::vector<std::pair<uint64_t, uint64_t>>> map_fallback_minimizers;   // 632
+    std::vector<std::array<uint64_t, 4>> pending_fallbacks;                   // vv_fallback_minimizers: applied at the next registration
     std::vector<GroupState> v_segments;
     uint32_t no_segments = 0;
     uint32_t processed_samples = 0;

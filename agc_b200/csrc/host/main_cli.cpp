@@ -1,6 +1,7 @@
 // agc-b200: `create` sub-command with the reference CLI's flags (src/app/application.cpp:125-169; defaults from
 // src/app/application.h:24-84).  Everything per-base runs on the GPU through libagcgpu.
 #include "compressor.h"
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <filesystem>
@@ -40,6 +41,9 @@ int main(int argc, char** argv)
         else if (x == "-d") {} else if (x == "-f") f = atof(next()); else if (x == "--device") dev = atoi(next()); else if (x == "--dump-parts") dump = next();
         else inputs.push_back(x);
     }
+    // b_value<T>::assign clamps every numeric option to its range (src/app/application.h:23-47, 63-71)
+    k = std::clamp(k, 17u, 32u); b = std::clamp(b, 1u, 1000000000u); s = std::clamp(s, 100u, 1000000u); l = std::clamp(l, 15u, 32u);
+    v = std::clamp(v, 0u, 2u); f = std::clamp(f, 0.0, 0.05);
     if (!list.empty()) { std::ifstream in(list); std::string ln; while (std::getline(in, ln)) if (!ln.empty()) inputs.push_back(ln); }
     if (out.empty() || inputs.empty()) { std::cerr << "need -o and at least the reference FASTA\n"; return 1; }
     { std::vector<std::string> u; std::unordered_set<std::string> seen; for (auto& x : inputs) if (seen.insert(x).second) u.push_back(x); inputs.swap(u); }

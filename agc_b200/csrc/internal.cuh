@@ -86,6 +86,12 @@ struct ScanHit {               // one k-mer occurrence that is a splitter
     uint32_t pad;
 };
 
+struct SplPos {                // where k_find_splitters found a splitter
+    uint64_t pos;              // end position of the k-mer, contig coordinates
+    uint32_t contig;           // index within the launch
+    uint32_t is_last;          // the right-most candidate added after the walk
+};
+
 struct LzReqDev {              // device form of agcgpu_seg_req
     uint64_t gstart;           // global base index of the segment's first base in the packed contig store
     uint32_t n;
@@ -121,6 +127,8 @@ struct agcgpu_ctx {
     // v_candidate_kmers and v_duplicated_kmers of the reference in one list (agc_compressor.cpp:493-494, 2066-2076)
     DevBuf ref_kmers;
     uint64_t n_ref_kmers = 0;
+    struct SplFound { uint32_t contig; uint64_t pos, kmer; uint8_t is_last; };
+    std::vector<SplFound> h_last_spl;      // splitters of the last determine / find_new call with their positions (-f mode)
 
     // resident contig batch
     DevBuf raw;                // raw FASTA bytes (only when uploaded through agcgpu_scan_contigs)
@@ -172,6 +180,7 @@ void agc_dev_trim(int dev);
 int agc_prep_and_scan(agcgpu_ctx* ctx, const uint8_t* raw_dev, uint64_t raw_bytes, const uint64_t* raw_offsets,
                       uint32_t n_contigs, bool do_scan, std::vector<ScanHit>* hits_out);
 int agc_scan_resident(agcgpu_ctx* ctx, std::vector<ScanHit>* hits_out);
+int agc_filtered_kmers(agcgpu_ctx* ctx, uint64_t gstart, uint64_t len, uint64_t thr, std::vector<agcgpu_fkmer>& out);
 // splitters of resident contigs [c0, c0+nc): candidates = singletons among the k-mers of those contigs, minus (exclude_ref)
 // the k-mers of the reference sample; keep_kmers moves the sorted k-mer list into ctx->ref_kmers
 int agc_enumerate_splitters(agcgpu_ctx* ctx, uint32_t c0, uint32_t nc, bool exclude_ref, bool keep_kmers, std::vector<uint64_t>& out_sorted);

@@ -88,12 +88,61 @@ __global__ void k_absent_flags(const uint64_t* __restrict__ cand, uint64_t n, co
     flags[i] = !in_sorted(ref, n_ref, cand[i]);
 }
 
+// -f mode: k-mers of one resident range that pass kmer_filter_t (agc_compressor.h:570-599); one thread per position,
+// appended in any order (the host sorts by position)
+__global__ void k_filter_kmers(const uint64_t* __restrict__ P, uint64_t gstart, uint64_t len, uint32_t k, uint64_t thr,
+                               const uint64_t* __restrict__ exc_pos, uint64_t n_exc, agcgpu_fkmer* __restrict__ out,
+                               uint32_t* __restrict__ out_count, uint32_t out_cap)
+{
+    const uint32_t shift = 64 - 2 * k;
+    for (uint64_t p = (uint64_t)(k - 1) + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; p < len; p += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t g = gstart + p;
+        if (last_exc_in(exc_pos, n_exc, g - (k - 1), g) != ~0ULL) continue;
+        uint64_t dir = agc_win(P, g - (k - 1)) & ((~0ULL) << shift);
+        uint64_t rc = (~agc_rev2(dir)) << shift;
+        uint64_t canon = dir < rc ? dir : rc;
+        if ((agc_murmur64(canon) ^ 0xD73F8BF11046C40EULL) >= thr) continue;
+        uint32_t idx = atomicAdd(out_count, 1u);
+        if (idx < out_cap) { agcgpu_fkmer f; f.pos = p; f.kmer = canon; f.is_dir_oriented = dir <= rc; f.is_symmetric = dir == rc; out[idx] = f; }
+    }
+}
+
+int agc_filtered_kmers(agcgpu_ctx* ctx, uint64_t gstart, uint64_t len, uint64_t thr, std::vector<agcgpu_fkmer>& out)
+{
+    out.clear();
+    const uint32_t k = ctx->prm.kmer_length;
+    if (len < k) return 0;
+    // expected count = len * thr / 2^64; room for 2x + slack, retried once with the exact count if that was not enough
+    uint64_t cap = (uint64_t)((double)len * ((double)thr / 18446744073709551616.0) * 2.0) + 1024;
+    if (cap > len) cap = len;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        if (cap > 0x7fffffffull) return agc_fail(ctx, AGCGPU_EUNSUPPORTED, "filtered_kmers: range too large");
+        if (int r = agc_reserve(ctx, ctx->scr_misc, cap * sizeof(agcgpu_fkmer) + 64)) return r;
+        if (int r = agc_reserve(ctx, ctx->counters, 64)) return r;
+        CK(cudaMemsetAsync(ctx->counters.p, 0, 64, ctx->st));
+        uint32_t grid = (uint32_t)std::min<uint64_t>((len + 255) / 256, (uint64_t)ctx->n_sm * 8);
+        k_filter_kmers<<<grid, 256, 0, ctx->st>>>((const uint64_t*)ctx->packed.p, gstart, len, k, thr, (const uint64_t*)ctx->exc_pos.p,
+                                                  ctx->n_exc, (agcgpu_fkmer*)ctx->scr_misc.p, (uint32_t*)ctx->counters.p, (uint32_t)cap);
+        CKL();
+        uint32_t cnt = 0;
+        CK(cudaMemcpyAsync(&cnt, ctx->counters.p, 4, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaStreamSynchronize(ctx->st));
+        if (cnt > cap) { cap = cnt; continue; }
+        out.resize(cnt);
+        if (cnt) { CK(cudaMemcpy(out.data(), ctx->scr_misc.p, (size_t)cnt * sizeof(agcgpu_fkmer), cudaMemcpyDeviceToHost)); ctx->stats.d2h_bytes += (size_t)cnt * sizeof(agcgpu_fkmer); }
+        std::sort(out.begin(), out.end(), [](const agcgpu_fkmer& a, const agcgpu_fkmer& b) { return a.pos < b.pos; });
+        return 0;
+    }
+    return agc_fail(ctx, AGCGPU_EUNSUPPORTED, "filtered_kmers: count changed between two passes");
+}
+
 // one warp per contig
 __global__ void __launch_bounds__(128) k_find_splitters(const uint64_t* __restrict__ P, const uint64_t* __restrict__ cstart,
                                                         uint32_t n_contigs, uint32_t k, uint64_t segment_size,
                                                         const uint64_t* __restrict__ singles, uint64_t n_singles,
                                                         const uint64_t* __restrict__ exc_pos, uint64_t n_exc,
-                                                        uint64_t* __restrict__ out, uint32_t* __restrict__ out_count, uint32_t out_cap)
+                                                        uint64_t* __restrict__ out, uint32_t* __restrict__ out_count, uint32_t out_cap,
+                                                        SplPos* __restrict__ out_where)
 {
     uint32_t c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (c >= n_contigs) return;
@@ -115,7 +164,7 @@ __global__ void __launch_bounds__(128) k_find_splitters(const uint64_t* __restri
             uint32_t L = __ffs(mk) - 1;
             uint64_t pa = q + L;
             uint64_t d = __shfl_sync(FULL, canon, L);
-            if (lane == 0) { uint32_t idx = atomicAdd(out_count, 1u); if (idx < out_cap) out[idx] = d; }
+            if (lane == 0) { uint32_t idx = atomicAdd(out_count, 1u); if (idx < out_cap) { out[idx] = d; out_where[idx] = SplPos{ pa, c, 0u }; } }
             last_acc = (int64_t)pa;
             q = pa + segment_size;
             continue;
@@ -148,7 +197,7 @@ __global__ void __launch_bounds__(128) k_find_splitters(const uint64_t* __restri
         if (mk) {
             uint32_t L = __ffs(mk) - 1;
             uint64_t d = __shfl_sync(FULL, canon, L);
-            if (lane == 0) { uint32_t idx = atomicAdd(out_count, 1u); if (idx < out_cap) out[idx] = d; }
+            if (lane == 0) { uint32_t idx = atomicAdd(out_count, 1u); if (idx < out_cap) { out[idx] = d; out_where[idx] = SplPos{ hi_pos - 1 - L, c, 1u }; } }
             return;
         }
         hi_pos -= span;
@@ -177,12 +226,13 @@ int agc_enumerate_splitters(agcgpu_ctx* ctx, uint32_t c0, uint32_t n_contigs, bo
     if (int r = agc_reserve(ctx, ctx->chunk_prefix, (n_contigs + 1) * 4)) return r;
     CK(cudaMemcpyAsync(ctx->chunk_prefix.p, cp.data(), (n_contigs + 1) * 4, cudaMemcpyHostToDevice, ctx->st));
     const uint64_t* d_cstart = (const uint64_t*)ctx->d_cstart.p + c0;
-    DevBuf keys_a, keys_b, flags, tmp, nsel, outb;
+    DevBuf keys_a, keys_b, flags, tmp, nsel, outb, whereb;
     int rc = 0;
-    auto cleanup = [&]() { for (DevBuf* b : { &keys_a, &keys_b, &flags, &tmp, &nsel, &outb }) if (b->p) { agc_dev_free(ctx->dev, b->p, b->cap + 64); ctx->device_bytes -= b->cap; b->p = nullptr; b->cap = 0; } };
+    auto cleanup = [&]() { for (DevBuf* b : { &keys_a, &keys_b, &flags, &tmp, &nsel, &outb, &whereb }) if (b->p) { agc_dev_free(ctx->dev, b->p, b->cap + 64); ctx->device_bytes -= b->cap; b->p = nullptr; b->cap = 0; } };
     uint32_t out_cap = (uint32_t)std::min<uint64_t>(0x7fffffff, total / std::max<uint32_t>(ctx->prm.segment_size, 1) + 2ull * n_contigs + 16);
     if ((rc = agc_reserve(ctx, keys_a, total * 8)) || (rc = agc_reserve(ctx, keys_b, total * 8)) || (rc = agc_reserve(ctx, flags, total)) ||
-        (rc = agc_reserve(ctx, nsel, 64)) || (rc = agc_reserve(ctx, outb, (size_t)out_cap * 8))) { cleanup(); return rc; }
+        (rc = agc_reserve(ctx, nsel, 64)) || (rc = agc_reserve(ctx, outb, (size_t)out_cap * 8)) ||
+        (rc = agc_reserve(ctx, whereb, (size_t)out_cap * sizeof(SplPos)))) { cleanup(); return rc; }
     uint32_t grid = std::min<uint32_t>(total_chunks, (uint32_t)ctx->n_sm * 8);
     k_enum_kmers<<<grid, 256, 0, ctx->st>>>((const uint64_t*)ctx->packed.p, d_cstart, n_contigs,
         (const uint32_t*)ctx->chunk_prefix.p, total_chunks, k, (const uint64_t*)ctx->exc_pos.p, ctx->n_exc, (uint64_t*)keys_a.p, base0);
@@ -223,12 +273,18 @@ int agc_enumerate_splitters(agcgpu_ctx* ctx, uint32_t c0, uint32_t n_contigs, bo
     uint32_t* d_cnt = (uint32_t*)nsel.p + 4;
     cudaMemsetAsync(nsel.p, 0, 64, ctx->st);
     k_find_splitters<<<(n_contigs + 3) / 4, 128, 0, ctx->st>>>((const uint64_t*)ctx->packed.p, d_cstart, n_contigs, k,
-        ctx->prm.segment_size, d_cand, n_singles, (const uint64_t*)ctx->exc_pos.p, ctx->n_exc, d_out, d_cnt, out_cap);
+        ctx->prm.segment_size, d_cand, n_singles, (const uint64_t*)ctx->exc_pos.p, ctx->n_exc, d_out, d_cnt, out_cap, (SplPos*)whereb.p);
     ctx->stats.kernel_launches++;
     uint32_t cnt = 0;
     e = cudaMemcpyAsync(&cnt, d_cnt, 4, cudaMemcpyDeviceToHost, ctx->st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->st);
-    if (e == cudaSuccess && cnt <= out_cap && cnt) { out_sorted.resize(cnt); e = cudaMemcpy(out_sorted.data(), d_out, (size_t)cnt * 8, cudaMemcpyDeviceToHost); }
+    if (e == cudaSuccess && cnt <= out_cap && cnt) {
+        out_sorted.resize(cnt); e = cudaMemcpy(out_sorted.data(), d_out, (size_t)cnt * 8, cudaMemcpyDeviceToHost);
+        std::vector<SplPos> where(cnt);
+        if (e == cudaSuccess) e = cudaMemcpy(where.data(), whereb.p, (size_t)cnt * sizeof(SplPos), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) for (uint32_t i = 0; i < cnt; ++i)       // where each splitter was found (agcgpu_last_splitter_positions)
+            ctx->h_last_spl.push_back(agcgpu_ctx::SplFound{ c0 + where[i].contig, where[i].pos, out_sorted[i], (uint8_t)where[i].is_last });
+    }
     if (keep_kmers && e == cudaSuccess) {                  // the sorted k-mer list of the reference sample stays on the device
         if (ctx->ref_kmers.p) { agc_dev_free(ctx->dev, ctx->ref_kmers.p, ctx->ref_kmers.cap + 64); ctx->device_bytes -= ctx->ref_kmers.cap; }
         ctx->ref_kmers = keys_b; keys_b.p = nullptr; keys_b.cap = 0;

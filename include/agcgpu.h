@@ -125,6 +125,29 @@ int agcgpu_set_splitters(agcgpu_ctx* ctx, const uint64_t* splitters, uint64_t n)
 int agcgpu_find_new_splitters(agcgpu_ctx* ctx, const uint32_t* contigs, uint32_t n, uint64_t* out_splitters, uint64_t cap,
                               uint64_t* out_n);
 
+/* -f mode (fallback minimizers).  One k-mer that passes CAGCCompressor::kmer_filter_t (agc_compressor.h:570-599):
+ * (MurMur64Hash(canonical k-mer) ^ 0xD73F8BF11046C40E) < threshold. */
+typedef struct {
+    uint64_t pos;                /* position of the k-mer's last base, relative to the range's first base */
+    uint64_t kmer;               /* canonical CKmer word */
+    uint32_t is_dir_oriented;    /* CKmer::is_dir_oriented(): kmer_dir <= kmer_rc */
+    uint32_t is_symmetric;       /* kmer_dir == kmer_rc (find_splitters_in_contig skips those, agc_compressor.cpp:788) */
+} agcgpu_fkmer;
+/* The filtered k-mers of resident ranges, in position order: the loops of find_cand_segment_using_fallback_minimizers
+ * (agc_compressor.cpp:1826-1855) and find_splitters_in_contig (776-789).  Range i = reqs[i] (contig, start, len; is_rc and
+ * group_id are ignored: the canonical k-mers of a reverse complement are the same ones, orientation flipped; len is
+ * clipped to the contig's end, so 0xFFFFFFFF means "to the end");
+ * k-mers that overlap a non-ACGT symbol do not exist.  Range i's k-mers = out[out_offsets[i] .. out_offsets[i+1]). */
+int agcgpu_filtered_kmers(agcgpu_ctx* ctx, const agcgpu_seg_req* reqs, uint32_t n, uint64_t threshold, agcgpu_fkmer* out,
+                          uint64_t cap, uint64_t* out_offsets);
+/* Where the splitters of the last agcgpu_determine_splitters / agcgpu_find_new_splitters call were found:
+ * (contig index in that call's batch, position of the k-mer's last base, canonical k-mer), ordered by (contig, position);
+ * is_last[i] = 1 for the right-most-candidate splitter that find_splitters_in_contig adds after its walk (816-824).
+ * The contigs of agcgpu_determine_splitters stay resident until the next scan call, so agcgpu_filtered_kmers can be
+ * applied to them: together these give the v_fallbacks of find_splitters_in_contig (797-802, 821-822). */
+int agcgpu_last_splitter_positions(agcgpu_ctx* ctx, uint32_t* out_contig, uint64_t* out_pos, uint64_t* out_kmer, uint8_t* out_is_last,
+                                   uint64_t cap, uint64_t* out_n);
+
 /* ---- contig batch: preprocess + scan ---------------------------------------------------------------------------- */
 /* preprocess_raw_contig (agc_compressor.cpp:907-951) + compress_contig's scan loop (1997-2051) for a batch of
  * contigs.  raw = concatenated raw bodies, contig i = raw[raw_offsets[i] .. raw_offsets[i+1]).  The preprocessed

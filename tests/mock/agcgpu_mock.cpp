@@ -36,8 +36,11 @@ uint64_t orc_scan_contig(const uint8_t* ctg, uint64_t n, uint32_t k, const uint6
 uint64_t orc_enumerate_kmers(const uint8_t* ctg, uint64_t n, uint32_t k, uint64_t* out);
 uint64_t orc_determine_splitters(const uint8_t* ctgs, const uint64_t* offs, uint32_t n_ctg, uint32_t k, uint64_t segment_size,
                                  uint64_t* out, uint64_t* singletons_out, uint64_t* n_singletons);
-uint64_t orc_find_new_splitters(const uint8_t* ctg, uint64_t n, uint32_t k, uint64_t segment_size, const uint64_t* ref_kmers,
-                                uint64_t n_ref, uint64_t* out);
+uint64_t orc_find_new_splitters_pos(const uint8_t* ctg, uint64_t n, uint32_t k, uint64_t segment_size, const uint64_t* ref_kmers,
+                                    uint64_t n_ref, uint64_t* out, uint64_t* out_pos, uint8_t* out_last);
+uint64_t orc_find_splitters_pos(const uint8_t* ctg, uint64_t n, uint32_t k, uint64_t segment_size, const uint64_t* cand, uint64_t n_cand,
+                                uint64_t* out, uint64_t* out_pos, uint8_t* out_last);
+uint64_t orc_filtered_kmers(const uint8_t* ctg, uint64_t n, uint32_t k, uint64_t thr, uint64_t* out_pos, uint64_t* out_kmer, uint8_t* out_flags);
 olz_t* orc_lz_prepare(const uint8_t* ref, uint32_t m, uint32_t min_match_len);
 void orc_lz_free(olz_t* z);
 uint64_t orc_lz_ht_size(const olz_t* z);
@@ -60,6 +63,8 @@ struct agcgpu_ctx {
     struct Group { std::vector<uint8_t> ref; olz_t* lz = nullptr; };
     std::map<uint32_t, Group> groups;
     std::vector<uint64_t> ref_kmers;                          // AGCGPU_F_ADAPTIVE: sorted k-mers of the reference sample
+    struct SplFound { uint32_t contig; uint64_t pos, kmer; uint8_t is_last; };
+    std::vector<SplFound> last_spl;
 };
 
 static thread_local std::string g_create_err;
@@ -158,7 +163,15 @@ int agcgpu_determine_splitters(agcgpu_ctx* ctx, const uint8_t* raw, const uint64
     for (uint32_t c = 0; c < n; ++c) { cat.insert(cat.end(), ctx->contigs[c].begin(), ctx->contigs[c].end()); co[c + 1] = cat.size(); }
     cat.push_back(0);
     std::vector<uint64_t> spl(cat.size() + 2 * n + 16);
-    uint64_t ns = orc_determine_splitters(cat.data(), co.data(), n, ctx->prm.kmer_length, ctx->prm.segment_size, spl.data(), nullptr, nullptr);
+    std::vector<uint64_t> singles(cat.size() + 2); uint64_t n_singles = 0;
+    uint64_t ns = orc_determine_splitters(cat.data(), co.data(), n, ctx->prm.kmer_length, ctx->prm.segment_size, spl.data(), singles.data(), &n_singles);
+    ctx->last_spl.clear();
+    for (uint32_t c = 0; c < n; ++c) {
+        uint64_t len = co[c + 1] - co[c];
+        std::vector<uint64_t> o(len + 2), op(len + 2); std::vector<uint8_t> ol(len + 2);
+        uint64_t no = orc_find_splitters_pos(cat.data() + co[c], len, ctx->prm.kmer_length, ctx->prm.segment_size, singles.data(), n_singles, o.data(), op.data(), ol.data());
+        for (uint64_t i = 0; i < no; ++i) ctx->last_spl.push_back(agcgpu_ctx::SplFound{ c, op[i], o[i], ol[i] });
+    }
     if (ctx->prm.flags & AGCGPU_F_ADAPTIVE) {
         ctx->ref_kmers.assign(cat.size() + 1, 0);
         uint64_t nk = 0;
@@ -166,8 +179,7 @@ int agcgpu_determine_splitters(agcgpu_ctx* ctx, const uint8_t* raw, const uint64
         ctx->ref_kmers.resize(nk);
         std::sort(ctx->ref_kmers.begin(), ctx->ref_kmers.end());
     }
-    ctx->contigs.clear();
-    *out_n = ns;
+    *out_n = ns;                                               // the contigs stay resident until the next scan (agcgpu.h)
     if (ns > cap) return fail(ctx, AGCGPU_EOVERFLOW, "determine_splitters: %llu splitters, buffer holds %llu", (unsigned long long)ns, (unsigned long long)cap);
     if (ns) memcpy(out, spl.data(), ns * 8);
     ctx->splitters.assign(spl.begin(), spl.begin() + ns);
@@ -179,19 +191,52 @@ int agcgpu_find_new_splitters(agcgpu_ctx* ctx, const uint32_t* contigs, uint32_t
     if (!ctx || !out_n || (n && !contigs)) return AGCGPU_EINVAL;
     if (!(ctx->prm.flags & AGCGPU_F_ADAPTIVE)) return fail(ctx, AGCGPU_EINVAL, "find_new_splitters needs AGCGPU_F_ADAPTIVE");
     std::vector<uint64_t> all;
+    ctx->last_spl.clear();
     for (uint32_t i = 0; i < n; ++i) {
         if (contigs[i] >= ctx->contigs.size()) return fail(ctx, AGCGPU_EINVAL, "find_new_splitters: contig %u is not resident", contigs[i]);
         auto& s = ctx->contigs[contigs[i]];
-        std::vector<uint64_t> o(s.size() + 2);
+        std::vector<uint64_t> o(s.size() + 2), op(s.size() + 2); std::vector<uint8_t> ol(s.size() + 2);
         std::vector<uint8_t> padded(s); padded.push_back(0);
-        uint64_t no = orc_find_new_splitters(padded.data(), s.size(), ctx->prm.kmer_length, ctx->prm.segment_size, ctx->ref_kmers.data(), ctx->ref_kmers.size(), o.data());
+        uint64_t no = orc_find_new_splitters_pos(padded.data(), s.size(), ctx->prm.kmer_length, ctx->prm.segment_size, ctx->ref_kmers.data(), ctx->ref_kmers.size(),
+                                                 o.data(), op.data(), ol.data());
         all.insert(all.end(), o.begin(), o.begin() + no);
+        for (uint64_t j = 0; j < no; ++j) ctx->last_spl.push_back(agcgpu_ctx::SplFound{ contigs[i], op[j], o[j], ol[j] });
     }
     std::sort(all.begin(), all.end());
     all.erase(std::unique(all.begin(), all.end()), all.end());
     *out_n = all.size();
     if (all.size() > cap) return fail(ctx, AGCGPU_EOVERFLOW, "find_new_splitters: %zu splitters, buffer holds %llu", all.size(), (unsigned long long)cap);
     if (!all.empty()) memcpy(out, all.data(), all.size() * 8);
+    return 0;
+}
+
+int agcgpu_filtered_kmers(agcgpu_ctx* ctx, const agcgpu_seg_req* reqs, uint32_t n, uint64_t thr, agcgpu_fkmer* out, uint64_t cap, uint64_t* out_offsets)
+{
+    if (!ctx || !out_offsets || (n && !reqs) || (cap && !out)) return AGCGPU_EINVAL;
+    out_offsets[0] = 0;
+    bool overflow = false;
+    for (uint32_t i = 0; i < n; ++i) {
+        std::vector<uint8_t> s;
+        if (reqs[i].contig >= ctx->contigs.size() || reqs[i].start > ctx->contigs[reqs[i].contig].size()) return fail(ctx, AGCGPU_EINVAL, "filtered_kmers: range outside the resident batch");
+        const uint32_t len = (uint32_t)std::min<uint64_t>(reqs[i].len, ctx->contigs[reqs[i].contig].size() - reqs[i].start);   // clipped like get_part
+        if (int r = fetch(ctx, reqs[i].contig, reqs[i].start, len, 0, s)) return r;
+        std::vector<uint64_t> pos(len + 1), km(len + 1); std::vector<uint8_t> fl(len + 1);
+        uint64_t c = orc_filtered_kmers(s.data(), len, ctx->prm.kmer_length, thr, pos.data(), km.data(), fl.data());
+        out_offsets[i + 1] = out_offsets[i] + c;
+        if (out_offsets[i + 1] > cap) { overflow = true; continue; }
+        for (uint64_t j = 0; j < c; ++j) { agcgpu_fkmer f; f.pos = pos[j]; f.kmer = km[j]; f.is_dir_oriented = fl[j] & 1; f.is_symmetric = (fl[j] >> 1) & 1; out[out_offsets[i] + j] = f; }
+    }
+    if (overflow) return fail(ctx, AGCGPU_EOVERFLOW, "filtered_kmers: buffer too small");
+    return 0;
+}
+int agcgpu_last_splitter_positions(agcgpu_ctx* ctx, uint32_t* out_contig, uint64_t* out_pos, uint64_t* out_kmer, uint8_t* out_is_last, uint64_t cap, uint64_t* out_n)
+{
+    if (!ctx || !out_n) return AGCGPU_EINVAL;
+    auto v = ctx->last_spl;
+    std::sort(v.begin(), v.end(), [](const agcgpu_ctx::SplFound& a, const agcgpu_ctx::SplFound& b) { return a.contig != b.contig ? a.contig < b.contig : a.pos < b.pos; });
+    *out_n = v.size();
+    if (v.size() > cap) return fail(ctx, AGCGPU_EOVERFLOW, "last_splitter_positions: buffer too small");
+    for (size_t i = 0; i < v.size(); ++i) { out_contig[i] = v[i].contig; out_pos[i] = v[i].pos; out_kmer[i] = v[i].kmer; out_is_last[i] = v[i].is_last; }
     return 0;
 }
 

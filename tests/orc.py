@@ -52,6 +52,12 @@ def oracle():
         L.orc_lz_estimate.restype = C.c_uint64; L.orc_lz_estimate.argtypes = [C.c_void_p, u8p, C.c_uint32, C.c_uint32]
         L.orc_lz_cost_vector.restype = C.c_uint64; L.orc_lz_cost_vector.argtypes = [C.c_void_p, u8p, C.c_uint32, C.c_int, u32p]
         L.orc_lz_decode.restype = C.c_uint64; L.orc_lz_decode.argtypes = [u8p, C.c_uint32, u8p, C.c_uint64, C.c_uint32, u8p]
+        L.orc_find_new_splitters.restype = C.c_uint64
+        L.orc_find_new_splitters.argtypes = [u8p, C.c_uint64, C.c_uint32, C.c_uint64, u64p, C.c_uint64, u64p]
+        L.orc_filtered_kmers.restype = C.c_uint64
+        L.orc_filtered_kmers.argtypes = [u8p, C.c_uint64, C.c_uint32, C.c_uint64, u64p, u64p, u8p]
+        L.orc_find_splitters_pos.restype = C.c_uint64
+        L.orc_find_splitters_pos.argtypes = [u8p, C.c_uint64, C.c_uint32, C.c_uint64, u64p, C.c_uint64, u64p, u64p, u8p]
         L.orc_bytes2tuples.restype = C.c_uint64; L.orc_bytes2tuples.argtypes = [u8p, C.c_uint64, u8p]
         L.orc_ref_use_tuples.restype = C.c_int; L.orc_ref_use_tuples.argtypes = [u8p, C.c_uint64]
         _ORC = L
@@ -204,3 +210,21 @@ def find_new_splitters(codes, k, segment_size, ref_kmers_sorted):
     out = np.empty(len(codes) + 2, np.uint64)
     n = oracle().orc_find_new_splitters(_p8(codes), len(codes), k, segment_size, rk.ctypes.data_as(u64p), len(rk), out.ctypes.data_as(u64p))
     return out[:n].copy()
+
+
+def filtered_kmers(codes, k, thr):
+    """-f mode: (pos, kmer, is_dir_oriented, is_symmetric) of the k-mers passing kmer_filter_t, in position order"""
+    codes = np.ascontiguousarray(codes, np.uint8)
+    pos = np.empty(len(codes) + 1, np.uint64); km = np.empty(len(codes) + 1, np.uint64); fl = np.empty(len(codes) + 1, np.uint8)
+    n = oracle().orc_filtered_kmers(_p8(codes), len(codes), k, int(thr), pos.ctypes.data_as(u64p), km.ctypes.data_as(u64p), _p8(fl))
+    return [(int(pos[i]), int(km[i]), int(fl[i] & 1), int(fl[i] >> 1)) for i in range(n)]
+
+
+def find_splitters_pos(codes, k, segment_size, cand_sorted):
+    """find_splitters_in_contig with positions: (pos, kmer, is_last) in the order they were found"""
+    codes = np.ascontiguousarray(codes, np.uint8)
+    cd = np.ascontiguousarray(cand_sorted, np.uint64)
+    out = np.empty(len(codes) + 2, np.uint64); pos = np.empty(len(codes) + 2, np.uint64); last = np.empty(len(codes) + 2, np.uint8)
+    n = oracle().orc_find_splitters_pos(_p8(codes), len(codes), k, segment_size, cd.ctypes.data_as(u64p), len(cd),
+                                        out.ctypes.data_as(u64p), pos.ctypes.data_as(u64p), _p8(last))
+    return [(int(pos[i]), int(out[i]), int(last[i])) for i in range(n)]

@@ -252,6 +252,44 @@ def test_find_new_splitters_and_rescan(dev_factory):
                    [(x.start, x.len, x.has_front, x.has_back, x.front_dir if x.has_front else 0, x.back_dir if x.has_back else 0, x.back_rc if x.has_back else 0) for x in exp], (k, seg, c)
 
 
+def test_filtered_kmers_and_splitter_positions(dev_factory):
+    """-f mode entry points: the k-mers that pass kmer_filter_t in resident ranges (orientation, symmetry, non-ACGT resets) and
+    where determine_splitters / find_new_splitters found their splitters (agc_compressor.cpp:776-802, 1826-1855)"""
+    rng = np.random.default_rng(22)
+    for k, seg, frac in ((21, 700, 0.05), (32, 3000, 0.01), (17, 500, 0.5)):
+        thr = int(float(0xFFFFFFFFFFFFFFFF) * frac)
+        dev = dev_factory(k=k, min_match_len=20, segment_size=seg, adaptive=True)
+        ref = [rng.integers(0, 4, n).astype(np.uint8) for n in (20000, 6000, k - 1, 0, k)]
+        ref[1] = mutate(rng, ref[1], 0, 0, 6)                       # non-ACGT symbols
+        pal = rng.integers(0, 4, k // 2).astype(np.uint8)
+        if k % 2 == 0:                                              # a k-mer that is its own reverse complement
+            ref[0][500:500 + k] = np.concatenate([pal, orc.revcomp(pal)])
+        spl, singles = orc.determine_splitters(ref, k, seg)
+        got = dev.determine_splitters([to_fasta_body(c, 70) for c in ref])
+        assert np.array_equal(got, spl)
+        exp_pos = sorted((c, p, km, last) for c, codes in enumerate(ref) for p, km, last in orc.find_splitters_pos(codes, k, seg, singles))
+        assert dev.last_splitter_positions() == exp_pos, (k, seg)
+        # the reference contigs are still resident: whole contigs (len clipped), inner ranges, ranges shorter than k
+        ranges = [(c, 0, 0xFFFFFFFF) for c in range(len(ref))] + [(0, 137, 5000), (0, 19990, 10), (1, 3, k), (1, 100, k - 1)]
+        res = dev.filtered_kmers(ranges, thr)
+        for (c, s, l), fk in zip(ranges, res):
+            codes = ref[c][s:s + min(l, len(ref[c]) - s)]
+            assert [(f.pos, f.kmer, f.is_dir_oriented, f.is_symmetric) for f in fk] == orc.filtered_kmers(codes, k, thr), (k, c, s, l)
+        # after a scan, find_new_splitters reports positions in the new batch
+        novel = [rng.integers(0, 4, 4 * seg + 77).astype(np.uint8), mutate(rng, rng.integers(0, 4, 3 * seg).astype(np.uint8), 0, 0, 3)]
+        dev.scan_contigs([to_fasta_body(c, 60) for c in [ref[0]] + novel])
+        ref_kmers = np.sort(np.concatenate([orc.enumerate_kmers(c, k) for c in ref]))
+        new = dev.find_new_splitters([1, 2])
+        where = dev.last_splitter_positions()
+        assert sorted(set(w[2] for w in where)) == list(new)
+        for c in (1, 2):
+            codes = novel[c - 1]
+            km = orc.enumerate_kmers(codes, k)
+            u, cnt = np.unique(km, return_counts=True)
+            cand = np.setdiff1d(u[cnt == 1], ref_kmers)
+            assert [w[1:] for w in where if w[0] == c] == sorted(orc.find_splitters_pos(codes, k, seg, cand)), (k, c)
+
+
 def test_assign(dev_factory):
     rng = np.random.default_rng(15)
     k = 25

@@ -53,11 +53,17 @@ def collection(case, tmp):
         return gen_data.concatenated_collection(d, seed=2, n_ctg=17, per_file=6), ["-c", "-k", "21", "-s", "2000", "-b", "4"]
     if case == "concatenated_adaptive":
         return gen_data.concatenated_collection(d, seed=3, n_ctg=22, per_file=8), ["-c", "-a", "-k", "21", "-s", "2000", "-b", "6"]
+    if case == "fallback":          # -f, segment_size <= 10000: candidates are decided by shared-minimizer counts (1908-1913)
+        return gen_data.fallback_collection(d, seed=11, seg=2000), ["-f", "0.05", "-k", "21", "-s", "2000", "-b", "4"]
+    if case == "fallback_estimates":    # -f, long segments: candidates are decided by CSegment::estimate (1919)
+        return gen_data.fallback_collection(d, seed=12, seg=12000, n_samples=6, ref_len=200000), ["-f", "0.02", "-k", "25", "-s", "12000"]
+    if case == "fallback_adaptive":
+        return gen_data.fallback_collection(d, seed=13, seg=2000), ["-f", "0.05", "-a", "-k", "21", "-s", "2000", "-b", "4"]
     raise KeyError(case)
 
 
 ALL_CASES = ["viral", "complex", "complex_n", "tiny", "smallpacks", "adaptive", "adaptive_big_segments", "adaptive_complex",
-             "concatenated", "concatenated_full_units", "concatenated_adaptive"]
+             "concatenated", "concatenated_full_units", "concatenated_adaptive", "fallback", "fallback_estimates", "fallback_adaptive"]
 
 
 @pytest.fixture(scope="module")
@@ -75,14 +81,23 @@ def test_host_pipeline_archives_match_reference(tmp_path, mock_agc, case):
     subprocess.check_call([mock_agc, "create", "-o", our_out] + flags + files)
     a = open(our_out, "rb").read(); b = open(ref_out, "rb").read()
     assert a == b, f"archives differ: {len(a)} vs {len(b)} bytes, first diff at {next((i for i, (x, y) in enumerate(zip(a, b)) if x != y), -1)}"
-    if "-a" in flags:               # the case must really exercise the adaptive path: the non-adaptive archive is a different one
-        plain = os.path.join(tmp, "plain.agc")
-        subprocess.check_call([REF_AGC, "create", "-t", "4", "-o", plain] + [f for f in flags if f != "-a"] + files, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-        assert open(plain, "rb").read() != b
+    for mode in ("-a", "-f"):       # the case must really exercise the mode: without the flag the reference writes a different archive
+        if mode in flags:
+            plain = os.path.join(tmp, "plain.agc")
+            i = flags.index(mode)
+            rest = flags[:i] + flags[i + (2 if mode == "-f" else 1):]
+            subprocess.check_call([REF_AGC, "create", "-t", "4", "-o", plain] + rest + files, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            assert open(plain, "rb").read() != b
 
 
-def test_refused_modes_fail_loudly(tmp_path, mock_agc):
-    files, flags = collection("tiny", str(tmp_path))
-    for extra in (["-f", "0.1"],):
-        r = subprocess.run([mock_agc, "create", "-o", os.path.join(str(tmp_path), "x.agc")] + extra + flags + files, capture_output=True)
-        assert r.returncode != 0 and b"not implemented" in r.stderr
+def test_cli_clamps_options_like_the_reference(tmp_path, mock_agc):
+    """b_value<T>::assign (src/app/application.h:23-47): -f 0.2 means -f 0.05, -k 40 means -k 32, ..."""
+    tmp = str(tmp_path)
+    files, _ = collection("fallback", tmp)
+    outs = []
+    for flags in (["-f", "0.2", "-k", "40", "-s", "50", "-l", "3"], ["-f", "0.05", "-k", "32", "-s", "100", "-l", "15"]):
+        for exe, name in ((REF_AGC, "ref"), (mock_agc, "our")):
+            out = os.path.join(tmp, f"{name}{len(outs)}.agc")
+            subprocess.check_call([exe, "create", "-o", out] + flags + files[:3], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            outs.append(open(out, "rb").read())
+    assert outs[0] == outs[1] == outs[2] == outs[3]

@@ -1,4 +1,4 @@
-"""Differential fuzzing of the host side of the path (TEST TOOL): random small collections and random `create` flags through
+"""Differential fuzzing of the host side of the path (TEST TOOL): random small collections and random `create` flags (k, l, s, b, -a, -c, -f) through
 tests/mock/agc-mock (product host objects + oracle-backed device ABI) and through the reference binary; archives must be
 byte-identical.  usage: python tools/fuzz_host_pipeline.py [n_cases] [first_seed] [agc binary]"""
 import os
@@ -28,6 +28,8 @@ def make_case(d, seed):
     conc = rng.random() < 0.3
     if conc:
         flags.append("-c")
+    if rng.random() < 0.4:
+        flags += ["-f", str(rng.choice([0.005, 0.02, 0.05, 0.2]))]      # the CLI clamps to 0.05
     n_ref = int(rng.integers(1, 4))
     ref = [rng.integers(0, 4, int(rng.integers(s // 2, 12 * s)), dtype=np.uint8) for _ in range(n_ref)]
     if rng.random() < 0.3 and len(ref[0]) > 4 * s:

@@ -120,6 +120,32 @@ def concatenated_collection(out_dir, seed=1, n_ctg=23, per_file=9):
     return files
 
 
+def fallback_collection(out_dir, seed=11, seg=2000, n_samples=8, ref_len=60000):
+    """-f mode: divergent samples (up to 6 % substitutions: most splitters are destroyed, so segments come with one or no
+    terminal splitter, or with a pair that is not in the map) plus reference fragments that contain no whole splitter pair:
+    the cases find_cand_segment_using_fallback_minimizers decides (agc_compressor.cpp:1290,1327,1352,1461)."""
+    os.makedirs(out_dir, exist_ok=True)
+    rng = np.random.default_rng(seed)
+    ref = [rng.integers(0, 4, ref_len // 2 + 901 * i, dtype=np.uint8) for i in range(2)]
+    files = [os.path.join(out_dir, "ref.fa")]
+    write_fasta(files[0], [(f"chr{i + 1}", c) for i, c in enumerate(ref)])
+    for s in range(n_samples):
+        ctgs = []
+        for i, c in enumerate(ref):
+            t = indels(rng, substitute(rng, c, [0.002, 0.02, 0.06][s % 3]), 4)
+            if s % 4 == 1:
+                t = (3 - t[::-1]).astype(np.uint8)
+            ctgs.append((f"f{s}_chr{i + 1}", t))
+        a = int(rng.integers(0, len(ref[0]) - 3 * seg))
+        frag = substitute(rng, ref[0][a:a + int(2.2 * seg)], 0.03)
+        ctgs.append((f"f{s}_frag", frag if s % 2 else (3 - frag[::-1]).astype(np.uint8)))
+        ctgs.append((f"f{s}_novel", rng.integers(0, 4, int(1.5 * seg), dtype=np.uint8)))
+        fn = os.path.join(out_dir, f"f{s:02d}.fa")
+        write_fasta(fn, ctgs)
+        files.append(fn)
+    return files
+
+
 def total_bases(files):
     n = 0
     for fn in files:
