@@ -76,6 +76,13 @@ int agcgpu_compressor_set_discard_parts(agcgpu_compressor* c, int discard)
     return 0;
 }
 
+int agcgpu_compressor_set_verify(agcgpu_compressor* c, int verify)
+{
+    if (!c) return AGCGPU_EINVAL;
+    c->impl.SetVerify(verify != 0);
+    return 0;
+}
+
 int agcgpu_compressor_add_cmd_line(agcgpu_compressor* c, const char* cmd_line)
 {
     if (!c || !cmd_line) return AGCGPU_EINVAL;

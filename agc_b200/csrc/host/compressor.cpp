@@ -549,6 +549,16 @@ bool CAGCCompressor::compress_tasks_local(std::vector<ZTask*>& tasks)
     if (!gpu_ok(agcgpu_zstd_compress_batch(ctx, src.data(), offs.data(), levels.data(), (uint32_t)tasks.size(), dst.data(), cap, doffs.data()),
                 "zstd_compress_batch")) return false;
     for (size_t i = 0; i < tasks.size(); ++i) tasks[i]->packed.assign(dst.begin() + doffs[i], dst.begin() + doffs[i + 1]);
+    if (verify) {                                            // decode-and-compare: the frames must give back exactly what went in
+        PhaseTimer pv("residual coder self check");
+        std::vector<uint8_t> back(offs.back() + 1);
+        std::vector<uint64_t> boffs(tasks.size() + 1, 0);
+        if (!gpu_ok(agcgpu_zstd_decompress_batch(ctx, dst.data(), doffs.data(), (uint32_t)tasks.size(), back.data(), offs.back(), boffs.data()),
+                    "zstd_decompress_batch (self check)")) return false;
+        for (size_t i = 0; i < tasks.size(); ++i)
+            if (boffs[i + 1] - boffs[i] != tasks[i]->raw.size() || (!tasks[i]->raw.empty() && memcmp(back.data() + boffs[i], tasks[i]->raw.data(), tasks[i]->raw.size()) != 0))
+                return fail("self check: frame " + std::to_string(i) + " of a residual-coder batch does not decode to its input");
+    }
     return true;
 }
 

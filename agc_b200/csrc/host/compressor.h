@@ -125,6 +125,7 @@ public:
     void SetAppMode(bool m) { is_app_mode = m; }
     void SetDumpParts(const std::string& path) { dump_path = path; }   // test hook: write every part's pre-zstd content
     void SetBatchBases(uint64_t b) { batch_bases = b; }
+    void SetVerify(bool v) { verify = v; }                             // decode every coded frame on the device and compare with its input
     // multi-GPU (include/agcgpu.h, agcgpu_set_exchange): this object is rank `rank` of `world` identical ones
     void SetExchange(uint32_t rank, uint32_t world, agcgpu_allgather_fn fn, void* user) { xrank = rank; xworld = fn && world > 1 ? world : 1; xfn = fn; xuser = user; }
     const std::string& LastError() const { return last_error; }
@@ -176,7 +177,7 @@ private:
     uint32_t xrank = 0, xworld = 1; agcgpu_allgather_fn xfn = nullptr; void* xuser = nullptr;
     uint64_t batch_bases = 1ull << 30;
     std::string dump_path, last_error;
-    bool discard_parts = false;
+    bool discard_parts = false, verify = false;
     FILE* dump_f = nullptr;
 
     agcgpu_ctx* ctx = nullptr;

@@ -26,10 +26,10 @@ static void remove_common_suffixes(std::string& s)        // application.cpp:606
 int main(int argc, char** argv)
 {
     if (argc < 3 || std::string(argv[1]) != "create") {
-        std::cerr << "usage: agc-b200 create [-k 31] [-l 20] [-s 60000] [-b 50] [-t n] [-v n] [-i list] [-d] [--device n] [--dump-parts file] -o out.agc ref.fa [samples...]\n";
+        std::cerr << "usage: agc-b200 create [-k 31] [-l 20] [-s 60000] [-b 50] [-t n] [-v n] [-i list] [-d] [-a] [-c] [-f frac] [--device n] [--verify] [--dump-parts file] -o out.agc ref.fa [samples...]\n";
         return 1;
     }
-    uint32_t k = 31, l = 20, s = 60000, b = 50, t = 1, v = 0; bool a = false, c = false; double f = 0.0; int dev = 0;
+    uint32_t k = 31, l = 20, s = 60000, b = 50, t = 1, v = 0; bool a = false, c = false, verify = false; double f = 0.0; int dev = 0;
     std::string out, list, dump;
     std::vector<std::string> inputs;
     for (int i = 2; i < argc; ++i) {
@@ -38,7 +38,7 @@ int main(int argc, char** argv)
         if (x == "-k") k = (uint32_t)atoi(next()); else if (x == "-l") l = (uint32_t)atoi(next()); else if (x == "-s") s = (uint32_t)atoi(next());
         else if (x == "-b") b = (uint32_t)atoi(next()); else if (x == "-t") t = (uint32_t)atoi(next()); else if (x == "-v") v = (uint32_t)atoi(next());
         else if (x == "-o") out = next(); else if (x == "-i") list = next(); else if (x == "-a") a = true; else if (x == "-c") c = true;
-        else if (x == "-d") {} else if (x == "-f") f = atof(next()); else if (x == "--device") dev = atoi(next()); else if (x == "--dump-parts") dump = next();
+        else if (x == "-d") {} else if (x == "-f") f = atof(next()); else if (x == "--device") dev = atoi(next()); else if (x == "--dump-parts") dump = next(); else if (x == "--verify") verify = true;
         else inputs.push_back(x);
     }
     // b_value<T>::assign clamps every numeric option to its range (src/app/application.h:23-47, 63-71)
@@ -50,6 +50,7 @@ int main(int argc, char** argv)
     agc_b200::CAGCCompressor agc;
     agc.SetDevice(dev);
     if (!dump.empty()) agc.SetDumpParts(dump);
+    agc.SetVerify(verify);
     if (!agc.Create(out, b, k, inputs.front(), s, l, c, a, v, t, f)) { std::cerr << "Cannot create archive " << out << std::endl; return 1; }
     std::vector<std::pair<std::string, std::string>> files;
     for (auto& fn : inputs) { std::string nm = std::filesystem::path(fn).stem().string(); remove_common_suffixes(nm); files.emplace_back(nm, fn); }

@@ -279,9 +279,12 @@ ZD_FN int decode_block(Work& w, const uint8_t* src, uint32_t n, uint8_t* dst_bas
         const uint32_t modes = p[0]; p += 1; left -= 1;
         if (modes & 3) return ZD_ESRC;
         int t;
-        if ((t = seq_table(w, 0, modes >> 6, w.ll, &w.ll_log, &w.have_ll, p, left)) < 0) return t; p += t; left -= t;
-        if ((t = seq_table(w, 1, (modes >> 4) & 3, w.of, &w.of_log, &w.have_of, p, left)) < 0) return t; p += t; left -= t;
-        if ((t = seq_table(w, 2, (modes >> 2) & 3, w.ml, &w.ml_log, &w.have_ml, p, left)) < 0) return t; p += t; left -= t;
+        if ((t = seq_table(w, 0, modes >> 6, w.ll, &w.ll_log, &w.have_ll, p, left)) < 0) return t;
+        p += t; left -= t;
+        if ((t = seq_table(w, 1, (modes >> 4) & 3, w.of, &w.of_log, &w.have_of, p, left)) < 0) return t;
+        p += t; left -= t;
+        if ((t = seq_table(w, 2, (modes >> 2) & 3, w.ml, &w.ml_log, &w.have_ml, p, left)) < 0) return t;
+        p += t; left -= t;
         const uint32_t LL_base[36] = { 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 18, 20, 22, 24, 28, 32, 40, 48, 64, 0x80, 0x100, 0x200, 0x400,
                                        0x800, 0x1000, 0x2000, 0x4000, 0x8000, 0x10000 };
         const uint8_t LL_bits[36] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 3, 3, 4, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16 };
@@ -331,6 +334,21 @@ ZD_FN int decode_block(Work& w, const uint8_t* src, uint32_t n, uint8_t* dst_bas
     out += tail;
     if (out - dst_pos > (128u << 10)) return ZD_ESRC;
     return (int)(out - dst_pos);
+}
+
+// Frame_Content_Size of a frame header, -1 when the header does not carry it (frames written by ZSTD_compressCCtx always do)
+ZD_FN int64_t frame_content_size(const uint8_t* src, uint64_t n)
+{
+    if (n < 6 || (src[0] | (src[1] << 8) | (src[2] << 16) | ((uint32_t)src[3] << 24)) != 0xFD2FB528u) return -1;
+    const uint32_t fhd = src[4], fcs_flag = fhd >> 6, single = (fhd >> 5) & 1, did = fhd & 3;
+    const uint32_t did_bytes = did == 3 ? 4 : did;
+    uint64_t p = 5 + (single ? 0 : 1) + did_bytes;
+    const uint32_t fcs_bytes = fcs_flag == 0 ? single : (fcs_flag == 1 ? 2 : (fcs_flag == 2 ? 4 : 8));
+    if (fcs_bytes == 0 || p + fcs_bytes > n) return -1;
+    uint64_t fcs = 0;
+    for (uint32_t i = 0; i < fcs_bytes; ++i) fcs |= (uint64_t)src[p + i] << (8 * i);
+    if (fcs_bytes == 2) fcs += 256;
+    return (int64_t)fcs;
 }
 
 // one frame; `w` needs no initialisation

@@ -209,6 +209,14 @@ int agcgpu_pack_ref_batch(agcgpu_ctx* ctx, const uint32_t* group_ids, uint32_t n
 int agcgpu_zstd_compress_batch(agcgpu_ctx* ctx, const uint8_t* src, const uint64_t* src_offsets, const int32_t* levels,
                                uint32_t n, uint8_t* dst, uint64_t dst_cap, uint64_t* dst_offsets);
 
+/* ZSTD_decompressDCtx (3rd_party/zstd/lib/decompress) for a batch of independent frames, as CSegment::unpack / get
+ * (src/common/segment.cpp:500-577, 220-399) and CCollection_V3 call it: the decode side of the residual coder, used by the
+ * decode-and-compare self check (agcgpu_compressor_set_verify).  Frame i = src[src_offsets[i] .. src_offsets[i+1]); every frame
+ * header must carry its content size (all frames of ZSTD_compressCCtx do); output i = dst[dst_offsets[i] .. dst_offsets[i+1]).
+ * dst_offsets is filled even when dst_cap is too small (AGCGPU_EOVERFLOW), so a caller can size the buffer with one call. */
+int agcgpu_zstd_decompress_batch(agcgpu_ctx* ctx, const uint8_t* src, const uint64_t* src_offsets, uint32_t n, uint8_t* dst,
+                                 uint64_t dst_cap, uint64_t* dst_offsets);
+
 /* ---- CAGCCompressor facade (src/core/agc_compressor.h:754-763) for non-C++ callers -------------------------------- */
 typedef struct agcgpu_compressor agcgpu_compressor;
 /* CAGCCompressor::Create; dump_parts_path (may be NULL) = test hook writing every part's pre-zstd content */
@@ -240,6 +248,9 @@ int agcgpu_set_exchange(uint32_t rank, uint32_t world, agcgpu_allgather_fn allga
 
 /* measurement hook: build every archive part but skip the residual coder and the file writes */
 int agcgpu_compressor_set_discard_parts(agcgpu_compressor* c, int discard);
+/* self check: every frame the residual coder writes is decoded again on the device and compared with its input before the
+ * part goes to the archive; a mismatch fails the call (AGC's own check is a later `agc getset`) */
+int agcgpu_compressor_set_verify(agcgpu_compressor* c, int verify);
 /* CAGCCompressor::AddCmdLine */
 int agcgpu_compressor_add_cmd_line(agcgpu_compressor* c, const char* cmd_line);
 /* CAGCCompressor::Close, then frees the object */

@@ -27,6 +27,8 @@
 #undef ZE_NS
 #undef ZE_WN_W
 
+#include "../../agc_b200/csrc/zstd_dec.cuh"
+
 extern "C" {
 typedef struct olz olz_t;
 typedef struct { uint64_t start, len, front_dir, front_rc, back_dir, back_rc; uint32_t has_front, has_back; } orc_cut_t;
@@ -427,6 +429,24 @@ int agcgpu_zstd_compress_batch(agcgpu_ctx* ctx, const uint8_t* src, const uint64
         memcpy(dst + o, fr.data(), r);
         o += r; dof[i + 1] = o;
         ctx->stats.zstd_input_mb += (float)len / 1e6f;
+    }
+    return 0;
+}
+
+int agcgpu_zstd_decompress_batch(agcgpu_ctx* ctx, const uint8_t* src, const uint64_t* so, uint32_t n, uint8_t* dst, uint64_t dst_cap, uint64_t* dof)
+{
+    if (!ctx || !so || !dof || (n && !src) || (dst_cap && !dst)) return AGCGPU_EINVAL;
+    dof[0] = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        int64_t fcs = zd::frame_content_size(src + so[i], so[i + 1] - so[i]);
+        if (fcs < 0) return fail(ctx, AGCGPU_EUNSUPPORTED, "zstd decode: frame %u has no content size in its header", i);
+        dof[i + 1] = dof[i] + (uint64_t)fcs;
+    }
+    if (dof[n] > dst_cap) return fail(ctx, AGCGPU_EOVERFLOW, "zstd decode: output buffer too small");
+    std::vector<zd::Work> w(1);
+    for (uint32_t i = 0; i < n; ++i) {
+        int64_t r = zd::decompress_frame(src + so[i], so[i + 1] - so[i], dst + dof[i], dof[i + 1] - dof[i], w[0]);
+        if (r < 0 || (uint64_t)r != dof[i + 1] - dof[i]) return fail(ctx, AGCGPU_EINVAL, "zstd decode: frame %u is malformed or truncated (code %lld)", i, (long long)r);
     }
     return 0;
 }

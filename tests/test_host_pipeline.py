@@ -90,6 +90,17 @@ def test_host_pipeline_archives_match_reference(tmp_path, mock_agc, case):
             assert open(plain, "rb").read() != b
 
 
+def test_self_check_mode(tmp_path, mock_agc):
+    """--verify: every coded frame is decoded again (device decoder; here its host build) and compared before it is written;
+    the archive is the same one"""
+    tmp = str(tmp_path)
+    files, flags = collection("complex", tmp)
+    a = os.path.join(tmp, "a.agc"); b = os.path.join(tmp, "b.agc")
+    subprocess.check_call([mock_agc, "create", "-o", a] + flags + files)
+    subprocess.check_call([mock_agc, "create", "--verify", "-o", b] + flags + files)
+    assert open(a, "rb").read() == open(b, "rb").read()
+
+
 def test_cli_clamps_options_like_the_reference(tmp_path, mock_agc):
     """b_value<T>::assign (src/app/application.h:23-47): -f 0.2 means -f 0.05, -k 40 means -k 32, ..."""
     tmp = str(tmp_path)

@@ -102,3 +102,66 @@ def test_host_btlazy2_class(ze):
     for kind, n in ((2, 270000), (5, 1200000), (0, 270000)):
         raw = _gen_adv(rng, kind, n)
         assert ze(raw, 13) == agc_parts.zstd_compress(raw, 13), f"adv kind {kind}, {n} bytes"
+
+
+# ---- the decoding side (agc_b200/csrc/zstd_dec.cuh, host build) -------------------------------------------------------
+@pytest.fixture(scope="module")
+def zd():
+    d = os.path.join(ROOT, "tests", "zstd_host")
+    so = os.path.join(d, "libzd_host.so")
+    src = [os.path.join(d, "zd_host.cpp"), os.path.join(ROOT, "agc_b200", "csrc", "zstd_dec.cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src):
+        subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-o", so, src[0]])
+    L = C.CDLL(so)
+    L.zd_host_decompress.restype = C.c_long
+    L.zd_host_decompress.argtypes = [C.c_char_p, C.c_ulong, C.c_char_p, C.c_ulong]
+
+    def decompress(frame, cap):
+        out = C.create_string_buffer(cap + 64)
+        r = L.zd_host_decompress(frame, len(frame), out, cap)
+        return r, out.raw[:max(r, 0)]
+    return decompress
+
+
+def test_decoder_against_libzstd_frames(zd):
+    """frames written by the reference's libzstd at fast, lazy and optimal levels (raw / RLE / Huffman / treeless literals,
+    predefined / RLE / FSE / repeat sequence tables, multi-block) decode to the input"""
+    rng = np.random.default_rng(31)
+    for level in (1, 3, 6, 9, 13, 17, 18, 19):
+        for gen, kinds in ((_gen, range(7)), (_gen_adv, range(6))):
+            for kind in kinds:
+                for n in (0, 1, 5, 200, 4000, 40000, 300000):
+                    if n > 40000 and (kind + level) % 2:
+                        continue
+                    raw = gen(rng, kind, n)
+                    r, out = zd(agc_parts.zstd_compress(raw, level), len(raw))
+                    assert r == len(raw) and out == raw, f"level {level} {gen.__name__} kind {kind} n {n}: {r}"
+
+
+def test_decoder_roundtrips_the_coder(ze, zd):
+    """frames of this repository's coder (both instantiations) decode to the input"""
+    rng = np.random.default_rng(32)
+    for kind in range(7):
+        for n, level, narrow in ((300, 17, True), (9000, 13, True), (30000, 19, True), (50000, 17, False), (300000, 19, False)):
+            raw = _gen(rng, kind, n)
+            r, out = zd(ze(raw, level, narrow=narrow), len(raw))
+            assert r == len(raw) and out == raw
+
+
+def test_decoder_rejects_damaged_frames(zd):
+    """truncated or corrupted input and short output buffers give an error code, never a wrong answer of the right size"""
+    rng = np.random.default_rng(33)
+    raw = _gen(rng, 2, 20000)
+    fr = agc_parts.zstd_compress(raw, 17)
+    assert zd(fr, len(raw))[0] == len(raw)
+    assert zd(fr, len(raw) - 1)[0] < 0                           # output buffer too small
+    for cut in (0, 3, 5, 9, len(fr) // 2, len(fr) - 1):
+        assert zd(fr[:cut], len(raw))[0] < 0
+    assert zd(b"\x00" * 20, 100)[0] < 0                          # not a zstd frame
+    hits = 0
+    for _ in range(200):                                         # random single-byte damage: an error, or (rarely) a different text
+        i = int(rng.integers(4, len(fr)))
+        bad = bytearray(fr); bad[i] ^= 1 << int(rng.integers(0, 8))
+        r, out = zd(bytes(bad), len(raw))
+        hits += (r < 0) or (out != raw)
+    assert hits >= 190
