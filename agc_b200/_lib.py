@@ -55,7 +55,7 @@ EXPORTED_SYMBOLS = [
     "agcgpu_group_put_reference", "agcgpu_group_get_index", "agcgpu_lz_encode_batch", "agcgpu_lz_estimate_batch",
     "agcgpu_lz_cost_vector", "agcgpu_pack_ref_batch", "agcgpu_zstd_compress_batch",
     "agcgpu_find_new_splitters", "agcgpu_rescan_contigs", "agcgpu_filtered_kmers", "agcgpu_last_splitter_positions",
-    "agcgpu_zstd_decompress_batch",
+    "agcgpu_zstd_decompress_batch", "agcgpu_lz_decode_batch",
 ]
 
 
@@ -87,6 +87,8 @@ def lib():
     L.agcgpu_scan_contigs.argtypes = [vp, u8p, u64p, C.c_uint32, u64p, C.POINTER(Cut), C.c_uint64, u64p]
     L.agcgpu_find_new_splitters.restype = C.c_int
     L.agcgpu_find_new_splitters.argtypes = [vp, u32p, C.c_uint32, u64p, C.c_uint64, u64p]
+    L.agcgpu_lz_decode_batch.restype = C.c_int
+    L.agcgpu_lz_decode_batch.argtypes = [vp, u32p, u8p, u64p, C.c_uint32, u8p, C.c_uint64, u64p]
     L.agcgpu_zstd_decompress_batch.restype = C.c_int
     L.agcgpu_zstd_decompress_batch.argtypes = [vp, u8p, u64p, C.c_uint32, u8p, C.c_uint64, u64p]
     L.agcgpu_filtered_kmers.restype = C.c_int
@@ -326,6 +328,22 @@ class Device:
         doffs = np.zeros(len(inputs) + 1, np.uint64)
         self._ck(self.L.agcgpu_zstd_compress_batch(self.h, _p(src, u8p), _p(offs, u64p), _p(lv, i32p), len(inputs), _p(dst, u8p), cap, _p(doffs, u64p)))
         return [dst[int(doffs[i]):int(doffs[i + 1])].tobytes() for i in range(len(inputs))]
+
+    def lz_decode(self, group_ids, deltas):
+        """CLZDiff_V2::Decode of every delta against its group's resident reference -> list of symbol arrays"""
+        g = np.ascontiguousarray(group_ids, np.uint32)
+        offs = np.zeros(len(deltas) + 1, np.uint64)
+        if deltas:
+            offs[1:] = np.cumsum([len(x) for x in deltas])
+        src = np.frombuffer(b"".join(deltas), np.uint8).copy() if offs[-1] else np.zeros(1, np.uint8)
+        ooffs = np.zeros(len(deltas) + 1, np.uint64)
+        out = np.zeros(1, np.uint8)
+        rc = self.L.agcgpu_lz_decode_batch(self.h, _p(g, u32p), _p(src, u8p), _p(offs, u64p), len(deltas), _p(out, u8p), 0, _p(ooffs, u64p))
+        if rc == -4:
+            out = np.zeros(int(ooffs[-1]) + 1, np.uint8)
+            rc = self.L.agcgpu_lz_decode_batch(self.h, _p(g, u32p), _p(src, u8p), _p(offs, u64p), len(deltas), _p(out, u8p), int(ooffs[-1]), _p(ooffs, u64p))
+        self._ck(rc)
+        return [out[int(ooffs[i]):int(ooffs[i + 1])].copy() for i in range(len(deltas))]
 
     def zstd_decompress(self, frames):
         """ZSTD_decompressDCtx of every frame on the device -> list of outputs (sizes come from the frame headers)"""

@@ -1218,6 +1218,23 @@ bool CAGCCompressor::process_batch_raw(const uint8_t* cat, bool is_device, const
     }
     std::vector<uint8_t> deltas; std::vector<uint64_t> doffs;
     if (!lz_encode(lz, deltas, doffs)) return false;
+    if (verify && !lz.empty()) {                             // decode-and-compare: every delta must give back its segment
+        PhaseTimer pv("LZ self check");
+        std::vector<uint32_t> gids(lz.size());
+        uint64_t cap = 0;
+        for (size_t i = 0; i < lz.size(); ++i) { gids[i] = lz[i].group_id; cap += lz[i].len; }
+        std::vector<uint8_t> back(cap + 1), sym;
+        std::vector<uint64_t> boffs(lz.size() + 1, 0);
+        if (!gpu_ok(agcgpu_lz_decode_batch(ctx, gids.data(), deltas.data(), doffs.data(), (uint32_t)lz.size(), back.data(), cap, boffs.data()),
+                    "lz_decode_batch (self check)")) return false;
+        for (size_t i = 0; i < lz.size(); ++i) {
+            if (doffs[i + 1] == doffs[i]) continue;          // empty delta = "equal to the reference" (segment.cpp:61-64)
+            sym.resize(lz[i].len ? lz[i].len : 1);
+            if (!gpu_ok(agcgpu_get_segment(ctx, lz[i].contig, lz[i].start, lz[i].len, lz[i].is_rc, sym.data()), "get_segment")) return false;
+            if (boffs[i + 1] - boffs[i] != lz[i].len || memcmp(back.data() + boffs[i], sym.data(), lz[i].len) != 0)
+                return fail("self check: LZ delta " + std::to_string(i) + " (group " + std::to_string(lz[i].group_id) + ") does not decode to its segment");
+        }
+    }
     // reference payloads (tuples or raw symbols) of the groups created in this batch
     std::vector<uint8_t> refpay; std::vector<uint64_t> roffs(ref_groups.size() + 1, 0); std::vector<uint8_t> ruse(ref_groups.size() + 1, 0);
     if (!ref_groups.empty()) {

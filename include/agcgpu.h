@@ -193,6 +193,13 @@ int agcgpu_lz_estimate_batch(agcgpu_ctx* ctx, const agcgpu_seg_req* reqs, uint32
  * (agc_compressor.cpp:1540-1571).  out has req->len entries. */
 int agcgpu_lz_cost_vector(agcgpu_ctx* ctx, const agcgpu_seg_req* req, int prefix_costs, uint32_t* out);
 
+/* CLZDiff_V2::Decode (lz_diff.cpp:801-836) as CSegment::get calls it (segment.cpp:220-399): delta i = deltas[delta_offsets[i] ..
+ * delta_offsets[i+1]) is decoded against the resident reference of group_ids[i]; symbols (1 byte each) of segment i =
+ * out[out_offsets[i] .. out_offsets[i+1]).  out_offsets is filled even when out_cap is too small (AGCGPU_EOVERFLOW).
+ * An empty delta decodes to nothing (CSegment stores "equal to the reference" that way, segment.cpp:61-64). */
+int agcgpu_lz_decode_batch(agcgpu_ctx* ctx, const uint32_t* group_ids, const uint8_t* deltas, const uint64_t* delta_offsets,
+                           uint32_t n, uint8_t* out, uint64_t out_cap, uint64_t* out_offsets);
+
 /* ---- packing of reference segments ------------------------------------------------------------------------------ */
 /* CSegment::store_in_archive(ref) up to the zstd call (src/common/segment.h:218-255): periodicity probe and
  * bytes2tuples (73-138).  For group i: out_use_tuples[i] = 1 -> payload = tuples (zstd level 13, marker 1),

@@ -52,6 +52,7 @@ void orc_free(void* p);
 uint64_t orc_lz_estimate(const olz_t* z, const uint8_t* text, uint32_t n, uint32_t bound);
 uint64_t orc_lz_cost_vector(const olz_t* z, const uint8_t* text, uint32_t n, int prefix_costs, uint32_t* v);
 uint64_t orc_bytes2tuples(const uint8_t* b, uint64_t n, uint8_t* out);
+uint64_t orc_lz_decode(const uint8_t* ref, uint32_t m, const uint8_t* enc, uint64_t en, uint32_t mml, uint8_t* out);
 int orc_ref_use_tuples(const uint8_t* d, uint64_t n);
 }
 
@@ -330,6 +331,7 @@ int agcgpu_group_get_index(agcgpu_ctx* ctx, uint32_t group_id, uint32_t* out_slo
     auto p = ctx->groups.find(group_id);
     if (p == ctx->groups.end()) return fail(ctx, AGCGPU_EINVAL, "group %u has no reference", group_id);
     *out_ht_size = orc_lz_ht_size(p->second.lz);
+    if (!out_slots) return 0;
     if (*out_ht_size > cap) return fail(ctx, AGCGPU_EOVERFLOW, "index larger than the caller's buffer");
     orc_lz_get_ht(p->second.lz, out_slots);
     return 0;
@@ -378,6 +380,32 @@ int agcgpu_lz_cost_vector(agcgpu_ctx* ctx, const agcgpu_seg_req* req, int prefix
     uint64_t vn = orc_lz_cost_vector(z, t.data(), req->len, prefix_costs, v.data());
     if (vn != req->len) return fail(ctx, AGCGPU_EINVAL, "cost vector has %llu entries for %u symbols", (unsigned long long)vn, req->len);
     if (req->len) memcpy(out, v.data(), (size_t)req->len * 4);
+    return 0;
+}
+
+int agcgpu_lz_decode_batch(agcgpu_ctx* ctx, const uint32_t* group_ids, const uint8_t* deltas, const uint64_t* dofs, uint32_t n, uint8_t* out,
+                           uint64_t out_cap, uint64_t* out_offsets)
+{
+    if (!ctx || !out_offsets || !dofs || (n && (!group_ids || !deltas)) || (out_cap && !out)) return AGCGPU_EINVAL;
+    out_offsets[0] = 0;
+    std::vector<std::vector<uint8_t>> dec(n);
+    for (uint32_t i = 0; i < n; ++i) {
+        auto p = ctx->groups.find(group_ids[i]);
+        if (p == ctx->groups.end()) return fail(ctx, AGCGPU_EINVAL, "lz_decode: group %u has no reference", group_ids[i]);
+        const uint64_t en = dofs[i + 1] - dofs[i];
+        std::vector<uint8_t> enc(deltas + dofs[i], deltas + dofs[i + 1]); enc.push_back(0);        // the oracle peeks one byte past a number
+        uint64_t bound = en + 64;                                                                   // literals: one symbol per byte
+        for (uint64_t j = 0; j < en; ++j) {
+            if (enc[j] == '.') bound += p->second.ref.size();                                        // a match copies at most the whole reference
+            if (enc[j] == 30) { uint64_t v = 0, q = j + 1; while (q < en && enc[q] >= '0' && enc[q] <= '9') v = v * 10 + (enc[q++] - '0'); bound += v + 4; }
+        }
+        dec[i].resize(bound);
+        uint64_t o = orc_lz_decode(p->second.ref.data(), (uint32_t)p->second.ref.size(), enc.data(), en, ctx->prm.min_match_len, dec[i].data());
+        dec[i].resize(o);
+        out_offsets[i + 1] = out_offsets[i] + o;
+    }
+    if (out_offsets[n] > out_cap) return fail(ctx, AGCGPU_EOVERFLOW, "lz_decode: output buffer too small");
+    for (uint32_t i = 0; i < n; ++i) if (!dec[i].empty()) memcpy(out + out_offsets[i], dec[i].data(), dec[i].size());
     return 0;
 }
 

@@ -39,7 +39,7 @@ def _mk_pairs(rng, n_pairs, dirty=False):
     return pairs
 
 
-def _run_pairs(dev, rng, pairs, mml, use_rc):
+def _run_pairs(dev, rng, pairs, mml, use_rc, check_decode=False):
     """upload refs and texts as contigs, build references from segments, encode/estimate/cost-vector on device"""
     contigs, reqs_ref, reqs_txt, expect_text = [], [], [], []
     for g, (ref, text) in enumerate(pairs):
@@ -79,6 +79,14 @@ def _run_pairs(dev, rng, pairs, mml, use_rc):
                 assert np.array_equal(cv, z.cost_vector(text, pf)), f"cost vector differs, pair {g} prefix={pf}"
         if len(text) and text.max() <= 20 and len(enc[g]):
             assert np.array_equal(orc.lz_decode(ref, enc[g], mml, len(text)), text)
+    if check_decode:                         # CLZDiff_V2::Decode on the device: every delta gives back its text
+        ok = [g for g, (ref, text) in enumerate(pairs) if len(text) == 0 or text.max() <= 20]     # literals above 'A'+20 have no decoding (lz_diff.h is_literal)
+        dec = dev.lz_decode([16 + g for g in ok], [enc[g] for g in ok])
+        for g, d in zip(ok, dec):
+            if len(enc[g]) == 0:
+                assert len(d) == 0           # "equal to the reference" is stored as an empty delta
+            else:
+                assert np.array_equal(d, pairs[g][1]), f"device decode differs, pair {g}"
 
 
 @pytest.mark.parametrize("mml", [15, 20, 32])
@@ -98,6 +106,14 @@ def test_lz_non_acgt(dev_factory):
     rng = np.random.default_rng(8)
     dev = dev_factory(k=21, min_match_len=18)
     _run_pairs(dev, rng, _mk_pairs(rng, 30, dirty=True), 18, use_rc=True)
+
+
+def test_lz_decode_roundtrip(dev_factory):
+    """agcgpu_lz_decode_batch (CLZDiff_V2::Decode): clean, reverse-complemented and non-ACGT pairs"""
+    rng = np.random.default_rng(23)
+    for mml, dirty, use_rc in ((20, False, False), (15, False, True), (24, True, False)):
+        dev = dev_factory(k=31, min_match_len=mml, segment_size=60000)
+        _run_pairs(dev, rng, _mk_pairs(rng, 24, dirty=dirty), mml, use_rc, check_decode=True)
 
 
 def test_lz_many_segments_one_group(dev_factory):
