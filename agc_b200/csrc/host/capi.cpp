@@ -48,6 +48,24 @@ int agcgpu_compressor_create(const char* out_file, uint32_t pack_cardinality, ui
     return 0;
 }
 
+int agcgpu_compressor_append(const char* in_archive, const char* out_file, uint32_t verbosity, int prefetch_archive, int concatenated_genomes,
+                             int adaptive_compression, uint32_t no_threads, double fallback_frac, int device, agcgpu_compressor** out)
+{
+    if (!in_archive || !out_file || !out) { g_err = "null argument"; return AGCGPU_EINVAL; }
+    CallTimer ct("compressor_append");
+    agcgpu_compressor* c = new agcgpu_compressor();
+    c->impl.SetAppMode(false);
+    c->impl.SetDevice(device);
+    c->impl.SetExchange(g_exchange.rank, g_exchange.world, g_exchange.fn, g_exchange.user);
+    if (!c->impl.Append(in_archive, out_file, verbosity, prefetch_archive != 0, concatenated_genomes != 0, adaptive_compression != 0, no_threads, fallback_frac)) {
+        g_err = c->impl.LastError();
+        delete c;
+        return AGCGPU_EUNSUPPORTED;
+    }
+    *out = c;
+    return 0;
+}
+
 int agcgpu_compressor_add_sample_files(agcgpu_compressor* c, const char* const* sample_names, const char* const* file_names,
                                        uint32_t n, uint32_t no_threads)
 {

@@ -352,7 +352,7 @@ bool CAGCCompressor::Create(const std::string& file_name, uint32_t _pack_cardina
     segment_size = _segment_size; verbosity = _verbosity;
     concatenated_genomes = _concatenated_genomes; adaptive_compression = _adaptive_compression;
     fallback_thr = fallback_frac == 0.0 ? 0ull : (uint64_t)(((double)~0ull) * fallback_frac);       // kmer_filter_t::reset
-    map_fallback_minimizers.clear(); pending_fallbacks.clear();
+    map_fallback_minimizers.clear(); pending_fallbacks.clear(); appending = false;
     agcgpu_params prm; memset(&prm, 0, sizeof prm);
     prm.kmer_length = kmer_length; prm.min_match_len = min_match_len; prm.segment_size = segment_size;
     prm.pack_cardinality = pack_cardinality; prm.device = device;
@@ -605,7 +605,8 @@ bool CAGCCompressor::flush_jobs(bool force)
                 if (j.fallback_raw.size() != j.fallback_size) return fail("internal: raw fallback of a large reference was not fetched");
                 out_archive.AddPart(j.stream_id, j.fallback_raw, 0);
             }
-        } else if (j.kind == 2) out_archive.AddPart(j.stream_id, j.tasks[0].packed, j.raw_size);
+        } else if (j.kind == 4) out_archive.AddPart(j.stream_id, j.fallback_raw, j.raw_size);
+        else if (j.kind == 2) out_archive.AddPart(j.stream_id, j.tasks[0].packed, j.raw_size);
         else {                                                  // store_batch_contig_details (collection_v3.cpp:225-257)
             std::vector<uint8_t> v;
             for (auto& t : j.tasks) { CCollection_V3::append(v, (uint32_t)t.raw.size()); CCollection_V3::append(v, (uint32_t)t.packed.size()); }
@@ -787,11 +788,14 @@ bool CAGCCompressor::find_cand_segment_using_fallback_minimizers(uint32_t bc, ui
         uint64_t es = 0;
         if (p != map_segments.end()) {                      // can fail if the mappings are to a segment of the same sample
             if (short_segments) { best_pair = x.second; best_es = 0; break; }
+            if (v_segments[p->second].lazy) { es = 0; }         // not unpacked yet: CSegment::estimate returns 0
+            else {
             agcgpu_seg_req e; memset(&e, 0, sizeof e);
             e.contig = bc; e.start = start; e.len = len; e.is_rc = is_seg_rc != rc_view; e.group_id = (uint32_t)p->second; e.bound = (uint32_t)best_es;
             uint32_t est = 0;
             if (!gpu_ok(agcgpu_lz_estimate_batch(ctx, &e, 1, &est), "lz_estimate")) return false;
             es = est;
+            }
         }
         if (es && es < best_es) { best_es = es; best_pair = x.second; }
     }
@@ -967,8 +971,15 @@ bool CAGCCompressor::process_batch_raw(const uint8_t* cat, bool is_device, const
             est_valid[x] = 1;
         }
         if (rq.empty()) return true;
-        std::vector<uint32_t> est(rq.size());
-        if (!gpu_ok(agcgpu_lz_estimate_batch(ctx, rq.data(), (uint32_t)rq.size(), est.data()), "lz_estimate")) return false;
+        std::vector<uint32_t> est(rq.size(), 0);
+        // groups reloaded by Append and not unpacked yet estimate to 0 (CSegment::estimate returns before it unpacks, segment.cpp:84-86)
+        std::vector<agcgpu_seg_req> live; std::vector<size_t> live_idx;
+        for (size_t i = 0; i < rq.size(); ++i) if (!v_segments[rq[i].group_id].lazy) { live.push_back(rq[i]); live_idx.push_back(i); }
+        if (!live.empty()) {
+            std::vector<uint32_t> le(live.size());
+            if (!gpu_ok(agcgpu_lz_estimate_batch(ctx, live.data(), (uint32_t)live.size(), le.data()), "lz_estimate")) return false;
+            for (size_t i = 0; i < live.size(); ++i) est[live_idx[i]] = le[i];
+        }
         for (size_t i = 0; i < rq.size(); ++i) est_cache[owner[i]].push_back(est[i]);
         return true;
     };
@@ -1012,9 +1023,12 @@ bool CAGCCompressor::process_batch_raw(const uint8_t* cat, bool is_device, const
         if (shared.empty()) return true;
         uint64_t mid = shared.front();
         uint32_t g1 = (uint32_t)map_segments[std::minmax(k1d, mid)], g2 = (uint32_t)map_segments[std::minmax(mid, k2d)];
-        std::vector<uint32_t> c1(len), c2(len);
+        // a group reloaded by Append and not unpacked yet gives no cost vector (get_coding_cost returns on ref_size == 0, segment.cpp:101-103)
+        const bool lazy1 = v_segments[g1].lazy, lazy2 = v_segments[g2].lazy;
+        std::vector<uint32_t> c1(lazy1 ? 0 : len), c2(lazy2 ? 0 : len);
         agcgpu_seg_req q;
-        if (k1d < mid) {
+        if (lazy1) {}
+        else if (k1d < mid) {
             q = seg_req(bc, start, len, dir_is_rc, g1, 0);
             if (!gpu_ok(agcgpu_lz_cost_vector(ctx, &q, 1, c1.data()), "lz_cost_vector")) return false;
         } else {
@@ -1023,7 +1037,8 @@ bool CAGCCompressor::process_batch_raw(const uint8_t* cat, bool is_device, const
             std::reverse(c1.begin(), c1.end());
         }
         std::partial_sum(c1.begin(), c1.end(), c1.begin());
-        if (mid < k2d) {
+        if (lazy2) {}
+        else if (mid < k2d) {
             q = seg_req(bc, start, len, dir_is_rc, g2, 0);
             if (!gpu_ok(agcgpu_lz_cost_vector(ctx, &q, 0, c2.data()), "lz_cost_vector")) return false;
             std::partial_sum(c2.rbegin(), c2.rend(), c2.rbegin());
@@ -1033,10 +1048,11 @@ bool CAGCCompressor::process_batch_raw(const uint8_t* cat, bool is_device, const
             std::partial_sum(c2.begin(), c2.end(), c2.begin());
             std::reverse(c2.begin(), c2.end());
         }
+        if (c1.size() != c2.size()) return true;                 // 1600-1603: no split
         uint32_t best_sum = ~0u, bp = 0;
-        for (uint32_t i = 0; i < len; ++i) { uint32_t cs = c1[i] + c2[i]; if (cs < best_sum) { best_sum = cs; bp = i; } }
+        for (uint32_t i = 0; i < c1.size(); ++i) { uint32_t cs = c1[i] + c2[i]; if (cs < best_sum) { best_sum = cs; bp = i; } }
         if (bp < kmer_length + 1u) bp = 0;
-        if ((size_t)bp + kmer_length + 1u > len) bp = len;
+        if ((size_t)bp + kmer_length + 1u > c1.size()) bp = (uint32_t)c1.size();
         middle = mid; best_pos = bp;
         return true;
     };
@@ -1173,6 +1189,7 @@ bool CAGCCompressor::process_batch_raw(const uint8_t* cat, bool is_device, const
         bool map_changed = false;
         for (auto& kv : by_group) {
             GroupState& g = v_segments[kv.first];
+            if (g.lazy) { g.lazy = false; map_changed = true; }     // store_segments' add() unpacks the group: estimates of later samples are real
             if (!g.exists) {
                 g.exists = true;
                 const Item& first = kv.second.front();
@@ -1192,9 +1209,11 @@ bool CAGCCompressor::process_batch_raw(const uint8_t* cat, bool is_device, const
         }
         no_segments += no_new;
         if (map_changed) {
-            if (!gpu_ok(agcgpu_map_insert(ctx, ins_k1.data(), ins_k2.data(), ins_g.data(), ins_g.size()), "map_insert")) return false;
-            if (!gpu_ok(agcgpu_group_put_reference_batch(ctx, new_refs.data(), (uint32_t)new_refs.size()), "put_reference")) return false;
-            if (!run_assign(cut_first[cj])) return false;
+            if (!ins_g.empty()) {
+                if (!gpu_ok(agcgpu_map_insert(ctx, ins_k1.data(), ins_k2.data(), ins_g.data(), ins_g.size()), "map_insert")) return false;
+                if (!gpu_ok(agcgpu_group_put_reference_batch(ctx, new_refs.data(), (uint32_t)new_refs.size()), "put_reference")) return false;
+                if (!run_assign(cut_first[cj])) return false;
+            }
             if (!prefetch_estimates(cut_first[cj])) return false;
         }
         regs.push_back(std::move(reg));
@@ -1248,6 +1267,7 @@ bool CAGCCompressor::process_batch_raw(const uint8_t* cat, bool is_device, const
     for (auto& reg : regs) {
         for (auto& rg : reg.groups) {
             GroupState& g = v_segments[rg.group];
+            if (!rg.items.empty()) g.packed_pending = false;        // CSegment::add / add_raw unpack the group (segment.cpp:18-19, 37-38)
             for (auto& it : rg.items) {
                 uint32_t in_group_id;
                 if (rg.group < NO_RAW_GROUPS) {                                   // add_raw
@@ -1297,7 +1317,13 @@ bool CAGCCompressor::Close(uint32_t)
     if (!working) return false;
     working = false;
     // close_compression (agc_compressor.cpp:2094-2114): CSegment::finish for all groups, flush, metadata
-    for (uint32_t i = 0; i < no_segments; ++i) if (!v_segments[i].pack.empty()) store_pack(i, v_segments[i], epoch);
+    for (uint32_t i = 0; i < no_segments; ++i) {
+        GroupState& g = v_segments[i];
+        if (g.packed_pending) {                                  // untouched since Append: store_compressed_delta_in_archive (segment.h:283-292)
+            PartJob j; j.epoch = epoch; j.kind = 4; j.stream_id = g.stream_delta; j.raw_size = g.packed_meta; j.fallback_raw = std::move(g.packed_delta);
+            add_job(std::move(j));
+        } else if (!g.pack.empty()) store_pack(i, g, epoch);
+    }
     ++epoch;
     auto a32 = [](std::vector<uint8_t>& v, uint32_t x) { for (int i = 0; i < 4; ++i) { v.push_back(x & 0xff); x >>= 8; } };
     auto a64 = [](std::vector<uint8_t>& v, uint64_t x) { for (int i = 0; i < 8; ++i) { v.push_back(x & 0xff); x >>= 8; } };
@@ -1310,9 +1336,12 @@ bool CAGCCompressor::Close(uint32_t)
     PartJob js; js.epoch = epoch; js.kind = 2; js.stream_id = collection_samples_id; js.tasks.emplace_back(); js.tasks[0].level = 19;
     collection.serialize_sample_names(js.tasks[0].raw); js.raw_size = js.tasks[0].raw.size();
     std::map<std::string, std::string> fti;
+    if (appending) fti = file_type_info;                         // store_file_type_info writes what load_file_type_info read
+    else {
     fti["producer"] = "agc"; fti["producer_version_major"] = "3"; fti["producer_version_minor"] = "2"; fti["producer_version_build"] = "20260326.1";
     fti["file_version_major"] = "3"; fti["file_version_minor"] = "0";
     fti["comment"] = "AGC (Assembled Genomes Compressor) v. 3.2.2 [build 20260326.1]";
+    }
     std::vector<uint8_t> v_fti; for (auto& x : fti) { astr(v_fti, x.first); astr(v_fti, x.second); }
     if (discard_parts) { flush_jobs(true); out_archive.Close(); return true; }
     if (dump_f) {

@@ -63,6 +63,10 @@ public:
     void serialize_contig_names(std::vector<uint8_t>& v, uint32_t id_from, uint32_t id_to) const;   // 468-497
     void serialize_contig_details(std::vector<uint8_t> (&v)[5], uint32_t id_from, uint32_t id_to);  // 539-586
     void clear_batch(uint32_t id_from, uint32_t id_to);
+    // append side (collection_v3.cpp:332-345, 498-536, 589-680)
+    bool deserialize_sample_names(const std::vector<uint8_t>& v);
+    bool deserialize_contig_names(const std::vector<uint8_t>& v, size_t i_sample, uint32_t& n_in_batch);
+    bool deserialize_contig_details(const std::vector<uint8_t> (&v)[5], size_t i_sample);
     std::vector<sample_desc_t> sample_desc;
     static void append(std::vector<uint8_t>& data, uint32_t num);                                   // collection.h:126-160
     static void append(std::vector<uint8_t>& data, const std::string& s);
@@ -110,6 +114,9 @@ public:
     bool Create(const std::string& file_name, uint32_t pack_cardinality, uint32_t kmer_length, const std::string& reference_file_name,
                 uint32_t segment_size, uint32_t min_match_len, bool concatenated_genomes, bool adaptive_compression,
                 uint32_t verbosity, uint32_t no_threads, double fallback_frac);
+    // CAGCCompressor::Append (agc_compressor.cpp:2330-2374): continue an existing archive (host/append.cpp)
+    bool Append(const std::string& in_archive_fn, const std::string& out_archive_fn, uint32_t verbosity, bool prefetch_archive,
+                bool concatenated_genomes, bool adaptive_compression, uint32_t no_threads, double fallback_frac);
     bool AddSampleFiles(std::vector<std::pair<std::string, std::string>> v_sample_file_name, uint32_t no_threads);
     // Same as AddSampleFiles for contigs that are already in memory (raw FASTA bodies as ReadContigRaw returns them):
     // contig i = raw[offsets[i] .. offsets[i+1]) belongs to sample_of_contig[i]; `raw` is a host pointer, or a device
@@ -145,6 +152,11 @@ private:
         std::vector<std::vector<uint8_t>> pack;      // v_lzp or v_raw
         int stream_ref = -1, stream_delta = -1;
         bool exists = false;
+        // append mode: the last pack of the input archive, written back verbatim unless the group is touched (segment.h:283-292)
+        std::vector<uint8_t> packed_delta; uint64_t packed_meta = 0; bool packed_pending = false;
+        // append mode: loaded but not unpacked yet.  CSegment::estimate / get_coding_cost test ref_size == 0 BEFORE they unpack
+        // (segment.cpp:84-86, 101-103), so until the first add() such a group estimates to 0 and returns no cost vector
+        bool lazy = false;
         uint32_t ref_size = 0;                       // symbols + 1 (segment.cpp:47)
     };
     struct BatchContig { uint32_t sample_id, contig_idx; uint32_t unit = 0; };   // unit: contigs registered at the same synchronisation token
@@ -183,7 +195,8 @@ private:
     agcgpu_ctx* ctx = nullptr;
     CArchive out_archive;
     CCollection_V3 collection;
-    bool working = false;
+    bool working = false, appending = false;
+    std::map<std::string, std::string> file_type_info;          // append: as loaded from the input archive (agc_basic.cpp:68-88)
 
     std::vector<uint64_t> splitters;                          // sorted
     std::map<std::pair<uint64_t, uint64_t>, int32_t> map_segments;            // agc_compressor.h:628

@@ -25,8 +25,10 @@ static void remove_common_suffixes(std::string& s)        // application.cpp:606
 
 int main(int argc, char** argv)
 {
-    if (argc < 3 || std::string(argv[1]) != "create") {
-        std::cerr << "usage: agc-b200 create [-k 31] [-l 20] [-s 60000] [-b 50] [-t n] [-v n] [-i list] [-d] [-a] [-c] [-f frac] [--device n] [--verify] [--dump-parts file] -o out.agc ref.fa [samples...]\n";
+    const bool is_append = argc >= 2 && std::string(argv[1]) == "append";
+    if (argc < 3 || (std::string(argv[1]) != "create" && !is_append)) {
+        std::cerr << "usage: agc-b200 append [-a] [-c] [-f frac] [-t n] [-v n] [-i list] [--device n] [--verify] -o out.agc in.agc [samples...]\n"
+                     "       agc-b200 create [-k 31] [-l 20] [-s 60000] [-b 50] [-t n] [-v n] [-i list] [-d] [-a] [-c] [-f frac] [--device n] [--verify] [--dump-parts file] -o out.agc ref.fa [samples...]\n";
         return 1;
     }
     uint32_t k = 31, l = 20, s = 60000, b = 50, t = 1, v = 0; bool a = false, c = false, verify = false; double f = 0.0; int dev = 0;
@@ -45,7 +47,20 @@ int main(int argc, char** argv)
     k = std::clamp(k, 17u, 32u); b = std::clamp(b, 1u, 1000000000u); s = std::clamp(s, 100u, 1000000u); l = std::clamp(l, 15u, 32u);
     v = std::clamp(v, 0u, 2u); f = std::clamp(f, 0.0, 0.05);
     if (!list.empty()) { std::ifstream in(list); std::string ln; while (std::getline(in, ln)) if (!ln.empty()) inputs.push_back(ln); }
-    if (out.empty() || inputs.empty()) { std::cerr << "need -o and at least the reference FASTA\n"; return 1; }
+    if (out.empty() || inputs.empty()) { std::cerr << "need -o and at least the reference FASTA (create) / the input archive (append)\n"; return 1; }
+    if (is_append) {                                           // src/app/main.cpp:124-160: the first positional argument is the archive to extend
+        const std::string in_archive = inputs.front();
+        inputs.erase(inputs.begin());
+        { std::vector<std::string> u; std::unordered_set<std::string> seen; for (auto& x : inputs) if (seen.insert(x).second) u.push_back(x); inputs.swap(u); }
+        agc_b200::CAGCCompressor agc;
+        agc.SetDevice(dev); agc.SetVerify(verify);
+        if (!agc.Append(in_archive, out, v, true, c, a, t, f)) { std::cerr << "Cannot extend archive " << in_archive << ": " << agc.LastError() << std::endl; return 1; }
+        std::vector<std::pair<std::string, std::string>> files;
+        for (auto& fn : inputs) { std::string nm = std::filesystem::path(fn).stem().string(); remove_common_suffixes(nm); files.emplace_back(nm, fn); }
+        bool r = agc.AddSampleFiles(files, t);
+        r &= agc.Close(t);
+        return r ? 0 : 1;
+    }
     { std::vector<std::string> u; std::unordered_set<std::string> seen; for (auto& x : inputs) if (seen.insert(x).second) u.push_back(x); inputs.swap(u); }
     agc_b200::CAGCCompressor agc;
     agc.SetDevice(dev);

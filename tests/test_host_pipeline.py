@@ -90,6 +90,46 @@ def test_host_pipeline_archives_match_reference(tmp_path, mock_agc, case):
             assert open(plain, "rb").read() != b
 
 
+def append_flags(flags):
+    """`append` takes the archive's own k / l / s / b"""
+    out, i = [], 0
+    while i < len(flags):
+        if flags[i] in ("-k", "-s", "-l", "-b"):
+            i += 2
+            continue
+        out.append(flags[i]); i += 1
+    return out
+
+
+APPEND_CASES = [("viral", 12, 1), ("complex", 5, 1), ("complex", 3, 2), ("complex_n", 7, 1), ("smallpacks", 10, 2), ("smallpacks", 7, 1),
+                ("concatenated", 2, 1), ("fallback", 4, 2), ("tiny", 2, 1)]
+
+
+def run_append_case(tmp, agc, case, n_first, steps):
+    """reference: create(first files) then append the rest in `steps` runs; `agc` extends the same base; -> (ours, reference) bytes"""
+    files, flags = collection(case, tmp)
+    base = os.path.join(tmp, "base.agc")
+    subprocess.check_call([REF_AGC, "create", "-t", "3", "-o", base] + flags + files[:n_first], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    rest = files[n_first:]
+    chunks = [rest] if steps == 1 else [rest[:len(rest) // 2], rest[len(rest) // 2:]]
+    rb = ob = base
+    for i, ch in enumerate(chunks):
+        r2 = os.path.join(tmp, f"ref{i}.agc"); o2 = os.path.join(tmp, f"our{i}.agc")
+        subprocess.check_call([REF_AGC, "append", "-t", "3", "-o", r2] + append_flags(flags) + [rb] + ch, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        subprocess.check_call([agc, "append", "-o", o2] + append_flags(flags) + [ob] + ch)
+        rb, ob = r2, o2
+    return open(ob, "rb").read(), open(rb, "rb").read(), files
+
+
+@pytest.mark.parametrize("case,n_first,steps", APPEND_CASES)
+def test_append_matches_reference(tmp_path, mock_agc, case, n_first, steps):
+    """CAGCCompressor::Append: the archive state is reloaded (zstd frames decoded, references handed back to the device, last
+    packs and the last contig batch unpacked) and the extended archive is byte-identical to the reference's -- including the
+    reference's behaviour that a reloaded group estimates to 0 until something is added to it (segment.cpp:84-86)"""
+    a, b, files = run_append_case(str(tmp_path), mock_agc, case, n_first, steps)
+    assert a == b, f"appended archives differ: {len(a)} vs {len(b)} bytes"
+
+
 def test_self_check_mode(tmp_path, mock_agc):
     """--verify: every coded frame is decoded again (device decoder; here its host build) and compared before it is written;
     the archive is the same one"""
