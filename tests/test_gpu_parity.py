@@ -108,14 +108,6 @@ def test_lz_non_acgt(dev_factory):
     _run_pairs(dev, rng, _mk_pairs(rng, 30, dirty=True), 18, use_rc=True)
 
 
-def test_lz_decode_roundtrip(dev_factory):
-    """agcgpu_lz_decode_batch (CLZDiff_V2::Decode): clean, reverse-complemented and non-ACGT pairs"""
-    rng = np.random.default_rng(23)
-    for mml, dirty, use_rc in ((20, False, False), (15, False, True), (24, True, False)):
-        dev = dev_factory(k=31, min_match_len=mml, segment_size=60000)
-        _run_pairs(dev, rng, _mk_pairs(rng, 24, dirty=dirty), mml, use_rc, check_decode=True)
-
-
 def test_lz_many_segments_one_group(dev_factory):
     """many texts against one reference: exercises the shared-memory staged path and unit splitting"""
     rng = np.random.default_rng(9)

@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 import gen_data
 import agc_parts
-from test_host_pipeline import collection, ALL_CASES, run_append_case
+from test_host_pipeline import collection, ALL_CASES
 
 pytestmark = pytest.mark.gpu
 
@@ -48,11 +48,3 @@ def test_parts_match_reference(tmp_path, case):
         sample = os.path.splitext(os.path.basename(files[-1]))[0]
     out = subprocess.run([REF_AGC, "getset", our, sample], capture_output=True).stdout
     assert out == last
-
-
-@pytest.mark.skipif(not os.path.exists(REF_AGC), reason="reference binary not built (make -f oracle/Makefile.ref)")
-@pytest.mark.parametrize("case,n_first,steps", [("viral", 12, 1), ("complex", 3, 2), ("complex_n", 7, 1), ("fallback", 4, 2), ("concatenated", 2, 1)])
-def test_append_matches_reference(tmp_path, case, n_first, steps):
-    """`agc-b200 append` on the device (frames decoded by k_zstd_decode, references re-indexed, packs continued) vs the reference's"""
-    a, b, files = run_append_case(str(tmp_path), OUR_AGC, case, n_first, steps)
-    assert a == b, f"appended archives differ: {len(a)} vs {len(b)} bytes"

@@ -113,28 +113,6 @@ def test_zstd_btlazy2_class(dev_factory):
         assert g == agc_parts.zstd_compress(raw, 13)
 
 
-def test_zstd_decode_on_device(dev_factory):
-    """agcgpu_zstd_decompress_batch: frames of the reference's libzstd (several levels) and of the device coder decode to
-    their inputs in one batch; a truncated frame fails the call"""
-    import agc_b200
-    rng = np.random.default_rng(41)
-    dev = dev_factory(k=31)
-    raws, frames = [], []
-    for level in (1, 5, 13, 17, 19):
-        for kind in range(7):
-            for n in (0, 1, 200, 4000, 40000, 200000):
-                if n > 4000 and (kind + level) % 3:
-                    continue
-                raw = _gen(rng, kind, n)
-                raws.append(raw); frames.append(agc_parts.zstd_compress(raw, level))
-    assert dev.zstd_decompress(frames) == raws
-    mine = [_gen(rng, k, n) for k in range(7) for n in (300, 30000, 150000)]
-    coded = dev.zstd_compress(mine, [17] * len(mine))
-    assert dev.zstd_decompress(coded) == mine
-    with pytest.raises(agc_b200.AgcGpuError):                   # a truncated frame fails the call
-        dev.zstd_decompress([frames[0], frames[-1][:-5]])
-
-
 def test_zstd_unsupported_is_loud(dev_factory):
     import agc_b200
     dev = dev_factory(k=21, min_match_len=20)
