@@ -9,6 +9,8 @@
 #include <algorithm>
 #include <cstring>
 #include <iostream>
+#include <map>
+#include <memory>
 
 namespace agc_b200 {
 
@@ -223,9 +225,6 @@ bool CAGCCompressor::Append(const std::string& in_archive_fn, const std::string&
 {
     if (working) return false;
     verbosity = _verbosity; concatenated_genomes = _concatenated_genomes; adaptive_compression = _adaptive_compression;
-    if (adaptive_compression)
-        return fail("agc-b200: append -a needs the reference sample decoded from the archive (build_candidate_kmers_from_archive, "
-                    "agc_compressor.cpp:828-847); not implemented, refusing rather than writing a different archive");
     fallback_thr = fallback_frac == 0.0 ? 0ull : (uint64_t)(((double)~0ull) * fallback_frac);
     map_fallback_minimizers.clear(); pending_fallbacks.clear();
     InArchive in;
@@ -244,6 +243,7 @@ bool CAGCCompressor::Append(const std::string& in_archive_fn, const std::string&
     agcgpu_params prm; memset(&prm, 0, sizeof prm);
     prm.kmer_length = kmer_length; prm.min_match_len = min_match_len; prm.segment_size = segment_size;
     prm.pack_cardinality = pack_cardinality; prm.device = device;
+    prm.flags = adaptive_compression ? AGCGPU_F_ADAPTIVE : 0;
     if (agcgpu_create(&prm, &ctx)) return fail(std::string("agcgpu_create: ") + agcgpu_last_error(nullptr));
     if (!out_archive.Open(xrank == 0 ? out_archive_fn : std::string("/dev/null"))) return fail("Cannot create archive " + out_archive_fn);
     collection.set_params(pack_cardinality, segment_size, kmer_length);
@@ -313,6 +313,30 @@ bool CAGCCompressor::Append(const std::string& in_archive_fn, const std::string&
         collection.clear_batch((uint32_t)i_sample, (uint32_t)std::min<size_t>(collection.sample_desc.size(), i_sample + pack_cardinality));
     }
 
+    // ---- -a: build_candidate_kmers_from_archive (agc_compressor.cpp:828-847) needs the reference sample (sample 0) again:
+    // its contig batch tells which references / pack items it is made of
+    CCollection_V3 ref_coll;
+    std::unordered_map<uint32_t, std::vector<uint8_t>> ref_syms;            // symbols of the references sample 0 uses
+    if (adaptive_compression) {
+        ref_coll.set_params(pack_cardinality, segment_size, kmer_length);
+        if (!ref_coll.deserialize_sample_names(f_samples.raw) || ref_coll.sample_desc.empty()) return fail("cannot deserialize the sample names");
+        Frame b_names, b_det[5];
+        std::vector<uint8_t> part; uint64_t pm = 0;
+        in.GetPart(in_contigs, 0, b_names.packed, b_names.raw_size);
+        in.GetPart(in_details, 0, part, pm);
+        const uint8_t* p = part.data(); const uint8_t* e = p + part.size();
+        uint32_t raw_sz[5], pk_sz[5];
+        for (int i = 0; i < 5; ++i) if (!rd_u32(p, e, raw_sz[i]) || !rd_u32(p, e, pk_sz[i])) return fail("bad collection-details part");
+        for (int i = 0; i < 5; ++i) { if (p + pk_sz[i] > e) return fail("bad collection-details part"); b_det[i].packed.assign(p, p + pk_sz[i]); b_det[i].raw_size = raw_sz[i]; p += pk_sz[i]; }
+        std::vector<Frame*> fr{ &b_names, &b_det[0], &b_det[1], &b_det[2], &b_det[3], &b_det[4] }, nz;
+        for (auto* f : fr) if (f->raw_size && !f->packed.empty()) nz.push_back(f);
+        if (!decode_all(nz)) return false;
+        uint32_t nb = 0;
+        std::vector<uint8_t> v5[5]; for (int i = 0; i < 5; ++i) v5[i] = b_det[i].raw;
+        if (!ref_coll.deserialize_contig_names(b_names.raw, 0, nb) || !ref_coll.deserialize_contig_details(v5, 0)) return fail("cannot deserialize the first contig batch");
+        for (auto& c : ref_coll.sample_desc[0].contigs) for (auto& sg : c.segments) if (sg.group_id >= 16) ref_syms[sg.group_id];
+    }
+
     // ---- appending_init (agc_compressor.cpp:303-380) + CSegment::appending_init (segment.cpp:418-470)
     v_segments.clear(); no_segments = 0;
     std::vector<std::unique_ptr<Frame>> ref_frames, pack_frames;
@@ -358,6 +382,8 @@ bool CAGCCompressor::Append(const std::string& in_archive_fn, const std::string&
             if (f.raw_size && markers[i] == 1) tuples2bytes(f.raw, sym); else sym = f.raw;
             if (!gpu_ok(agcgpu_group_put_reference(ctx, ref_group[i], sym.empty() ? (const uint8_t*)"" : sym.data(), (uint32_t)sym.size()), "group_put_reference")) return false;
             v_segments[ref_group[i]].ref_size = (uint32_t)sym.size() + 1;
+            auto rs = ref_syms.find(ref_group[i]);
+            if (rs != ref_syms.end()) rs->second = sym;
         }
         for (size_t i = 0; i < pack_frames.size(); ++i) {
             GroupState& g = v_segments[pack_group[i]];
@@ -368,6 +394,70 @@ bool CAGCCompressor::Append(const std::string& in_archive_fn, const std::string&
             } else if (!dl.empty()) g.pack.emplace_back(dl.begin(), dl.end() - 1);
             g.no_seqs += (uint32_t)g.pack.size();
         } }
+
+    // ---- -a: the reference sample's contigs, put together as CAGCDecompressorLibrary::decompress_contig does
+    // (src/common/agc_decompressor_lib.cpp:172-288: segments in order, reverse-complemented where flagged, k symbols of overlap
+    // dropped), go through agcgpu_determine_splitters once more: it leaves the sorted k-mer list of the reference sample on the
+    // device (count_kmers, agc_compressor.cpp:566-630); the splitter set it computes is replaced by the archive's below
+    if (adaptive_compression) {
+        auto& ctgs = ref_coll.sample_desc[0].contigs;
+        // pack items that are needed: (group, pack index) -> decoded pack
+        std::map<std::pair<uint32_t, uint32_t>, std::unique_ptr<Frame>> packs;
+        for (auto& c : ctgs) for (auto& sg : c.segments) {
+            if (sg.group_id >= 16 && sg.in_group_id == 0) continue;
+            const uint32_t idx = sg.group_id < 16 ? sg.in_group_id : sg.in_group_id - 1;
+            auto key = std::make_pair(sg.group_id, idx / pack_cardinality);
+            if (packs.count(key)) continue;
+            auto f = std::make_unique<Frame>();
+            if (!in.GetPart(in.GetStreamId(ss_base(sg.group_id) + "d"), key.second, f->packed, f->raw_size)) return fail("the reference sample points at a pack that is not in the archive");
+            packs[key] = std::move(f);
+        }
+        {   std::vector<Frame*> fr; for (auto& kv : packs) fr.push_back(kv.second.get());
+            if (!decode_all(fr)) return false; }
+        auto item_of = [&](uint32_t group, uint32_t idx, std::vector<uint8_t>& out) -> bool {
+            const std::vector<uint8_t>& dl = packs[std::make_pair(group, idx / pack_cardinality)]->raw;
+            uint32_t want = idx % pack_cardinality, cur = 0; size_t b_pos = 0;
+            if (pack_cardinality == 1) { if (dl.empty()) return false; out.assign(dl.begin(), dl.end() - 1); return true; }
+            for (size_t j = 0; j < dl.size(); ++j) if (dl[j] == 0xff) { if (cur == want) { out.assign(dl.begin() + b_pos, dl.begin() + j); return true; } ++cur; b_pos = j + 1; }
+            return false;
+        };
+        // deltas of sample 0 (two segments of the reference genome with the same splitter pair): one device decode batch
+        std::vector<uint32_t> dg; std::vector<uint8_t> dblob; std::vector<uint64_t> doff(1, 0); std::vector<uint8_t> item;
+        for (auto& c : ctgs) for (auto& sg : c.segments) if (sg.group_id >= 16 && sg.in_group_id > 0) {
+            if (!item_of(sg.group_id, sg.in_group_id - 1, item)) return fail("the reference sample points at a pack item that is not in the archive");
+            dg.push_back(sg.group_id); dblob.insert(dblob.end(), item.begin(), item.end()); doff.push_back(dblob.size());
+        }
+        std::vector<uint8_t> dec(1); std::vector<uint64_t> deco(dg.size() + 1, 0);
+        if (!dg.empty()) {
+            dblob.push_back(0);
+            int rc = agcgpu_lz_decode_batch(ctx, dg.data(), dblob.data(), doff.data(), (uint32_t)dg.size(), dec.data(), 0, deco.data());
+            if (rc == AGCGPU_EOVERFLOW) { dec.resize(deco.back() + 1); rc = agcgpu_lz_decode_batch(ctx, dg.data(), dblob.data(), doff.data(), (uint32_t)dg.size(), dec.data(), deco.back(), deco.data()); }
+            if (!gpu_ok(rc, "lz_decode_batch")) return false;
+        }
+        static const char alpha[] = "ACGTNRYSWKMBDHVU";
+        std::vector<uint8_t> raw; std::vector<uint64_t> roffs(1, 0); std::vector<uint8_t> seg;
+        size_t di = 0;
+        for (auto& c : ctgs) {
+            bool first = true;
+            for (auto& sg : c.segments) {
+                if (sg.group_id < 16) { if (!item_of(sg.group_id, sg.in_group_id, seg)) return fail("the reference sample points at a raw item that is not in the archive"); }
+                else if (sg.in_group_id == 0) seg = ref_syms[sg.group_id];
+                else {
+                    if (doff[di + 1] == doff[di]) seg = ref_syms[sg.group_id];       // (never stored: an empty delta is in_group_id 0)
+                    else seg.assign(dec.begin() + deco[di], dec.begin() + deco[di + 1]);
+                    ++di;
+                }
+                if (sg.is_rev_comp) { std::reverse(seg.begin(), seg.end()); for (auto& x : seg) if (x < 4) x = 3 - x; }
+                size_t from = first ? 0 : std::min<size_t>(kmer_length, seg.size());
+                for (size_t j = from; j < seg.size(); ++j) raw.push_back(seg[j] < 16 ? (uint8_t)alpha[seg[j]] : (uint8_t)'N');
+                first = false;
+            }
+            roffs.push_back(raw.size());
+        }
+        if (raw.empty()) raw.push_back(0);
+        std::vector<uint64_t> tmp_spl(raw.size() / std::max<uint32_t>(segment_size, 1) + 2 * roffs.size() + 64); uint64_t n_tmp = 0;
+        if (!gpu_ok(agcgpu_determine_splitters(ctx, raw.data(), roffs.data(), (uint32_t)roffs.size() - 1, tmp_spl.data(), tmp_spl.size(), &n_tmp), "determine_splitters (reference k-mers)")) return false;
+    }
 
     // splitters and segment map (agc_compressor.cpp:332-378)
     if (!in.GetPart(in.GetStreamId("splitters"), 0, d, meta) || d.size() < meta * 8) return fail("archive has no splitters");

@@ -232,8 +232,7 @@ int agcgpu_compressor_create(const char* out_file, uint32_t pack_cardinality, ui
                              uint32_t verbosity, uint32_t no_threads, double fallback_frac, int device,
                              const char* dump_parts_path, agcgpu_compressor** out);
 /* CAGCCompressor::Append (src/core/agc_compressor.cpp:2330-2374): continue the archive in_archive into out_file; afterwards
- * add_sample_files / close as after create.  adaptive_compression is refused (it needs the reference sample decoded from
- * the archive, build_candidate_kmers_from_archive). */
+ * add_sample_files / close as after create. */
 int agcgpu_compressor_append(const char* in_archive, const char* out_file, uint32_t verbosity, int prefetch_archive, int concatenated_genomes,
                              int adaptive_compression, uint32_t no_threads, double fallback_frac, int device, agcgpu_compressor** out);
 /* CAGCCompressor::AddSampleFiles */

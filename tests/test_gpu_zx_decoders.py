@@ -61,7 +61,7 @@ def test_create_with_self_check(tmp_path):
 
 
 @pytest.mark.skipif(not os.path.exists(REF_AGC), reason="reference binary not built (make -f oracle/Makefile.ref)")
-@pytest.mark.parametrize("case,n_first,steps", [("viral", 12, 1), ("complex", 3, 2), ("complex_n", 7, 1), ("fallback", 4, 2), ("concatenated", 2, 1)])
+@pytest.mark.parametrize("case,n_first,steps", [("viral", 12, 1), ("complex", 3, 2), ("complex_n", 7, 1), ("fallback", 4, 2), ("concatenated", 2, 1), ("adaptive", 4, 1), ("fallback_adaptive", 4, 1)])
 def test_append_matches_reference(tmp_path, case, n_first, steps):
     """`agc-b200 append` on the device (frames decoded by k_zstd_decode, references re-indexed, packs continued) vs the reference's"""
     a, b, files = run_append_case(str(tmp_path), OUR_AGC, case, n_first, steps)

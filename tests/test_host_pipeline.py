@@ -102,7 +102,10 @@ def append_flags(flags):
 
 
 APPEND_CASES = [("viral", 12, 1), ("complex", 5, 1), ("complex", 3, 2), ("complex_n", 7, 1), ("smallpacks", 10, 2), ("smallpacks", 7, 1),
-                ("concatenated", 2, 1), ("fallback", 4, 2), ("tiny", 2, 1)]
+                ("concatenated", 2, 1), ("fallback", 4, 2), ("tiny", 2, 1),
+                # append -a: the reference sample is decoded from the archive to rebuild the reference k-mer list (828-847)
+                ("adaptive", 4, 1), ("adaptive", 2, 2), ("adaptive_big_segments", 3, 1), ("adaptive_complex", 5, 1), ("fallback_adaptive", 4, 1),
+                ("concatenated_adaptive", 2, 1)]
 
 
 def run_append_case(tmp, agc, case, n_first, steps):

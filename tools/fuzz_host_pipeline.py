@@ -96,7 +96,7 @@ def main():
         # agc_compressor.cpp:1142-1156); the reference's own append then indexes sample_desc out of bounds (it crashed in 2 of 5
         # such cases): out of the envelope, agc-b200 refuses those archives
         conc_bad = "-c" in flags and n_contigs(files[:cut0]) % int(flags[flags.index("-b") + 1]) == 0
-        if same and "-a" not in flags and len(files) >= 3 and seed % 2 == 0 and not conc_bad:
+        if same and len(files) >= 3 and seed % 2 == 0 and not conc_bad:
             # `append`: the reference creates a base from the first files and extends it (in one or two steps); so must we
             cut = 1 + seed % (len(files) - 1)
             aflags = [x for i, x in enumerate(flags) if x not in ("-k", "-l", "-s", "-b") and (i == 0 or flags[i - 1] not in ("-k", "-l", "-s", "-b"))]
@@ -108,6 +108,8 @@ def main():
                 r2 = os.path.join(tmp, f"ref_app{si}.agc"); o2 = os.path.join(tmp, f"our_app{si}.agc")
                 rr = subprocess.run([REF, "append", "-t", "3", "-o", r2] + aflags + [rb] + step, capture_output=True)
                 ro = subprocess.run([OUR, "append", "-o", o2] + aflags + [ob] + step, capture_output=True)
+                if rr.returncode != 0 and ro.returncode != 0:       # the reference crashed on its own archive (see conc_bad) and we refused it
+                    break
                 same = same and rr.returncode == 0 and ro.returncode == 0 and open(r2, "rb").read() == open(o2, "rb").read()
                 rb, ob = r2, o2
             flags = flags + ["(append at %d, %d steps)" % (cut, len(steps))]
