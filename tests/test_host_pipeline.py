@@ -133,6 +133,33 @@ def test_append_matches_reference(tmp_path, mock_agc, case, n_first, steps):
     assert a == b, f"appended archives differ: {len(a)} vs {len(b)} bytes"
 
 
+def test_append_survives_damaged_archives(tmp_path, mock_agc):
+    """bit flips, truncation and footer damage of the input archive: `append` fails with a message (or succeeds when the damage
+    sits in a part that is copied verbatim), it never crashes"""
+    tmp = str(tmp_path)
+    files, flags = collection("complex", tmp)
+    base = os.path.join(tmp, "base.agc")
+    subprocess.check_call([REF_AGC, "create", "-t", "3", "-o", base] + flags + files[:5], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    good = open(base, "rb").read()
+    rng = np.random.default_rng(1)
+    failed = 0
+    for it in range(45):
+        b = bytearray(good)
+        if it % 3 == 0:
+            for _ in range(int(rng.integers(1, 4))):
+                b[int(rng.integers(0, len(b)))] ^= 1 << int(rng.integers(0, 8))
+        elif it % 3 == 1:
+            b = b[:int(rng.integers(0, len(b)))]
+        else:
+            b[int(rng.integers(len(b) - 600, len(b)))] = int(rng.integers(0, 256))
+        bad = os.path.join(tmp, "bad.agc")
+        open(bad, "wb").write(bytes(b))
+        r = subprocess.run([mock_agc, "append", "-o", os.path.join(tmp, "o.agc"), bad] + files[5:7], capture_output=True, timeout=120)
+        assert 0 <= r.returncode < 128, f"append crashed (exit {r.returncode}) on damaged archive, iteration {it}"
+        failed += r.returncode != 0
+    assert failed >= 15
+
+
 def test_self_check_mode(tmp_path, mock_agc):
     """--verify: every coded frame is decoded again (device decoder; here its host build) and compared before it is written;
     the archive is the same one"""
