@@ -42,14 +42,21 @@ def test_gloo_world2(tmp_path):
     assert "ok0" in out.stdout and "ok1" in out.stdout
 
 
-def _sharded_create(tmp, case, world, port, so, device):
+def _sharded_create(tmp, case, world, port, so, device, append_after=0):
     """one archive from `world` ranks (agcgpu_set_exchange + torch.distributed all-gather over gloo); returns (archive bytes,
-    reference archive bytes, per-rank residual-coder input in MB)"""
+    reference archive bytes, per-rank residual-coder input in MB).  append_after = n: the reference creates a base from the
+    first n files and the ranks extend it (`append`) with the rest."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from test_host_pipeline import collection, REF_AGC
+    from test_host_pipeline import collection, REF_AGC, append_flags
     files, flags = collection(case, tmp)
     ref = os.path.join(tmp, "ref.agc"); out = os.path.join(tmp, "our.agc")
-    subprocess.check_call([REF_AGC, "create", "-t", "4", "-o", ref] + flags + files, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    if append_after:
+        base = os.path.join(tmp, "base.agc")
+        subprocess.check_call([REF_AGC, "create", "-t", "4", "-o", base] + flags + files[:append_after], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        subprocess.check_call([REF_AGC, "append", "-t", "4", "-o", ref] + append_flags(flags) + [base] + files[append_after:], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        files = [base] + files[append_after:]
+    else:
+        subprocess.check_call([REF_AGC, "create", "-t", "4", "-o", ref] + flags + files, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
                         "--master-port", str(port), os.path.join(ROOT, "tests", "sharded_create_worker.py"), so, out, str(device)] + flags + ["--"] + files,
                        capture_output=True, text=True, timeout=900)
@@ -70,9 +77,9 @@ def test_sharded_create_gloo(tmp_path):
         pytest.skip("reference binary not built")
     subprocess.check_call(["make", "-C", MOCK_DIR, "-j4"], stdout=subprocess.DEVNULL)
     so = os.path.join(MOCK_DIR, "libagcgpu_mock.so")
-    for case, world, port in (("complex", 2, 29541), ("adaptive", 3, 29542)):
+    for case, world, port, app in (("complex", 2, 29541, 0), ("adaptive", 3, 29542, 0), ("fallback", 2, 29543, 4)):
         tmp = os.path.join(str(tmp_path), case); os.makedirs(tmp)
-        a, b, mb = _sharded_create(tmp, case, world, port, so, -1)
+        a, b, mb = _sharded_create(tmp, case, world, port, so, -1, append_after=app)
         assert a == b, f"{case}: archive of {world} ranks differs from the reference's ({len(a)} vs {len(b)} bytes)"
         total = sum(mb.values())
         assert total > 0 and all(v > 0.5 * total / world for v in mb.values()), mb     # every rank coded its share of the parts
