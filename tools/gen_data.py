@@ -186,3 +186,26 @@ def adaptive_collection(out_dir, seed=2, n_samples=8, ref_len=60000, n_ctg=2, no
         write_fasta(fn, ctgs)
         files.append(fn)
     return files
+
+
+def bacterial_adaptive(out_dir, seed=2, n_samples=63, ref_len=5_000_000, p=0.01, novel_len=120_000, n_indels=20):
+    """BASELINE configs[2] / SURVEY C3: ref 5 Mb; every sample = the reference with 1 % substitutions and 20 random 1-50 b indels
+    plus one NOVEL random 120 kb contig (>= segment_size: `-a` finds new splitters in it).  Returns the file list (ref first)."""
+    os.makedirs(out_dir, exist_ok=True)
+    rng = np.random.default_rng(seed)
+    ref = rng.integers(0, 4, ref_len, dtype=np.uint8)
+    files = [os.path.join(out_dir, "ref.fa")]
+    write_fasta(files[0], [("ref_chr", ref)])
+    for s in range(n_samples):
+        t = substitute(rng, ref, p)
+        pos = np.sort(rng.integers(0, len(t), n_indels))[::-1]
+        for q in pos:                                     # few large-array edits instead of list surgery
+            L = int(rng.integers(1, 51))
+            if rng.random() < 0.5:
+                t = np.concatenate([t[:q], t[q + L:]])
+            else:
+                t = np.concatenate([t[:q], rng.integers(0, 4, L, dtype=np.uint8), t[q:]])
+        fn = os.path.join(out_dir, f"b{s:02d}.fa")
+        write_fasta(fn, [(f"b{s:02d}_chr", t), (f"b{s:02d}_novel", rng.integers(0, 4, novel_len, dtype=np.uint8))])
+        files.append(fn)
+    return files
