@@ -29,9 +29,20 @@ while i < len(flags):
         opt[flags[i]] = int(flags[i + 1]); i += 1
     i += 1
 
-dist.init_process_group("gloo")
-L = C.CDLL(so)
-rank, world = adist.install_exchange(L)
+# AGC_EXCHANGE=nccl: one GPU per rank, blocks staged through HBM and gathered with NCCL; AGC_EXCHANGE=staged-cpu: the same staging
+# code path over gloo with CPU tensors (CPU suite); default: gloo on host memory
+mode = os.environ.get("AGC_EXCHANGE", "gloo")
+if mode == "nccl":
+    import torch
+    device = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(device)
+    dist.init_process_group("nccl")
+    L = C.CDLL(so)
+    rank, world = adist.install_exchange(L, device=f"cuda:{device}")
+else:
+    dist.init_process_group("gloo")
+    L = C.CDLL(so)
+    rank, world = adist.install_exchange(L, device="cpu" if mode == "staged-cpu" else None)
 vp = C.c_void_p
 L.agcgpu_compressor_create.restype = C.c_int
 L.agcgpu_compressor_create.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_char_p, C.c_uint32, C.c_uint32, C.c_int, C.c_int,

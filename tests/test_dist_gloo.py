@@ -42,7 +42,7 @@ def test_gloo_world2(tmp_path):
     assert "ok0" in out.stdout and "ok1" in out.stdout
 
 
-def _sharded_create(tmp, case, world, port, so, device, append_after=0):
+def _sharded_create(tmp, case, world, port, so, device, append_after=0, exchange="gloo"):
     """one archive from `world` ranks (agcgpu_set_exchange + torch.distributed all-gather over gloo); returns (archive bytes,
     reference archive bytes, per-rank residual-coder input in MB).  append_after = n: the reference creates a base from the
     first n files and the ranks extend it (`append`) with the rest."""
@@ -59,7 +59,7 @@ def _sharded_create(tmp, case, world, port, so, device, append_after=0):
         subprocess.check_call([REF_AGC, "create", "-t", "4", "-o", ref] + flags + files, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
                         "--master-port", str(port), os.path.join(ROOT, "tests", "sharded_create_worker.py"), so, out, str(device)] + flags + ["--"] + files,
-                       capture_output=True, text=True, timeout=900)
+                       capture_output=True, text=True, timeout=900, env=dict(os.environ, AGC_EXCHANGE=exchange))
     assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-3000:]
     import re
     mb = {int(m.group(1)): float(m.group(2)) for m in re.finditer(r"rank(\d+)/\d+ zstd_input_mb=([0-9.]+)", r.stdout)}
@@ -77,9 +77,10 @@ def test_sharded_create_gloo(tmp_path):
         pytest.skip("reference binary not built")
     subprocess.check_call(["make", "-C", MOCK_DIR, "-j4"], stdout=subprocess.DEVNULL)
     so = os.path.join(MOCK_DIR, "libagcgpu_mock.so")
-    for case, world, port, app in (("complex", 2, 29541, 0), ("adaptive", 3, 29542, 0), ("fallback", 2, 29543, 4)):
+    # the third run takes the staging path of install_exchange (the one NCCL uses on a GPU box) with CPU tensors
+    for case, world, port, app, exch in (("complex", 2, 29541, 0, "gloo"), ("adaptive", 3, 29542, 0, "gloo"), ("fallback", 2, 29543, 4, "staged-cpu")):
         tmp = os.path.join(str(tmp_path), case); os.makedirs(tmp)
-        a, b, mb = _sharded_create(tmp, case, world, port, so, -1, append_after=app)
+        a, b, mb = _sharded_create(tmp, case, world, port, so, -1, append_after=app, exchange=exch)
         assert a == b, f"{case}: archive of {world} ranks differs from the reference's ({len(a)} vs {len(b)} bytes)"
         total = sum(mb.values())
         assert total > 0 and all(v > 0.5 * total / world for v in mb.values()), mb     # every rank coded its share of the parts

@@ -21,3 +21,22 @@ def test_two_ranks_one_archive(tmp_path, case):
     assert a == b, f"{case}: archive of 2 ranks differs from the reference's ({len(a)} vs {len(b)} bytes)"
     total = sum(mb.values())
     assert total > 0 and all(v > 0.25 * total for v in mb.values()), mb
+
+
+def _n_gpus():
+    try:
+        import subprocess
+        return len(subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True).stdout.strip().splitlines())
+    except Exception:
+        return 0
+
+
+@pytest.mark.skipif(not os.path.exists(REF_AGC), reason="reference binary not built (make -f oracle/Makefile.ref)")
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs two GPUs (NCCL cannot put two ranks on one device)")
+def test_two_gpus_nccl(tmp_path):
+    """one GPU per rank, the exchange step over NCCL (all_gather_into_tensor on HBM-staged blocks)"""
+    import agc_b200
+    a, b, mb = _sharded_create(str(tmp_path), "complex", 2, 29553, agc_b200.lib_path(), 0, exchange="nccl")
+    assert a == b
+    total = sum(mb.values())
+    assert total > 0 and all(v > 0.25 * total for v in mb.values()), mb
