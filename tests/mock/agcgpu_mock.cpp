@@ -71,6 +71,8 @@ struct agcgpu_ctx {
 };
 
 static thread_local std::string g_create_err;
+static std::map<std::string, std::pair<uint64_t, uint64_t>> g_calls;     // AGC_MOCK_COUNT=1: calls and items per entry point, printed at destroy
+#define COUNT(name, items) do { auto& c_ = g_calls[name]; c_.first++; c_.second += (items); } while (0)
 
 static int fail(agcgpu_ctx* c, int code, const char* fmt, ...)
 {
@@ -143,6 +145,7 @@ void agcgpu_destroy(agcgpu_ctx* ctx)
 {
     if (!ctx) return;
     for (auto& g : ctx->groups) orc_lz_free(g.second.lz);
+    if (getenv("AGC_MOCK_COUNT")) for (auto& c : g_calls) fprintf(stderr, "[mock] %-28s %8llu calls %12llu items\n", c.first.c_str(), (unsigned long long)c.second.first, (unsigned long long)c.second.second);
     delete ctx;
 }
 const char* agcgpu_last_error(const agcgpu_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
@@ -215,6 +218,7 @@ int agcgpu_find_new_splitters(agcgpu_ctx* ctx, const uint32_t* contigs, uint32_t
 
 int agcgpu_filtered_kmers(agcgpu_ctx* ctx, const agcgpu_seg_req* reqs, uint32_t n, uint64_t thr, agcgpu_fkmer* out, uint64_t cap, uint64_t* out_offsets)
 {
+    COUNT("agcgpu_filtered_kmers", n);
     if (!ctx || !out_offsets || (n && !reqs) || (cap && !out)) return AGCGPU_EINVAL;
     out_offsets[0] = 0;
     bool overflow = false;
@@ -268,6 +272,7 @@ int agcgpu_rescan_contigs(agcgpu_ctx* ctx, agcgpu_cut* out_cuts, uint64_t cap, u
 
 int agcgpu_get_segment(agcgpu_ctx* ctx, uint32_t contig, uint64_t start, uint32_t len, uint32_t is_rc, uint8_t* out)
 {
+    COUNT("agcgpu_get_segment", 1);
     if (!ctx || (len && !out)) return AGCGPU_EINVAL;
     std::vector<uint8_t> s;
     if (int r = fetch(ctx, contig, start, len, is_rc, s)) return r;
@@ -277,6 +282,7 @@ int agcgpu_get_segment(agcgpu_ctx* ctx, uint32_t contig, uint64_t start, uint32_
 
 int agcgpu_map_insert(agcgpu_ctx* ctx, const uint64_t* k1, const uint64_t* k2, const int32_t* gid, uint64_t n)
 {
+    COUNT("agcgpu_map_insert", n);
     if (!ctx || (n && (!k1 || !k2 || !gid))) return AGCGPU_EINVAL;
     for (uint64_t i = 0; i < n; ++i) {
         if (gid[i] < 0) return fail(ctx, AGCGPU_EINVAL, "map_insert: negative group id");
@@ -289,6 +295,7 @@ int agcgpu_map_insert(agcgpu_ctx* ctx, const uint64_t* k1, const uint64_t* k2, c
 
 int agcgpu_assign_cuts(agcgpu_ctx* ctx, const agcgpu_cut* cuts, uint64_t n, agcgpu_assign* out)
 {
+    COUNT("agcgpu_assign_cuts", n);
     if (!ctx || (n && (!cuts || !out))) return AGCGPU_EINVAL;
     for (uint64_t i = 0; i < n; ++i) {                          // add_segment key construction (agc_compressor.cpp:1287-1313)
         const agcgpu_cut& c = cuts[i];
@@ -317,6 +324,7 @@ int agcgpu_group_put_reference(agcgpu_ctx* ctx, uint32_t group_id, const uint8_t
 }
 int agcgpu_group_put_reference_batch(agcgpu_ctx* ctx, const agcgpu_seg_req* reqs, uint32_t n)
 {
+    COUNT("agcgpu_group_put_reference_batch", n);
     if (!ctx || (n && !reqs)) return AGCGPU_EINVAL;
     for (uint32_t i = 0; i < n; ++i) {
         std::vector<uint8_t> s;
@@ -347,6 +355,7 @@ static int lz_prep(agcgpu_ctx* ctx, const agcgpu_seg_req& q, std::vector<uint8_t
 
 int agcgpu_lz_encode_batch(agcgpu_ctx* ctx, const agcgpu_seg_req* reqs, uint32_t n, uint8_t* out, uint64_t out_cap, uint64_t* out_offsets)
 {
+    COUNT("agcgpu_lz_encode_batch", n);
     if (!ctx || !out_offsets || (n && (!reqs || !out))) return AGCGPU_EINVAL;
     uint64_t o = 0; out_offsets[0] = 0;
     for (uint32_t i = 0; i < n; ++i) {
@@ -363,6 +372,7 @@ int agcgpu_lz_encode_batch(agcgpu_ctx* ctx, const agcgpu_seg_req* reqs, uint32_t
 }
 int agcgpu_lz_estimate_batch(agcgpu_ctx* ctx, const agcgpu_seg_req* reqs, uint32_t n, uint32_t* out)
 {
+    COUNT("agcgpu_lz_estimate_batch", n);
     if (!ctx || (n && (!reqs || !out))) return AGCGPU_EINVAL;
     for (uint32_t i = 0; i < n; ++i) {
         std::vector<uint8_t> t; olz_t* z;
@@ -373,6 +383,7 @@ int agcgpu_lz_estimate_batch(agcgpu_ctx* ctx, const agcgpu_seg_req* reqs, uint32
 }
 int agcgpu_lz_cost_vector(agcgpu_ctx* ctx, const agcgpu_seg_req* req, int prefix_costs, uint32_t* out)
 {
+    COUNT("agcgpu_lz_cost_vector", 1);
     if (!ctx || !req || (req->len && !out)) return AGCGPU_EINVAL;
     std::vector<uint8_t> t; olz_t* z;
     if (int r = lz_prep(ctx, *req, t, &z)) return r;
@@ -412,6 +423,7 @@ int agcgpu_lz_decode_batch(agcgpu_ctx* ctx, const uint32_t* group_ids, const uin
 int agcgpu_pack_ref_batch(agcgpu_ctx* ctx, const uint32_t* group_ids, uint32_t n, uint8_t* out, uint64_t out_cap, uint64_t* out_offsets,
                           uint8_t* out_use_tuples)
 {
+    COUNT("agcgpu_pack_ref_batch", n);
     if (!ctx || !out_offsets || (n && (!group_ids || !out || !out_use_tuples))) return AGCGPU_EINVAL;
     uint64_t o = 0; out_offsets[0] = 0;
     for (uint32_t i = 0; i < n; ++i) {
@@ -433,6 +445,7 @@ int agcgpu_pack_ref_batch(agcgpu_ctx* ctx, const uint32_t* group_ids, uint32_t n
 int agcgpu_zstd_compress_batch(agcgpu_ctx* ctx, const uint8_t* src, const uint64_t* so, const int32_t* levels, uint32_t n, uint8_t* dst,
                                uint64_t dst_cap, uint64_t* dof)
 {
+    COUNT("agcgpu_zstd_compress_batch", n);
     if (!ctx || !so || !dof || (n && (!src || !levels || !dst))) return AGCGPU_EINVAL;
     uint64_t o = 0; dof[0] = 0;
     for (uint32_t i = 0; i < n; ++i) {

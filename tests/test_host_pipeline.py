@@ -160,6 +160,27 @@ def test_append_survives_damaged_archives(tmp_path, mock_agc):
     assert failed >= 15
 
 
+def test_golden_archives(tmp_path, mock_agc):
+    """the committed hashes of the reference's archives (tools/make_golden_modes.py): create in every mode, and the appended
+    archives -- this check does not execute the reference binary for the create cases"""
+    import hashlib
+    import json
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "archives_modes.json")))
+    for case, g in gold["create"].items():
+        tmp = os.path.join(str(tmp_path), case); os.makedirs(tmp)
+        files, flags = collection(case, tmp)
+        assert hashlib.sha256(b"".join(open(f, "rb").read() for f in files)).hexdigest() == g["fasta_sha256"], f"{case}: generator drifted"
+        out = os.path.join(tmp, "o.agc")
+        subprocess.check_call([mock_agc, "create", "-o", out] + flags + files)
+        b = open(out, "rb").read()
+        assert len(b) == g["agc_size"] and hashlib.sha256(b).hexdigest() == g["agc_sha256"], f"{case}: archive differs from the reference's golden hash"
+    for (case, n_first, steps) in APPEND_CASES:
+        g = gold["append"][f"{case}:{n_first}:{steps}"]
+        tmp = os.path.join(str(tmp_path), f"app_{case}_{n_first}_{steps}"); os.makedirs(tmp)
+        a, _, _ = run_append_case(tmp, mock_agc, case, n_first, steps)
+        assert len(a) == g["agc_size"] and hashlib.sha256(a).hexdigest() == g["agc_sha256"], f"append {case}:{n_first}:{steps} differs from the golden hash"
+
+
 def test_self_check_mode(tmp_path, mock_agc):
     """--verify: every coded frame is decoded again (device decoder; here its host build) and compared before it is written;
     the archive is the same one"""
