@@ -458,16 +458,24 @@ bool CAGCCompressor::exchange(const std::vector<uint8_t>& mine, std::vector<std:
     return true;
 }
 
-// residual coder over all ranks: the frames of a drain are dealt out by size (largest first, round-robin), coded where
-// they land and all-gathered; every rank ends up with every frame (only rank 0 writes them)
+// residual coder over all ranks: the frames of a drain are dealt out by size (largest first, to the least loaded rank), coded
+// where they land and all-gathered; every rank ends up with every frame (only rank 0 writes them)
 bool CAGCCompressor::compress_tasks(std::vector<ZTask*>& tasks)
 {
     if (xworld <= 1 || tasks.empty()) return compress_tasks_local(tasks);
+    // longest-processing-time-first: frames sorted by size, each to the rank with the least bytes so far (ties: lowest rank);
+    // every rank computes the same assignment from the same task list
     std::vector<size_t> order(tasks.size());
     std::iota(order.begin(), order.end(), (size_t)0);
     std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return tasks[a]->raw.size() > tasks[b]->raw.size(); });
+    std::vector<uint64_t> load(xworld, 0);
+    std::vector<std::vector<size_t>> of_rank(xworld);
+    for (size_t i : order) {
+        uint32_t r = (uint32_t)(std::min_element(load.begin(), load.end()) - load.begin());
+        of_rank[r].push_back(i); load[r] += tasks[i]->raw.size() + 512;     // + a per-frame constant: empty and tiny frames are not free
+    }
     std::vector<ZTask*> mine;
-    for (size_t i = xrank; i < order.size(); i += xworld) mine.push_back(tasks[order[i]]);
+    for (size_t i : of_rank[xrank]) mine.push_back(tasks[i]);
     if (!compress_tasks_local(mine)) return false;
     std::vector<uint8_t> blob;
     for (auto* t : mine) { uint64_t n = t->packed.size(); const uint8_t* p = (const uint8_t*)&n; blob.insert(blob.end(), p, p + 8); blob.insert(blob.end(), t->packed.begin(), t->packed.end()); }
@@ -475,12 +483,12 @@ bool CAGCCompressor::compress_tasks(std::vector<ZTask*>& tasks)
     if (!exchange(blob, all)) return false;
     for (uint32_t r = 0; r < xworld; ++r) {
         size_t o = 0;
-        for (size_t i = r; i < order.size(); i += xworld) {
+        for (size_t i : of_rank[r]) {
             uint64_t n;
             if (o + 8 > all[r].size()) return fail("exchange: truncated frame block");
             memcpy(&n, all[r].data() + o, 8); o += 8;
             if (o + n > all[r].size()) return fail("exchange: truncated frame block");
-            if (r != xrank) tasks[order[i]]->packed.assign(all[r].begin() + o, all[r].begin() + o + n);
+            if (r != xrank) tasks[i]->packed.assign(all[r].begin() + o, all[r].begin() + o + n);
             o += n;
         }
     }
