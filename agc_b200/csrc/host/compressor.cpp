@@ -24,9 +24,10 @@ namespace agc_b200 {
 bool CArchive::Open(const std::string& file_name)
 {
     if (f) return false;
-    f = fopen(file_name.c_str(), "wb");
+    use_stdout = file_name.empty();                          // COutFile::Open (src/common/io.h:281-300): no name = stdout
+    f = use_stdout ? stdout : fopen(file_name.c_str(), "wb");
     if (!f) return false;
-    setvbuf(f, nullptr, _IOFBF, 32 << 20);
+    if (!use_stdout) setvbuf(f, nullptr, _IOFBF, 32 << 20);
     f_offset = 0;
     return true;
 }
@@ -89,7 +90,7 @@ bool CArchive::Close()
         for (auto& p : s.parts) { footer_size += write_varint(p.offset); footer_size += write_varint(p.size); }
     }
     for (int i = 0; i < 8; ++i) putc((int)((footer_size >> (8 * i)) & 0xff), f);     // io.h:371-380 WriteUInt little endian
-    bool ok = fclose(f) == 0;
+    bool ok = use_stdout ? fflush(f) == 0 : fclose(f) == 0;
     f = nullptr;
     return ok;
 }

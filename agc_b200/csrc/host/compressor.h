@@ -40,6 +40,7 @@ public:
 private:
     size_t write_varint(uint64_t x);                          // archive.h:110-125: [n][big-endian bytes]
     FILE* f = nullptr;
+    bool use_stdout = false;
     uint64_t f_offset = 0;
     std::vector<stream_t> v_streams;
     std::unordered_map<std::string, int> rm_streams;

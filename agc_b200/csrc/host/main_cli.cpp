@@ -47,7 +47,7 @@ int main(int argc, char** argv)
     k = std::clamp(k, 17u, 32u); b = std::clamp(b, 1u, 1000000000u); s = std::clamp(s, 100u, 1000000u); l = std::clamp(l, 15u, 32u);
     v = std::clamp(v, 0u, 2u); f = std::clamp(f, 0.0, 0.05);
     if (!list.empty()) { std::ifstream in(list); std::string ln; while (std::getline(in, ln)) if (!ln.empty()) inputs.push_back(ln); }
-    if (out.empty() || inputs.empty()) { std::cerr << "need -o and at least the reference FASTA (create) / the input archive (append)\n"; return 1; }
+    if (inputs.empty()) { std::cerr << "need at least the reference FASTA (create) / the input archive (append)\n"; return 1; }   // no -o: the archive goes to stdout
     if (is_append) {                                           // src/app/main.cpp:124-160: the first positional argument is the archive to extend
         const std::string in_archive = inputs.front();
         inputs.erase(inputs.begin());

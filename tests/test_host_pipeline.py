@@ -192,6 +192,14 @@ def test_self_check_mode(tmp_path, mock_agc):
     assert open(a, "rb").read() == open(b, "rb").read()
 
 
+def test_archive_to_stdout(tmp_path, mock_agc):
+    """no -o: the archive goes to stdout (COutFile::Open with an empty name, src/common/io.h:281-300)"""
+    files, flags = collection("smallpacks", str(tmp_path))
+    a = subprocess.run([mock_agc, "create"] + flags + files, capture_output=True).stdout
+    b = subprocess.run([REF_AGC, "create", "-t", "2"] + flags + files, capture_output=True).stdout
+    assert a == b and len(a) > 1000
+
+
 def test_cli_clamps_options_like_the_reference(tmp_path, mock_agc):
     """b_value<T>::assign (src/app/application.h:23-47): -f 0.2 means -f 0.05, -k 40 means -k 32, ..."""
     tmp = str(tmp_path)
