@@ -192,6 +192,21 @@ def test_self_check_mode(tmp_path, mock_agc):
     assert open(a, "rb").read() == open(b, "rb").read()
 
 
+def test_gzipped_inputs(tmp_path, mock_agc):
+    """.fa.gz inputs (CGenomeIO through zlib; sample names lose .gz and .fa, application.cpp:606-630): same archive"""
+    import gzip
+    import shutil
+    files, flags = collection("smallpacks", str(tmp_path))
+    gz = []
+    for f in files:
+        with open(f, "rb") as i, gzip.open(f + ".gz", "wb") as o:
+            shutil.copyfileobj(i, o)
+        gz.append(f + ".gz")
+    a = subprocess.run([mock_agc, "create"] + flags + gz, capture_output=True).stdout
+    b = subprocess.run([REF_AGC, "create", "-t", "2"] + flags + gz, capture_output=True).stdout
+    assert a == b and len(a) > 1000
+
+
 def test_archive_to_stdout(tmp_path, mock_agc):
     """no -o: the archive goes to stdout (COutFile::Open with an empty name, src/common/io.h:281-300)"""
     files, flags = collection("smallpacks", str(tmp_path))
