@@ -38,7 +38,7 @@ def make_case(d, seed):
     files = [os.path.join(d, "ref.fa")]
     gen_data.write_fasta(files[0], [(f"r{i} x", c) for i, c in enumerate(ref)])
     pool = list(ref)
-    n_samples = int(rng.integers(1, 7))
+    n_samples = int(rng.integers(1, 7 * int(os.environ.get("AGC_FUZZ_SCALE", "1"))))          # AGC_FUZZ_SCALE=3: up to 20 samples
     uid = 0
     for si in range(n_samples):
         ctgs = []
