@@ -32,6 +32,11 @@ class SegReq(C.Structure):
                 ("group_id", C.c_uint32), ("bound", C.c_uint32), ("reserved", C.c_uint32)]
 
 
+class SplitReq(C.Structure):
+    _fields_ = [("contig", C.c_uint32), ("len", C.c_uint32), ("start", C.c_uint64), ("group1", C.c_uint32), ("group2", C.c_uint32),
+                ("flags", C.c_uint32), ("reserved", C.c_uint32)]
+
+
 class Assign(C.Structure):
     _fields_ = [("key1", C.c_uint64), ("key2", C.c_uint64), ("group_id", C.c_int32), ("is_rc", C.c_uint32),
                 ("klass", C.c_uint32), ("reserved", C.c_uint32)]
@@ -53,7 +58,7 @@ EXPORTED_SYMBOLS = [
     "agcgpu_determine_splitters", "agcgpu_set_splitters", "agcgpu_scan_contigs", "agcgpu_scan_contigs_dev",
     "agcgpu_get_segment", "agcgpu_map_insert", "agcgpu_assign_cuts", "agcgpu_group_put_reference_batch",
     "agcgpu_group_put_reference", "agcgpu_group_get_index", "agcgpu_lz_encode_batch", "agcgpu_lz_estimate_batch",
-    "agcgpu_lz_cost_vector", "agcgpu_pack_ref_batch", "agcgpu_zstd_compress_batch",
+    "agcgpu_lz_cost_vector", "agcgpu_lz_cost_split_batch", "agcgpu_pack_ref_batch", "agcgpu_zstd_compress_batch",
     "agcgpu_find_new_splitters", "agcgpu_rescan_contigs", "agcgpu_filtered_kmers", "agcgpu_last_splitter_positions",
     "agcgpu_zstd_decompress_batch", "agcgpu_lz_decode_batch",
 ]
@@ -110,6 +115,7 @@ def lib():
     L.agcgpu_lz_encode_batch.argtypes = [vp, C.POINTER(SegReq), C.c_uint32, u8p, C.c_uint64, u64p]
     L.agcgpu_lz_estimate_batch.restype = C.c_int; L.agcgpu_lz_estimate_batch.argtypes = [vp, C.POINTER(SegReq), C.c_uint32, u32p]
     L.agcgpu_lz_cost_vector.restype = C.c_int; L.agcgpu_lz_cost_vector.argtypes = [vp, C.POINTER(SegReq), C.c_int, u32p]
+    L.agcgpu_lz_cost_split_batch.restype = C.c_int; L.agcgpu_lz_cost_split_batch.argtypes = [vp, C.POINTER(SplitReq), C.c_uint32, u32p, u32p]
     L.agcgpu_pack_ref_batch.restype = C.c_int
     L.agcgpu_pack_ref_batch.argtypes = [vp, u32p, C.c_uint32, u8p, C.c_uint64, u64p, u8p]
     L.agcgpu_zstd_compress_batch.restype = C.c_int
@@ -315,6 +321,15 @@ class Device:
         out = np.zeros(max(req[2], 1), np.uint32)
         self._ck(self.L.agcgpu_lz_cost_vector(self.h, arr, int(bool(prefix_costs)), _p(out, u32p)))
         return out[:req[2]].copy()
+
+    def lz_cost_split(self, reqs):
+        """reqs: (contig, start, len, group1, group2, flags) -> (best_pos[], best_sum[]) of agcgpu_lz_cost_split_batch"""
+        arr = (SplitReq * max(len(reqs), 1))()
+        for i, (c, st, ln, g1, g2, fl) in enumerate(reqs):
+            arr[i].contig, arr[i].start, arr[i].len, arr[i].group1, arr[i].group2, arr[i].flags = c, st, ln, g1, g2, fl
+        pos = np.zeros(max(len(reqs), 1), np.uint32); sm = np.zeros(max(len(reqs), 1), np.uint32)
+        self._ck(self.L.agcgpu_lz_cost_split_batch(self.h, arr, len(reqs), _p(pos, u32p), _p(sm, u32p)))
+        return pos[:len(reqs)].copy(), sm[:len(reqs)].copy()
 
     def zstd_compress(self, inputs, levels):
         """ZSTD_compressCCtx(level) of every input on the device -> list of frames"""

@@ -429,7 +429,17 @@ int agcgpu_lz_cost_vector(agcgpu_ctx* ctx, const agcgpu_seg_req* req, int prefix
     if (!ctx || !req || (req->len && !out)) return AGCGPU_EINVAL;
     cudaSetDevice(ctx->dev);
     if (req->len == 0) return 0;
-    return agc_lz_run(ctx, 2, req, 1, prefix_costs, nullptr, 0, nullptr, out);
+    agcgpu_seg_req q = *req;
+    q.bound = prefix_costs ? 1u : 0u;                    // the cost-vector kernels take prefix_costs per request
+    return agc_lz_run(ctx, 2, &q, 1, prefix_costs, nullptr, 0, nullptr, out);
+}
+
+int agcgpu_lz_cost_split_batch(agcgpu_ctx* ctx, const agcgpu_split_req* reqs, uint32_t n, uint32_t* out_best_pos, uint32_t* out_best_sum)
+{
+    if (!ctx || (n && (!reqs || !out_best_pos || !out_best_sum))) return AGCGPU_EINVAL;
+    cudaSetDevice(ctx->dev);
+    if (n == 0) return 0;
+    return agc_lz_cost_split(ctx, reqs, n, out_best_pos, out_best_sum);
 }
 
 int agcgpu_pack_ref_batch(agcgpu_ctx* ctx, const uint32_t* group_ids, uint32_t n, uint8_t* out, uint64_t out_cap,

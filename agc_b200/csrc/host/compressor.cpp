@@ -16,6 +16,18 @@ struct PhaseTimer {
     explicit PhaseTimer(const char* n) : name(n), t0(std::chrono::steady_clock::now()), on(getenv("AGCGPU_TRACE") != nullptr) {}
     ~PhaseTimer() { if (on) fprintf(stderr, "[agcgpu] phase %-22s %8.1f ms\n", name, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count()); }
 };
+// accumulated timers (AGCGPU_TRACE): total ms and call count per label, printed by Close
+struct AccTimers {
+    std::map<std::string, std::pair<double, uint64_t>> acc;
+    bool on = getenv("AGCGPU_TRACE") != nullptr;
+    void report() { if (!on) return; for (auto& kv : acc) fprintf(stderr, "[agcgpu] total %-26s %9.1f ms in %llu calls\n", kv.first.c_str(), kv.second.first, (unsigned long long)kv.second.second); acc.clear(); }
+};
+static AccTimers g_acc;
+struct AccTimer {
+    const char* name; std::chrono::steady_clock::time_point t0;
+    explicit AccTimer(const char* n) : name(n), t0(std::chrono::steady_clock::now()) {}
+    ~AccTimer() { if (!g_acc.on) return; auto& a = g_acc.acc[name]; a.first += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); ++a.second; }
+};
 namespace agc_b200 {
 
 // =====================================================================================================================
@@ -992,7 +1004,7 @@ bool CAGCCompressor::process_batch_raw(const uint8_t* cat, bool is_device, const
         for (size_t i = 0; i < rq.size(); ++i) est_cache[owner[i]].push_back(est[i]);
         return true;
     };
-    if (!prefetch_estimates(0)) return false;
+    { AccTimer at("prefetch_estimates(0)"); if (!prefetch_estimates(0)) return false; }
     auto one_splitter = [&](uint64_t x, uint64_t kdir, uint64_t krc, uint32_t len,
                             std::pair<uint64_t, uint64_t>& best_pk, bool& is_best_rc) -> bool {
         const uint64_t kd = canon(kdir, krc);
@@ -1019,50 +1031,77 @@ bool CAGCCompressor::process_batch_raw(const uint8_t* cat, bool is_device, const
         return true;
     };
 
-    // find_cand_segment_with_missing_middle_splitter (agc_compressor.cpp:1502-1627); dir_is_rc tells which orientation
-    // of the resident segment plays "segment_dir"
-    auto missing_middle = [&](uint64_t k1d, uint64_t k2d, uint32_t bc, uint64_t start, uint32_t len, bool dir_is_rc,
-                              uint64_t& middle, uint32_t& best_pos) -> bool {
-        middle = EMPTY; best_pos = 0;
+    // The decisions of one registration unit are independent of each other (the maps only change at the registration), so all of
+    // them go to the device as ONE agcgpu_lz_cost_split_batch call before the unit's add_segment pass; the device returns the
+    // split position of each (prefix / suffix sums and the argmin run there), 8 bytes per decision.
+    struct SplitPlan { uint64_t mid; uint32_t g1, g2, flags; };
+    auto split_plan = [&](uint64_t k1d, uint64_t k2d, bool dir_is_rc, SplitPlan& sp) -> bool {      // false: no shared splitter
         auto pf = map_segments_terminators.find(k1d), pb = map_segments_terminators.find(k2d);
-        if (pf == map_segments_terminators.end() || pb == map_segments_terminators.end()) return true;
+        if (pf == map_segments_terminators.end() || pb == map_segments_terminators.end()) return false;
         std::vector<uint64_t> shared;
         std::set_intersection(pf->second.begin(), pf->second.end(), pb->second.begin(), pb->second.end(), std::back_inserter(shared));
         shared.erase(std::remove(shared.begin(), shared.end(), EMPTY), shared.end());
-        if (shared.empty()) return true;
-        uint64_t mid = shared.front();
-        uint32_t g1 = (uint32_t)map_segments[std::minmax(k1d, mid)], g2 = (uint32_t)map_segments[std::minmax(mid, k2d)];
+        if (shared.empty()) return false;
+        sp.mid = shared.front();
+        sp.g1 = (uint32_t)map_segments[std::minmax(k1d, sp.mid)]; sp.g2 = (uint32_t)map_segments[std::minmax(sp.mid, k2d)];
+        sp.flags = 0;
+        if (k1d < sp.mid) sp.flags |= (dir_is_rc ? AGCGPU_SPLIT_RC1 : 0u) | AGCGPU_SPLIT_PREFIX1;
+        else sp.flags |= (dir_is_rc ? 0u : AGCGPU_SPLIT_RC1) | AGCGPU_SPLIT_REV1;
+        if (sp.mid < k2d) sp.flags |= (dir_is_rc ? AGCGPU_SPLIT_RC2 : 0u);
+        else sp.flags |= (dir_is_rc ? 0u : AGCGPU_SPLIT_RC2) | AGCGPU_SPLIT_PREFIX2 | AGCGPU_SPLIT_REV2;
+        return true;
+    };
+    std::unordered_map<uint64_t, std::pair<uint64_t, uint32_t>> split_cache;        // cut -> (middle splitter, best position before snapping)
+    auto prefetch_splits = [&](uint32_t c_from, uint32_t c_to) -> bool {
+        split_cache.clear();
+        if (concatenated_genomes) return true;
+        AccTimer at("missing_middle (batched)");
+        std::vector<agcgpu_split_req> rq; std::vector<uint64_t> owner; std::vector<uint64_t> mids;
+        for (uint64_t x = cut_first[c_from]; x < cut_first[c_to]; ++x) {
+            const agcgpu_cut& c = cuts[x];
+            if (!c.has_front || !c.has_back || assign[x].group_id >= 0) continue;
+            const uint64_t fc = canon(c.front_dir, c.front_rc), bcn = canon(c.back_dir, c.back_rc);
+            if (fc == bcn || fc == EMPTY || bcn == EMPTY) continue;
+            if (!map_segments_terminators.count(fc) || !map_segments_terminators.count(bcn)) continue;
+            SplitPlan sp;
+            if (!split_plan(std::min(fc, bcn), std::max(fc, bcn), fc > bcn, sp)) continue;
+            if (v_segments[sp.g1].lazy || v_segments[sp.g2].lazy) continue;          // append: decided on the host (no cost vector exists)
+            agcgpu_split_req q; q.contig = c.contig; q.len = (uint32_t)c.len; q.start = c.start; q.group1 = sp.g1; q.group2 = sp.g2;
+            q.flags = sp.flags; q.reserved = 0;
+            rq.push_back(q); owner.push_back(x); mids.push_back(sp.mid);
+        }
+        if (rq.empty()) return true;
+        std::vector<uint32_t> bpos(rq.size()), bsum(rq.size());
+        if (!gpu_ok(agcgpu_lz_cost_split_batch(ctx, rq.data(), (uint32_t)rq.size(), bpos.data(), bsum.data()), "lz_cost_split_batch")) return false;
+        for (size_t i = 0; i < rq.size(); ++i) split_cache[owner[i]] = std::make_pair(mids[i], bpos[i]);
+        return true;
+    };
+
+    // find_cand_segment_with_missing_middle_splitter (agc_compressor.cpp:1502-1627); dir_is_rc tells which orientation
+    // of the resident segment plays "segment_dir"
+    auto missing_middle = [&](uint64_t x, uint64_t k1d, uint64_t k2d, uint32_t bc, uint64_t start, uint32_t len, bool dir_is_rc,
+                              uint64_t& middle, uint32_t& best_pos) -> bool {
+        middle = EMPTY; best_pos = 0;
+        auto snap = [&](uint32_t bp, uint32_t n_costs) {          // 1621-1624
+            if (bp < kmer_length + 1u) bp = 0;
+            if ((size_t)bp + kmer_length + 1u > n_costs) bp = n_costs;
+            return bp; };
+        auto pc = split_cache.find(x);
+        if (pc != split_cache.end()) { middle = pc->second.first; best_pos = snap(pc->second.second, len); return true; }
+        SplitPlan sp;
+        if (!split_plan(k1d, k2d, dir_is_rc, sp)) return true;
         // a group reloaded by Append and not unpacked yet gives no cost vector (get_coding_cost returns on ref_size == 0, segment.cpp:101-103)
-        const bool lazy1 = v_segments[g1].lazy, lazy2 = v_segments[g2].lazy;
-        std::vector<uint32_t> c1(lazy1 ? 0 : len), c2(lazy2 ? 0 : len);
-        agcgpu_seg_req q;
-        if (lazy1) {}
-        else if (k1d < mid) {
-            q = seg_req(bc, start, len, dir_is_rc, g1, 0);
-            if (!gpu_ok(agcgpu_lz_cost_vector(ctx, &q, 1, c1.data()), "lz_cost_vector")) return false;
-        } else {
-            q = seg_req(bc, start, len, !dir_is_rc, g1, 0);
-            if (!gpu_ok(agcgpu_lz_cost_vector(ctx, &q, 0, c1.data()), "lz_cost_vector")) return false;
-            std::reverse(c1.begin(), c1.end());
+        const bool lazy1 = v_segments[sp.g1].lazy, lazy2 = v_segments[sp.g2].lazy;
+        if (lazy1 != lazy2) return true;                          // 1600-1603: vectors of different sizes, no split
+        uint32_t bp = 0, n_costs = 0;
+        if (!lazy1) {
+            AccTimer at("missing_middle (single)");
+            agcgpu_split_req q; q.contig = bc; q.len = len; q.start = start; q.group1 = sp.g1; q.group2 = sp.g2; q.flags = sp.flags; q.reserved = 0;
+            uint32_t bs = 0;
+            if (!gpu_ok(agcgpu_lz_cost_split_batch(ctx, &q, 1, &bp, &bs), "lz_cost_split_batch")) return false;
+            n_costs = len;
         }
-        std::partial_sum(c1.begin(), c1.end(), c1.begin());
-        if (lazy2) {}
-        else if (mid < k2d) {
-            q = seg_req(bc, start, len, dir_is_rc, g2, 0);
-            if (!gpu_ok(agcgpu_lz_cost_vector(ctx, &q, 0, c2.data()), "lz_cost_vector")) return false;
-            std::partial_sum(c2.rbegin(), c2.rend(), c2.rbegin());
-        } else {
-            q = seg_req(bc, start, len, !dir_is_rc, g2, 0);
-            if (!gpu_ok(agcgpu_lz_cost_vector(ctx, &q, 1, c2.data()), "lz_cost_vector")) return false;
-            std::partial_sum(c2.begin(), c2.end(), c2.begin());
-            std::reverse(c2.begin(), c2.end());
-        }
-        if (c1.size() != c2.size()) return true;                 // 1600-1603: no split
-        uint32_t best_sum = ~0u, bp = 0;
-        for (uint32_t i = 0; i < c1.size(); ++i) { uint32_t cs = c1[i] + c2[i]; if (cs < best_sum) { best_sum = cs; bp = i; } }
-        if (bp < kmer_length + 1u) bp = 0;
-        if ((size_t)bp + kmer_length + 1u > c1.size()) bp = (uint32_t)c1.size();
-        middle = mid; best_pos = bp;
+        middle = sp.mid; best_pos = snap(bp, n_costs);
         return true;
     };
 
@@ -1072,6 +1111,7 @@ bool CAGCCompressor::process_batch_raw(const uint8_t* cat, bool is_device, const
         uint32_t cj = ci;
         while (cj < nc && owners[cj].unit == unit) ++cj;
         std::vector<Item> known, fresh;
+        if (!prefetch_splits(ci, cj)) return false;
         // ---- add_segment for every cut of the sample (agc_compressor.cpp:1275-1499)
         for (uint32_t bc = ci; bc < cj; ++bc) {
             uint32_t part_no = 0;
@@ -1123,7 +1163,7 @@ bool CAGCCompressor::process_batch_raw(const uint8_t* cat, bool is_device, const
                         uint64_t k1d = fc, k2d = bcn; bool use_rc = false;
                         if (k1d > k2d) { std::swap(k1d, k2d); use_rc = true; }
                         uint64_t mid; uint32_t bp;
-                        if (!missing_middle(k1d, k2d, bc, it.start, it.len, use_rc, mid, bp)) return false;
+                        if (!missing_middle(x, k1d, k2d, bc, it.start, it.len, use_rc, mid, bp)) return false;
                         if (mid != EMPTY) {
                             uint32_t left = bp, right = it.len - bp;
                             if (left == 0) { store_rc = (mid < k2d) ? use_rc : !use_rc; pk = std::minmax(mid, k2d); }
@@ -1218,6 +1258,7 @@ bool CAGCCompressor::process_batch_raw(const uint8_t* cat, bool is_device, const
         }
         no_segments += no_new;
         if (map_changed) {
+            AccTimer at("map_insert+put_ref+reassign");
             if (!ins_g.empty()) {
                 if (!gpu_ok(agcgpu_map_insert(ctx, ins_k1.data(), ins_k2.data(), ins_g.data(), ins_g.size()), "map_insert")) return false;
                 if (!gpu_ok(agcgpu_group_put_reference_batch(ctx, new_refs.data(), (uint32_t)new_refs.size()), "put_reference")) return false;
@@ -1245,7 +1286,7 @@ bool CAGCCompressor::process_batch_raw(const uint8_t* cat, bool is_device, const
         }
     }
     std::vector<uint8_t> deltas; std::vector<uint64_t> doffs;
-    if (!lz_encode(lz, deltas, doffs)) return false;
+    { AccTimer at("lz_encode"); if (!lz_encode(lz, deltas, doffs)) return false; }
     if (verify && !lz.empty()) {                             // decode-and-compare: every delta must give back its segment
         PhaseTimer pv("LZ self check");
         std::vector<uint32_t> gids(lz.size());
@@ -1268,10 +1309,12 @@ bool CAGCCompressor::process_batch_raw(const uint8_t* cat, bool is_device, const
     if (!ref_groups.empty()) {
         uint64_t cap = 64; for (auto g : ref_groups) cap += v_segments[g].ref_size + 2;
         refpay.resize(cap);
+        AccTimer at("pack_ref_batch");
         if (!gpu_ok(agcgpu_pack_ref_batch(ctx, ref_groups.data(), (uint32_t)ref_groups.size(), refpay.data(), cap, roffs.data(), ruse.data()), "pack_ref_batch")) return false;
     }
 
     // ---- store_segments part 2 (CSegment::add / add_raw, segment.cpp:14-80) in sample order + collection placement
+    AccTimer at_store("store_segments part 2");
     size_t lz_i = 0, ref_i = 0;
     for (auto& reg : regs) {
         for (auto& rg : reg.groups) {
@@ -1323,6 +1366,7 @@ bool CAGCCompressor::process_batch_raw(const uint8_t* cat, bool is_device, const
 bool CAGCCompressor::Close(uint32_t)
 {
     PhaseTimer pt("close");
+    g_acc.report();
     if (!working) return false;
     working = false;
     // close_compression (agc_compressor.cpp:2094-2114): CSegment::finish for all groups, flush, metadata

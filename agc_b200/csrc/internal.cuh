@@ -194,6 +194,7 @@ int agc_refs_from_segments(agcgpu_ctx* ctx, const agcgpu_seg_req* reqs, uint32_t
 int agc_ref_from_host(agcgpu_ctx* ctx, uint32_t group, const uint8_t* symbols, uint32_t len);
 int agc_lz_run(agcgpu_ctx* ctx, int mode, const agcgpu_seg_req* reqs, uint32_t n, int prefix_costs,
                uint8_t* out_bytes, uint64_t out_cap, uint64_t* out_offsets, uint32_t* out_u32);
+int agc_lz_cost_split(agcgpu_ctx* ctx, const agcgpu_split_req* reqs, uint32_t n, uint32_t* out_pos, uint32_t* out_sum);
 int agc_pack_refs(agcgpu_ctx* ctx, const uint32_t* group_ids, uint32_t n, uint8_t* out, uint64_t out_cap,
                   uint64_t* out_offsets, uint8_t* out_use_tuples);
 bool agc_segment_dirty(agcgpu_ctx* ctx, uint64_t gstart, uint32_t n);

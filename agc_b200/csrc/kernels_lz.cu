@@ -461,7 +461,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 2) k_lz_packed(
         }
         PackedAcc a; a.T = P; a.gs = (int64_t)q.gstart; a.n = q.n; a.rc = q.is_rc; a.R = (const uint64_t*)refp; a.m = g.m;
         Sink s; s.out = slab + q.out_off; s.olen = 0; s.cap = q.out_cap; s.ovf = 0; s.est = 0; s.bound = q.bound;
-        s.v = costv + q.out_off; s.prefix = prefix;
+        s.v = costv + q.out_off; s.prefix = MODE == 2 ? (int)q.bound : prefix;       // cost vectors: prefix_costs travels per request
         lz_parse<PackedAcc, MODE>(a, ht, mml, lane, s);
         if (lane == 0) {
             res[q.orig] = MODE == 1 ? s.est : s.olen;
@@ -484,7 +484,7 @@ __global__ void __launch_bounds__(128) k_lz_bytes(const ByteReq* __restrict__ re
     ByteAcc a; a.T = q.text; a.n = q.n; a.R = q.ref; a.m = q.m;
     HT ht; ht.tab = q.ht; ht.mask = q.ht_size - 1; ht.is_short = q.is_short;
     Sink s; s.out = slab + q.out_off; s.olen = 0; s.cap = q.out_cap; s.ovf = 0; s.est = 0; s.bound = q.bound;
-    s.v = costv + q.out_off; s.prefix = prefix;
+    s.v = costv + q.out_off; s.prefix = MODE == 2 ? (int)q.bound : prefix;
     lz_parse<ByteAcc, MODE>(a, ht, mml, lane, s);
     if (lane == 0) { res[q.orig] = MODE == 1 ? s.est : s.olen; if (s.ovf) atomicOr(err, 1u); }
 }
@@ -971,9 +971,11 @@ int agc_lz_run(agcgpu_ctx* ctx, int mode, const agcgpu_seg_req* reqs, uint32_t n
         CK(cudaStreamSynchronize(ctx->st));
         ctx->stats.d2h_bytes += (size_t)n * 4;
     } else if (mode == 2) {
-        CK(cudaMemcpyAsync(out_u32, costv, (size_t)reqs[0].len * 4, cudaMemcpyDeviceToHost, ctx->st));
-        CK(cudaStreamSynchronize(ctx->st));
-        ctx->stats.d2h_bytes += (size_t)reqs[0].len * 4;
+        if (out_u32) {                                   // single vector to the host (agcgpu_lz_cost_vector)
+            CK(cudaMemcpyAsync(out_u32, costv, (size_t)reqs[0].len * 4, cudaMemcpyDeviceToHost, ctx->st));
+            CK(cudaStreamSynchronize(ctx->st));
+            ctx->stats.d2h_bytes += (size_t)reqs[0].len * 4;
+        }                                                // else: vector i stays at scr_out (u32 index = sum of the lengths before it)
     } else {
         if (int r = agc_reserve(ctx, ctx->scr_offs, ((size_t)n + 1) * 16)) return r;
         uint64_t* d_dst = (uint64_t*)ctx->scr_offs.p;
@@ -998,8 +1000,104 @@ int agc_lz_run(agcgpu_ctx* ctx, int mode, const agcgpu_seg_req* reqs, uint32_t n
         ctx->stats.d2h_bytes += total + ((size_t)n + 1) * 8;
         alg_bytes += total;
     }
+    if (mode == 2 && !out_u32) return 0;                 // nothing was synchronised: the caller queues its reduction behind the launch
     cudaEventElapsedTime(&ctx->stats.last_lz_kernel_ms, ctx->ev0, ctx->ev1);
     ctx->stats.lz_alg_bytes = alg_bytes;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ missing-middle split
+// find_cand_segment_with_missing_middle_splitter (agc_compressor.cpp:1540-1610) after the two get_coding_cost calls: v1 (reversed
+// when the segment was coded in the other orientation) is cumulated from the left, v2 from the right, and the first position
+// with the smallest sum wins.  One CTA per decision; thread t owns the strip [t*S, (t+1)*S).
+struct SplitJob { uint64_t off1, off2; uint32_t len, rev1, rev2, pad; };
+
+__global__ void __launch_bounds__(1024) k_split_reduce(const uint32_t* __restrict__ costv, const SplitJob* __restrict__ jobs,
+                                                       uint32_t* __restrict__ out_pos, uint32_t* __restrict__ out_sum)
+{
+    __shared__ uint32_t s_a[1024], s_b[1024];
+    __shared__ unsigned long long s_best[32];
+    const SplitJob j = jobs[blockIdx.x];
+    const uint32_t len = j.len, t = threadIdx.x;
+    const uint32_t* v1 = costv + j.off1; const uint32_t* v2 = costv + j.off2;
+    const uint32_t S = (len + 1023u) / 1024u;
+    const uint32_t lo = min(len, t * S), hi = min(len, lo + S);
+    auto u1 = [&](uint32_t i) { return j.rev1 ? v1[len - 1 - i] : v1[i]; };
+    auto u2 = [&](uint32_t i) { return j.rev2 ? v2[len - 1 - i] : v2[i]; };
+    uint32_t a = 0, b = 0;
+    for (uint32_t i = lo; i < hi; ++i) { a += u1(i); b += u2(i); }
+    s_a[t] = a; s_b[t] = b;
+    __syncthreads();
+    // exclusive prefix of the strip sums of v1, exclusive suffix of those of v2 (Hillis-Steele over 1024 entries, u32 wrap-around
+    // like the reference's partial_sum on vector<uint32_t>)
+    for (uint32_t o = 1; o < 1024; o <<= 1) {
+        uint32_t xa = t >= o ? s_a[t - o] : 0u, xb = t + o < 1024 ? s_b[t + o] : 0u;
+        __syncthreads();
+        s_a[t] += xa; s_b[t] += xb;
+        __syncthreads();
+    }
+    uint32_t run1 = s_a[t] - a, rest2 = s_b[t];          // sum of u1 before the strip; sum of u2 from the strip's first entry on
+    uint32_t best = 0xffffffffu, bpos = 0;
+    for (uint32_t i = lo; i < hi; ++i) {
+        run1 += u1(i);
+        const uint32_t cs = run1 + rest2;
+        if (cs < best) { best = cs; bpos = i; }
+        rest2 -= u2(i);
+    }
+    // first minimum: smallest (sum, position) pair; a strip that saw nothing keeps (~0, ~0)
+    unsigned long long key = lo < hi ? ((unsigned long long)best << 32) | bpos : ~0ull;
+    if (lo < hi && best == 0xffffffffu) key = ~0ull;     // "cs < ~0u" never fired: not a candidate (the reference starts from ~0u too)
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { unsigned long long x = __shfl_xor_sync(FULL, key, o); key = x < key ? x : key; }
+    if ((t & 31) == 0) s_best[t >> 5] = key;
+    __syncthreads();
+    if (t < 32) {
+        key = s_best[t];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) { unsigned long long x = __shfl_xor_sync(FULL, key, o); key = x < key ? x : key; }
+        if (t == 0) {
+            if (key == ~0ull) { out_pos[blockIdx.x] = 0; out_sum[blockIdx.x] = 0xffffffffu; }
+            else { out_pos[blockIdx.x] = (uint32_t)key; out_sum[blockIdx.x] = (uint32_t)(key >> 32); }
+        }
+    }
+}
+
+int agc_lz_cost_split(agcgpu_ctx* ctx, const agcgpu_split_req* reqs, uint32_t n, uint32_t* out_pos, uint32_t* out_sum)
+{
+    // sub-batches bounded by the size of the cost vectors (2 x len x 4 bytes per decision)
+    const uint64_t budget = 1ull << 30;
+    for (uint32_t a = 0; a < n;) {
+        uint32_t b = a; uint64_t bytes = 0;
+        while (b < n && (b == a || bytes + (uint64_t)reqs[b].len * 8 <= budget)) { bytes += (uint64_t)reqs[b].len * 8; ++b; }
+        const uint32_t cnt = b - a;
+        std::vector<agcgpu_seg_req> sr(2 * (size_t)cnt);
+        std::vector<SplitJob> jobs(cnt);
+        uint64_t off = 0;
+        for (uint32_t i = 0; i < cnt; ++i) {
+            const agcgpu_split_req& q = reqs[a + i];
+            for (int h = 0; h < 2; ++h) {
+                agcgpu_seg_req& s = sr[2 * (size_t)i + h];
+                const uint32_t f = h ? q.flags >> 3 : q.flags;
+                s.contig = q.contig; s.start = q.start; s.len = q.len; s.is_rc = f & 1u; s.group_id = h ? q.group2 : q.group1;
+                s.bound = (f >> 1) & 1u; s.reserved = 0;
+            }
+            jobs[i].off1 = off; jobs[i].off2 = off + q.len; jobs[i].len = q.len;
+            jobs[i].rev1 = (q.flags >> 2) & 1u; jobs[i].rev2 = (q.flags >> 5) & 1u; jobs[i].pad = 0;
+            off += 2ull * q.len;
+        }
+        if (int r = agc_lz_run(ctx, 2, sr.data(), 2 * cnt, 0, nullptr, 0, nullptr, nullptr)) return r;
+        if (int r = agc_reserve(ctx, ctx->scr_offs, cnt * (sizeof(SplitJob) + 8) + 64)) return r;
+        SplitJob* d_jobs = (SplitJob*)ctx->scr_offs.p;
+        uint32_t* d_pos = (uint32_t*)(d_jobs + cnt); uint32_t* d_sum = d_pos + cnt;
+        CK(cudaMemcpyAsync(d_jobs, jobs.data(), cnt * sizeof(SplitJob), cudaMemcpyHostToDevice, ctx->st));
+        k_split_reduce<<<cnt, 1024, 0, ctx->st>>>((const uint32_t*)ctx->scr_out.p, d_jobs, d_pos, d_sum);
+        CKL();
+        CK(cudaMemcpyAsync(out_pos + a, d_pos, cnt * 4, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaMemcpyAsync(out_sum + a, d_sum, cnt * 4, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaStreamSynchronize(ctx->st));
+        ctx->stats.d2h_bytes += cnt * 8ull; ctx->stats.h2d_bytes += cnt * sizeof(SplitJob);
+        a = b;
+    }
     return 0;
 }
 

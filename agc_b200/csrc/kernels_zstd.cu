@@ -29,12 +29,14 @@ struct ZTaskDev {
     uint64_t n, dst_cap;
     int32_t level; int32_t err;
     uint64_t out_size;
+    uint64_t t_start, t_end;          // %globaltimer at CTA start / end (trace output only)
 #ifdef ZE_PROF
     uint64_t prof[32];
 #endif
 };
 
 static const uint32_t ZS_THREADS = 512;
+__device__ __forceinline__ uint64_t zs_globaltimer() { uint64_t t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 
 __global__ void __launch_bounds__(ZS_THREADS, 1) k_zstd(ZTaskDev* __restrict__ tasks, uint32_t n_tasks, uint32_t smem_bytes)
 {
@@ -56,12 +58,13 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) k_zstd(ZTaskDev* __restrict__ t
     }
     ZTaskDev k = tasks[t];
     int err = 0;
+    if (threadIdx.x == 0) tasks[t].t_start = zs_globaltimer();
 #ifdef ZE_PROF
     uint64_t r = ze::compress_frame(k.src, k.n, k.level, k.dst, k.dst_cap, k.mem, &err, tasks[t].prof, zs_smem, smem_bytes);
 #else
     uint64_t r = ze::compress_frame(k.src, k.n, k.level, k.dst, k.dst_cap, k.mem, &err, nullptr, zs_smem, smem_bytes);
 #endif
-    if (threadIdx.x == 0) { tasks[t].err = err; tasks[t].out_size = r; reinterpret_cast<ze::Win*>(zs_smem)->job = ze::WJ_EXIT; }
+    if (threadIdx.x == 0) { tasks[t].err = err; tasks[t].out_size = r; tasks[t].t_end = zs_globaltimer(); reinterpret_cast<ze::Win*>(zs_smem)->job = ze::WJ_EXIT; }
     __syncwarp();
     ze::ze_bar_arrive(1, ZS_THREADS);
 }
@@ -74,12 +77,13 @@ __global__ void __launch_bounds__(32) k_zstd_narrow(ZTaskDev* __restrict__ tasks
     extern __shared__ __align__(16) uint8_t zs_smem[];
     ZTaskDev k = tasks[t];
     int err = 0;
+    if (threadIdx.x == 0) tasks[t].t_start = zs_globaltimer();
 #ifdef ZE_PROF
     uint64_t r = zen::compress_frame(k.src, k.n, k.level, k.dst, k.dst_cap, k.mem, &err, tasks[t].prof, zs_smem, smem_bytes);
 #else
     uint64_t r = zen::compress_frame(k.src, k.n, k.level, k.dst, k.dst_cap, k.mem, &err, nullptr, zs_smem, smem_bytes);
 #endif
-    if (threadIdx.x == 0) { tasks[t].err = err; tasks[t].out_size = r; }
+    if (threadIdx.x == 0) { tasks[t].err = err; tasks[t].out_size = r; tasks[t].t_end = zs_globaltimer(); }
 }
 // inputs up to this size take the narrow coder (AGCGPU_ZSTD_NARROW_MAX overrides it: diagnostics)
 static uint64_t zs_narrow_max()
@@ -139,7 +143,7 @@ extern "C" int agcgpu_zstd_compress_batch(agcgpu_ctx* ctx, const uint8_t* src, c
             ZTaskDev& k = tasks[j];
             k.src = (const uint8_t*)ctx->scr_bytes.p + src_offsets[i]; k.n = src_offsets[i + 1] - src_offsets[i];
             k.dst = (uint8_t*)ctx->scr_dense.p + oo; k.dst_cap = ob[i]; k.mem = (uint8_t*)ctx->scr_out.p + wo;
-            k.level = levels[i]; k.err = 0; k.out_size = 0;
+            k.level = levels[i]; k.err = 0; k.out_size = 0; k.t_start = k.t_end = 0;
             wo += ws[i]; oo += ob[i];
         }
         CK(cudaMemcpyAsync(ctx->scr_req.p, tasks.data(), cnt * sizeof(ZTaskDev), cudaMemcpyHostToDevice, ctx->st));
@@ -173,6 +177,14 @@ extern "C" int agcgpu_zstd_compress_batch(agcgpu_ctx* ctx, const uint8_t* src, c
                 uint64_t tot = 0; for (uint32_t j = 0; j < cnt; ++j) tot += tasks[j].n;
                 fprintf(stderr, "[agcgpu] zstd wave: %u inputs, %llu bytes, largest %llu (level %d), kernel %.1f ms\n", cnt,
                         (unsigned long long)tot, (unsigned long long)tasks[0].n, tasks[0].level, ms);
+                uint64_t t0 = ~0ull, tw = 0, tn = 0, endw = 0, endn = 0;
+                for (uint32_t j = 0; j < cnt; ++j) t0 = std::min<uint64_t>(t0, tasks[j].t_start);
+                for (uint32_t j = 0; j < cnt; ++j) { uint64_t d = tasks[j].t_end - tasks[j].t_start; if (j < n_wide) { tw += d; endw = std::max(endw, tasks[j].t_end - t0); } else { tn += d; endn = std::max(endn, tasks[j].t_end - t0); } }
+                fprintf(stderr, "[agcgpu]   wide: %u frames, sum of frame times %.1f ms, last ends at %.1f ms | narrow: %u frames, sum %.1f ms, last ends at %.1f ms\n",
+                        n_wide, tw * 1e-6, endw * 1e-6, cnt - n_wide, tn * 1e-6, endn * 1e-6);
+                for (uint32_t j = 0; j < cnt; j += (j < 8 ? 1 : std::max<uint32_t>(1, cnt / 24)))
+                    fprintf(stderr, "[agcgpu]   frame %u: %llu B L%d start %.1f ms dur %.1f ms (%.2f us/B)\n", j, (unsigned long long)tasks[j].n, tasks[j].level,
+                            (tasks[j].t_start - t0) * 1e-6, (tasks[j].t_end - tasks[j].t_start) * 1e-6, (tasks[j].t_end - tasks[j].t_start) * 1e-3 / std::max<uint64_t>(1, tasks[j].n));
 #ifdef ZE_PROF
                 for (uint32_t j = 0; j < cnt && j < 4; ++j) {
                     const uint64_t* p = tasks[j].prof; const double us = 1.0 / 1965.0;     // ticks at the max SM clock

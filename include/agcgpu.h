@@ -193,6 +193,28 @@ int agcgpu_lz_estimate_batch(agcgpu_ctx* ctx, const agcgpu_seg_req* reqs, uint32
  * (agc_compressor.cpp:1540-1571).  out has req->len entries. */
 int agcgpu_lz_cost_vector(agcgpu_ctx* ctx, const agcgpu_seg_req* req, int prefix_costs, uint32_t* out);
 
+/* One decision of find_cand_segment_with_missing_middle_splitter (agc_compressor.cpp:1502-1627), everything between the two
+ * get_coding_cost calls (1540-1571) and the argmin loop (1605-1616): v1 = cost vector of the resident segment against group1,
+ * v2 = against group2; each is taken in the orientation / prefix_costs mode the reference picks from the order of the splitters,
+ * reversed when it was computed on the reverse complement; v1 is cumulated from the left (partial_sum), v2 from the right, and
+ * best_pos = the FIRST i with the smallest v1cum[i] + v2cum[i] (u32 arithmetic), best_sum = that value (~0 when len == 0).
+ * The host applies the k+1 snapping (1621-1624) itself.  Only 8 bytes per decision come back instead of 2 x len x 4. */
+typedef struct {
+    uint32_t contig;
+    uint32_t len;
+    uint64_t start;
+    uint32_t group1, group2;
+    uint32_t flags;              /* AGCGPU_SPLIT_* */
+    uint32_t reserved;
+} agcgpu_split_req;
+#define AGCGPU_SPLIT_RC1      1u   /* v1: code the reverse complement of the segment */
+#define AGCGPU_SPLIT_PREFIX1  2u   /* v1: get_coding_cost(..., prefix_costs = true) */
+#define AGCGPU_SPLIT_REV1     4u   /* v1: reverse the vector before cumulating (1551-1552) */
+#define AGCGPU_SPLIT_RC2      8u
+#define AGCGPU_SPLIT_PREFIX2 16u
+#define AGCGPU_SPLIT_REV2    32u
+int agcgpu_lz_cost_split_batch(agcgpu_ctx* ctx, const agcgpu_split_req* reqs, uint32_t n, uint32_t* out_best_pos, uint32_t* out_best_sum);
+
 /* CLZDiff_V2::Decode (lz_diff.cpp:801-836) as CSegment::get calls it (segment.cpp:220-399): delta i = deltas[delta_offsets[i] ..
  * delta_offsets[i+1]) is decoded against the resident reference of group_ids[i]; symbols (1 byte each) of segment i =
  * out[out_offsets[i] .. out_offsets[i+1]).  out_offsets is filled even when out_cap is too small (AGCGPU_EOVERFLOW).

@@ -14,6 +14,7 @@
 #include <map>
 #include <string>
 #include <vector>
+#include <numeric>
 #include "../../include/agcgpu.h"
 
 #define ZE_NS ze
@@ -391,6 +392,31 @@ int agcgpu_lz_cost_vector(agcgpu_ctx* ctx, const agcgpu_seg_req* req, int prefix
     uint64_t vn = orc_lz_cost_vector(z, t.data(), req->len, prefix_costs, v.data());
     if (vn != req->len) return fail(ctx, AGCGPU_EINVAL, "cost vector has %llu entries for %u symbols", (unsigned long long)vn, req->len);
     if (req->len) memcpy(out, v.data(), (size_t)req->len * 4);
+    return 0;
+}
+
+int agcgpu_lz_cost_split_batch(agcgpu_ctx* ctx, const agcgpu_split_req* reqs, uint32_t n, uint32_t* out_best_pos, uint32_t* out_best_sum)
+{
+    COUNT("agcgpu_lz_cost_split_batch", n);
+    if (!ctx || (n && (!reqs || !out_best_pos || !out_best_sum))) return AGCGPU_EINVAL;
+    for (uint32_t i = 0; i < n; ++i) {
+        const agcgpu_split_req& q = reqs[i];
+        std::vector<uint32_t> c[2];
+        for (int h = 0; h < 2; ++h) {
+            const uint32_t f = h ? q.flags >> 3 : q.flags;
+            agcgpu_seg_req r; memset(&r, 0, sizeof r);
+            r.contig = q.contig; r.start = q.start; r.len = q.len; r.is_rc = f & 1u; r.group_id = h ? q.group2 : q.group1;
+            c[h].assign((size_t)q.len + 64, 0);
+            if (q.len) { if (int rc = agcgpu_lz_cost_vector(ctx, &r, (f >> 1) & 1, c[h].data())) return rc; }
+            c[h].resize(q.len);
+            if (f & 4u) std::reverse(c[h].begin(), c[h].end());
+        }
+        std::partial_sum(c[0].begin(), c[0].end(), c[0].begin());
+        std::partial_sum(c[1].rbegin(), c[1].rend(), c[1].rbegin());
+        uint32_t best = ~0u, bp = 0;
+        for (uint32_t k = 0; k < q.len; ++k) { uint32_t cs = c[0][k] + c[1][k]; if (cs < best) { best = cs; bp = k; } }
+        out_best_pos[i] = bp; out_best_sum[i] = best;
+    }
     return 0;
 }
 
