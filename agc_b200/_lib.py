@@ -49,7 +49,10 @@ class FKmer(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("device_bytes_in_use", C.c_uint64), ("lz_alg_bytes", C.c_uint64), ("last_lz_kernel_ms", C.c_float),
-                ("last_scan_kernel_ms", C.c_float), ("zstd_kernel_ms", C.c_float), ("zstd_input_mb", C.c_float)]
+                ("last_scan_kernel_ms", C.c_float), ("zstd_kernel_ms", C.c_float), ("zstd_input_mb", C.c_float),
+                ("lz_chunk_segments", C.c_uint64), ("lz_sequential_segments", C.c_uint64),
+                ("lz_alg_bytes_total", C.c_uint64), ("scan_bytes_total", C.c_uint64), ("lz_kernel_ms_total", C.c_float),
+                ("scan_kernel_ms_total", C.c_float), ("lz_encode_launches", C.c_uint32), ("scan_launches", C.c_uint32)]
 
 
 # every symbol include/agcgpu.h declares (tests/test_abi.py checks header <-> library <-> this list)
@@ -58,7 +61,9 @@ EXPORTED_SYMBOLS = [
     "agcgpu_determine_splitters", "agcgpu_set_splitters", "agcgpu_scan_contigs", "agcgpu_scan_contigs_dev",
     "agcgpu_get_segment", "agcgpu_map_insert", "agcgpu_assign_cuts", "agcgpu_group_put_reference_batch",
     "agcgpu_group_put_reference", "agcgpu_group_get_index", "agcgpu_lz_encode_batch", "agcgpu_lz_estimate_batch",
-    "agcgpu_lz_cost_vector", "agcgpu_lz_cost_split_batch", "agcgpu_pack_ref_batch", "agcgpu_zstd_compress_batch",
+    "agcgpu_lz_cost_vector", "agcgpu_lz_cost_split_batch", "agcgpu_debug_lz_chunk_records", "agcgpu_lz_encode_batch_sharded",
+    "agcgpu_zstd_compress_batch_sharded", "agcgpu_comm_unique_id", "agcgpu_comm_init", "agcgpu_comm_destroy", "agcgpu_comm_get_stats",
+    "agcgpu_comm_last_error", "agcgpu_comm_world", "agcgpu_comm_rank", "agcgpu_pack_ref_batch", "agcgpu_zstd_compress_batch",
     "agcgpu_find_new_splitters", "agcgpu_rescan_contigs", "agcgpu_filtered_kmers", "agcgpu_last_splitter_positions",
     "agcgpu_zstd_decompress_batch", "agcgpu_lz_decode_batch",
 ]

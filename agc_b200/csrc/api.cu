@@ -148,7 +148,7 @@ void agcgpu_destroy(agcgpu_ctx* ctx)
     DevBuf* bufs[] = { &ctx->spl_keys, &ctx->spl_filter, &ctx->raw, &ctx->packed, &ctx->exc_pos, &ctx->exc_code, &ctx->tile_desc,
                        &ctx->tile_cnt, &ctx->tile_base, &ctx->d_cstart, &ctx->chunk_prefix, &ctx->hits, &ctx->counters, &ctx->map_k1,
                        &ctx->map_k2, &ctx->map_val, &ctx->d_groups, &ctx->scr_req, &ctx->scr_units, &ctx->scr_out, &ctx->scr_sizes,
-                       &ctx->scr_offs, &ctx->scr_dense, &ctx->scr_misc, &ctx->scr_bytes, &ctx->ref_kmers };
+                       &ctx->scr_offs, &ctx->scr_dense, &ctx->scr_misc, &ctx->scr_bytes, &ctx->scr_chunk, &ctx->scr_rec, &ctx->scr_gsz, &ctx->scr_gather, &ctx->scr_zkeep, &ctx->ref_kmers };
     for (DevBuf* b : bufs) if (b->p) agc_dev_free(ctx->dev, b->p, b->cap + 64);
     for (auto& c : ctx->arena_chunks) agc_dev_free(ctx->dev, c.first, c.second);
     if (ctx->pin) {
@@ -416,6 +416,28 @@ int agcgpu_lz_encode_batch(agcgpu_ctx* ctx, const agcgpu_seg_req* reqs, uint32_t
     cudaSetDevice(ctx->dev);
     return agc_lz_run(ctx, 0, reqs, n, 0, out, out_cap, out_offsets, nullptr);
 }
+
+int agcgpu_lz_encode_batch_sharded(agcgpu_ctx* ctx, const agcgpu_seg_req* reqs, uint32_t n, uint8_t* out, uint64_t out_cap, uint64_t* out_offsets)
+{
+    if (!ctx || !out_offsets || (n && (!reqs || !out))) return AGCGPU_EINVAL;
+    cudaSetDevice(ctx->dev);
+    if (!agc_comm_active() || n == 0) return agc_lz_run(ctx, 0, reqs, n, 0, out, out_cap, out_offsets, nullptr);
+    return agc_lz_encode_sharded(ctx, reqs, n, out, out_cap, out_offsets);
+}
+
+int agcgpu_debug_lz_chunk_records(agcgpu_ctx* ctx, void* out, uint64_t cap_bytes, uint64_t* out_n_records)
+{
+    if (!ctx || !out_n_records) return AGCGPU_EINVAL;
+    cudaSetDevice(ctx->dev);
+    *out_n_records = ctx->last_lzc_chunks;
+    const uint64_t need = ctx->last_lzc_chunks * 64;
+    if (!out || cap_bytes < need) return need ? AGCGPU_EOVERFLOW : 0;
+    if (need) CK(cudaMemcpy(out, ctx->scr_rec.p, need, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int agcgpu_comm_world(void) { return agc_comm_active() ? (int)agc_comm_world() : 1; }
+int agcgpu_comm_rank(void) { return agc_comm_active() ? (int)agc_comm_rank() : 0; }
 
 int agcgpu_lz_estimate_batch(agcgpu_ctx* ctx, const agcgpu_seg_req* reqs, uint32_t n, uint32_t* out)
 {

@@ -245,6 +245,7 @@ bool CAGCCompressor::Append(const std::string& in_archive_fn, const std::string&
     prm.pack_cardinality = pack_cardinality; prm.device = device;
     prm.flags = adaptive_compression ? AGCGPU_F_ADAPTIVE : 0;
     if (agcgpu_create(&prm, &ctx)) return fail(std::string("agcgpu_create: ") + agcgpu_last_error(nullptr));
+    if (agcgpu_comm_world() > 1) xrank = (uint32_t)agcgpu_comm_rank();
     if (!out_archive.Open(xrank == 0 ? out_archive_fn : std::string("/dev/null"))) return fail("Cannot create archive " + out_archive_fn);
     collection.set_params(pack_cardinality, segment_size, kmer_length);
 

@@ -400,6 +400,7 @@ bool CAGCCompressor::Create(const std::string& file_name, uint32_t _pack_cardina
         if (!dump_f) return fail("cannot open dump file " + dump_path);
     }
     // multi-GPU: every rank keeps the identical bookkeeping, rank 0 alone owns the output file
+    if (agcgpu_comm_world() > 1) xrank = (uint32_t)agcgpu_comm_rank();
     if (!out_archive.Open(xrank == 0 ? file_name : std::string("/dev/null"))) return fail("Cannot create archive " + file_name);
     working = true;
     collection.set_params(pack_cardinality, segment_size, kmer_length);
@@ -475,7 +476,7 @@ bool CAGCCompressor::exchange(const std::vector<uint8_t>& mine, std::vector<std:
 // where they land and all-gathered; every rank ends up with every frame (only rank 0 writes them)
 bool CAGCCompressor::compress_tasks(std::vector<ZTask*>& tasks)
 {
-    if (xworld <= 1 || tasks.empty()) return compress_tasks_local(tasks);
+    if (xworld <= 1 || tasks.empty() || agcgpu_comm_world() > 1) return compress_tasks_local(tasks);
     // longest-processing-time-first: frames sorted by size, each to the rank with the least bytes so far (ties: lowest rank);
     // every rank computes the same assignment from the same task list
     std::vector<size_t> order(tasks.size());
@@ -525,6 +526,18 @@ bool CAGCCompressor::lz_encode_local(const agcgpu_seg_req* lz, size_t n, std::ve
 // LZ-diff encoding over all ranks: contiguous runs of requests (they are grouped by reference), balanced by bases
 bool CAGCCompressor::lz_encode(std::vector<agcgpu_seg_req>& lz, std::vector<uint8_t>& deltas, std::vector<uint64_t>& doffs)
 {
+    if (agcgpu_comm_world() > 1 && !lz.empty()) {
+        // NCCL communicator inside the library: the split, the device-to-device all-gather and the one copy to the host are
+        // agcgpu_lz_encode_batch_sharded's business; every rank gets every delta
+        const size_t n = lz.size();
+        doffs.assign(n + 1, 0);
+        uint64_t cap = 64; for (size_t i = 0; i < n; ++i) cap += (uint64_t)lz[i].len * 3 / 2 + 32;
+        uint64_t try_cap = std::max<uint64_t>(cap / 16, 1 << 20);
+        deltas.resize(try_cap);
+        int rc2 = agcgpu_lz_encode_batch_sharded(ctx, lz.data(), (uint32_t)n, deltas.data(), try_cap, doffs.data());
+        if (rc2 == AGCGPU_EOVERFLOW) { deltas.resize(cap); rc2 = agcgpu_lz_encode_batch_sharded(ctx, lz.data(), (uint32_t)n, deltas.data(), cap, doffs.data()); }
+        return gpu_ok(rc2, "lz_encode_batch_sharded");
+    }
     if (xworld <= 1 || lz.empty()) return lz_encode_local(lz.data(), lz.size(), deltas, doffs);
     std::vector<uint64_t> cum(lz.size() + 1, 0);
     for (size_t i = 0; i < lz.size(); ++i) cum[i + 1] = cum[i] + lz[i].len + 64;
@@ -567,7 +580,9 @@ bool CAGCCompressor::compress_tasks_local(std::vector<ZTask*>& tasks)
     uint64_t cap = offs.back() + offs.back() / 128 + 1024 * (tasks.size() + 1);
     std::vector<uint8_t> dst(cap);
     std::vector<uint64_t> doffs(tasks.size() + 1, 0);
-    if (!gpu_ok(agcgpu_zstd_compress_batch(ctx, src.data(), offs.data(), levels.data(), (uint32_t)tasks.size(), dst.data(), cap, doffs.data()),
+    // with an NCCL communicator the frames are dealt out over the ranks and all-gathered between device buffers (every rank passes
+    // the same batch); without one this is the plain call
+    if (!gpu_ok(agcgpu_zstd_compress_batch_sharded(ctx, src.data(), offs.data(), levels.data(), (uint32_t)tasks.size(), dst.data(), cap, doffs.data()),
                 "zstd_compress_batch")) return false;
     for (size_t i = 0; i < tasks.size(); ++i) tasks[i]->packed.assign(dst.begin() + doffs[i], dst.begin() + doffs[i + 1]);
     if (verify) {                                            // decode-and-compare: the frames must give back exactly what went in

@@ -157,8 +157,9 @@ struct agcgpu_ctx {
     size_t device_bytes = 0;
 
     // scratch
-    DevBuf scr_req, scr_units, scr_out, scr_sizes, scr_offs, scr_dense, scr_misc, scr_bytes;
+    DevBuf scr_req, scr_units, scr_out, scr_sizes, scr_offs, scr_dense, scr_misc, scr_bytes, scr_chunk, scr_rec, scr_gsz, scr_gather, scr_zkeep;
     void* pin = nullptr; size_t pin_cap = 0;   // pinned host staging
+    uint64_t last_lzc_chunks = 0;              // chunk records of the last chunk-parallel encode (diagnostics)
 };
 
 // ------------------------------------------------------------------------------------------------ internal API
@@ -189,11 +190,19 @@ int agc_upload_splitters(agcgpu_ctx* ctx, const uint64_t* s, uint64_t n);
 int agc_map_rebuild(agcgpu_ctx* ctx);
 int agc_assign_launch(agcgpu_ctx* ctx, const agcgpu_cut* cuts, uint64_t n, agcgpu_assign* out);
 
+// comm.cu (NCCL exchange)
+bool agc_comm_active();
+uint32_t agc_comm_rank();
+uint32_t agc_comm_world();
+int agc_comm_allgather(agcgpu_ctx* ctx, const void* d_send, void* d_recv, size_t bytes, cudaStream_t st);
+int agc_comm_allgatherv(agcgpu_ctx* ctx, const void* d_mine, uint64_t my_bytes, int local_status, std::vector<uint64_t>& sizes, uint64_t* stride_out);
+
 // kernels_lz.cu
 int agc_refs_from_segments(agcgpu_ctx* ctx, const agcgpu_seg_req* reqs, uint32_t n);
 int agc_ref_from_host(agcgpu_ctx* ctx, uint32_t group, const uint8_t* symbols, uint32_t len);
 int agc_lz_run(agcgpu_ctx* ctx, int mode, const agcgpu_seg_req* reqs, uint32_t n, int prefix_costs,
                uint8_t* out_bytes, uint64_t out_cap, uint64_t* out_offsets, uint32_t* out_u32);
+int agc_lz_encode_sharded(agcgpu_ctx* ctx, const agcgpu_seg_req* reqs, uint32_t n, uint8_t* out, uint64_t out_cap, uint64_t* out_offsets);
 int agc_lz_cost_split(agcgpu_ctx* ctx, const agcgpu_split_req* reqs, uint32_t n, uint32_t* out_pos, uint32_t* out_sum);
 int agc_pack_refs(agcgpu_ctx* ctx, const uint32_t* group_ids, uint32_t n, uint8_t* out, uint64_t out_cap,
                   uint64_t* out_offsets, uint8_t* out_use_tuples);

@@ -15,6 +15,7 @@
 //
 // Integer/byte work only; the roofline is HBM: B_lz = ceil(n/4) + ceil(m/4) + e bytes per segment.
 #include "internal.cuh"
+#include "lz_chunk.cuh"
 #include <algorithm>
 #include <cstring>
 
@@ -577,6 +578,54 @@ __global__ void __launch_bounds__(128) k_index(const RefJob* __restrict__ jobs, 
     }
 }
 
+// make_index16/32 for references without non-ACGT symbols, all insertions of one reference in parallel (one CTA per reference).
+// The stored value of a key IS its insertion rank (ref_pos / 4), and sequential first-come linear probing has one defining
+// property: key k sits in the first slot from its home that no key j < k occupies (64 tries, else it is dropped).  So the table
+// is built with atomicMin on the slot values: a key that meets a larger value takes the slot and carries the displaced key on
+// (its try count = its displacement from its own home), a key that meets a smaller value moves on.  The fixed point satisfies
+// the defining property for every key, hence equals the sequential layout (tests: test_index_layout_parity).
+// Tables of up to LZ_IDX_SMEM_SLOTS slots are built in shared memory and written out once (u16 or u32 slots).
+#define LZ_IDX_THREADS 512
+#define LZ_IDX_SMEM_SLOTS 32768u
+__global__ void __launch_bounds__(LZ_IDX_THREADS) k_index_par(const RefJob* __restrict__ jobs, GroupRefDev* __restrict__ groups, uint32_t mml,
+                                                              uint32_t* __restrict__ gtab_all)
+{
+    extern __shared__ uint32_t s_tab[];
+    const RefJob j = jobs[blockIdx.x];
+    if (j.codes != nullptr) return;                               // references with non-ACGT symbols: k_index<true>
+    const uint32_t kl = mml - 3u, m = j.n;
+    const bool is_short = (m / 4u) < 65535u;
+    const uint32_t cnt = m >= kl ? (m - kl) / 4u + 1u : 0u;
+    const uint32_t hs = (uint32_t)ht_size_for(cnt), mask = hs - 1;
+    // where the u32 working table lives: shared memory (small tables), the final table itself (u32 slots), or a scratch slice
+    // (u16 tables too large for shared memory; ht_cap = this job's offset into the scratch)
+    uint32_t* tab = hs <= LZ_IDX_SMEM_SLOTS ? s_tab : (is_short ? gtab_all + j.ht_cap : (uint32_t*)j.ht);
+    for (uint32_t i = threadIdx.x; i < hs; i += LZ_IDX_THREADS) tab[i] = AGC_EMPTY32;
+    __syncthreads();
+    const uint64_t* R = (const uint64_t*)j.packed;
+    auto home = [&](uint32_t v) { return (uint32_t)agc_murmur64(agc_win(R, (uint64_t)v * 4u) >> (64 - 2 * kl)) & mask; };
+    for (uint32_t v0 = threadIdx.x; v0 < cnt; v0 += LZ_IDX_THREADS) {
+        uint32_t cur = v0, s = home(cur), tries = 0;
+        while (tries < 64) {
+            const uint32_t old = atomicMin(&tab[s], cur);
+            if (old == AGC_EMPTY32) break;                        // placed in an empty slot
+            if (old > cur) { cur = old; tries = ((s - home(cur)) & mask) + 1u; }   // took the slot: the displaced key moves on
+            else ++tries;                                         // an earlier key owns it
+            s = (s + 1u) & mask;
+        }
+    }
+    __syncthreads();
+    if (is_short) { uint16_t* o = (uint16_t*)j.ht; for (uint32_t i = threadIdx.x; i < hs; i += LZ_IDX_THREADS) { const uint32_t v = tab[i]; o[i] = v == AGC_EMPTY32 ? (uint16_t)0xffffu : (uint16_t)v; } }
+    else if (tab != (uint32_t*)j.ht) { uint32_t* o = (uint32_t*)j.ht; for (uint32_t i = threadIdx.x; i < hs; i += LZ_IDX_THREADS) o[i] = tab[i]; }
+    if (threadIdx.x == 0) {
+        GroupRefDev g;
+        g.packed = j.packed; g.ht = j.ht; g.codes = nullptr; g.m = m; g.ht_size = hs;
+        g.flags = GRF_PRESENT | (is_short ? GRF_SHORT : 0u);
+        g.packed_bytes = ((m + 3) / 4 + 15) / 16 * 16 + 16;
+        groups[j.group] = g;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ output gather
 __global__ void __launch_bounds__(1024) k_excl_scan_u32(const uint32_t* __restrict__ in, uint32_t n, uint64_t* __restrict__ out)
 {
@@ -744,8 +793,23 @@ static int build_refs(agcgpu_ctx* ctx, std::vector<RefJob>& jobs, bool from_segm
         for (auto& j : jobs) if (j.codes) if (int r = agc_expand_segment(ctx, j.gstart, j.n, j.is_rc, j.codes, mml - 3)) return r;
     }
     uint32_t nb = (uint32_t)((jobs.size() + 3) / 4);
-    k_index<false><<<nb, 128, 0, ctx->st>>>(d_jobs, (uint32_t)jobs.size(), (GroupRefDev*)ctx->d_groups.p, mml);
-    CKL();
+    {
+        // scratch slices for u16 tables that do not fit in shared memory (references of 115 k .. 262 k symbols)
+        uint64_t scratch = 0;
+        for (auto& j : jobs) {
+            const uint64_t hs = clean_ht_size(j.n, mml);
+            if (!j.codes && (j.n / 4) < 65535 && hs > LZ_IDX_SMEM_SLOTS) { j.ht_cap = (uint32_t)scratch; scratch += hs; }
+        }
+        if (scratch) {
+            if (scratch >= 0xffffffffull) return agc_fail(ctx, AGCGPU_ENOMEM, "index build: too many large references in one batch");
+            if (int r = agc_reserve(ctx, ctx->scr_dense, scratch * 4 + 64)) return r;
+            CK(cudaMemcpyAsync(ctx->scr_misc.p, jobs.data(), jobs.size() * sizeof(RefJob), cudaMemcpyHostToDevice, ctx->st));
+        }
+        static bool attr_set = false;
+        if (!attr_set) { cudaFuncSetAttribute(k_index_par, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(LZ_IDX_SMEM_SLOTS * 4)); attr_set = true; }
+        k_index_par<<<(uint32_t)jobs.size(), LZ_IDX_THREADS, LZ_IDX_SMEM_SLOTS * 4, ctx->st>>>(d_jobs, (GroupRefDev*)ctx->d_groups.p, mml, (uint32_t*)ctx->scr_dense.p);
+        CKL();
+    }
     bool any_dirty = false;
     for (auto& j : jobs) any_dirty |= j.codes != nullptr;
     if (any_dirty) { k_index<true><<<nb, 128, 0, ctx->st>>>(d_jobs, (uint32_t)jobs.size(), (GroupRefDev*)ctx->d_groups.p, mml); CKL(); }
@@ -887,26 +951,8 @@ int agc_lz_run(agcgpu_ctx* ctx, int mode, const agcgpu_seg_req* reqs, uint32_t n
         packed_reqs.push_back(d);
     }
     std::stable_sort(packed_reqs.begin(), packed_reqs.end(), [](const LzReqDev& a, const LzReqDev& b) { return a.group < b.group; });
-    // units: requests of one group, at most UNIT_MAX per CTA; longest-first inside a group helps the tail
-    // A CTA has 16 warps and two CTAs fit on an SM: give every warp a request while the batch fits in one wave of CTAs, and make
-    // the warps loop over several requests (instead of launching a second, mostly empty wave) when it does not.
-    const size_t resident = 2 * (size_t)ctx->n_sm;
-    const uint32_t UNIT_MAX = (uint32_t)std::max<size_t>(16, ((packed_reqs.size() + resident - 1) / resident + 15) / 16 * 16);
-    std::vector<LzUnit> units;
-    size_t smem_need = 0;
-    for (size_t a = 0; a < packed_reqs.size();) {
-        size_t b = a;
-        while (b < packed_reqs.size() && packed_reqs[b].group == packed_reqs[a].group) ++b;
-        const GroupRefDev& g = ctx->h_groups[packed_reqs[a].group];
-        size_t need = (size_t)g.packed_bytes + (size_t)g.ht_size * ((g.flags & GRF_SHORT) ? 2 : 4);
-        if (need <= LZ_STAGE_LIMIT) smem_need = std::max(smem_need, need);
-        size_t cnt = b - a, nun = (cnt + UNIT_MAX - 1) / UNIT_MAX, per = (cnt + nun - 1) / nun;
-        for (size_t s0 = a; s0 < b; s0 += per) {
-            LzUnit u; u.group = packed_reqs[a].group; u.first = (uint32_t)s0; u.count = (uint32_t)std::min(per, b - s0); u.pad = 0;
-            units.push_back(u);
-        }
-        a = b;
-    }
+    const size_t resident = 2 * (size_t)ctx->n_sm;            // CTAs of the sequential kernel that fit on the device
+    bool chunk_timed = false;
     // ---- device buffers
     if (int r = agc_reserve(ctx, ctx->scr_out, slab_total * (mode == 2 ? 4 : 1) + 64)) return r;
     if (int r = agc_reserve(ctx, ctx->scr_sizes, (size_t)n * 4 + 64)) return r;
@@ -918,22 +964,103 @@ int agc_lz_run(agcgpu_ctx* ctx, int mode, const agcgpu_seg_req* reqs, uint32_t n
     uint32_t* res = (uint32_t*)ctx->scr_sizes.p;
     uint32_t* err = (uint32_t*)ctx->counters.p + 8;
     CK(cudaEventRecord(ctx->ev0, ctx->st));
-    if (!packed_reqs.empty()) {
-        if (int r = agc_reserve(ctx, ctx->scr_req, packed_reqs.size() * sizeof(LzReqDev))) return r;
-        if (int r = agc_reserve(ctx, ctx->scr_units, units.size() * sizeof(LzUnit))) return r;
-        CK(cudaMemcpyAsync(ctx->scr_req.p, packed_reqs.data(), packed_reqs.size() * sizeof(LzReqDev), cudaMemcpyHostToDevice, ctx->st));
-        CK(cudaMemcpyAsync(ctx->scr_units.p, units.data(), units.size() * sizeof(LzUnit), cudaMemcpyHostToDevice, ctx->st));
-        ctx->stats.h2d_bytes += packed_reqs.size() * sizeof(LzReqDev) + units.size() * sizeof(LzUnit);
-        CK(cudaEventRecord(ctx->ev0, ctx->st));
+    // the sequential (warp per segment) kernel over packed_reqs[sel]; sel == nullptr: all of them
+    auto run_sequential = [&](const std::vector<LzReqDev>& rq) -> int {
+        if (rq.empty()) return 0;
+        std::vector<LzUnit> un;
+        size_t smem_seq = 0;
+        const uint32_t umax = (uint32_t)std::max<size_t>(16, ((rq.size() + resident - 1) / resident + 15) / 16 * 16);
+        for (size_t a = 0; a < rq.size();) {
+            size_t b = a;
+            while (b < rq.size() && rq[b].group == rq[a].group) ++b;
+            const GroupRefDev& g = ctx->h_groups[rq[a].group];
+            size_t need = (size_t)g.packed_bytes + (size_t)g.ht_size * ((g.flags & GRF_SHORT) ? 2 : 4);
+            if (need <= LZ_STAGE_LIMIT) smem_seq = std::max(smem_seq, need);
+            size_t cnt = b - a, nun = (cnt + umax - 1) / umax, per = (cnt + nun - 1) / nun;
+            for (size_t s0 = a; s0 < b; s0 += per) {
+                LzUnit u; u.group = rq[a].group; u.first = (uint32_t)s0; u.count = (uint32_t)std::min(per, b - s0); u.pad = 0;
+                un.push_back(u);
+            }
+            a = b;
+        }
+        if (int r = agc_reserve(ctx, ctx->scr_req, rq.size() * sizeof(LzReqDev))) return r;
+        if (int r = agc_reserve(ctx, ctx->scr_units, un.size() * sizeof(LzUnit))) return r;
+        CK(cudaMemcpyAsync(ctx->scr_req.p, rq.data(), rq.size() * sizeof(LzReqDev), cudaMemcpyHostToDevice, ctx->st));
+        CK(cudaMemcpyAsync(ctx->scr_units.p, un.data(), un.size() * sizeof(LzUnit), cudaMemcpyHostToDevice, ctx->st));
+        ctx->stats.h2d_bytes += rq.size() * sizeof(LzReqDev) + un.size() * sizeof(LzUnit);
         const LzReqDev* d_req = (const LzReqDev*)ctx->scr_req.p;
         const LzUnit* d_units = (const LzUnit*)ctx->scr_units.p;
-        size_t smem = std::max<size_t>(smem_need, 1024);
-        if (mode == 0) launch_packed<0>(ctx, (uint32_t)units.size(), smem, d_req, d_units, slab, res, costv, prefix_costs, err);
-        else if (mode == 1) launch_packed<1>(ctx, (uint32_t)units.size(), smem, d_req, d_units, slab, res, costv, prefix_costs, err);
-        else launch_packed<2>(ctx, (uint32_t)units.size(), smem, d_req, d_units, slab, res, costv, prefix_costs, err);
+        size_t smem = std::max<size_t>(smem_seq, 1024);
+        if (mode == 0) launch_packed<0>(ctx, (uint32_t)un.size(), smem, d_req, d_units, slab, res, costv, prefix_costs, err);
+        else if (mode == 1) launch_packed<1>(ctx, (uint32_t)un.size(), smem, d_req, d_units, slab, res, costv, prefix_costs, err);
+        else launch_packed<2>(ctx, (uint32_t)un.size(), smem, d_req, d_units, slab, res, costv, prefix_costs, err);
         CKL();
+        return 0;
+    };
+    static const bool no_chunks = getenv("AGCGPU_LZ_SEQUENTIAL") != nullptr;          // diagnostics: force the sequential kernel
+    if (!packed_reqs.empty() && mode == 0 && !no_chunks) {
+        // ---- chunk-parallel encode (kernels_lz_chunk.cu): thread per chunk, then thread per segment; segments the stitcher
+        // could not prove identical to the sequential parse are redone by the sequential kernel
+        const size_t nr = packed_reqs.size();
+        std::vector<LzcReq> cr(nr);
+        std::vector<LzcUnit> cu;
+        uint64_t n_chunks = 0; size_t smem_c = 0;
+        const uint32_t UNIT_ITEMS = 4 * LZC_THREADS;
+        for (size_t a = 0; a < nr;) {
+            size_t b = a;
+            while (b < nr && packed_reqs[b].group == packed_reqs[a].group) ++b;
+            const GroupRefDev& g = ctx->h_groups[packed_reqs[a].group];
+            size_t need = (size_t)g.packed_bytes + (size_t)g.ht_size * ((g.flags & GRF_SHORT) ? 2 : 4);
+            if (need <= LZC_STAGE_LIMIT) smem_c = std::max(smem_c, need);
+            uint32_t base = 0;
+            for (size_t i = a; i < b; ++i) {
+                const LzReqDev& q = packed_reqs[i];
+                LzcReq& c = cr[i];
+                c.gstart = q.gstart; c.n = q.n; c.is_rc = q.is_rc; c.group = q.group; c.chunk_first = (uint32_t)n_chunks;
+                c.nch = std::max<uint32_t>(1u, (q.n + LZC_CHUNK - 1) / LZC_CHUNK); c.unit_base = base; c.out_off = q.out_off; c.out_cap = q.out_cap; c.orig = q.orig;
+                base += c.nch; n_chunks += c.nch;
+            }
+            // all requests of the group share one running chunk count; a unit is a slice of UNIT_ITEMS chunks of it
+            for (uint32_t i0 = 0; i0 < base; i0 += UNIT_ITEMS) {
+                LzcUnit u; u.group = packed_reqs[a].group; u.first = (uint32_t)a; u.count = (uint32_t)(b - a); u.item0 = i0;
+                u.n_items = std::min(UNIT_ITEMS, base - i0); u.pad = 0;
+                cu.push_back(u);
+            }
+            a = b;
+        }
+        if (n_chunks >= 0xffffffffull) return agc_fail(ctx, AGCGPU_EINVAL, "lz: batch too large (%llu chunks)", (unsigned long long)n_chunks);
+        if (int r = agc_reserve(ctx, ctx->scr_req, nr * sizeof(LzcReq))) return r;
+        if (int r = agc_reserve(ctx, ctx->scr_units, cu.size() * sizeof(LzcUnit))) return r;
+        if (int r = agc_reserve(ctx, ctx->scr_chunk, n_chunks * (uint64_t)LZC_CSLAB + 256)) return r;
+        if (int r = agc_reserve(ctx, ctx->scr_rec, n_chunks * sizeof(LzcRec) + nr * 4 + 256)) return r;
+        CK(cudaMemcpyAsync(ctx->scr_req.p, cr.data(), nr * sizeof(LzcReq), cudaMemcpyHostToDevice, ctx->st));
+        CK(cudaMemcpyAsync(ctx->scr_units.p, cu.data(), cu.size() * sizeof(LzcUnit), cudaMemcpyHostToDevice, ctx->st));
+        ctx->stats.h2d_bytes += nr * sizeof(LzcReq) + cu.size() * sizeof(LzcUnit);
+        CK(cudaEventRecord(ctx->ev0, ctx->st));
+        LzcRec* d_rec = (LzcRec*)ctx->scr_rec.p;
+        uint32_t* d_fb = (uint32_t*)(d_rec + n_chunks);
+        uint32_t* cnt2 = (uint32_t*)ctx->counters.p;                       // [0] segments for the sequential kernel, [1] overflow
+        if (int r = agc_lzc_launch(ctx, (const LzcReq*)ctx->scr_req.p, (uint32_t)nr, (const LzcUnit*)ctx->scr_units.p, (uint32_t)cu.size(),
+                                   std::max<size_t>(smem_c, 1024), (uint8_t*)ctx->scr_chunk.p, d_rec, slab, res, d_fb, cnt2)) return r;
+        CK(cudaEventRecord(ctx->ev1, ctx->st));
+        uint32_t h_cnt[2] = { 0, 0 };
+        CK(cudaMemcpyAsync(h_cnt, cnt2, 8, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaStreamSynchronize(ctx->st));
+        if (h_cnt[1]) return agc_fail(ctx, AGCGPU_EOVERFLOW, "lz encode: per-segment output bound exceeded");
+        ctx->stats.lz_chunk_segments += nr; ctx->stats.lz_sequential_segments += h_cnt[0];
+        if (h_cnt[0]) {
+            std::vector<uint32_t> h_fb(nr);
+            CK(cudaMemcpy(h_fb.data(), d_fb, nr * 4, cudaMemcpyDeviceToHost));
+            std::vector<LzReqDev> redo;
+            for (size_t i = 0; i < nr; ++i) if (h_fb[i]) redo.push_back(packed_reqs[i]);
+            if (int r = run_sequential(redo)) return r;
+        }
+        chunk_timed = true; ctx->last_lzc_chunks = n_chunks;
+    } else if (!packed_reqs.empty()) {
+        CK(cudaEventRecord(ctx->ev0, ctx->st));
+        if (int r = run_sequential(packed_reqs)) return r;
     }
-    CK(cudaEventRecord(ctx->ev1, ctx->st));
+    if (!chunk_timed) CK(cudaEventRecord(ctx->ev1, ctx->st));
     if (!dirty_idx.empty()) {
         // byte path: expand text (and, for clean references, the reference) to 1 byte / symbol
         size_t tbytes = 0;
@@ -988,21 +1115,25 @@ int agc_lz_run(agcgpu_ctx* ctx, int mode, const agcgpu_seg_req* reqs, uint32_t n
         CK(cudaStreamSynchronize(ctx->st));
         if (h_err) return agc_fail(ctx, AGCGPU_EOVERFLOW, "lz encode: per-segment output bound exceeded");
         uint64_t total = out_offsets[n];
-        if (total > out_cap) return agc_fail(ctx, AGCGPU_EOVERFLOW, "lz encode: need %llu bytes, caller gave %llu",
-                                             (unsigned long long)total, (unsigned long long)out_cap);
-        if (total) {
-            if (int r = agc_reserve(ctx, ctx->scr_dense, total)) return r;
-            k_gather<<<(n + 3) / 4, 128, 0, ctx->st>>>(slab, d_src, d_dst, n, (uint8_t*)ctx->scr_dense.p);
-            CKL();
-            CK(cudaMemcpyAsync(out_bytes, ctx->scr_dense.p, total, cudaMemcpyDeviceToHost, ctx->st));
-            CK(cudaStreamSynchronize(ctx->st));
+        if (out_bytes && total > out_cap) return agc_fail(ctx, AGCGPU_EOVERFLOW, "lz encode: need %llu bytes, caller gave %llu",
+                                                          (unsigned long long)total, (unsigned long long)out_cap);
+        // out_bytes == nullptr (sharded encode): the dense deltas stay in scr_dense behind `out_cap` bytes the caller fills in
+        const uint64_t lead = out_bytes ? 0 : out_cap;
+        if (total || lead) {
+            if (int r = agc_reserve(ctx, ctx->scr_dense, lead + total + 64)) return r;
+            if (total) { k_gather<<<(n + 3) / 4, 128, 0, ctx->st>>>(slab, d_src, d_dst, n, (uint8_t*)ctx->scr_dense.p + lead); CKL(); }
+            if (out_bytes && total) {
+                CK(cudaMemcpyAsync(out_bytes, ctx->scr_dense.p, total, cudaMemcpyDeviceToHost, ctx->st));
+                CK(cudaStreamSynchronize(ctx->st));
+            }
         }
-        ctx->stats.d2h_bytes += total + ((size_t)n + 1) * 8;
+        ctx->stats.d2h_bytes += (out_bytes ? total : 0) + ((size_t)n + 1) * 8;
         alg_bytes += total;
     }
     if (mode == 2 && !out_u32) return 0;                 // nothing was synchronised: the caller queues its reduction behind the launch
     cudaEventElapsedTime(&ctx->stats.last_lz_kernel_ms, ctx->ev0, ctx->ev1);
     ctx->stats.lz_alg_bytes = alg_bytes;
+    if (mode == 0) { ctx->stats.lz_alg_bytes_total += alg_bytes; ctx->stats.lz_kernel_ms_total += ctx->stats.last_lz_kernel_ms; ctx->stats.lz_encode_launches++; }
     return 0;
 }
 
@@ -1097,6 +1228,51 @@ int agc_lz_cost_split(agcgpu_ctx* ctx, const agcgpu_split_req* reqs, uint32_t n,
         CK(cudaStreamSynchronize(ctx->st));
         ctx->stats.d2h_bytes += cnt * 8ull; ctx->stats.h2d_bytes += cnt * sizeof(SplitJob);
         a = b;
+    }
+    return 0;
+}
+
+// LZ-diff encoding split across the ranks of the NCCL communicator: every rank holds the same request list, encodes
+// a contiguous share balanced by bases, and the shares are all-gathered device-to-device: block of rank r =
+// [u64 offsets of its deltas (count+1)][dense deltas].  One D2H of the gathered blocks on every rank.
+int agc_lz_encode_sharded(agcgpu_ctx* ctx, const agcgpu_seg_req* reqs, uint32_t n, uint8_t* out, uint64_t out_cap, uint64_t* out_offsets)
+{
+    const uint32_t W = agc_comm_world(), me = agc_comm_rank();
+    std::vector<uint64_t> cum((size_t)n + 1, 0);
+    for (uint32_t i = 0; i < n; ++i) cum[i + 1] = cum[i] + reqs[i].len + 64;
+    std::vector<uint32_t> cutp(W + 1, n);
+    cutp[0] = 0;
+    for (uint32_t r = 1; r < W; ++r) cutp[r] = (uint32_t)(std::lower_bound(cum.begin(), cum.end(), cum.back() / W * r) - cum.begin());
+    for (uint32_t r = 1; r <= W; ++r) if (cutp[r] < cutp[r - 1]) cutp[r] = cutp[r - 1];
+    cutp[W] = n;
+    const uint32_t lo = cutp[me], cnt = cutp[me + 1] - lo;
+    const uint64_t hdr = ((uint64_t)(cnt + 1) * 8 + 15) / 16 * 16;
+    std::vector<uint64_t> my_offs((size_t)cnt + 1, 0);
+    uint64_t my_bytes = hdr;
+    int local = 0;                                       // a local failure still enters the collective (all ranks fail together)
+    if (cnt) {
+        local = agc_lz_run(ctx, 0, reqs + lo, cnt, 0, nullptr, hdr, my_offs.data(), nullptr);
+        if (!local) my_bytes = hdr + my_offs[cnt];
+    } else local = agc_reserve(ctx, ctx->scr_dense, hdr + 64);
+    if (!local && cudaMemcpyAsync(ctx->scr_dense.p, my_offs.data(), (size_t)(cnt + 1) * 8, cudaMemcpyHostToDevice, ctx->st) != cudaSuccess) local = AGCGPU_ECUDA;
+    std::vector<uint64_t> sizes; uint64_t stride = 0;
+    if (int r = agc_comm_allgatherv(ctx, ctx->scr_dense.p, my_bytes, local, sizes, &stride)) return r;
+    std::vector<uint8_t> host((size_t)stride * W);
+    if (stride) CK(cudaMemcpyAsync(host.data(), ctx->scr_gather.p, (size_t)stride * W, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    ctx->stats.d2h_bytes += (size_t)stride * W;
+    out_offsets[0] = 0;
+    uint64_t o = 0;
+    for (uint32_t r = 0; r < W; ++r) {
+        const uint32_t c = cutp[r + 1] - cutp[r];
+        const uint64_t h = ((uint64_t)(c + 1) * 8 + 15) / 16 * 16;
+        if (sizes[r] < h) return agc_fail(ctx, AGCGPU_ECUDA, "sharded encode: truncated block from rank %u", r);
+        const uint64_t* offs = (const uint64_t*)(host.data() + (size_t)stride * r);
+        if (sizes[r] != h + offs[c]) return agc_fail(ctx, AGCGPU_ECUDA, "sharded encode: block of rank %u has the wrong size", r);
+        if (o + offs[c] > out_cap) return agc_fail(ctx, AGCGPU_EOVERFLOW, "lz encode: output buffer too small");
+        for (uint32_t i = 0; i < c; ++i) out_offsets[cutp[r] + i + 1] = o + offs[i + 1];
+        if (offs[c]) memcpy(out + o, host.data() + (size_t)stride * r + h, offs[c]);
+        o += offs[c];
     }
     return 0;
 }

@@ -423,6 +423,7 @@ int agc_scan_resident(agcgpu_ctx* ctx, std::vector<ScanHit>* hits_out)
         CK(cudaMemcpyAsync(&h_count, ctx->counters.p, 4, cudaMemcpyDeviceToHost, ctx->st));
         CK(cudaStreamSynchronize(ctx->st));
         cudaEventElapsedTime(&ctx->stats.last_scan_kernel_ms, ctx->ev0, ctx->ev1);
+        ctx->stats.scan_kernel_ms_total += ctx->stats.last_scan_kernel_ms; ctx->stats.scan_bytes_total += totals[0] / 4; ctx->stats.scan_launches++;
     } else CK(cudaStreamSynchronize(ctx->st));
     if (h_count > hit_cap) return agc_fail(ctx, AGCGPU_EUNSUPPORTED, "splitter hits (%u) exceed capacity (%u)", h_count, hit_cap);
     hits_out->resize(h_count);

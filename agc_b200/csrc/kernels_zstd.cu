@@ -92,11 +92,12 @@ static uint64_t zs_narrow_max()
     return v;
 }
 
-extern "C" int agcgpu_zstd_compress_batch(agcgpu_ctx* ctx, const uint8_t* src, const uint64_t* src_offsets, const int32_t* levels,
-                                          uint32_t n, uint8_t* dst, uint64_t dst_cap, uint64_t* dst_offsets)
+// keep_lead == ~0: frames go to the host (dst / dst_offsets).  Otherwise (sharded coder) they stay on the device, back to back in input
+// order in ctx->scr_zkeep behind keep_lead bytes the caller fills in; dst_offsets still receives their offsets.
+static int zstd_compress_batch_impl(agcgpu_ctx* ctx, const uint8_t* src, const uint64_t* src_offsets, const int32_t* levels,
+                                    uint32_t n, uint8_t* dst, uint64_t dst_cap, uint64_t* dst_offsets, uint64_t keep_lead)
 {
-    if (!ctx || !src_offsets || !dst_offsets || (n && (!src || !levels || !dst))) return AGCGPU_EINVAL;
-    cudaSetDevice(ctx->dev);
+    const bool keep = keep_lead != ~0ull;
     dst_offsets[0] = 0;
     if (n == 0) return 0;
     // per-input parameters, workspace and output sizes
@@ -125,6 +126,7 @@ extern "C" int agcgpu_zstd_compress_batch(agcgpu_ctx* ctx, const uint8_t* src, c
     ctx->stats.zstd_input_mb += (float)(total_src * 1e-6);
     std::vector<uint64_t> out_size(n, 0);
     std::vector<std::vector<uint8_t>> frames(n);
+    std::vector<const uint8_t*> keep_src(n, nullptr);
     size_t pos = 0;
     while (pos < n) {
         size_t end = pos; uint64_t wsum = 0, osum = 0;
@@ -203,7 +205,19 @@ extern "C" int agcgpu_zstd_compress_batch(agcgpu_ctx* ctx, const uint8_t* src, c
             if (tasks[j].err) return agc_fail(ctx, AGCGPU_EUNSUPPORTED, "zstd: device coder failed on input %u (code %d)", i, tasks[j].err);
             out_size[i] = tasks[j].out_size; out_total += out_size[i];
         }
-        if (osum <= (64ull << 20) || out_total * 2 >= osum) {
+        if (keep) {
+            // sharded coder: note where each frame lies; they are compacted on the device once every wave is done
+            for (uint32_t j = 0; j < cnt; ++j) { uint32_t i = order[pos + j]; keep_src[i] = tasks[j].dst; }
+            if (end < n) {     // more waves will reuse scr_dense: park this wave's frames
+                for (uint32_t j = 0; j < cnt; ++j) {
+                    uint32_t i = order[pos + j];
+                    frames[i].resize(out_size[i]);
+                    CK(cudaMemcpyAsync(frames[i].data(), tasks[j].dst, out_size[i], cudaMemcpyDeviceToHost, ctx->st));
+                    keep_src[i] = nullptr;
+                }
+                CK(cudaStreamSynchronize(ctx->st));
+            }
+        } else if (osum <= (64ull << 20) || out_total * 2 >= osum) {
             std::vector<uint8_t> host(osum);
             CK(cudaMemcpyAsync(host.data(), ctx->scr_dense.p, osum, cudaMemcpyDeviceToHost, ctx->st));
             CK(cudaStreamSynchronize(ctx->st));
@@ -225,7 +239,81 @@ extern "C" int agcgpu_zstd_compress_batch(agcgpu_ctx* ctx, const uint8_t* src, c
         pos = end;
     }
     for (uint32_t i = 0; i < n; ++i) dst_offsets[i + 1] = dst_offsets[i] + out_size[i];
+    if (keep) {
+        if (int r = agc_reserve(ctx, ctx->scr_zkeep, keep_lead + dst_offsets[n] + 64)) return r;
+        uint8_t* base = (uint8_t*)ctx->scr_zkeep.p + keep_lead;
+        for (uint32_t i = 0; i < n; ++i) {
+            if (!out_size[i]) continue;
+            if (keep_src[i]) CK(cudaMemcpyAsync(base + dst_offsets[i], keep_src[i], out_size[i], cudaMemcpyDeviceToDevice, ctx->st));
+            else CK(cudaMemcpyAsync(base + dst_offsets[i], frames[i].data(), out_size[i], cudaMemcpyHostToDevice, ctx->st));
+        }
+        CK(cudaStreamSynchronize(ctx->st));
+        return 0;
+    }
     if (dst_offsets[n] > dst_cap) return agc_fail(ctx, AGCGPU_EOVERFLOW, "zstd: need %llu output bytes", (unsigned long long)dst_offsets[n]);
     for (uint32_t i = 0; i < n; ++i) if (out_size[i]) memcpy(dst + dst_offsets[i], frames[i].data(), out_size[i]);
+    return 0;
+}
+
+extern "C" int agcgpu_zstd_compress_batch(agcgpu_ctx* ctx, const uint8_t* src, const uint64_t* src_offsets, const int32_t* levels,
+                                          uint32_t n, uint8_t* dst, uint64_t dst_cap, uint64_t* dst_offsets)
+{
+    if (!ctx || !src_offsets || !dst_offsets || (n && (!src || !levels || !dst))) return AGCGPU_EINVAL;
+    cudaSetDevice(ctx->dev);
+    return zstd_compress_batch_impl(ctx, src, src_offsets, levels, n, dst, dst_cap, dst_offsets, ~0ull);
+}
+
+// The residual coder over the ranks of the NCCL communicator: frames are dealt out by size (largest first, each to the least
+// loaded rank; every rank computes the same assignment), coded where they land, and all-gathered between device buffers:
+// block of rank r = [u64 offsets of its frames (count+1)][frames back to back].
+extern "C" int agcgpu_zstd_compress_batch_sharded(agcgpu_ctx* ctx, const uint8_t* src, const uint64_t* src_offsets, const int32_t* levels,
+                                                  uint32_t n, uint8_t* dst, uint64_t dst_cap, uint64_t* dst_offsets)
+{
+    if (!ctx || !src_offsets || !dst_offsets || (n && (!src || !levels || !dst))) return AGCGPU_EINVAL;
+    cudaSetDevice(ctx->dev);
+    if (!agc_comm_active() || n == 0) return zstd_compress_batch_impl(ctx, src, src_offsets, levels, n, dst, dst_cap, dst_offsets, ~0ull);
+    const uint32_t W = agc_comm_world(), me = agc_comm_rank();
+    std::vector<uint32_t> order(n);
+    std::iota(order.begin(), order.end(), 0u);
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+        return src_offsets[a + 1] - src_offsets[a] > src_offsets[b + 1] - src_offsets[b]; });
+    std::vector<uint64_t> load(W, 0);
+    std::vector<std::vector<uint32_t>> of_rank(W);
+    for (uint32_t i : order) {
+        uint32_t r = (uint32_t)(std::min_element(load.begin(), load.end()) - load.begin());
+        of_rank[r].push_back(i); load[r] += src_offsets[i + 1] - src_offsets[i] + 512;      // + a per-frame constant: tiny frames are not free
+    }
+    const std::vector<uint32_t>& mine = of_rank[me];
+    const uint32_t cnt = (uint32_t)mine.size();
+    std::vector<uint64_t> so((size_t)cnt + 1, 0), fo((size_t)cnt + 1, 0);
+    std::vector<int32_t> lv(cnt);
+    for (uint32_t j = 0; j < cnt; ++j) { so[j + 1] = so[j] + (src_offsets[mine[j] + 1] - src_offsets[mine[j]]); lv[j] = levels[mine[j]]; }
+    std::vector<uint8_t> sub(so[cnt] + 1);
+    for (uint32_t j = 0; j < cnt; ++j) if (so[j + 1] > so[j]) memcpy(sub.data() + so[j], src + src_offsets[mine[j]], so[j + 1] - so[j]);
+    const uint64_t hdr = ((uint64_t)(cnt + 1) * 8 + 15) / 16 * 16;
+    int local = 0;                                       // a local failure still enters the collective (all ranks fail together)
+    if (cnt) local = zstd_compress_batch_impl(ctx, sub.data(), so.data(), lv.data(), cnt, nullptr, 0, fo.data(), hdr);
+    else local = agc_reserve(ctx, ctx->scr_zkeep, hdr + 64);
+    if (!local && cudaMemcpyAsync(ctx->scr_zkeep.p, fo.data(), (size_t)(cnt + 1) * 8, cudaMemcpyHostToDevice, ctx->st) != cudaSuccess) local = AGCGPU_ECUDA;
+    std::vector<uint64_t> sizes; uint64_t stride = 0;
+    if (int r = agc_comm_allgatherv(ctx, ctx->scr_zkeep.p, hdr + fo[cnt], local, sizes, &stride)) return r;
+    std::vector<uint8_t> host((size_t)stride * W);
+    if (stride) CK(cudaMemcpyAsync(host.data(), ctx->scr_gather.p, (size_t)stride * W, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    ctx->stats.d2h_bytes += (size_t)stride * W;
+    std::vector<uint64_t> fsize(n, 0);
+    std::vector<const uint8_t*> fptr(n, nullptr);
+    for (uint32_t r = 0; r < W; ++r) {
+        const uint32_t c = (uint32_t)of_rank[r].size();
+        const uint64_t h = ((uint64_t)(c + 1) * 8 + 15) / 16 * 16;
+        if (sizes[r] < h) return agc_fail(ctx, AGCGPU_ECUDA, "sharded coder: truncated block from rank %u", r);
+        const uint64_t* offs = (const uint64_t*)(host.data() + (size_t)stride * r);
+        if (sizes[r] != h + offs[c]) return agc_fail(ctx, AGCGPU_ECUDA, "sharded coder: block of rank %u has the wrong size", r);
+        for (uint32_t j = 0; j < c; ++j) { fsize[of_rank[r][j]] = offs[j + 1] - offs[j]; fptr[of_rank[r][j]] = host.data() + (size_t)stride * r + h + offs[j]; }
+    }
+    dst_offsets[0] = 0;
+    for (uint32_t i = 0; i < n; ++i) dst_offsets[i + 1] = dst_offsets[i] + fsize[i];
+    if (dst_offsets[n] > dst_cap) return agc_fail(ctx, AGCGPU_EOVERFLOW, "zstd: need %llu output bytes", (unsigned long long)dst_offsets[n]);
+    for (uint32_t i = 0; i < n; ++i) if (fsize[i]) memcpy(dst + dst_offsets[i], fptr[i], fsize[i]);
     return 0;
 }

@@ -18,10 +18,47 @@ def env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
 
-def install_exchange(L, device=None):
-    """Register torch.distributed's all-gather as the exchange step of library `L` (agcgpu_set_exchange).  The process group
-    must be initialised.  device=None: CPU tensors (gloo); device="cuda:i": blocks are staged through HBM and gathered with
-    NCCL (all_gather_into_tensor).  Returns (rank, world)."""
+def install_exchange(device_index):
+    """GPU runs: create the NCCL communicator INSIDE libagcgpu (agc_b200/csrc/comm.cu): rank 0 asks the library for an ncclUniqueId,
+    torch.distributed (already initialised, any backend) carries the 128 bytes to the other ranks, every rank calls
+    agcgpu_comm_init.  From then on compressors of this process split LZ-diff encoding and residual coding over the ranks and
+    all-gather the results between device buffers from C++ -- no Python on the data path.  Returns a dict for bench.py."""
+    import torch
+    import torch.distributed as dist
+    from . import lib
+    L = lib()
+    rank, world = dist.get_rank(), dist.get_world_size()
+    L.agcgpu_comm_unique_id.restype = C.c_int; L.agcgpu_comm_unique_id.argtypes = [C.c_void_p]
+    L.agcgpu_comm_init.restype = C.c_int; L.agcgpu_comm_init.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p, C.c_int]
+    L.agcgpu_comm_last_error.restype = C.c_char_p
+    buf = (C.c_uint8 * 128)()
+    if rank == 0 and L.agcgpu_comm_unique_id(buf) != 0:
+        raise RuntimeError("agcgpu_comm_unique_id: " + L.agcgpu_comm_last_error().decode())
+    t = torch.tensor(list(buf), dtype=torch.uint8, device=f"cuda:{device_index}" if dist.get_backend() == "nccl" else "cpu")
+    dist.broadcast(t, src=0)
+    ident = (C.c_uint8 * 128)(*t.cpu().tolist())
+    if L.agcgpu_comm_init(rank, world, ident, device_index) != 0:
+        raise RuntimeError("agcgpu_comm_init: " + L.agcgpu_comm_last_error().decode())
+    return comm_stats()
+
+
+class CommStats(C.Structure):
+    _fields_ = [("nranks", C.c_uint32), ("rank", C.c_uint32), ("collectives", C.c_uint64), ("bytes_gathered", C.c_uint64)]
+
+
+def comm_stats():
+    from . import lib
+    L = lib()
+    st = CommStats()
+    L.agcgpu_comm_get_stats.restype = C.c_int; L.agcgpu_comm_get_stats.argtypes = [C.POINTER(CommStats)]
+    L.agcgpu_comm_get_stats(C.byref(st))
+    return {"library": "NCCL (ncclAllGather from C++, device buffers)", "comm_nranks_seen": int(st.nranks), "rank": int(st.rank),
+            "collectives": int(st.collectives), "bytes_gathered": int(st.bytes_gathered)}
+
+
+def install_exchange_callback(L, device=None):
+    """CPU tests (gloo): register torch.distributed's all-gather as the exchange step of library `L` through the callback entry
+    (agcgpu_set_exchange).  The process group must be initialised.  device=None: CPU tensors.  Returns (rank, world)."""
     import torch
     import torch.distributed as dist
     rank, world = dist.get_rank(), dist.get_world_size()

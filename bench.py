@@ -1,22 +1,27 @@
 #!/usr/bin/env python
 """bench.py -- input Gbp/s of the AGC compression hot path on B200 (BASELINE.json metric), one JSON line on rank 0.
 
-A "step" is one complete `agc create` of the workload through the reference-facing API of this repo
-(agc_b200's CAGCCompressor mirror behind the C ABI): splitter determination on the reference sample, ingest + 2-bit
-packing, splitter scan, hash-assign, reference index build, LZ-diff encoding of every segment, reference tuple packing,
-residual coding (when the device coder is built) and archive assembly.
+A "step" is one complete `agc create` of the workload through the reference-facing API of this repo (agc_b200's
+CAGCCompressor mirror behind the C ABI): splitter determination on the reference sample, ingest + 2-bit packing, splitter
+scan, hash-assign, reference index build, LZ-diff encoding of every segment, reference tuple packing, residual coding
+(bit-exact zstd frames) and archive assembly.  The archive is written in every step; its sha256 is compared IN THE RUN with
+the archive the reference binary writes for the same files (cpu_baseline leg) -- a mismatch aborts the bench.
   value : whole-job throughput with the raw FASTA bodies already resident in HBM when the timed region starts
-  e2e   : the same call with HOST (pinned) buffers: host->device copies of every input byte and device->host copies of
-          all deltas / packed references inside the timed region
-Workload (config.workload): BASELINE.json configs[1] = 1000 synthetic 30 kb viral genomes (1 % SNP from one random
-reference), k=25, 1 GPU.  N>1 (torchrun): every rank compresses its own replica of the workload (weak scaling, no
-data-path collective; see DESIGN.md "multi-GPU").
+  e2e   : the same create from the FASTA FILES (tmpfs): file read + parse + host->device copies + device->host copies +
+          archive write inside the timed region -- what `agc create` does, and what the reference arm is timed on
+Workload (config.workload): BASELINE.json configs[2] = 64 synthetic 5 Mb bacterial genomes, adaptive mode (-a), k=29 -- the
+largest single-GPU configuration of BASELINE.json.  `other_workloads` carries configs[1] (1000 x 30 kb viral, k=25) measured
+the same way with fewer steps.
+N>1 (torchrun): ONE create sharded over the N GPUs (strong scaling): every rank keeps the O(#segments) bookkeeping, the
+per-base device work (LZ-diff encoding, residual coding) is split across the ranks and all-gathered over NCCL from C++
+(agc_b200/csrc/comm.cu); rank 0 writes the archive, whose sha256 is checked like at N=1.
 
---impl reference : the UNMODIFIED reference binary (oracle/_ref/agc, built from /root/reference by oracle/Makefile.ref)
-on the host cores, same files / flags / metric.
+--impl reference : the UNMODIFIED reference binary (oracle/_ref/agc, built from /root/reference by oracle/Makefile.ref) on
+the host cores, same files / flags / metric.
 """
 import argparse
 import ctypes as C
+import hashlib
 import json
 import os
 import shutil
@@ -32,19 +37,29 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 
-K, MML, SEG, PACK = 25, 20, 60000, 50
-N_SAMPLES, REF_LEN, P_SNP, SEED = 1000, 30000, 0.01, 1
+MML, SEG, PACK = 20, 60000, 50
+WORKLOADS = {
+    # name: (description, generator kwargs, k, adaptive)
+    "c3": ("BASELINE configs[2]: 63 synthetic 5 Mb bacterial genomes (1% SNP, 20 indels, one novel 120 kb contig each) + 5 Mb reference, "
+           "seed 2, agc create -a -k 29 (l=20 s=60000 b=50)", dict(kind="bacterial", seed=2, n_samples=63, ref_len=5_000_000), 29, 1),
+    "c2": ("BASELINE configs[1]: 1000 synthetic 30 kb viral genomes (1% SNP) + reference, seed 1, agc create -k 25 (l=20 s=60000 b=50)",
+           dict(kind="viral", seed=1, n_samples=1000, ref_len=30000), 25, 0),
+}
 
 
 def dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
 
-def make_workload(tmp):
+def make_workload(tmp, name):
     import gen_data
-    files, _ = gen_data.viral(os.path.join(tmp, "data"), n_samples=N_SAMPLES, ref_len=REF_LEN, p=P_SNP, seed=SEED)
-    total = (N_SAMPLES + 1) * REF_LEN
-    return files, total
+    kw = dict(WORKLOADS[name][1]); kind = kw.pop("kind")
+    d = os.path.join(tmp, "data_" + name)
+    if kind == "viral":
+        files, _ = gen_data.viral(d, n_samples=kw["n_samples"], ref_len=kw["ref_len"], p=0.01, seed=kw["seed"])
+    else:
+        files = gen_data.bacterial_adaptive(d, seed=kw["seed"], n_samples=kw["n_samples"], ref_len=kw["ref_len"])
+    return files, gen_data.total_bases(files)
 
 
 def read_bodies(files):
@@ -52,9 +67,8 @@ def read_bodies(files):
     names, soc, ids, bodies = [], [], [], []
     for fn in files:
         nm = os.path.basename(fn)
-        for suf in (".fa",):
-            if nm.endswith(suf):
-                nm = nm[:-len(suf)]
+        if nm.endswith(".fa"):
+            nm = nm[:-3]
         names.append(nm)
         data = open(fn, "rb").read()
         for rec in data.split(b">")[1:]:
@@ -65,6 +79,14 @@ def read_bodies(files):
     offs = np.zeros(len(bodies) + 1, np.uint64)
     offs[1:] = np.cumsum([len(b) for b in bodies])
     return names, np.array(soc, np.uint32), ids, b"".join(bodies), offs
+
+
+def sha256_file(path):
+    h = hashlib.sha256()
+    with open(path, "rb") as f:
+        for blk in iter(lambda: f.read(1 << 22), b""):
+            h.update(blk)
+    return h.hexdigest()
 
 
 class ClockSampler(threading.Thread):
@@ -90,30 +112,48 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_sm, "reasons": sorted(self.reasons)}
 
 
+def workload_config(name, world):
+    return {"workload": WORKLOADS[name][0],
+            "l2_policy": "inputs re-uploaded / outputs re-written every step and a 256 MiB L2 flush write between steps; working set per step (raw FASTA + packed + deltas) exceeds L2",
+            "parallelism": "single GPU" if world == 1 else f"one create sharded over {world} GPUs (LZ-diff encoding and residual coding split across ranks, NCCL all-gather from C++; rank 0 writes the archive)"}
+
+
+def ref_cmd(ref_bin, name, cores, out, lst, ref_fa):
+    k, adaptive = WORKLOADS[name][2], WORKLOADS[name][3]
+    return [ref_bin, "create"] + (["-a"] if adaptive else []) + ["-k", str(k), "-t", str(cores), "-o", out, "-i", lst, ref_fa]
+
+
+def run_reference_once(files, tmp, name, tag):
+    """the unmodified reference binary on the whole workload with every host core -> (seconds, sha256 of its archive)"""
+    ref_bin = os.path.join(ROOT, "oracle", "_ref", "agc")
+    cores = os.cpu_count() or 1
+    lst = os.path.join(tmp, f"list_{name}.txt")
+    open(lst, "w").write("\n".join(files[1:]) + "\n")
+    out = os.path.join(tmp, f"ref_{name}_{tag}.agc")
+    t0 = time.perf_counter()
+    subprocess.check_call(ref_cmd(ref_bin, name, cores, out, lst, files[0]), stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    dt = time.perf_counter() - t0
+    return dt, sha256_file(out), cores
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    ref_bin = os.path.join(ROOT, "oracle", "_ref", "agc")
+    name = args.workload
     tmp = tempfile.mkdtemp(prefix="agcbench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
     try:
-        files, total = make_workload(tmp)
-        cores = os.cpu_count() or 1
-        lst = os.path.join(tmp, "list.txt")
-        open(lst, "w").write("\n".join(files[1:]) + "\n")
-        cmd = [ref_bin, "create", "-k", str(K), "-t", str(cores), "-o", os.path.join(tmp, "ref.agc"), "-i", lst, files[0]]
-        times = []
+        files, total = make_workload(tmp, name)
+        times, sha, cores = [], None, 1
         for it in range(args.warmup + args.steps):
-            t0 = time.perf_counter()
-            subprocess.check_call(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-            dt = time.perf_counter() - t0
+            dt, sha, cores = run_reference_once(files, tmp, name, "arm")
             if it >= args.warmup:
                 times.append(dt)
         ms = 1e3 * sum(times) / len(times)
         val = total / (ms * 1e-3) / 1e9
         line = {"impl": "reference", "metric": "input Gbp/s (agc create, bit-exact .agc)", "value": val, "unit": "Gbp/s", "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak" if args.gpus == 1 else "strong",
                 "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": workload_config(), "gpu_launches": 0,
+                "config": workload_config(name, args.gpus), "gpu_launches": 0, "archive_sha256": sha,
                 "cpu_baseline": {"value": val, "unit": "Gbp/s", "cores": cores, "kind": "reference",
                                  "sample": f"full workload ({total} bases), oracle/_ref/agc create -t {cores}, files in tmpfs"},
                 "e2e": {"value": val, "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -122,18 +162,107 @@ def run_reference(args, rank, world):
         shutil.rmtree(tmp, ignore_errors=True)
 
 
-def workload_config():
-    return {"workload": f"BASELINE configs[1]: {N_SAMPLES} synthetic {REF_LEN} b viral genomes + reference, {P_SNP:.0%} SNP, seed {SEED}, agc create -k {K} (l={MML} s={SEG} b={PACK})",
-            "l2_policy": "inputs re-uploaded / outputs re-written every step; working set per step (raw FASTA 30.4 MB + packed + deltas) plus a 256 MiB L2 flush write between steps",
-            "parallelism": "one process per GPU, replicas"}
+STAT_KEYS = ("kernel_launches", "h2d_bytes", "d2h_bytes", "zstd_kernel_ms", "zstd_input_mb", "lz_alg_bytes_total", "lz_kernel_ms_total",
+             "scan_bytes_total", "scan_kernel_ms_total", "lz_encode_launches", "scan_launches", "lz_chunk_segments", "lz_sequential_segments")
+
+
+class Runner:
+    """one workload through the CAGCCompressor facade of the C ABI"""
+
+    def __init__(self, L, name, tmp, local_rank, rank, world):
+        import torch
+        import agc_b200
+        self.torch, self.agc, self.L, self.name, self.rank, self.world, self.local_rank = torch, agc_b200, L, name, rank, world, local_rank
+        self.k, self.adaptive = WORKLOADS[name][2], WORKLOADS[name][3]
+        self.files, self.total = make_workload(tmp, name)
+        names, self.soc, ids, raw, self.offs = read_bodies(self.files)
+        self.n_ctg = len(ids)
+        self.c_names = (C.c_char_p * len(names))(*[n.encode() for n in names]); self.n_names = len(names)
+        self.c_ids = (C.c_char_p * self.n_ctg)(*[i.encode() for i in ids])
+        raw_np = np.frombuffer(raw, np.uint8)
+        self.raw_len = len(raw_np)
+        self.pinned = torch.empty(self.raw_len + 64, dtype=torch.uint8).pin_memory()
+        self.pinned[:self.raw_len] = torch.from_numpy(raw_np.copy())
+        self.dev_raw = torch.empty(self.raw_len + 64, dtype=torch.uint8, device="cuda")
+        self.c_files = (C.c_char_p * (len(self.files) - 1))(*[f.encode() for f in self.files[1:]])
+        self.c_snames = (C.c_char_p * (len(self.files) - 1))(*[n.encode() for n in names[1:]])
+        self.out_path = os.path.join(tmp, f"out_{name}_{rank}.agc")
+
+    def step(self, resident, flush):
+        """returns (seconds, stats); the archive is at self.out_path afterwards (rank 0)"""
+        torch, L, vp = self.torch, self.L, C.c_void_p
+        flush.fill_(1)                                   # L2 flush between timed iterations
+        if resident:
+            self.dev_raw[:self.raw_len].copy_(self.pinned[:self.raw_len])
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        h = vp()
+        rc = L.agcgpu_compressor_create(self.out_path.encode(), PACK, self.k, self.files[0].encode(), SEG, MML, 0, self.adaptive, 0, 1, 0.0,
+                                        self.local_rank, None, C.byref(h))
+        if rc:
+            raise SystemExit("compressor_create failed: " + L.agcgpu_compressor_last_error(None).decode())
+        if resident:
+            # sample 0 (the reference file) is added by Create's caller in `agc create` as well: all samples go through here
+            rc = L.agcgpu_compressor_add_samples_memory(h, self.c_names, self.n_names, self.soc.ctypes.data_as(C.POINTER(C.c_uint32)), self.c_ids,
+                                                        self.n_ctg, vp(self.dev_raw.data_ptr()), self.offs.ctypes.data_as(C.POINTER(C.c_uint64)), 1)
+        else:
+            all_files = (C.c_char_p * len(self.files))(*[f.encode() for f in self.files])
+            all_names = (C.c_char_p * len(self.files))(*[self.c_names[i] for i in range(self.n_names)])
+            rc = L.agcgpu_compressor_add_sample_files(h, all_names, all_files, len(self.files), 1)
+        if rc:
+            raise SystemExit("add_samples failed: " + L.agcgpu_compressor_last_error(h).decode())
+        rc = L.agcgpu_compressor_close(h, 1)
+        if rc:
+            raise SystemExit("close failed: " + L.agcgpu_compressor_last_error(None).decode())
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        st = self.agc.Stats()
+        L.agcgpu_compressor_last_stats(C.byref(st))      # counters of the compressor just closed (incl. the residual coder in close)
+        return dt, {k: getattr(st, k) for k in STAT_KEYS}
+
+    def timed(self, resident, steps, warmup, flush, dist):
+        torch = self.torch
+        for _ in range(warmup):
+            self.step(resident, flush)
+        if self.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        times, last = [], None
+        for _ in range(steps):
+            dt, last = self.step(resident, flush)
+            times.append(dt)
+        torch.cuda.synchronize()
+        t = torch.tensor([sum(times)], dtype=torch.float64, device="cuda")
+        if self.world > 1:
+            dist.barrier()
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / steps, last
+
+
+def bind(L):
+    vp = C.c_void_p
+    import agc_b200
+    L.agcgpu_compressor_create.restype = C.c_int
+    L.agcgpu_compressor_create.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_char_p, C.c_uint32, C.c_uint32, C.c_int, C.c_int,
+                                           C.c_uint32, C.c_uint32, C.c_double, C.c_int, C.c_char_p, C.POINTER(vp)]
+    L.agcgpu_compressor_add_samples_memory.restype = C.c_int
+    L.agcgpu_compressor_add_samples_memory.argtypes = [vp, C.POINTER(C.c_char_p), C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_char_p),
+                                                       C.c_uint32, vp, C.POINTER(C.c_uint64), C.c_int]
+    L.agcgpu_compressor_add_sample_files.restype = C.c_int
+    L.agcgpu_compressor_add_sample_files.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_uint32, C.c_uint32]
+    L.agcgpu_compressor_close.restype = C.c_int; L.agcgpu_compressor_close.argtypes = [vp, C.c_uint32]
+    L.agcgpu_compressor_last_error.restype = C.c_char_p; L.agcgpu_compressor_last_error.argtypes = [vp]
+    L.agcgpu_compressor_last_stats.restype = C.c_int; L.agcgpu_compressor_last_stats.argtypes = [C.POINTER(agc_b200.Stats)]
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary workload and the LZ micro-batch")
     args = ap.parse_args()
     rank, local_rank, world = dist_env()
     if args.impl == "reference":
@@ -149,98 +278,22 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     L = agc_b200.lib()
-    vp = C.c_void_p
-    L.agcgpu_compressor_create.restype = C.c_int
-    L.agcgpu_compressor_create.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_char_p, C.c_uint32, C.c_uint32, C.c_int, C.c_int,
-                                           C.c_uint32, C.c_uint32, C.c_double, C.c_int, C.c_char_p, C.POINTER(vp)]
-    L.agcgpu_compressor_add_samples_memory.restype = C.c_int
-    L.agcgpu_compressor_add_samples_memory.argtypes = [vp, C.POINTER(C.c_char_p), C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_char_p),
-                                                       C.c_uint32, vp, C.POINTER(C.c_uint64), C.c_int]
-    L.agcgpu_compressor_set_discard_parts.restype = C.c_int; L.agcgpu_compressor_set_discard_parts.argtypes = [vp, C.c_int]
-    L.agcgpu_compressor_close.restype = C.c_int; L.agcgpu_compressor_close.argtypes = [vp, C.c_uint32]
-    L.agcgpu_compressor_last_error.restype = C.c_char_p; L.agcgpu_compressor_last_error.argtypes = [vp]
-    L.agcgpu_compressor_ctx.restype = vp; L.agcgpu_compressor_ctx.argtypes = [vp]
-    L.agcgpu_compressor_total_bases.restype = C.c_uint64; L.agcgpu_compressor_total_bases.argtypes = [vp]
-    L.agcgpu_compressor_last_stats.restype = C.c_int; L.agcgpu_compressor_last_stats.argtypes = [C.POINTER(agc_b200.Stats)]
+    bind(L)
+    comm_info = None
+    if world > 1:
+        from agc_b200 import dist as agc_dist
+        comm_info = agc_dist.install_exchange(local_rank)          # NCCL communicator inside libagcgpu (C++), bootstrap over torch.distributed
 
     tmp = tempfile.mkdtemp(prefix=f"agcbench{rank}_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
     try:
-        files, total = make_workload(tmp)
-        names, soc, ids, raw, offs = read_bodies(files)
-        n_ctg = len(ids)
-        c_names = (C.c_char_p * len(names))(*[n.encode() for n in names])
-        c_ids = (C.c_char_p * n_ctg)(*[i.encode() for i in ids])
-        raw_np = np.frombuffer(raw, np.uint8)
-        pinned = torch.empty(len(raw_np) + 64, dtype=torch.uint8).pin_memory()
-        pinned[:len(raw_np)] = torch.from_numpy(raw_np.copy())
-        dev_raw = torch.empty(len(raw_np) + 64, dtype=torch.uint8, device="cuda")
         flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-        has_zstd = os.environ.get("AGC_BENCH_RESIDUAL", "auto")
-        out_path = os.path.join(tmp, "out.agc")
-
-        def one_step(resident):
-            """returns (seconds, stats)"""
-            flush.fill_(1)                      # L2 flush between timed iterations
-            if resident:
-                dev_raw[:len(raw_np)].copy_(pinned[:len(raw_np)])
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            h = vp()
-            rc = L.agcgpu_compressor_create(out_path.encode(), PACK, K, files[0].encode(), SEG, MML, 0, 0, 0, 1, 0.0, local_rank, None, C.byref(h))
-            if rc:
-                raise SystemExit("compressor_create failed: " + L.agcgpu_compressor_last_error(None).decode())
-            if not RESIDUAL:
-                L.agcgpu_compressor_set_discard_parts(h, 1)
-            ptr = vp(dev_raw.data_ptr()) if resident else vp(pinned.data_ptr())
-            rc = L.agcgpu_compressor_add_samples_memory(h, c_names, len(names), soc.ctypes.data_as(C.POINTER(C.c_uint32)), c_ids, n_ctg,
-                                                        ptr, offs.ctypes.data_as(C.POINTER(C.c_uint64)), 1 if resident else 0)
-            if rc:
-                raise SystemExit("add_samples failed: " + L.agcgpu_compressor_last_error(h).decode())
-            st = agc_b200.Stats()
-            L.agcgpu_get_stats(L.agcgpu_compressor_ctx(h), C.byref(st))
-            stats = {k: getattr(st, k) for k in ("kernel_launches", "h2d_bytes", "d2h_bytes", "lz_alg_bytes", "last_lz_kernel_ms", "last_scan_kernel_ms")}
-            rc = L.agcgpu_compressor_close(h, 1)
-            if rc:
-                raise SystemExit("close failed: " + L.agcgpu_compressor_last_error(None).decode())
-            torch.cuda.synchronize()
-            dt = time.perf_counter() - t0
-            L.agcgpu_compressor_last_stats(C.byref(st))          # counters incl. the residual coder, which runs inside close
-            for k in ("kernel_launches", "h2d_bytes", "d2h_bytes", "zstd_kernel_ms", "zstd_input_mb"):
-                stats[k] = getattr(st, k)
-            return dt, stats
-
-        # is the device residual coder available?  (probe once; without it the step stops before zstd and says so)
-        global RESIDUAL
-        RESIDUAL = True
-        if has_zstd == "0":
-            RESIDUAL = False
-        elif has_zstd == "auto":
-            try:
-                one_step(True)
-            except SystemExit:
-                RESIDUAL = False
-
-        def timed(resident):
-            for _ in range(args.warmup):
-                one_step(resident)
-            if world > 1:
-                dist.barrier()
-            torch.cuda.synchronize()
-            times, last = [], None
-            for _ in range(args.steps):
-                dt, last = one_step(resident)
-                times.append(dt)
-            torch.cuda.synchronize()
-            t = torch.tensor([sum(times)], dtype=torch.float64, device="cuda")
-            if world > 1:
-                dist.barrier()
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            return float(t.item()) / args.steps, last
-
+        run = Runner(L, args.workload, tmp, local_rank, rank, world)
         sampler = ClockSampler(local_rank)
         sampler.start()
-        sec_res, st_res = timed(True)
-        sec_e2e, st_e2e = timed(False)
+        sec_res, st_res = run.timed(True, args.steps, args.warmup, flush, dist)
+        sha_res = sha256_file(run.out_path) if rank == 0 else None
+        sec_e2e, st_e2e = run.timed(False, args.steps, args.warmup, flush, dist)
+        sha_e2e = sha256_file(run.out_path) if rank == 0 else None
         sampler.stop_flag = True
         sampler.join(timeout=2)
 
@@ -250,33 +303,55 @@ def main():
                 peak = json.load(open(peaks_path))["hbm_gbs"]; peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
             else:
                 peak = 6650.0; peak_src = "fallback (B200_PROFILING.md)"
-            lz_gbs = st_res["lz_alg_bytes"] / (st_res["last_lz_kernel_ms"] * 1e-3) / 1e9 if st_res["last_lz_kernel_ms"] else 0.0
-            prof = os.path.join(ROOT, "profiles", "r01_lz_traffic.json")
-            traffic = json.load(open(prof)).get("traffic_bytes_per_launch") if os.path.exists(prof) else None
-            # the same LZ kernel on a batch shaped like one HPP-scale device batch (context for the roofline figure: the C2
-            # launch above holds 16 MB of algorithmic bytes, less than a launch latency worth of HBM traffic)
-            lz_hpp = lz_hpp_batch(local_rank, peak)
-            # bounded CPU sample of the same workload: reference binary on the first 200 samples
-            cpu = cpu_baseline(files, tmp)
-            cfg = workload_config()
-            cfg["stages"] = ("determine_splitters, ingest+2bit pack, splitter scan, hash-assign, LZ index, LZ-diff encode, ref tuple pack, "
-                             + ("residual coder (zstd frames), archive write" if RESIDUAL else "archive part assembly -- residual coder (zstd, SURVEY a24) NOT yet in the step"))
-            line = {"metric": "input Gbp/s (agc create" + (", bit-exact .agc)" if RESIDUAL else ", residual coder excluded)"),
-                    "value": world * total / sec_res / 1e9, "unit": "Gbp/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                    "ms_per_step": sec_res * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
-                    "data": "synthetic", "config": cfg,
-                    "e2e": {"value": world * total / sec_e2e / 1e9, "unit": "Gbp/s", "h2d_bytes_per_step": int(st_e2e["h2d_bytes"]),
-                            "d2h_bytes_per_step": int(st_e2e["d2h_bytes"]), "ms_per_step": sec_e2e * 1e3},
+            # the reference binary on the WHOLE workload with every host core: the CPU baseline and the bit-exactness oracle of the run
+            ref_dt, ref_sha, cores = run_reference_once(run.files, tmp, args.workload, "cpu")
+            if sha_res != ref_sha or sha_e2e != ref_sha:
+                raise SystemExit(f"bench.py: archive differs from the reference's (ours {sha_res} / {sha_e2e}, reference {ref_sha}): no valid number")
+            cpu = {"value": run.total / ref_dt / 1e9, "unit": "Gbp/s", "cores": cores, "kind": "reference",
+                   "sample": f"full workload ({run.total} bases), oracle/_ref/agc create -t {cores}, files in tmpfs, one run"}
+            total = run.total
+            lz_ms, lz_b = st_res["lz_kernel_ms_total"], st_res["lz_alg_bytes_total"]
+            lz_gbs = lz_b / (lz_ms * 1e-3) / 1e9 if lz_ms else 0.0
+            sc_ms, sc_b = st_res["scan_kernel_ms_total"], st_res["scan_bytes_total"]
+            sc_gbs = sc_b / (sc_ms * 1e-3) / 1e9 if sc_ms else 0.0
+            prof = os.path.join(ROOT, "profiles", "r02_lz_traffic.json")
+            traffic = json.load(open(prof)) if os.path.exists(prof) else {}
+            line = {"metric": "input Gbp/s (agc create, bit-exact .agc)", "value": total / sec_res / 1e9, "unit": "Gbp/s", "n_gpus": world,
+                    "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec_res * 1e3, "higher_is_better": True,
+                    "scaling": "weak" if world == 1 else "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                    "config": workload_config(args.workload, world),
+                    "e2e": {"value": total / sec_e2e / 1e9, "unit": "Gbp/s", "h2d_bytes_per_step": int(st_e2e["h2d_bytes"]),
+                            "d2h_bytes_per_step": int(st_e2e["d2h_bytes"]), "ms_per_step": sec_e2e * 1e3,
+                            "includes": "FASTA file read + parse, H2D/D2H, archive write"},
                     "gpu_launches": int(st_res["kernel_launches"]) * args.steps,
-                    "roofline": {"kernel": "k_lz_packed<0> (LZ-diff encode)", "bound": "hbm", "achieved": lz_gbs, "peak": peak, "unit": "GB/s",
-                                 "frac": lz_gbs / peak, "traffic": traffic, "peak_source": peak_src,
-                                 "algorithmic_bytes_per_launch": int(st_res["lz_alg_bytes"]), "kernel_ms": st_res["last_lz_kernel_ms"]},
-                    "lz_kernel_hpp_like_batch": lz_hpp,
-                    "residual_coder": {"kernel": "k_zstd (bit-exact zstd frames; one CTA per part: parser warp + 15 warps of tree walks)", "ms_per_step": float(st_res["zstd_kernel_ms"]),
-                                       "input_bytes_per_step": int(st_res["zstd_input_mb"] * 1e6),
-                                       "share_of_step": float(st_res["zstd_kernel_ms"]) / (sec_res * 1e3),
-                                       "note": "critical path of the step = the largest frame (1.35 MB raw-group pack, btopt): the optimal parse is sequential per frame; latency bound, not an HBM-roofline kernel (DESIGN.md section 5)"},
+                    "archive_sha256": sha_e2e, "reference_sha256": ref_sha, "bit_exact": True,
+                    "roofline": {"kernel": "k_lzc_parse + k_lzc_stitch (LZ-diff encode, all launches of the step)", "bound": "hbm", "achieved": lz_gbs, "peak": peak,
+                                 "unit": "GB/s", "frac": lz_gbs / peak, "traffic": traffic.get("step_traffic_bytes_per_launch"), "peak_source": peak_src,
+                                 "algorithmic_bytes_per_step": int(lz_b), "kernel_ms_per_step": lz_ms, "launches_per_step": int(st_res["lz_encode_launches"]),
+                                 "segments_chunk_parallel": int(st_res["lz_chunk_segments"]), "segments_sequential_kernel": int(st_res["lz_sequential_segments"]),
+                                 "note": "-a mode: one device batch per sample, so a launch holds ~90 segments (2.7 MB algorithmic): launch-latency bound; the HBM figure of the kernel is lz_kernel_hpp_like_batch"},
+                    "scan_roofline": {"kernel": "k_scan (splitter scan over 2-bit packed contigs)", "bound": "hbm", "achieved": sc_gbs, "peak": peak, "unit": "GB/s",
+                                      "frac": sc_gbs / peak, "algorithmic_bytes_per_step": int(sc_b), "kernel_ms_per_step": sc_ms, "launches_per_step": int(st_res["scan_launches"])},
+                    "residual_coder": {"kernel": "k_zstd / k_zstd_narrow (bit-exact zstd frames, one CTA per part)", "ms_per_step": float(st_res["zstd_kernel_ms"]),
+                                       "input_bytes_per_step": int(st_res["zstd_input_mb"] * 1e6), "share_of_step": float(st_res["zstd_kernel_ms"]) / (sec_res * 1e3)},
                     "cpu_baseline": cpu, "clocks": sampler.summary()}
+            if comm_info:
+                line["comm"] = comm_info
+            if not args.no_extra and world == 1:
+                line["lz_kernel_hpp_like_batch"] = lz_hpp_batch(local_rank, peak, traffic)
+                line["other_workloads"] = {}
+                for other in sorted(WORKLOADS):
+                    if other == args.workload:
+                        continue
+                    r2 = Runner(L, other, tmp, local_rank, rank, world)
+                    s_res, _ = r2.timed(True, 2, 1, flush, dist)
+                    s_e2e, _ = r2.timed(False, 2, 1, flush, dist)
+                    sha2 = sha256_file(r2.out_path)
+                    rdt, rsha, _ = run_reference_once(r2.files, tmp, other, "cpu")
+                    if sha2 != rsha:
+                        raise SystemExit(f"bench.py: {other} archive differs from the reference's")
+                    line["other_workloads"][other] = {"workload": WORKLOADS[other][0], "value": r2.total / s_res / 1e9, "e2e": r2.total / s_e2e / 1e9,
+                                                      "unit": "Gbp/s", "steps": 2, "warmup": 1, "reference_cpu": r2.total / rdt / 1e9, "bit_exact": True}
             print(json.dumps(line))
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
@@ -284,61 +359,15 @@ def main():
             dist.destroy_process_group()
 
 
-def lz_hpp_batch(device, peak):
-    """k_lz_packed<0> on 4096 segments of 60 031 bases (0.1 % SNP, 64 reference segments): CUDA-event time of the launch"""
-    import agc_b200
-    import gen_data
-    n_seg, seg_len, n_groups = 4096, 60031, 64
-    rng = np.random.default_rng(1)
-    LET = np.frombuffer(b"ACGT", np.uint8)
-    refs = [rng.integers(0, 4, seg_len, dtype=np.uint8) for _ in range(n_groups)]
-    contigs = [LET[r].tobytes() for r in refs] + [LET[gen_data.substitute(rng, refs[i % n_groups], 0.001)].tobytes() for i in range(n_seg)]
-    dev = agc_b200.Device(k=31, min_match_len=20, device=device)
-    try:
-        dev.set_splitters(np.zeros(0, np.uint64))
-        dev.scan_contigs(contigs)
-        dev.put_references([(g, 0, seg_len, False, 16 + g) for g in range(n_groups)])
-        arr = dev._reqs([(n_groups + i, 0, seg_len, False, 16 + (i % n_groups)) for i in range(n_seg)])
-        out = np.zeros(n_seg * (seg_len // 8 + 64), np.uint8)
-        offs = np.zeros(n_seg + 1, np.uint64)
-        ms = []
-        for _ in range(5):
-            dev.lz_encode_raw(arr, n_seg, out, offs)
-            st = dev.stats()
-            ms.append(st.last_lz_kernel_ms)
-        ms = sorted(ms[2:])[len(ms[2:]) // 2]
-        gbs = st.lz_alg_bytes / (ms * 1e-3) / 1e9
-        tp = os.path.join(ROOT, "profiles", "r01_lz_traffic_hpp.json")
-        traffic = json.load(open(tp)).get("traffic_bytes_per_launch") if os.path.exists(tp) else None
-        return {"workload": f"{n_seg} segments x {seg_len} bases, 0.1% SNP, {n_groups} reference segments (working set 125 MB ~ L2 size, 2 warm-up launches)",
-                "kernel_ms": ms, "algorithmic_bytes_per_launch": int(st.lz_alg_bytes), "achieved": gbs, "unit": "GB/s", "frac": gbs / peak,
-                "traffic": traffic}
-    finally:
-        dev.close()
+def lz_hpp_batch(device, peak, traffic):
+    """the LZ-diff encode kernels on 16384 segments of 60 031 bases (0.1 % SNP, 256 reference segments; 0.98 Gbase, one HPP-scale device
+    batch): CUDA-event time of the launch (k_lzc_parse + k_lzc_stitch), L2 flushed before every launch (working set 0.5 GB > L2 anyway)"""
+    import lz_hpp_bench
+    r = lz_hpp_bench.run(16384, 0.001, 256, reps=5, device=device, flush=True)
+    return {"workload": f"{r['n_seg']} segments x {r['seg_len']} bases, 0.1% SNP, {r['groups']} reference segments (one HPP-scale device batch; working set >> L2, L2 flushed between launches)",
+            "kernel_ms": r["kernel_ms"], "algorithmic_bytes_per_launch": r["alg_bytes"], "achieved": r["GBps"], "unit": "GB/s", "frac": r["GBps"] / peak,
+            "Gbase_per_s": r["Gbase_per_s"], "segments_sequential_kernel": r["sequential_segments"], "traffic": traffic.get("hpp_traffic_bytes_per_launch")}
 
-
-def cpu_baseline(files, tmp):
-    ref_bin = os.path.join(ROOT, "oracle", "_ref", "agc")
-    if not os.path.exists(ref_bin):
-        return {"value": None, "unit": "Gbp/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref/agc not built"}
-    cores = os.cpu_count() or 1
-    n = 200
-    sub = files[:n + 1]
-    bases = (n + 1) * REF_LEN
-    lst = os.path.join(tmp, "cpu_list.txt")
-    open(lst, "w").write("\n".join(sub[1:]) + "\n")
-    best = None
-    for _ in range(2):
-        t0 = time.perf_counter()
-        subprocess.check_call([ref_bin, "create", "-k", str(K), "-t", str(cores), "-o", os.path.join(tmp, "cpu.agc"), "-i", lst, sub[0]],
-                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-    return {"value": bases / best / 1e9, "unit": "Gbp/s", "cores": cores, "kind": "reference",
-            "sample": f"first {n} samples + reference of the workload ({bases} bases), oracle/_ref/agc create -t {cores}, best of 2"}
-
-
-RESIDUAL = True
 
 if __name__ == "__main__":
     main()

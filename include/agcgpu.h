@@ -96,6 +96,14 @@ typedef struct {
     float    last_scan_kernel_ms;
     float    zstd_kernel_ms;     /* device time spent in the residual coder since agcgpu_create (sum over batches) */
     float    zstd_input_mb;      /* bytes handed to the residual coder since agcgpu_create, in 10^6 bytes */
+    uint64_t lz_chunk_segments;       /* segments encoded by the chunk-parallel kernels since agcgpu_create ... */
+    uint64_t lz_sequential_segments;  /* ... of which the stitcher handed to the sequential kernel */
+    /* sums since agcgpu_create (a step of the bench = one create): LZ-diff encode launches and splitter-scan launches */
+    uint64_t lz_alg_bytes_total;      /* sum of ceil(n/4)+ceil(m/4)+e over all encode requests */
+    uint64_t scan_bytes_total;        /* 2-bit packed bytes read by k_scan (bases / 4) */
+    float    lz_kernel_ms_total;      /* device time of the encode kernels (CUDA events) */
+    float    scan_kernel_ms_total;
+    uint32_t lz_encode_launches, scan_launches;
 } agcgpu_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------------------------------- */
@@ -187,6 +195,10 @@ int agcgpu_group_get_index(agcgpu_ctx* ctx, uint32_t group_id, uint32_t* out_slo
  * out_offsets has n+1 entries; delta i = out[out_offsets[i] .. out_offsets[i+1]). */
 int agcgpu_lz_encode_batch(agcgpu_ctx* ctx, const agcgpu_seg_req* reqs, uint32_t n,
                            uint8_t* out, uint64_t out_cap, uint64_t* out_offsets);
+/* diagnostics: the chunk records (agc_b200/csrc/lz_chunk.cuh, LzcRec, 64 bytes each) the last agcgpu_lz_encode_batch left on the
+ * device, in request order as sorted by group; tests compare them with the host build of the same source */
+int agcgpu_debug_lz_chunk_records(agcgpu_ctx* ctx, void* out, uint64_t cap_bytes, uint64_t* out_n_records);
+
 /* CLZDiff_V2::Estimate (lz_diff.cpp:839-946) as called from CSegment::estimate (agc_compressor.cpp:1705,1733,1757) */
 int agcgpu_lz_estimate_batch(agcgpu_ctx* ctx, const agcgpu_seg_req* reqs, uint32_t n, uint32_t* out);
 /* CLZDiffBase::GetCodingCostVector (lz_diff.cpp:159-284) as called from CSegment::get_coding_cost
@@ -278,6 +290,33 @@ int agcgpu_compressor_add_samples_memory(agcgpu_compressor* c, const char* const
  * afterwards; world <= 1 or allgather == NULL switches it off. */
 typedef int (*agcgpu_allgather_fn)(void* user, const void* send, void* recv, uint64_t bytes);
 int agcgpu_set_exchange(uint32_t rank, uint32_t world, agcgpu_allgather_fn allgather, void* user);
+
+/* The exchange over NCCL, inside the library (agc_b200/csrc/comm.cu): one communicator per process, device-to-device
+ * ncclAllGather on the library's stream.  One rank calls agcgpu_comm_unique_id and hands the 128 bytes to the others over any
+ * side channel (torch.distributed broadcast, MPI, a file); every rank then calls agcgpu_comm_init, after which compressors
+ * created in this process split LZ-diff encoding and residual coding across the ranks: the deltas / frames a rank produced stay
+ * in HBM, are all-gathered there and come to the host once.  Takes precedence over agcgpu_set_exchange. */
+#define AGCGPU_UNIQUE_ID_BYTES 128
+int agcgpu_comm_unique_id(uint8_t* out_id);
+int agcgpu_comm_init(uint32_t rank, uint32_t world, const uint8_t* id, int device);
+int agcgpu_comm_destroy(void);
+typedef struct {
+    uint32_t nranks;             /* ncclCommCount of the live communicator (1 without one) */
+    uint32_t rank;
+    uint64_t collectives;        /* ncclAllGather calls issued by the data path since agcgpu_comm_init */
+    uint64_t bytes_gathered;     /* bytes received through them on this rank */
+} agcgpu_comm_stats;
+int agcgpu_comm_get_stats(agcgpu_comm_stats* out);
+int agcgpu_comm_world(void);     /* ranks of the live communicator, 1 without one */
+int agcgpu_comm_rank(void);
+/* agcgpu_lz_encode_batch / agcgpu_zstd_compress_batch with the work split across the ranks of the communicator: every rank passes
+ * the SAME arguments, works on its share (requests: contiguous runs balanced by bases; frames: largest first to the least loaded
+ * rank) and receives everything; the results are all-gathered between device buffers.  Without a communicator they are the
+ * plain calls. */
+int agcgpu_lz_encode_batch_sharded(agcgpu_ctx* ctx, const agcgpu_seg_req* reqs, uint32_t n, uint8_t* out, uint64_t out_cap, uint64_t* out_offsets);
+int agcgpu_zstd_compress_batch_sharded(agcgpu_ctx* ctx, const uint8_t* src, const uint64_t* src_offsets, const int32_t* levels,
+                                       uint32_t n, uint8_t* dst, uint64_t dst_cap, uint64_t* dst_offsets);
+const char* agcgpu_comm_last_error(void);
 
 /* measurement hook: build every archive part but skip the residual coder and the file writes */
 int agcgpu_compressor_set_discard_parts(agcgpu_compressor* c, int discard);

@@ -395,6 +395,13 @@ int agcgpu_lz_cost_vector(agcgpu_ctx* ctx, const agcgpu_seg_req* req, int prefix
     return 0;
 }
 
+int agcgpu_comm_world(void) { return 1; }
+int agcgpu_comm_rank(void) { return 0; }
+int agcgpu_lz_encode_batch_sharded(agcgpu_ctx* ctx, const agcgpu_seg_req* reqs, uint32_t n, uint8_t* out, uint64_t out_cap, uint64_t* out_offsets)
+{ return agcgpu_lz_encode_batch(ctx, reqs, n, out, out_cap, out_offsets); }
+int agcgpu_zstd_compress_batch_sharded(agcgpu_ctx* ctx, const uint8_t* src, const uint64_t* src_offsets, const int32_t* levels, uint32_t n, uint8_t* dst,
+                                       uint64_t dst_cap, uint64_t* dst_offsets)
+{ return agcgpu_zstd_compress_batch(ctx, src, src_offsets, levels, n, dst, dst_cap, dst_offsets); }
 int agcgpu_lz_cost_split_batch(agcgpu_ctx* ctx, const agcgpu_split_req* reqs, uint32_t n, uint32_t* out_best_pos, uint32_t* out_best_sum)
 {
     COUNT("agcgpu_lz_cost_split_batch", n);

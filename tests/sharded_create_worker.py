@@ -29,20 +29,21 @@ while i < len(flags):
         opt[flags[i]] = int(flags[i + 1]); i += 1
     i += 1
 
-# AGC_EXCHANGE=nccl: one GPU per rank, blocks staged through HBM and gathered with NCCL; AGC_EXCHANGE=staged-cpu: the same staging
-# code path over gloo with CPU tensors (CPU suite); default: gloo on host memory
+# AGC_EXCHANGE=nccl: one GPU per rank, NCCL communicator inside the library, device-to-device all-gathers from C++;
+# AGC_EXCHANGE=staged-cpu / default: the callback entry (agcgpu_set_exchange) over gloo (CPU suite)
 mode = os.environ.get("AGC_EXCHANGE", "gloo")
 if mode == "nccl":
     import torch
     device = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(device)
     dist.init_process_group("nccl")
-    L = C.CDLL(so)
-    rank, world = adist.install_exchange(L, device=f"cuda:{device}")
+    L = agc_b200.lib()                                   # the NCCL communicator lives inside libagcgpu (agc_b200/csrc/comm.cu)
+    info = adist.install_exchange(device)
+    rank, world = info["rank"], info["comm_nranks_seen"]
 else:
     dist.init_process_group("gloo")
     L = C.CDLL(so)
-    rank, world = adist.install_exchange(L, device="cpu" if mode == "staged-cpu" else None)
+    rank, world = adist.install_exchange_callback(L, device="cpu" if mode == "staged-cpu" else None)
 vp = C.c_void_p
 L.agcgpu_compressor_create.restype = C.c_int
 L.agcgpu_compressor_create.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_char_p, C.c_uint32, C.c_uint32, C.c_int, C.c_int,
@@ -71,5 +72,7 @@ assert rc == 0, L.agcgpu_compressor_last_error(None)
 st = agc_b200.Stats()
 L.agcgpu_compressor_last_stats(C.byref(st))
 dist.barrier()
+if mode == "nccl":
+    print(f"rank{rank} comm {adist.comm_stats()}", flush=True)
 print(f"rank{rank}/{world} zstd_input_mb={st.zstd_input_mb:.6f}", flush=True)
 dist.destroy_process_group()

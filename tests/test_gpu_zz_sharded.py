@@ -1,6 +1,6 @@
 """SURVEY 8e on the device: two ranks (two processes, two contexts -- both on cuda:0, so the test also runs on a one-GPU box;
 the exchange step goes over gloo) write ONE archive through libagcgpu.so, byte-identical to the reference's.  On a multi-GPU
-box the same calls run with one GPU per rank and agc_b200.dist.install_exchange(L, device="cuda:<local rank>") (NCCL)."""
+box test_two_gpus_nccl runs one GPU per rank with the NCCL communicator inside the library (agc_b200.dist.install_exchange)."""
 import os
 import sys
 import pytest
@@ -34,7 +34,7 @@ def _n_gpus():
 @pytest.mark.skipif(not os.path.exists(REF_AGC), reason="reference binary not built (make -f oracle/Makefile.ref)")
 @pytest.mark.skipif(_n_gpus() < 2, reason="needs two GPUs (NCCL cannot put two ranks on one device)")
 def test_two_gpus_nccl(tmp_path):
-    """one GPU per rank, the exchange step over NCCL (all_gather_into_tensor on HBM-staged blocks)"""
+    """one GPU per rank, the exchange step = ncclAllGather between device buffers from C++ (agc_b200/csrc/comm.cu)"""
     import agc_b200
     a, b, mb = _sharded_create(str(tmp_path), "complex", 2, 29553, agc_b200.lib_path(), 0, exchange="nccl")
     assert a == b
