@@ -148,7 +148,7 @@ void agcgpu_destroy(agcgpu_ctx* ctx)
     DevBuf* bufs[] = { &ctx->spl_keys, &ctx->spl_filter, &ctx->raw, &ctx->packed, &ctx->exc_pos, &ctx->exc_code, &ctx->tile_desc,
                        &ctx->tile_cnt, &ctx->tile_base, &ctx->d_cstart, &ctx->chunk_prefix, &ctx->hits, &ctx->counters, &ctx->map_k1,
                        &ctx->map_k2, &ctx->map_val, &ctx->d_groups, &ctx->scr_req, &ctx->scr_units, &ctx->scr_out, &ctx->scr_sizes,
-                       &ctx->scr_offs, &ctx->scr_dense, &ctx->scr_misc, &ctx->scr_bytes, &ctx->scr_chunk, &ctx->scr_rec, &ctx->scr_gsz, &ctx->scr_gather, &ctx->scr_zkeep, &ctx->ref_kmers };
+                       &ctx->scr_offs, &ctx->scr_dense, &ctx->scr_misc, &ctx->scr_bytes, &ctx->scr_chunk, &ctx->scr_rec, &ctx->scr_gsz, &ctx->scr_gather, &ctx->scr_zkeep, &ctx->scr_cost, &ctx->ref_kmers };
     for (DevBuf* b : bufs) if (b->p) agc_dev_free(ctx->dev, b->p, b->cap + 64);
     for (auto& c : ctx->arena_chunks) agc_dev_free(ctx->dev, c.first, c.second);
     if (ctx->pin) {

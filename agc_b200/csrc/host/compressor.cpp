@@ -1382,6 +1382,8 @@ bool CAGCCompressor::Close(uint32_t)
 {
     PhaseTimer pt("close");
     g_acc.report();
+    if (g_acc.on && ctx) { agcgpu_stats st; if (!agcgpu_get_stats(ctx, &st)) fprintf(stderr, "[agcgpu] LZ encode: %llu segments chunk-parallel, %llu of them redone by the sequential kernel; %u launches, %.1f ms of kernels\n",
+        (unsigned long long)st.lz_chunk_segments, (unsigned long long)st.lz_sequential_segments, st.lz_encode_launches, st.lz_kernel_ms_total); }
     if (!working) return false;
     working = false;
     // close_compression (agc_compressor.cpp:2094-2114): CSegment::finish for all groups, flush, metadata

@@ -157,8 +157,9 @@ struct agcgpu_ctx {
     size_t device_bytes = 0;
 
     // scratch
-    DevBuf scr_req, scr_units, scr_out, scr_sizes, scr_offs, scr_dense, scr_misc, scr_bytes, scr_chunk, scr_rec, scr_gsz, scr_gather, scr_zkeep;
+    DevBuf scr_req, scr_units, scr_out, scr_sizes, scr_offs, scr_dense, scr_misc, scr_bytes, scr_chunk, scr_rec, scr_gsz, scr_gather, scr_zkeep, scr_cost;
     void* pin = nullptr; size_t pin_cap = 0;   // pinned host staging
+    std::vector<uint64_t> last_slab_off;       // device-only encode: slab offset of every delta (request order)
     uint64_t last_lzc_chunks = 0;              // chunk records of the last chunk-parallel encode (diagnostics)
 };
 

@@ -17,6 +17,8 @@
 #include "internal.cuh"
 #include "lz_chunk.cuh"
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #define FULL 0xffffffffu
@@ -573,7 +575,7 @@ __global__ void __launch_bounds__(128) k_index(const RefJob* __restrict__ jobs, 
         GroupRefDev g;
         g.packed = j.packed; g.ht = j.ht; g.codes = j.codes; g.m = m; g.ht_size = hs;
         g.flags = GRF_PRESENT | (is_short ? GRF_SHORT : 0u) | (BYTES ? GRF_DIRTY : 0u);
-        g.packed_bytes = ((m + 3) / 4 + 15) / 16 * 16 + 16;
+        g.packed_bytes = ((m + 3) / 4 + 15) / 16 * 16 + 32;
         groups[j.group] = g;
     }
 }
@@ -621,7 +623,7 @@ __global__ void __launch_bounds__(LZ_IDX_THREADS) k_index_par(const RefJob* __re
         GroupRefDev g;
         g.packed = j.packed; g.ht = j.ht; g.codes = nullptr; g.m = m; g.ht_size = hs;
         g.flags = GRF_PRESENT | (is_short ? GRF_SHORT : 0u);
-        g.packed_bytes = ((m + 3) / 4 + 15) / 16 * 16 + 16;
+        g.packed_bytes = ((m + 3) / 4 + 15) / 16 * 16 + 32;
         groups[j.group] = g;
     }
 }
@@ -825,7 +827,7 @@ static int build_refs(agcgpu_ctx* ctx, std::vector<RefJob>& jobs, bool from_segm
 static int alloc_ref_job(agcgpu_ctx* ctx, RefJob& j, bool dirty)
 {
     const uint32_t mml = ctx->prm.min_match_len;
-    size_t pbytes = ((size_t)(j.n + 3) / 4 + 15) / 16 * 16 + 16;
+    size_t pbytes = ((size_t)(j.n + 3) / 4 + 15) / 16 * 16 + 32;
     uint64_t hs = clean_ht_size(j.n, mml);
     bool is_short = (j.n / 4) < 65535;
     size_t hbytes = hs * (is_short ? 2 : 4);
@@ -924,7 +926,7 @@ static void launch_bytes(agcgpu_ctx* ctx, const ByteReq* d_req, uint32_t n, uint
 int agc_lz_run(agcgpu_ctx* ctx, int mode, const agcgpu_seg_req* reqs, uint32_t n, int prefix_costs,
                uint8_t* out_bytes, uint64_t out_cap, uint64_t* out_offsets, uint32_t* out_u32)
 {
-    if (n == 0) { if (mode == 0) out_offsets[0] = 0; return 0; }
+    if (n == 0) { if (mode == 0 && out_offsets) out_offsets[0] = 0; return 0; }
     const uint32_t mml = ctx->prm.min_match_len;
     // ---- classify + order by group
     std::vector<LzReqDev> packed_reqs; packed_reqs.reserve(n);
@@ -1103,6 +1105,14 @@ int agc_lz_run(agcgpu_ctx* ctx, int mode, const agcgpu_seg_req* reqs, uint32_t n
             CK(cudaStreamSynchronize(ctx->st));
             ctx->stats.d2h_bytes += (size_t)reqs[0].len * 4;
         }                                                // else: vector i stays at scr_out (u32 index = sum of the lengths before it)
+    } else if (!out_offsets) {
+        // device-only encode (cost-split path): delta i stays in the slab at last_slab_off[i], its size in scr_sizes[i]
+        CK(cudaMemcpyAsync(&h_err, err, 4, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaStreamSynchronize(ctx->st));
+        if (h_err) return agc_fail(ctx, AGCGPU_EOVERFLOW, "lz encode: per-segment output bound exceeded");
+        ctx->last_slab_off = slab_off;
+        cudaEventElapsedTime(&ctx->stats.last_lz_kernel_ms, ctx->ev0, ctx->ev1);
+        return 0;
     } else {
         if (int r = agc_reserve(ctx, ctx->scr_offs, ((size_t)n + 1) * 16)) return r;
         uint64_t* d_dst = (uint64_t*)ctx->scr_offs.p;
@@ -1193,8 +1203,59 @@ __global__ void __launch_bounds__(1024) k_split_reduce(const uint32_t* __restric
     }
 }
 
+// GetCodingCostVector (lz_diff.cpp:159-284) runs the same parse as Encode (with the rewind), so its vector is a function of the
+// delta: a literal (letter or '!') costs 1 at its position, an N-run / match token costs its printed length at the first
+// (prefix_costs) or last position it covers -- coding_cost_match always counts the length field, which Encode omits for a match
+// that reaches both ends (lz_diff.cpp:781-784), and Encode's "equal sequences" shortcut (678-680) is one match over everything.
+// One thread walks one delta; the vectors were zero-filled before.
+struct CostJob { uint64_t delta_off, cost_off; uint32_t len, m, prefix, pad; };
+__device__ __forceinline__ uint32_t int_len_dev(uint32_t x)
+{
+    return x < 10 ? 1 : x < 100 ? 2 : x < 1000 ? 3 : x < 10000 ? 4 : x < 100000 ? 5 : x < 1000000 ? 6 : x < 10000000 ? 7
+         : x < 100000000 ? 8 : x < 1000000000 ? 9 : 10;
+}
+__global__ void k_delta_costs(const uint8_t* __restrict__ slab, const uint32_t* __restrict__ sizes, const CostJob* __restrict__ jobs, uint32_t n_jobs,
+                              uint32_t mml, uint32_t* __restrict__ costv, uint32_t* __restrict__ bad)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_jobs) return;
+    const CostJob j = jobs[r];
+    const uint8_t* d = slab + j.delta_off;
+    const uint32_t e = sizes[r], n = j.len;
+    uint32_t* v = costv + j.cost_off;
+    auto put = [&](uint32_t pos, uint32_t len, uint32_t tc) { if (pos + len <= n && len) v[j.prefix ? pos : pos + len - 1] = tc; else atomicOr(bad, 1u); };
+    if (e == 0) { if (n) atomicOr(bad, 2u); return; }    // Encode's "equal sequences" shortcut: the sequential kernel makes this vector
+    uint32_t pos = 0, i = 0;
+    while (i < e) {
+        const uint8_t c = d[i];
+        if ((c >= 'A' && c <= 'A' + 30) || c == '!') { if (pos < n) v[pos] = 1; else atomicOr(bad, 1u); ++pos; ++i; continue; }
+        if (c == 30) {                                   // N-run: 0x1e <len - 4> 0x04 (lz_diff.h:152-157)
+            uint32_t k = i + 1, val = 0;
+            while (k < e && d[k] >= '0' && d[k] <= '9') { val = val * 10 + (d[k] - '0'); ++k; }
+            const uint32_t len = val + 4;
+            put(pos, len, k + 1 - i);
+            pos += len; i = k + 1;
+            continue;
+        }
+        // match: <signed dif>[,<len - min_match_len>].
+        uint32_t k = i;
+        while (k < e && d[k] != ',' && d[k] != '.') ++k;
+        uint32_t tc = k - i, len;
+        if (k < e && d[k] == ',') {
+            uint32_t val = 0; ++k;
+            const uint32_t k0 = k;
+            while (k < e && d[k] != '.') { val = val * 10 + (d[k] - '0'); ++k; }
+            len = val + mml; tc += 1 + (k - k0) + 1;
+        } else { len = n - pos; tc += int_len_dev(len - mml) + 2; }
+        put(pos, len, tc);
+        pos += len; i = k + 1;
+    }
+    if (pos != n) atomicOr(bad, 1u);
+}
+
 int agc_lz_cost_split(agcgpu_ctx* ctx, const agcgpu_split_req* reqs, uint32_t n, uint32_t* out_pos, uint32_t* out_sum)
 {
+    static const bool seq_costs = getenv("AGCGPU_LZ_SEQUENTIAL") != nullptr;        // diagnostics: cost vectors from the sequential kernel
     // sub-batches bounded by the size of the cost vectors (2 x len x 4 bytes per decision)
     const uint64_t budget = 1ull << 30;
     for (uint32_t a = 0; a < n;) {
@@ -1216,16 +1277,46 @@ int agc_lz_cost_split(agcgpu_ctx* ctx, const agcgpu_split_req* reqs, uint32_t n,
             jobs[i].rev1 = (q.flags >> 2) & 1u; jobs[i].rev2 = (q.flags >> 5) & 1u; jobs[i].pad = 0;
             off += 2ull * q.len;
         }
-        if (int r = agc_lz_run(ctx, 2, sr.data(), 2 * cnt, 0, nullptr, 0, nullptr, nullptr)) return r;
+        const uint32_t* d_costs = nullptr;
+        bool use_seq = seq_costs;
+      again:
+        if (use_seq) {
+            if (int r = agc_lz_run(ctx, 2, sr.data(), 2 * cnt, 0, nullptr, 0, nullptr, nullptr)) return r;
+            d_costs = (const uint32_t*)ctx->scr_out.p;
+        } else {
+            // the chunk-parallel encoder produces the deltas (they stay in its slab), one thread per delta turns it into the vector
+            if (int r = agc_lz_run(ctx, 0, sr.data(), 2 * cnt, 0, nullptr, 0, nullptr, nullptr)) return r;
+            std::vector<CostJob> cj(2 * (size_t)cnt);
+            for (uint32_t i = 0; i < 2 * cnt; ++i) {
+                cj[i].delta_off = ctx->last_slab_off[i]; cj[i].cost_off = (i & 1) ? jobs[i / 2].off2 : jobs[i / 2].off1;
+                cj[i].len = sr[i].len; cj[i].m = 0; cj[i].prefix = sr[i].bound; cj[i].pad = 0;
+            }
+            if (int r = agc_reserve(ctx, ctx->scr_cost, off * 4 + 64)) return r;
+            if (int r = agc_reserve(ctx, ctx->scr_misc, cj.size() * sizeof(CostJob) + 64)) return r;
+            if (int r = agc_reserve(ctx, ctx->counters, 64)) return r;
+            CK(cudaMemsetAsync(ctx->scr_cost.p, 0, off * 4, ctx->st));
+            CK(cudaMemsetAsync(ctx->counters.p, 0, 64, ctx->st));
+            CK(cudaMemcpyAsync(ctx->scr_misc.p, cj.data(), cj.size() * sizeof(CostJob), cudaMemcpyHostToDevice, ctx->st));
+            k_delta_costs<<<(2 * cnt + 63) / 64, 64, 0, ctx->st>>>((const uint8_t*)ctx->scr_out.p, (const uint32_t*)ctx->scr_sizes.p, (const CostJob*)ctx->scr_misc.p,
+                                                                   2 * cnt, ctx->prm.min_match_len, (uint32_t*)ctx->scr_cost.p, (uint32_t*)ctx->counters.p);
+            CKL();
+            d_costs = (const uint32_t*)ctx->scr_cost.p;
+        }
         if (int r = agc_reserve(ctx, ctx->scr_offs, cnt * (sizeof(SplitJob) + 8) + 64)) return r;
         SplitJob* d_jobs = (SplitJob*)ctx->scr_offs.p;
         uint32_t* d_pos = (uint32_t*)(d_jobs + cnt); uint32_t* d_sum = d_pos + cnt;
         CK(cudaMemcpyAsync(d_jobs, jobs.data(), cnt * sizeof(SplitJob), cudaMemcpyHostToDevice, ctx->st));
-        k_split_reduce<<<cnt, 1024, 0, ctx->st>>>((const uint32_t*)ctx->scr_out.p, d_jobs, d_pos, d_sum);
+        k_split_reduce<<<cnt, 1024, 0, ctx->st>>>(d_costs, d_jobs, d_pos, d_sum);
         CKL();
+        uint32_t h_bad = 0;
         CK(cudaMemcpyAsync(out_pos + a, d_pos, cnt * 4, cudaMemcpyDeviceToHost, ctx->st));
         CK(cudaMemcpyAsync(out_sum + a, d_sum, cnt * 4, cudaMemcpyDeviceToHost, ctx->st));
+        if (!use_seq) CK(cudaMemcpyAsync(&h_bad, ctx->counters.p, 4, cudaMemcpyDeviceToHost, ctx->st));
         CK(cudaStreamSynchronize(ctx->st));
+        if (getenv("AGCGPU_TRACE_SPLIT")) fprintf(stderr, "[agcgpu] cost split: %u decisions, %llu cost entries, lz kernels %.2f ms, sequential segments so far %llu of %llu\n", cnt,
+                                                  (unsigned long long)off, ctx->stats.last_lz_kernel_ms, (unsigned long long)ctx->stats.lz_sequential_segments, (unsigned long long)ctx->stats.lz_chunk_segments);
+        if (h_bad & 1u) return agc_fail(ctx, AGCGPU_ECUDA, "cost split: a delta does not cover its segment (internal error)");
+        if (h_bad & 2u) { use_seq = true; goto again; }  // a segment equal to its reference: take the vectors of the sequential parse
         ctx->stats.d2h_bytes += cnt * 8ull; ctx->stats.h2d_bytes += cnt * sizeof(SplitJob);
         a = b;
     }

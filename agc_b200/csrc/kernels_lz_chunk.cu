@@ -65,25 +65,28 @@ __global__ void __launch_bounds__(LZC_THREADS, 2) k_lzc_parse(
         }
         lzc_mbar_wait(&bar, 0);
     }
-    for (uint32_t it = threadIdx.x; it < u.n_items; it += LZC_THREADS) {
+    // every lane of a warp enters the parser together (its scheduler votes); lanes beyond the unit's last item only vote
+    for (uint32_t it0 = 0; it0 < u.n_items; it0 += LZC_THREADS) {
+        const uint32_t it = it0 + threadIdx.x;
+        const bool active = it < u.n_items;
         // item -> (request, chunk): requests of the unit carry the running chunk count (unit_base)
         uint32_t lo = 0, hi = u.count - 1;
         while (lo < hi) { const uint32_t mid = (lo + hi + 1) >> 1; if (reqs[u.first + mid].unit_base <= it + u.item0) lo = mid; else hi = mid - 1; }
         const LzcReq q = reqs[u.first + lo];
-        const uint32_t ch = it + u.item0 - q.unit_base;
+        const uint32_t ch = active ? it + u.item0 - q.unit_base : 0u;
         const uint32_t c0 = ch * LZC_CHUNK, c1 = lzc_min(q.n, c0 + LZC_CHUNK);
         LzcRec R;
         uint8_t* out = cslab + (uint64_t)(q.chunk_first + ch) * LZC_CSLAB;
         if (stage) {
             LzcView<true> a; a.T = P; a.gs = (int64_t)q.gstart; a.n = q.n; a.rc = q.is_rc; a.R = nullptr; a.r_s = lzc_smem_u32(smem);
             a.ht = nullptr; a.ht_s = lzc_smem_u32(smem + g.packed_bytes); a.mask = g.ht_size - 1; a.is_short = g.flags & GRF_SHORT; a.m = g.m;
-            lzc_parse_chunk<true>(a, c0, c1, mml, out, R);
+            lzc_parse_chunk<true>(a, c0, c1, mml, out, R, active);
         } else {
             LzcView<false> a; a.T = P; a.gs = (int64_t)q.gstart; a.n = q.n; a.rc = q.is_rc; a.R = (const uint64_t*)g.packed; a.r_s = 0;
             a.ht = g.ht; a.ht_s = 0; a.mask = g.ht_size - 1; a.is_short = g.flags & GRF_SHORT; a.m = g.m;
-            lzc_parse_chunk<false>(a, c0, c1, mml, out, R);
+            lzc_parse_chunk<false>(a, c0, c1, mml, out, R, active);
         }
-        recs[q.chunk_first + ch] = R;
+        if (active) recs[q.chunk_first + ch] = R;
     }
 }
 

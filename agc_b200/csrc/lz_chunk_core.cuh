@@ -12,6 +12,14 @@
 #ifndef AGC_EMPTY32
 #define AGC_EMPTY32 0xffffffffu
 #endif
+// warp votes of the parser's scheduler: the whole warp calls lzc_parse_chunk together on the device; one lane on the host
+#ifdef __CUDA_ARCH__
+#define LZC_BALLOT(p) __ballot_sync(0xffffffffu, (p))
+#define LZC_POPC(x) __popc(x)
+#else
+#define LZC_BALLOT(p) ((p) ? 1u : 0u)
+#define LZC_POPC(x) ((x) ? 1 : 0)
+#endif
 
 // ---- portable forms of the intrinsics the device code uses
 LZC_HD uint32_t lzc_min(uint32_t a, uint32_t b) { return a < b ? a : b; }
@@ -173,80 +181,115 @@ LZC_HD bool lzc_best_match_full(const LzcView<STAGED>& a, uint32_t h, uint64_t x
 
 // ------------------------------------------------------------------------------------------------ phase 1: one thread, one chunk
 template <bool STAGED>
-LZC_HD void lzc_parse_chunk(const LzcView<STAGED>& a, uint32_t c0, uint32_t c1, uint32_t mml, uint8_t* __restrict__ out, LzcRec& R)
+LZC_HD void lzc_parse_chunk(const LzcView<STAGED>& a, uint32_t c0, uint32_t c1, uint32_t mml, uint8_t* __restrict__ out, LzcRec& R, bool active = true)
 {
     const uint32_t kl = mml - 3u, n = a.n, m = a.m;
     uint32_t i = c0, np = 0, pred = 0, olen = 0, flags = 0;
     bool have_first = false, neq_checked = (n != m), ended_open = false;
     int32_t end_diag = 0;
     R.lit0 = 0; R.first_p = R.first_ts = R.first_mp = R.first_len = 0; R.open_ts = R.open_mp = R.open_predb = 0;
-    while (i < c1 && i + kl < n) {
-        const uint64_t x = a.twin(i) >> (64 - 2 * kl);
-        const uint32_t h = (uint32_t)lzc_murmur64(x) & a.mask;
-        // candidates: slots until the first empty one whose key equals the text's (find_best_match's "f_len >= key_len")
-        uint32_t ncand = 0, hp0 = 0;
-        for (uint32_t t = 0; t < 64; ++t) {
-            const uint32_t v = a.slot((h + t) & a.mask);
-            if (v == AGC_EMPTY32) break;
-            if ((a.rwin(v * 4u) >> (64 - 2 * kl)) == x) { if (!ncand) hp0 = v * 4u; ++ncand; if (ncand > 1) break; }
-        }
-        bool ok = false, open = false;
-        uint32_t hp = 0, b = 0, f = 0;
-        bool np_limited = false, multi = false;
-        if (ncand == 1) {
-            hp = hp0;
-            const uint32_t maxlen = lzc_min(n - i, m - hp);
-            const uint32_t cap = lzc_max(c1 - i, mml + 1u);                 // enough to decide "b + f > min_match_len" whatever b is
-            const uint32_t lim_f = lzc_min(maxlen, cap);
-            f = a.lcp_fwd(i, hp, lim_f);
-            const uint32_t lim = lzc_min(np, hp);
-            b = lim ? a.lcp_bwd(i, hp, lim) : 0u;
-            np_limited = (b == np && np < hp);
-            ok = b + f > mml;
-            open = ok && f == lim_f && lim_f < maxlen;
-        } else if (ncand > 1) {
-            multi = true;
-            ok = lzc_best_match_full<STAGED>(a, h, x, i, np, kl, mml, hp, b, f, np_limited);
-        }
-        if (!ok) {
-            // a candidate that failed although its backward extension was cut short by no_prev_literals: with the true (possibly
-            // larger) count it might have succeeded -- only matters before the chunk's first match
-            if (!have_first && np_limited) flags |= LZC_SENS;
-            if (!neq_checked) { neq_checked = true; if (a.tsym(i) != a.rsym(i)) flags |= LZC_NEQ; }
-            ++i; ++np;
+    // Warp-cooperative state machine.  A lane is EXTENDING (stepping a forward extension, 64 bases per step -- almost all of the
+    // work), in NEED of the rare path (resolve a finished extension: backward part, decision, token output; then probe positions
+    // until the next extension starts) or DONE.  The lanes of a warp are all at different places of their chunks, so left alone
+    // every iteration would pay for both paths with a handful of lanes active in each.  Instead the warp votes: extension steps run
+    // while at least half of the lanes extend; lanes that need the rare path park until 16 of them wait (or nobody extends) and are
+    // then served together.  Both paths run with most lanes active.  (Host build: one lane, the votes are trivial.)
+    enum { ST_NEED = 0, ST_EXT = 1, ST_DONE = 2 };
+    int st = active ? ST_NEED : ST_DONE;
+    bool pending = false;                                 // a finished extension waits for its resolve
+    uint32_t e_hp = 0, e_off = 0, e_lim = 0, e_maxlen = 0, e_f = 0;
+    for (;;) {
+        const uint32_t m_ext = LZC_BALLOT(st == ST_EXT), m_need = LZC_BALLOT(st == ST_NEED);
+        if (!(m_ext | m_need)) break;
+        if (m_ext != 0 && LZC_POPC(m_need) < 16) {
+            if (st == ST_EXT) {
+                // matching_length(text + i, ref + e_hp, e_lim), two 32-base windows per step
+                const uint64_t x0 = a.twin((int64_t)i + e_off) ^ a.rwin((int64_t)e_hp + e_off);
+                const uint64_t x1 = a.twin((int64_t)i + e_off + 32) ^ a.rwin((int64_t)e_hp + e_off + 32);
+                bool fin = true;
+                if (x0) e_f = e_off + (lzc_clz64(x0) >> 1);
+                else if (x1) e_f = e_off + 32u + (lzc_clz64(x1) >> 1);
+                else { e_off += 64; if (e_off < e_lim) fin = false; else e_f = e_lim; }
+                if (fin) { if (e_f > e_lim) e_f = e_lim; pending = true; st = ST_NEED; }
+            }
             continue;
         }
-        const uint32_t ts = i - b, mp = hp - b, len = b + f;
-        np -= b;                                                         // literals [ts - np, ts) stay pending
-        if (!have_first) {
-            have_first = true;
-            flags |= LZC_HAS_FIRST | (open ? LZC_FIRST_OPEN : 0u) | (multi ? LZC_FIRST_MULTI : 0u);
-            if (np_limited && ts == c0) flags |= LZC_FIRST_BLIM;        // back extension reached the chunk start: may go on before it
-            if (multi && np_limited) flags |= LZC_SENS;                 // candidate choice depends on the true no_prev_literals
-            R.lit0 = np; R.first_p = i; R.first_ts = ts; R.first_mp = mp; R.first_len = len;
-            for (uint32_t j = 0; j < np; ++j) out[olen + j] = (uint8_t)('A' + a.tsym(ts - np + j));
-            olen += np;
-            if (!(n == m && ts == c0 && mp == c0)) { if (!neq_checked && np) { neq_checked = true; if (a.tsym(ts - np) != a.rsym(ts - np)) flags |= LZC_NEQ; } }
-        } else {
-            const uint32_t pred_now = pred + np;
-            const bool bang = (mp == pred_now);
-            for (uint32_t j = 0; j < np; ++j) {
-                const uint32_t q = ts - np + j, sy = a.tsym(q);
-                uint8_t ch = (uint8_t)('A' + sy);
-                const uint32_t d = np - j;                               // distance back from the match (lz_diff.cpp:772)
-                if (bang && d < mp && sy == a.rsym(mp - d)) ch = '!';
-                out[olen + j] = ch;
+        while (st == ST_NEED) {
+            bool ok = false, open = false;
+            uint32_t hp = 0, b = 0, f = 0;
+            bool np_limited = false, multi = false;
+            if (pending) {
+                pending = false;
+                hp = e_hp; f = e_f;
+                const uint32_t lim = lzc_min(np, hp);
+                b = lim ? a.lcp_bwd(i, hp, lim) : 0u;
+                np_limited = (b == np && np < hp);
+                ok = b + f > mml;
+                open = ok && f == e_lim && e_lim < e_maxlen;
+            } else {
+                if (!(i < c1 && i + kl < n)) { st = ST_DONE; break; }
+                const uint64_t x = a.twin(i) >> (64 - 2 * kl);
+                const uint32_t h = (uint32_t)lzc_murmur64(x) & a.mask;
+                // candidates: slots until the first empty one whose key equals the text's (find_best_match's "f_len >= key_len")
+                uint32_t ncand = 0, hp0 = 0;
+                for (uint32_t t = 0; t < 64; ++t) {
+                    const uint32_t v = a.slot((h + t) & a.mask);
+                    if (v == AGC_EMPTY32) break;
+                    if ((a.rwin(v * 4u) >> (64 - 2 * kl)) == x) { if (!ncand) hp0 = v * 4u; ++ncand; if (ncand > 1) break; }
+                }
+                if (ncand == 1) {
+                    e_hp = hp0; e_off = 0;
+                    e_maxlen = lzc_min(n - i, m - hp0);
+                    e_lim = lzc_min(e_maxlen, lzc_max(c1 - i, mml + 1u));   // cap: enough to decide "b + f > min_match_len" whatever b is
+                    st = ST_EXT;
+                    break;
+                }
+                if (ncand > 1) {
+                    multi = true;
+                    ok = lzc_best_match_full<STAGED>(a, h, x, i, np, kl, mml, hp, b, f, np_limited);
+                }
             }
-            olen += np;
-            if (open) { flags |= LZC_END_OPEN; R.open_ts = ts; R.open_mp = mp; R.open_predb = pred_now; }
-            else {
-                const bool to_end = (ts + len == n) && (mp + len == m);
-                olen += lzc_put_match(out + olen, (int64_t)(int)mp - (int64_t)(int)pred_now, !to_end, len - mml);
+            if (!ok) {
+                // a candidate that failed although its backward extension was cut short by no_prev_literals: with the true (possibly
+                // larger) count it might have succeeded -- only matters before the chunk's first match
+                if (!have_first && np_limited) flags |= LZC_SENS;
+                if (!neq_checked) { neq_checked = true; if (a.tsym(i) != a.rsym(i)) flags |= LZC_NEQ; }
+                ++i; ++np;
+                continue;
             }
+            const uint32_t ts = i - b, mp = hp - b, len = b + f;
+            np -= b;                                                         // literals [ts - np, ts) stay pending
+            if (!have_first) {
+                have_first = true;
+                flags |= LZC_HAS_FIRST | (open ? LZC_FIRST_OPEN : 0u) | (multi ? LZC_FIRST_MULTI : 0u);
+                if (np_limited && ts == c0) flags |= LZC_FIRST_BLIM;        // back extension reached the chunk start: may go on before it
+                if (multi && np_limited) flags |= LZC_SENS;                 // candidate choice depends on the true no_prev_literals
+                R.lit0 = np; R.first_p = i; R.first_ts = ts; R.first_mp = mp; R.first_len = len;
+                for (uint32_t j = 0; j < np; ++j) out[olen + j] = (uint8_t)('A' + a.tsym(ts - np + j));
+                olen += np;
+                if (!(n == m && ts == c0 && mp == c0)) { if (!neq_checked && np) { neq_checked = true; if (a.tsym(ts - np) != a.rsym(ts - np)) flags |= LZC_NEQ; } }
+            } else {
+                const uint32_t pred_now = pred + np;
+                const bool bang = (mp == pred_now);
+                for (uint32_t j = 0; j < np; ++j) {
+                    const uint32_t q = ts - np + j, sy = a.tsym(q);
+                    uint8_t ch = (uint8_t)('A' + sy);
+                    const uint32_t d = np - j;                               // distance back from the match (lz_diff.cpp:772)
+                    if (bang && d < mp && sy == a.rsym(mp - d)) ch = '!';
+                    out[olen + j] = ch;
+                }
+                olen += np;
+                if (open) { flags |= LZC_END_OPEN; R.open_ts = ts; R.open_mp = mp; R.open_predb = pred_now; }
+                else {
+                    const bool to_end = (ts + len == n) && (mp + len == m);
+                    olen += lzc_put_match(out + olen, (int64_t)(int)mp - (int64_t)(int)pred_now, !to_end, len - mml);
+                }
+            }
+            pred = mp + len; i = ts + len; np = 0; end_diag = (int32_t)mp - (int32_t)ts;
+            if (open) { ended_open = true; st = ST_DONE; }
         }
-        pred = mp + len; i = ts + len; np = 0; end_diag = (int32_t)mp - (int32_t)ts;
-        if (open) { ended_open = true; break; }
     }
+    if (!active) return;
     // tail of the text (positions the sequential loop never probes) and literals pending at the chunk's end: raw letters
     if (!ended_open && i < c1 && i + kl >= n) { const uint32_t e = lzc_min(c1, n); np += e - i; i = e; }
     if (np) {

@@ -1,7 +1,5 @@
 mkdir -p gpurun_out
-timeout 300 python tools/lzc_debug.py 1 9000 2>&1 | tail -8
-timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_pipeline.py -m gpu -x -q 2>&1 | tail -8 > gpurun_out/c8_tests.log; cat gpurun_out/c8_tests.log
-(timeout 300 python tools/lz_hpp_bench.py 4096 0.001 64; timeout 300 python tools/lz_hpp_bench.py 16384 0.001 256; timeout 300 python tools/lz_hpp_bench.py 4096 0.01 64; AGCGPU_LZC_NOSTAGE=1 timeout 300 python tools/lz_hpp_bench.py 16384 0.001 256) > gpurun_out/c8_lz.log 2>&1; cat gpurun_out/c8_lz.log
-sed -i 's/| tail -12//; s/grep -E "real|wave|phase"/grep -vE "phase (scan|assign|find_new|add_seg)|agcgpu.   frame"/' tools/run_c3_cli.sh
-THREADS=$(nproc) timeout 600 bash tools/run_c3_cli.sh > gpurun_out/c8_c3.log 2>&1
-tail -22 gpurun_out/c8_c3.log
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_lzc_parse -s 2 -c 1 -o gpurun_out/c12_parse_1pct python tools/lz_hpp_bench.py 4096 0.01 64 > /dev/null 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_lzc_parse -s 2 -c 1 -o gpurun_out/c12_parse_01pct python tools/lz_hpp_bench.py 16384 0.001 256 > /dev/null 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_lzc_stitch -s 2 -c 1 -o gpurun_out/c12_stitch_01pct python tools/lz_hpp_bench.py 16384 0.001 256 > /dev/null 2>&1
+ls -la gpurun_out/*.ncu-rep
