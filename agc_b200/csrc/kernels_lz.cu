@@ -1000,9 +1000,9 @@ int agc_lz_run(agcgpu_ctx* ctx, int mode, const agcgpu_seg_req* reqs, uint32_t n
         return 0;
     };
     static const bool no_chunks = getenv("AGCGPU_LZ_SEQUENTIAL") != nullptr;          // diagnostics: force the sequential kernel
-    if (!packed_reqs.empty() && mode == 0 && !no_chunks) {
-        // ---- chunk-parallel encode (kernels_lz_chunk.cu): thread per chunk, then thread per segment; segments the stitcher
-        // could not prove identical to the sequential parse are redone by the sequential kernel
+    if (!packed_reqs.empty() && (mode == 0 || mode == 2) && !no_chunks) {
+        // ---- chunk-parallel encode / cost vectors (kernels_lz_chunk.cu): thread per chunk, then thread per segment; segments the
+        // stitcher could not prove identical to the sequential parse are redone by the sequential kernel
         const size_t nr = packed_reqs.size();
         std::vector<LzcReq> cr(nr);
         std::vector<LzcUnit> cu;
@@ -1019,7 +1019,7 @@ int agc_lz_run(agcgpu_ctx* ctx, int mode, const agcgpu_seg_req* reqs, uint32_t n
                 const LzReqDev& q = packed_reqs[i];
                 LzcReq& c = cr[i];
                 c.gstart = q.gstart; c.n = q.n; c.is_rc = q.is_rc; c.group = q.group; c.chunk_first = (uint32_t)n_chunks;
-                c.nch = std::max<uint32_t>(1u, (q.n + LZC_CHUNK - 1) / LZC_CHUNK); c.unit_base = base; c.out_off = q.out_off; c.out_cap = q.out_cap; c.orig = q.orig;
+                c.nch = std::max<uint32_t>(1u, (q.n + LZC_CHUNK - 1) / LZC_CHUNK); c.unit_base = base; c.out_off = q.out_off; c.out_cap = mode == 2 ? q.bound : q.out_cap; c.orig = q.orig;
                 base += c.nch; n_chunks += c.nch;
             }
             // all requests of the group share one running chunk count; a unit is a slice of UNIT_ITEMS chunks of it
@@ -1038,12 +1038,13 @@ int agc_lz_run(agcgpu_ctx* ctx, int mode, const agcgpu_seg_req* reqs, uint32_t n
         CK(cudaMemcpyAsync(ctx->scr_req.p, cr.data(), nr * sizeof(LzcReq), cudaMemcpyHostToDevice, ctx->st));
         CK(cudaMemcpyAsync(ctx->scr_units.p, cu.data(), cu.size() * sizeof(LzcUnit), cudaMemcpyHostToDevice, ctx->st));
         ctx->stats.h2d_bytes += nr * sizeof(LzcReq) + cu.size() * sizeof(LzcUnit);
+        if (mode == 2) CK(cudaMemsetAsync(costv, 0, slab_total * 4, ctx->st));      // the chunks only write the non-zero entries
         CK(cudaEventRecord(ctx->ev0, ctx->st));
         LzcRec* d_rec = (LzcRec*)ctx->scr_rec.p;
         uint32_t* d_fb = (uint32_t*)(d_rec + n_chunks);
         uint32_t* cnt2 = (uint32_t*)ctx->counters.p;                       // [0] segments for the sequential kernel, [1] overflow
         if (int r = agc_lzc_launch(ctx, (const LzcReq*)ctx->scr_req.p, (uint32_t)nr, (const LzcUnit*)ctx->scr_units.p, (uint32_t)cu.size(),
-                                   std::max<size_t>(smem_c, 1024), (uint8_t*)ctx->scr_chunk.p, d_rec, slab, res, d_fb, cnt2)) return r;
+                                   std::max<size_t>(smem_c, 1024), (uint8_t*)ctx->scr_chunk.p, d_rec, slab, res, d_fb, cnt2, mode == 2 ? costv : nullptr)) return r;
         CK(cudaEventRecord(ctx->ev1, ctx->st));
         uint32_t h_cnt[2] = { 0, 0 };
         CK(cudaMemcpyAsync(h_cnt, cnt2, 8, cudaMemcpyDeviceToHost, ctx->st));
@@ -1203,59 +1204,8 @@ __global__ void __launch_bounds__(1024) k_split_reduce(const uint32_t* __restric
     }
 }
 
-// GetCodingCostVector (lz_diff.cpp:159-284) runs the same parse as Encode (with the rewind), so its vector is a function of the
-// delta: a literal (letter or '!') costs 1 at its position, an N-run / match token costs its printed length at the first
-// (prefix_costs) or last position it covers -- coding_cost_match always counts the length field, which Encode omits for a match
-// that reaches both ends (lz_diff.cpp:781-784), and Encode's "equal sequences" shortcut (678-680) is one match over everything.
-// One thread walks one delta; the vectors were zero-filled before.
-struct CostJob { uint64_t delta_off, cost_off; uint32_t len, m, prefix, pad; };
-__device__ __forceinline__ uint32_t int_len_dev(uint32_t x)
-{
-    return x < 10 ? 1 : x < 100 ? 2 : x < 1000 ? 3 : x < 10000 ? 4 : x < 100000 ? 5 : x < 1000000 ? 6 : x < 10000000 ? 7
-         : x < 100000000 ? 8 : x < 1000000000 ? 9 : 10;
-}
-__global__ void k_delta_costs(const uint8_t* __restrict__ slab, const uint32_t* __restrict__ sizes, const CostJob* __restrict__ jobs, uint32_t n_jobs,
-                              uint32_t mml, uint32_t* __restrict__ costv, uint32_t* __restrict__ bad)
-{
-    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n_jobs) return;
-    const CostJob j = jobs[r];
-    const uint8_t* d = slab + j.delta_off;
-    const uint32_t e = sizes[r], n = j.len;
-    uint32_t* v = costv + j.cost_off;
-    auto put = [&](uint32_t pos, uint32_t len, uint32_t tc) { if (pos + len <= n && len) v[j.prefix ? pos : pos + len - 1] = tc; else atomicOr(bad, 1u); };
-    if (e == 0) { if (n) atomicOr(bad, 2u); return; }    // Encode's "equal sequences" shortcut: the sequential kernel makes this vector
-    uint32_t pos = 0, i = 0;
-    while (i < e) {
-        const uint8_t c = d[i];
-        if ((c >= 'A' && c <= 'A' + 30) || c == '!') { if (pos < n) v[pos] = 1; else atomicOr(bad, 1u); ++pos; ++i; continue; }
-        if (c == 30) {                                   // N-run: 0x1e <len - 4> 0x04 (lz_diff.h:152-157)
-            uint32_t k = i + 1, val = 0;
-            while (k < e && d[k] >= '0' && d[k] <= '9') { val = val * 10 + (d[k] - '0'); ++k; }
-            const uint32_t len = val + 4;
-            put(pos, len, k + 1 - i);
-            pos += len; i = k + 1;
-            continue;
-        }
-        // match: <signed dif>[,<len - min_match_len>].
-        uint32_t k = i;
-        while (k < e && d[k] != ',' && d[k] != '.') ++k;
-        uint32_t tc = k - i, len;
-        if (k < e && d[k] == ',') {
-            uint32_t val = 0; ++k;
-            const uint32_t k0 = k;
-            while (k < e && d[k] != '.') { val = val * 10 + (d[k] - '0'); ++k; }
-            len = val + mml; tc += 1 + (k - k0) + 1;
-        } else { len = n - pos; tc += int_len_dev(len - mml) + 2; }
-        put(pos, len, tc);
-        pos += len; i = k + 1;
-    }
-    if (pos != n) atomicOr(bad, 1u);
-}
-
 int agc_lz_cost_split(agcgpu_ctx* ctx, const agcgpu_split_req* reqs, uint32_t n, uint32_t* out_pos, uint32_t* out_sum)
 {
-    static const bool seq_costs = getenv("AGCGPU_LZ_SEQUENTIAL") != nullptr;        // diagnostics: cost vectors from the sequential kernel
     // sub-batches bounded by the size of the cost vectors (2 x len x 4 bytes per decision)
     const uint64_t budget = 1ull << 30;
     for (uint32_t a = 0; a < n;) {
@@ -1277,46 +1227,20 @@ int agc_lz_cost_split(agcgpu_ctx* ctx, const agcgpu_split_req* reqs, uint32_t n,
             jobs[i].rev1 = (q.flags >> 2) & 1u; jobs[i].rev2 = (q.flags >> 5) & 1u; jobs[i].pad = 0;
             off += 2ull * q.len;
         }
-        const uint32_t* d_costs = nullptr;
-        bool use_seq = seq_costs;
-      again:
-        if (use_seq) {
-            if (int r = agc_lz_run(ctx, 2, sr.data(), 2 * cnt, 0, nullptr, 0, nullptr, nullptr)) return r;
-            d_costs = (const uint32_t*)ctx->scr_out.p;
-        } else {
-            // the chunk-parallel encoder produces the deltas (they stay in its slab), one thread per delta turns it into the vector
-            if (int r = agc_lz_run(ctx, 0, sr.data(), 2 * cnt, 0, nullptr, 0, nullptr, nullptr)) return r;
-            std::vector<CostJob> cj(2 * (size_t)cnt);
-            for (uint32_t i = 0; i < 2 * cnt; ++i) {
-                cj[i].delta_off = ctx->last_slab_off[i]; cj[i].cost_off = (i & 1) ? jobs[i / 2].off2 : jobs[i / 2].off1;
-                cj[i].len = sr[i].len; cj[i].m = 0; cj[i].prefix = sr[i].bound; cj[i].pad = 0;
-            }
-            if (int r = agc_reserve(ctx, ctx->scr_cost, off * 4 + 64)) return r;
-            if (int r = agc_reserve(ctx, ctx->scr_misc, cj.size() * sizeof(CostJob) + 64)) return r;
-            if (int r = agc_reserve(ctx, ctx->counters, 64)) return r;
-            CK(cudaMemsetAsync(ctx->scr_cost.p, 0, off * 4, ctx->st));
-            CK(cudaMemsetAsync(ctx->counters.p, 0, 64, ctx->st));
-            CK(cudaMemcpyAsync(ctx->scr_misc.p, cj.data(), cj.size() * sizeof(CostJob), cudaMemcpyHostToDevice, ctx->st));
-            k_delta_costs<<<(2 * cnt + 63) / 64, 64, 0, ctx->st>>>((const uint8_t*)ctx->scr_out.p, (const uint32_t*)ctx->scr_sizes.p, (const CostJob*)ctx->scr_misc.p,
-                                                                   2 * cnt, ctx->prm.min_match_len, (uint32_t*)ctx->scr_cost.p, (uint32_t*)ctx->counters.p);
-            CKL();
-            d_costs = (const uint32_t*)ctx->scr_cost.p;
-        }
+        // the cost vectors come from the chunk-parallel parse in cost mode (agc_lz_run mode 2) and stay on the device
+        if (int r = agc_lz_run(ctx, 2, sr.data(), 2 * cnt, 0, nullptr, 0, nullptr, nullptr)) return r;
+        const uint32_t* d_costs = (const uint32_t*)ctx->scr_out.p;
         if (int r = agc_reserve(ctx, ctx->scr_offs, cnt * (sizeof(SplitJob) + 8) + 64)) return r;
         SplitJob* d_jobs = (SplitJob*)ctx->scr_offs.p;
         uint32_t* d_pos = (uint32_t*)(d_jobs + cnt); uint32_t* d_sum = d_pos + cnt;
         CK(cudaMemcpyAsync(d_jobs, jobs.data(), cnt * sizeof(SplitJob), cudaMemcpyHostToDevice, ctx->st));
         k_split_reduce<<<cnt, 1024, 0, ctx->st>>>(d_costs, d_jobs, d_pos, d_sum);
         CKL();
-        uint32_t h_bad = 0;
         CK(cudaMemcpyAsync(out_pos + a, d_pos, cnt * 4, cudaMemcpyDeviceToHost, ctx->st));
         CK(cudaMemcpyAsync(out_sum + a, d_sum, cnt * 4, cudaMemcpyDeviceToHost, ctx->st));
-        if (!use_seq) CK(cudaMemcpyAsync(&h_bad, ctx->counters.p, 4, cudaMemcpyDeviceToHost, ctx->st));
         CK(cudaStreamSynchronize(ctx->st));
         if (getenv("AGCGPU_TRACE_SPLIT")) fprintf(stderr, "[agcgpu] cost split: %u decisions, %llu cost entries, lz kernels %.2f ms, sequential segments so far %llu of %llu\n", cnt,
                                                   (unsigned long long)off, ctx->stats.last_lz_kernel_ms, (unsigned long long)ctx->stats.lz_sequential_segments, (unsigned long long)ctx->stats.lz_chunk_segments);
-        if (h_bad & 1u) return agc_fail(ctx, AGCGPU_ECUDA, "cost split: a delta does not cover its segment (internal error)");
-        if (h_bad & 2u) { use_seq = true; goto again; }  // a segment equal to its reference: take the vectors of the sequential parse
         ctx->stats.d2h_bytes += cnt * 8ull; ctx->stats.h2d_bytes += cnt * sizeof(SplitJob);
         a = b;
     }

@@ -45,12 +45,39 @@ __device__ __forceinline__ void lzc_mbar_wait(uint64_t* bar, uint32_t phase)
         "DONE_%=:\n\t}" :: "r"(lzc_smem_u32(bar)), "r"(phase) : "memory");
 }
 
+// hands the chunks of a unit to the lanes: item -> (request, chunk) through the running chunk count the requests carry (unit_base)
+template <bool COSTS>
+struct DevFetch {
+    const LzcReq* reqs; LzcUnit u; uint32_t* next; uint8_t* cslab; LzcRec* recs; uint32_t* costv;
+    template <bool STAGED>
+    __device__ __forceinline__ bool operator()(LzcView<STAGED>& a, LzcItem& it)
+    {
+        const uint32_t k = atomicAdd(next, 1u);
+        if (k >= u.n_items) return false;
+        uint32_t lo = 0, hi = u.count - 1;
+        while (lo < hi) { const uint32_t mid = (lo + hi + 1) >> 1; if (reqs[u.first + mid].unit_base <= k + u.item0) lo = mid; else hi = mid - 1; }
+        const LzcReq q = reqs[u.first + lo];
+        const uint32_t ch = k + u.item0 - q.unit_base;
+        a.gs = (int64_t)q.gstart; a.n = q.n; a.rc = q.is_rc;
+        it.c0 = ch * LZC_CHUNK; it.c1 = lzc_min(q.n, it.c0 + LZC_CHUNK);
+        it.out = cslab + (uint64_t)(q.chunk_first + ch) * LZC_CSLAB;
+        it.rec = recs + q.chunk_first + ch;
+        it.v = COSTS ? costv + q.out_off : nullptr; it.prefix = q.out_cap;
+        return true;
+    }
+};
+
+// COSTS: cost vectors instead of deltas (GetCodingCostVector): request q's vector starts at costv + q.out_off, q.out_cap = prefix_costs
+template <bool COSTS>
 __global__ void __launch_bounds__(LZC_THREADS, 2) k_lzc_parse(
     const uint64_t* __restrict__ P, const GroupRefDev* __restrict__ groups, const LzcReq* __restrict__ reqs,
-    const LzcUnit* __restrict__ units, uint32_t mml, uint32_t stage_limit, uint8_t* __restrict__ cslab, LzcRec* __restrict__ recs)
+    const LzcUnit* __restrict__ units, uint32_t mml, uint32_t stage_limit, uint8_t* __restrict__ cslab, LzcRec* __restrict__ recs,
+    uint32_t* __restrict__ costv)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t s_next;
+    if (threadIdx.x == 0) s_next = 0;
     const LzcUnit u = units[blockIdx.x];
     const GroupRefDev g = groups[u.group];
     const uint32_t ht_bytes = g.ht_size * ((g.flags & GRF_SHORT) ? 2u : 4u);
@@ -65,36 +92,26 @@ __global__ void __launch_bounds__(LZC_THREADS, 2) k_lzc_parse(
         }
         lzc_mbar_wait(&bar, 0);
     }
-    // every lane of a warp enters the parser together (its scheduler votes); lanes beyond the unit's last item only vote
-    for (uint32_t it0 = 0; it0 < u.n_items; it0 += LZC_THREADS) {
-        const uint32_t it = it0 + threadIdx.x;
-        const bool active = it < u.n_items;
-        // item -> (request, chunk): requests of the unit carry the running chunk count (unit_base)
-        uint32_t lo = 0, hi = u.count - 1;
-        while (lo < hi) { const uint32_t mid = (lo + hi + 1) >> 1; if (reqs[u.first + mid].unit_base <= it + u.item0) lo = mid; else hi = mid - 1; }
-        const LzcReq q = reqs[u.first + lo];
-        const uint32_t ch = active ? it + u.item0 - q.unit_base : 0u;
-        const uint32_t c0 = ch * LZC_CHUNK, c1 = lzc_min(q.n, c0 + LZC_CHUNK);
-        LzcRec R;
-        uint8_t* out = cslab + (uint64_t)(q.chunk_first + ch) * LZC_CSLAB;
-        if (stage) {
-            LzcView<true> a; a.T = P; a.gs = (int64_t)q.gstart; a.n = q.n; a.rc = q.is_rc; a.R = nullptr; a.r_s = lzc_smem_u32(smem);
-            a.ht = nullptr; a.ht_s = lzc_smem_u32(smem + g.packed_bytes); a.mask = g.ht_size - 1; a.is_short = g.flags & GRF_SHORT; a.m = g.m;
-            lzc_parse_chunk<true>(a, c0, c1, mml, out, R, active);
-        } else {
-            LzcView<false> a; a.T = P; a.gs = (int64_t)q.gstart; a.n = q.n; a.rc = q.is_rc; a.R = (const uint64_t*)g.packed; a.r_s = 0;
-            a.ht = g.ht; a.ht_s = 0; a.mask = g.ht_size - 1; a.is_short = g.flags & GRF_SHORT; a.m = g.m;
-            lzc_parse_chunk<false>(a, c0, c1, mml, out, R, active);
-        }
-        if (active) recs[q.chunk_first + ch] = R;
+    // every lane pulls chunks from the unit's counter until none is left (lzc_parse_stream)
+    __syncthreads();
+    DevFetch<COSTS> fetch; fetch.reqs = reqs; fetch.u = u; fetch.next = &s_next; fetch.cslab = cslab; fetch.recs = recs; fetch.costv = costv;
+    if (stage) {
+        LzcView<true> a; a.T = P; a.gs = 0; a.n = 0; a.rc = 0; a.R = nullptr; a.r_s = lzc_smem_u32(smem);
+        a.ht = nullptr; a.ht_s = lzc_smem_u32(smem + g.packed_bytes); a.mask = g.ht_size - 1; a.is_short = g.flags & GRF_SHORT; a.m = g.m;
+        lzc_parse_stream<true, COSTS>(a, mml, fetch);
+    } else {
+        LzcView<false> a; a.T = P; a.gs = 0; a.n = 0; a.rc = 0; a.R = (const uint64_t*)g.packed; a.r_s = 0;
+        a.ht = g.ht; a.ht_s = 0; a.mask = g.ht_size - 1; a.is_short = g.flags & GRF_SHORT; a.m = g.m;
+        lzc_parse_stream<false, COSTS>(a, mml, fetch);
     }
 }
 
 // ------------------------------------------------------------------------------------------------ phase 2: one thread, one segment
+template <bool COSTS>
 __global__ void __launch_bounds__(128) k_lzc_stitch(
     const uint64_t* __restrict__ P, const GroupRefDev* __restrict__ groups, const LzcReq* __restrict__ reqs, uint32_t n_req,
     uint32_t mml, const uint8_t* __restrict__ cslab, const LzcRec* __restrict__ recs, uint8_t* __restrict__ slab,
-    uint32_t* __restrict__ res, uint32_t* __restrict__ fb, uint32_t* __restrict__ counters)
+    uint32_t* __restrict__ res, uint32_t* __restrict__ fb, uint32_t* __restrict__ counters, uint32_t* __restrict__ costv)
 {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_req) return;
@@ -102,7 +119,8 @@ __global__ void __launch_bounds__(128) k_lzc_stitch(
     const GroupRefDev g = groups[q.group];
     LzcView<false> a; a.T = P; a.gs = (int64_t)q.gstart; a.n = q.n; a.rc = q.is_rc; a.R = (const uint64_t*)g.packed; a.r_s = 0;
     a.ht = g.ht; a.ht_s = 0; a.mask = g.ht_size - 1; a.is_short = g.flags & GRF_SHORT; a.m = g.m;
-    const int64_t o = lzc_stitch_segment(a, q, mml, recs + q.chunk_first, cslab + (uint64_t)q.chunk_first * LZC_CSLAB, slab + q.out_off, q.out_cap);
+    const int64_t o = COSTS ? lzc_stitch_segment<LzcView<false>, true>(a, q, mml, recs + q.chunk_first, nullptr, nullptr, 0, costv + q.out_off, q.out_cap)
+                            : lzc_stitch_segment<LzcView<false>, false>(a, q, mml, recs + q.chunk_first, cslab + (uint64_t)q.chunk_first * LZC_CSLAB, slab + q.out_off, q.out_cap);
     if (o <= -10) { fb[r] = 1; atomicAdd(counters + 0, 1u); res[q.orig] = 0; return; }
     fb[r] = 0;
     if (o == -2) { atomicOr(counters + 1, 1u); res[q.orig] = 0; return; }
@@ -111,16 +129,23 @@ __global__ void __launch_bounds__(128) k_lzc_stitch(
 
 // ------------------------------------------------------------------------------------------------ host side
 int agc_lzc_launch(agcgpu_ctx* ctx, const LzcReq* d_reqs, uint32_t n_req, const LzcUnit* d_units, uint32_t n_units, size_t smem,
-                   uint8_t* cslab, LzcRec* recs, uint8_t* slab, uint32_t* res, uint32_t* fb, uint32_t* counters)
+                   uint8_t* cslab, LzcRec* recs, uint8_t* slab, uint32_t* res, uint32_t* fb, uint32_t* counters, uint32_t* costv)
 {
     static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(k_lzc_parse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LZC_STAGE_LIMIT); attr_set = true; }
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_lzc_parse<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LZC_STAGE_LIMIT);
+        cudaFuncSetAttribute(k_lzc_parse<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LZC_STAGE_LIMIT);
+        attr_set = true;
+    }
     static const bool no_stage = getenv("AGCGPU_LZC_NOSTAGE") != nullptr;        // diagnostics: read reference and table from global memory
-    k_lzc_parse<<<n_units, LZC_THREADS, smem, ctx->st>>>((const uint64_t*)ctx->packed.p, (const GroupRefDev*)ctx->d_groups.p, d_reqs, d_units,
-                                                         ctx->prm.min_match_len, no_stage ? 0u : (uint32_t)smem, cslab, recs);
+    const GroupRefDev* groups = (const GroupRefDev*)ctx->d_groups.p;
+    const uint64_t* P = (const uint64_t*)ctx->packed.p;
+    const uint32_t mml = ctx->prm.min_match_len, sl = no_stage ? 0u : (uint32_t)smem;
+    if (costv) k_lzc_parse<true><<<n_units, LZC_THREADS, smem, ctx->st>>>(P, groups, d_reqs, d_units, mml, sl, cslab, recs, costv);
+    else k_lzc_parse<false><<<n_units, LZC_THREADS, smem, ctx->st>>>(P, groups, d_reqs, d_units, mml, sl, cslab, recs, nullptr);
     CKL();
-    k_lzc_stitch<<<(n_req + 127) / 128, 128, 0, ctx->st>>>((const uint64_t*)ctx->packed.p, (const GroupRefDev*)ctx->d_groups.p, d_reqs, n_req,
-                                                           ctx->prm.min_match_len, cslab, recs, slab, res, fb, counters);
+    if (costv) k_lzc_stitch<true><<<(n_req + 127) / 128, 128, 0, ctx->st>>>(P, groups, d_reqs, n_req, mml, cslab, recs, slab, res, fb, counters, costv);
+    else k_lzc_stitch<false><<<(n_req + 127) / 128, 128, 0, ctx->st>>>(P, groups, d_reqs, n_req, mml, cslab, recs, slab, res, fb, counters, nullptr);
     CKL();
     return 0;
 }

@@ -36,8 +36,8 @@ struct LzcReq {                    // one segment to encode
     uint32_t chunk_first;          // index of its first chunk record / chunk slab
     uint32_t nch;
     uint32_t unit_base;            // chunks of the requests before it in its unit
-    uint64_t out_off;              // byte offset of its delta in the output slab
-    uint32_t out_cap;
+    uint64_t out_off;              // byte offset of its delta in the output slab (cost vectors: u32 index of its vector)
+    uint32_t out_cap;              // (cost vectors: prefix_costs)
     uint32_t orig;                 // index in the caller's request array
 };
 
@@ -45,4 +45,4 @@ struct LzcUnit { uint32_t group, first, count, item0, n_items, pad; };   // one 
 
 struct agcgpu_ctx;
 int agc_lzc_launch(agcgpu_ctx* ctx, const LzcReq* d_reqs, uint32_t n_req, const LzcUnit* d_units, uint32_t n_units, size_t smem,
-                   uint8_t* cslab, LzcRec* recs, uint8_t* slab, uint32_t* res, uint32_t* fb, uint32_t* counters);
+                   uint8_t* cslab, LzcRec* recs, uint8_t* slab, uint32_t* res, uint32_t* fb, uint32_t* counters, uint32_t* costv = nullptr);

@@ -54,4 +54,37 @@ long lzc_host_encode_rec(const unsigned char* text, unsigned n, const unsigned c
     q.gstart = lead; q.n = n; q.is_rc = is_rc; q.nch = nch; q.out_cap = cap;
     return (long)lzc_stitch_segment(a, q, mml, rec.data(), cslab.data(), out, cap);
 }
+// GetCodingCostVector through the same chunk parse + stitch in cost mode; costs has n entries (zero-filled here).
+// returns 0, or <= -10 when the stitcher hands the segment to the sequential kernel
+__attribute__((visibility("default"))) long lzc_host_costs(const unsigned char* text, unsigned n, const unsigned char* ref, unsigned m,
+                                                           const unsigned* ht, unsigned ht_size, int is_short, unsigned mml, int is_rc, unsigned lead,
+                                                           int prefix, unsigned* costs)
+{
+    auto pack = [](const std::vector<unsigned char>& sym, std::vector<uint64_t>& w) {
+        w.assign(sym.size() / 32 + 4, 0);
+        unsigned char* b = (unsigned char*)w.data();
+        for (size_t i = 0; i < sym.size(); ++i) b[i >> 2] |= (unsigned char)((sym[i] & 3u) << (6 - 2 * (i & 3)));
+    };
+    std::vector<unsigned char> store(lead, 1);
+    if (!is_rc) store.insert(store.end(), text, text + n);
+    else for (unsigned i = 0; i < n; ++i) store.push_back((unsigned char)(3 - text[n - 1 - i]));
+    for (int i = 0; i < 40; ++i) store.push_back(2);
+    std::vector<unsigned char> rs(ref, ref + m);
+    std::vector<uint64_t> T, R; pack(store, T); pack(rs, R);
+    std::vector<uint16_t> h16; std::vector<uint32_t> h32;
+    if (is_short) { h16.resize(ht_size); for (unsigned i = 0; i < ht_size; ++i) h16[i] = ht[i] == 0xffffffffu ? 0xffffu : (uint16_t)ht[i]; }
+    else h32.assign(ht, ht + ht_size);
+    LzcView<false> a; a.T = T.data(); a.gs = lead; a.n = n; a.rc = is_rc; a.R = R.data(); a.r_s = 0;
+    a.ht = is_short ? (const void*)h16.data() : (const void*)h32.data(); a.ht_s = 0; a.mask = ht_size - 1; a.is_short = is_short; a.m = m;
+    const unsigned nch = n ? (n + LZC_CHUNK - 1) / LZC_CHUNK : 1;
+    std::vector<LzcRec> rec(nch);
+    for (unsigned i = 0; i < n; ++i) costs[i] = 0;
+    for (unsigned k = 0; k < nch; ++k) {
+        const unsigned c0 = k * LZC_CHUNK, c1 = lzc_min(n, c0 + LZC_CHUNK);
+        lzc_parse_chunk<false, true>(a, c0, c1, mml, nullptr, rec[k], costs, (unsigned)prefix);
+    }
+    LzcReq q; memset(&q, 0, sizeof q);
+    q.gstart = lead; q.n = n; q.is_rc = is_rc; q.nch = nch; q.out_cap = prefix;
+    return (long)lzc_stitch_segment<LzcView<false>, true>(a, q, mml, rec.data(), nullptr, nullptr, 0, costs, (unsigned)prefix);
+}
 }

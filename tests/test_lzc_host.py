@@ -21,7 +21,18 @@ def lzc():
     L = C.CDLL(os.path.join(d, "liblzc_host.so"))
     L.lzc_host_encode.restype = C.c_long
     L.lzc_host_encode.argtypes = [u8p, C.c_uint, u8p, C.c_uint, u32p, C.c_uint, C.c_int, C.c_uint, C.c_int, C.c_uint, u8p, C.c_uint]
+    L.lzc_host_costs.restype = C.c_long
+    L.lzc_host_costs.argtypes = [u8p, C.c_uint, u8p, C.c_uint, u32p, C.c_uint, C.c_int, C.c_uint, C.c_int, C.c_uint, C.c_int, u32p]
     return L
+
+
+def costs(L, text, ref, mml, z, prefix, is_rc=0, lead=0):
+    ht, short = z.ht()
+    text = np.ascontiguousarray(text, np.uint8); ref = np.ascontiguousarray(ref, np.uint8)
+    out = np.zeros(max(len(text), 1), np.uint32)
+    r = L.lzc_host_costs(text.ctypes.data_as(u8p), len(text), ref.ctypes.data_as(u8p), len(ref), ht.ctypes.data_as(u32p), len(ht),
+                         int(short), mml, is_rc, lead, int(prefix), out.ctypes.data_as(u32p))
+    return r, out[:len(text)]
 
 
 def enc(L, text, ref, mml, z, is_rc=0, lead=0):
@@ -101,3 +112,18 @@ def test_chunk_encoder_edges(lzc):
         for rc in (0, 1):
             r, got = enc(lzc, t, ref, 20, z, rc, 13)
             if r > -10: assert got == z.encode(np.ascontiguousarray(t)), f"edge case {i} rc={rc}"
+
+
+def test_chunk_cost_vectors_fuzz(lzc):
+    """GetCodingCostVector through the chunk parse in cost mode (the missing-middle path): identical vectors, both modes"""
+    n_seq = 0
+    for s in range(240):
+        rng, mml, ref, t = make_case(s)
+        if s % 8 == 5 and len(ref) > 4000:          # the missing-middle shape: the second half of the text does not match this reference
+            t = np.concatenate([t[:len(t) // 2], rng.integers(0, 4, int(rng.integers(500, 9000))).astype(np.uint8)])
+        z = orc.LZ(ref, mml)
+        for prefix in (0, 1):
+            r, got = costs(lzc, t, ref, mml, z, prefix, int(rng.random() < 0.4), int(rng.integers(0, 70)))
+            if r <= -10: n_seq += 1
+            else: assert np.array_equal(got, z.cost_vector(t, prefix)), f"seed {s} prefix {prefix}: cost vector differs from the oracle"
+    assert n_seq <= 24

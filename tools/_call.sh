@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_lzc_parse -s 2 -c 1 -o gpurun_out/c12_parse_1pct python tools/lz_hpp_bench.py 4096 0.01 64 > /dev/null 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_lzc_parse -s 2 -c 1 -o gpurun_out/c12_parse_01pct python tools/lz_hpp_bench.py 16384 0.001 256 > /dev/null 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_lzc_stitch -s 2 -c 1 -o gpurun_out/c12_stitch_01pct python tools/lz_hpp_bench.py 16384 0.001 256 > /dev/null 2>&1
-ls -la gpurun_out/*.ncu-rep
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 > gpurun_out/c16_tests.log; cat gpurun_out/c16_tests.log
+(timeout 300 python tools/lz_hpp_bench.py 16384 0.001 256; timeout 300 python tools/lz_hpp_bench.py 4096 0.01 64) 2>&1 | cut -c1-330
+timeout 900 python bench.py --steps 2 --warmup 1 > gpurun_out/c16_bench.json 2> gpurun_out/c16_bench.err; tail -3 gpurun_out/c16_bench.err; cat gpurun_out/c16_bench.json | cut -c1-3000
+timeout 300 python bench.py --impl reference --steps 1 --warmup 0 | cut -c1-600

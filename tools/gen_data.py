@@ -209,3 +209,40 @@ def bacterial_adaptive(out_dir, seed=2, n_samples=63, ref_len=5_000_000, p=0.01,
         write_fasta(fn, [(f"b{s:02d}_chr", t), (f"b{s:02d}_novel", rng.integers(0, 4, novel_len, dtype=np.uint8))])
         files.append(fn)
     return files
+
+
+def human_chromosome(out_dir, seed=3, n_samples=1, ctg_len=250_000_000, n_repeats=200, p=0.001, indel_every=10_000):
+    """BASELINE configs[3] / SURVEY C4 in shape: the reference is ONE long contig with repeat content (n_repeats random 1-10 kb
+    blocks copied to random places); every sample = the reference with substitutions at rate p and one random 1-50 b indel per
+    indel_every bases.  Returns the file list (ref first)."""
+    os.makedirs(out_dir, exist_ok=True)
+    rng = np.random.default_rng(seed)
+    ref = rng.integers(0, 4, ctg_len, dtype=np.uint8)
+    for _ in range(n_repeats):
+        L = int(rng.integers(1000, 10001))
+        a = int(rng.integers(0, ctg_len - L)); b = int(rng.integers(0, ctg_len - L))
+        ref[b:b + L] = ref[a:a + L]
+    files = [os.path.join(out_dir, "ref.fa")]
+    write_fasta(files[0], [("chr1", ref)])
+    for s in range(n_samples):
+        t = substitute(rng, ref, p)
+        n_ind = max(1, ctg_len // indel_every)
+        pos = np.sort(rng.integers(0, len(t), n_ind))
+        lens = rng.integers(1, 51, n_ind)
+        dele = rng.random(n_ind) < 0.5
+        pieces, prev = [], 0
+        for q, L, d in zip(pos, lens, dele):                # one pass: pieces between the edit points
+            q = int(q)
+            if q < prev:
+                continue
+            pieces.append(t[prev:q])
+            if d:
+                prev = min(len(t), q + int(L))
+            else:
+                pieces.append(rng.integers(0, 4, int(L), dtype=np.uint8)); prev = q
+        pieces.append(t[prev:])
+        t = np.concatenate(pieces)
+        fn = os.path.join(out_dir, f"h{s:02d}.fa")
+        write_fasta(fn, [(f"h{s:02d}_chr1", t)])
+        files.append(fn)
+    return files
