@@ -1008,6 +1008,12 @@ int agc_lz_run(agcgpu_ctx* ctx, int mode, const agcgpu_seg_req* reqs, uint32_t n
         std::vector<LzcUnit> cu;
         uint64_t n_chunks = 0; size_t smem_c = 0;
         const uint32_t UNIT_ITEMS = 4 * LZC_THREADS;
+        // chunk size: large batches take LZC_CHUNK; a batch that would not even give every resident lane a chunk (one sample of a
+        // collection) is latency bound -- smaller chunks mean more lanes and fewer tokens per lane
+        uint64_t big_chunks = 0;
+        for (size_t i = 0; i < nr; ++i) big_chunks += (packed_reqs[i].n + LZC_CHUNK - 1) / LZC_CHUNK;
+        uint32_t chunk = LZC_CHUNK;
+        while (chunk > LZC_CHUNK_MIN && big_chunks * (LZC_CHUNK / chunk) < 2ull * 1024 * (uint64_t)ctx->n_sm) chunk >>= 1;
         for (size_t a = 0; a < nr;) {
             size_t b = a;
             while (b < nr && packed_reqs[b].group == packed_reqs[a].group) ++b;
@@ -1019,7 +1025,7 @@ int agc_lz_run(agcgpu_ctx* ctx, int mode, const agcgpu_seg_req* reqs, uint32_t n
                 const LzReqDev& q = packed_reqs[i];
                 LzcReq& c = cr[i];
                 c.gstart = q.gstart; c.n = q.n; c.is_rc = q.is_rc; c.group = q.group; c.chunk_first = (uint32_t)n_chunks;
-                c.nch = std::max<uint32_t>(1u, (q.n + LZC_CHUNK - 1) / LZC_CHUNK); c.unit_base = base; c.out_off = q.out_off; c.out_cap = mode == 2 ? q.bound : q.out_cap; c.orig = q.orig;
+                c.chunk = chunk; c.pad = 0; c.nch = std::max<uint32_t>(1u, (q.n + chunk - 1) / chunk); c.unit_base = base; c.out_off = q.out_off; c.out_cap = mode == 2 ? q.bound : q.out_cap; c.orig = q.orig;
                 base += c.nch; n_chunks += c.nch;
             }
             // all requests of the group share one running chunk count; a unit is a slice of UNIT_ITEMS chunks of it

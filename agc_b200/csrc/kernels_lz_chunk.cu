@@ -59,7 +59,7 @@ struct DevFetch {
         const LzcReq q = reqs[u.first + lo];
         const uint32_t ch = k + u.item0 - q.unit_base;
         a.gs = (int64_t)q.gstart; a.n = q.n; a.rc = q.is_rc;
-        it.c0 = ch * LZC_CHUNK; it.c1 = lzc_min(q.n, it.c0 + LZC_CHUNK);
+        it.c0 = ch * q.chunk; it.c1 = lzc_min(q.n, it.c0 + q.chunk);
         it.out = cslab + (uint64_t)(q.chunk_first + ch) * LZC_CSLAB;
         it.rec = recs + q.chunk_first + ch;
         it.v = COSTS ? costv + q.out_off : nullptr; it.prefix = q.out_cap;
@@ -111,9 +111,13 @@ template <bool COSTS>
 __global__ void __launch_bounds__(128) k_lzc_stitch(
     const uint64_t* __restrict__ P, const GroupRefDev* __restrict__ groups, const LzcReq* __restrict__ reqs, uint32_t n_req,
     uint32_t mml, const uint8_t* __restrict__ cslab, const LzcRec* __restrict__ recs, uint8_t* __restrict__ slab,
-    uint32_t* __restrict__ res, uint32_t* __restrict__ fb, uint32_t* __restrict__ counters, uint32_t* __restrict__ costv)
+    uint32_t* __restrict__ res, uint32_t* __restrict__ fb, uint32_t* __restrict__ counters, uint32_t* __restrict__ costv, uint32_t per_warp)
 {
-    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    // per_warp: one segment per WARP (lane 0 works).  The stitcher is a serial, latency-bound walk; 32 of them in one warp run
+    // their divergent paths one after the other, so small batches (one sample of a collection) spread over warps instead.
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (per_warp && (threadIdx.x & 31u)) return;
+    const uint32_t r = per_warp ? t >> 5 : t;
     if (r >= n_req) return;
     const LzcReq q = reqs[r];
     const GroupRefDev g = groups[q.group];
@@ -144,8 +148,10 @@ int agc_lzc_launch(agcgpu_ctx* ctx, const LzcReq* d_reqs, uint32_t n_req, const 
     if (costv) k_lzc_parse<true><<<n_units, LZC_THREADS, smem, ctx->st>>>(P, groups, d_reqs, d_units, mml, sl, cslab, recs, costv);
     else k_lzc_parse<false><<<n_units, LZC_THREADS, smem, ctx->st>>>(P, groups, d_reqs, d_units, mml, sl, cslab, recs, nullptr);
     CKL();
-    if (costv) k_lzc_stitch<true><<<(n_req + 127) / 128, 128, 0, ctx->st>>>(P, groups, d_reqs, n_req, mml, cslab, recs, slab, res, fb, counters, costv);
-    else k_lzc_stitch<false><<<(n_req + 127) / 128, 128, 0, ctx->st>>>(P, groups, d_reqs, n_req, mml, cslab, recs, slab, res, fb, counters, nullptr);
+    const uint32_t per_warp = n_req <= 32u * (uint32_t)ctx->n_sm ? 1u : 0u;
+    const uint32_t n_thr = per_warp ? n_req * 32u : n_req;
+    if (costv) k_lzc_stitch<true><<<(n_thr + 127) / 128, 128, 0, ctx->st>>>(P, groups, d_reqs, n_req, mml, cslab, recs, slab, res, fb, counters, costv, per_warp);
+    else k_lzc_stitch<false><<<(n_thr + 127) / 128, 128, 0, ctx->st>>>(P, groups, d_reqs, n_req, mml, cslab, recs, slab, res, fb, counters, nullptr, per_warp);
     CKL();
     return 0;
 }

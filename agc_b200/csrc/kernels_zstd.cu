@@ -112,10 +112,31 @@ static int zstd_compress_batch_impl(agcgpu_ctx* ctx, const uint8_t* src, const u
         ws[i] = (ze::work_sizes(cp).total + 255) / 256 * 256;
         ob[i] = (ze::compress_bound(len) + 64 + 255) / 256 * 256;
     }
-    // schedule: biggest inputs first; waves bounded by a workspace budget
+    // Which coder.  Inputs above 32 KB take the wide one (a whole SM per frame: 15 warps of tree walks feed the parser) as long as
+    // every such frame gets an SM of its own.  When there are more of them than SMs, the frames of LZ-diff delta text
+    // ("0,85.C0,33.A...": the match-finder windows are cut after a few dozen positions, the helper warps idle, and the one-warp
+    // coder is as fast per frame -- 4.9 vs 5.8 us/B on C3's packs) go to the narrow coder, 11 of which fit on an SM, instead of
+    // waiting for a second round of SMs (C3: 223 frames, wave 2.74 s -> 2.20 s).  Packs of raw sequences (1 byte per base; C2's
+    // 1.35 MB raw-group pack: 0.71 us/B wide) always stay wide.  Both coders produce the same bytes; this is scheduling only.
+    std::vector<uint8_t> is_wide(n, 0), is_text(n, 0);
+    uint32_t n_big = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint64_t len = src_offsets[i + 1] - src_offsets[i];
+        if (len <= zs_narrow_max()) continue;
+        ++n_big;
+        const uint8_t* p = src + src_offsets[i];
+        uint32_t sym = 0; const uint32_t probe = 64;
+        for (uint32_t k = 0; k < probe; ++k) { const uint8_t c = p[(uint64_t)k * (len / probe)]; sym += c < 32u || c == 0xffu; }
+        is_text[i] = sym * 2 <= probe;               // mostly printable: digits, ',', '.', letters
+        is_wide[i] = 1;
+    }
+    if (n_big > (uint32_t)ctx->n_sm && !getenv("AGCGPU_ZSTD_WIDE_ALL"))
+        for (uint32_t i = 0; i < n; ++i) if (is_text[i]) is_wide[i] = 0;
+    // schedule: wide frames first, biggest inputs first; waves bounded by a workspace budget
     std::vector<uint32_t> order(n);
     std::iota(order.begin(), order.end(), 0u);
     std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+        if (is_wide[a] != is_wide[b]) return is_wide[a] > is_wide[b];
         return src_offsets[a + 1] - src_offsets[a] > src_offsets[b + 1] - src_offsets[b]; });
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
@@ -154,7 +175,7 @@ static int zstd_compress_batch_impl(agcgpu_ctx* ctx, const uint8_t* src, const u
         // inputs are sorted by size: the first n_wide take the wide coder, the rest the narrow one on a second stream so that
         // the two kernels share the device
         uint32_t n_wide = 0;
-        while (n_wide < cnt && tasks[n_wide].n > zs_narrow_max()) ++n_wide;
+        while (n_wide < cnt && is_wide[order[pos + n_wide]]) ++n_wide;
         if (n_wide) {
             const uint32_t smem_bytes = ze::fast_sizes().total;
             CK(cudaFuncSetAttribute(k_zstd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));

@@ -3,7 +3,8 @@
 #include <stdint.h>
 #include <stddef.h>
 
-#define LZC_CHUNK 2048u            // text positions per chunk (a multiple of 4: diagonal-0 matches start on an indexed position)
+#define LZC_CHUNK 2048u            // text positions per chunk of a large batch (a multiple of 4: diagonal-0 matches start on an indexed position)
+#define LZC_CHUNK_MIN 512u         // ... of a small batch: more lanes, fewer tokens per lane (the chunk size travels in LzcReq::chunk)
 #define LZC_CSLAB 2560u            // bytes of token output a chunk can produce: (LZC_CHUNK + min_match_len) positions, <= 23 bytes per 21
 #define LZC_THREADS 512
 #define LZC_STAGE_LIMIT (110u * 1024u)
@@ -39,6 +40,8 @@ struct LzcReq {                    // one segment to encode
     uint64_t out_off;              // byte offset of its delta in the output slab (cost vectors: u32 index of its vector)
     uint32_t out_cap;              // (cost vectors: prefix_costs)
     uint32_t orig;                 // index in the caller's request array
+    uint32_t chunk;                // text positions per chunk (LZC_CHUNK_MIN .. LZC_CHUNK, a multiple of 4)
+    uint32_t pad;
 };
 
 struct LzcUnit { uint32_t group, first, count, item0, n_items, pad; };   // one CTA: chunks [item0, item0 + n_items) of requests [first, first+count)

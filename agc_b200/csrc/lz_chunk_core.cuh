@@ -514,7 +514,7 @@ LZC_HD int64_t lzc_stitch_segment(const View& a, const LzcReq& q, uint32_t mml, 
 
     for (uint32_t k = 0; k < nch && !fail; ++k) {
         const LzcRec R = rec[k];
-        const uint32_t c0 = k * LZC_CHUNK, c1 = lzc_min(n, c0 + LZC_CHUNK);
+        const uint32_t c0 = k * q.chunk, c1 = lzc_min(n, c0 + q.chunk);
         const uint8_t* cb = cslab + (uint64_t)k * LZC_CSLAB;
         const bool has_first = (R.flags & LZC_HAS_FIRST) != 0;
         // state after the chunk's own last token

@@ -12,6 +12,8 @@ extern "C" {
 __attribute__((visibility("default"))) long lzc_host_encode(const unsigned char* text, unsigned n, const unsigned char* ref, unsigned m,
                                                             const unsigned* ht, unsigned ht_size, int is_short, unsigned mml, int is_rc, unsigned lead,
                                                             unsigned char* out, unsigned cap);
+static unsigned g_chunk = LZC_CHUNK;
+__attribute__((visibility("default"))) void lzc_host_set_chunk(unsigned c) { g_chunk = c; }
 // same, also returning the chunk records (64 bytes each)
 __attribute__((visibility("default"))) long lzc_host_encode_rec(const unsigned char* text, unsigned n, const unsigned char* ref, unsigned m,
                                                                 const unsigned* ht, unsigned ht_size, int is_short, unsigned mml, int is_rc, unsigned lead,
@@ -41,17 +43,17 @@ long lzc_host_encode_rec(const unsigned char* text, unsigned n, const unsigned c
     else h32.assign(ht, ht + ht_size);
     LzcView<false> a; a.T = T.data(); a.gs = lead; a.n = n; a.rc = is_rc; a.R = R.data(); a.r_s = 0;
     a.ht = is_short ? (const void*)h16.data() : (const void*)h32.data(); a.ht_s = 0; a.mask = ht_size - 1; a.is_short = is_short; a.m = m;
-    const unsigned nch = n ? (n + LZC_CHUNK - 1) / LZC_CHUNK : 1;
+    const unsigned nch = n ? (n + g_chunk - 1) / g_chunk : 1;
     std::vector<LzcRec> rec(nch);
     std::vector<unsigned char> cslab((size_t)nch * LZC_CSLAB + 64, 0xEE);
     for (unsigned k = 0; k < nch; ++k) {
-        const unsigned c0 = k * LZC_CHUNK, c1 = lzc_min(n, c0 + LZC_CHUNK);
+        const unsigned c0 = k * g_chunk, c1 = lzc_min(n, c0 + g_chunk);
         lzc_parse_chunk<false>(a, c0, c1, mml, cslab.data() + (size_t)k * LZC_CSLAB, rec[k]);
         if (rec[k].bytes > LZC_CSLAB) return -3;
     }
     if (recs_out && recs_cap >= nch) memcpy(recs_out, rec.data(), (size_t)nch * sizeof(LzcRec));
     LzcReq q; memset(&q, 0, sizeof q);
-    q.gstart = lead; q.n = n; q.is_rc = is_rc; q.nch = nch; q.out_cap = cap;
+    q.gstart = lead; q.n = n; q.is_rc = is_rc; q.nch = nch; q.out_cap = cap; q.chunk = g_chunk;
     return (long)lzc_stitch_segment(a, q, mml, rec.data(), cslab.data(), out, cap);
 }
 // GetCodingCostVector through the same chunk parse + stitch in cost mode; costs has n entries (zero-filled here).
@@ -76,15 +78,15 @@ __attribute__((visibility("default"))) long lzc_host_costs(const unsigned char* 
     else h32.assign(ht, ht + ht_size);
     LzcView<false> a; a.T = T.data(); a.gs = lead; a.n = n; a.rc = is_rc; a.R = R.data(); a.r_s = 0;
     a.ht = is_short ? (const void*)h16.data() : (const void*)h32.data(); a.ht_s = 0; a.mask = ht_size - 1; a.is_short = is_short; a.m = m;
-    const unsigned nch = n ? (n + LZC_CHUNK - 1) / LZC_CHUNK : 1;
+    const unsigned nch = n ? (n + g_chunk - 1) / g_chunk : 1;
     std::vector<LzcRec> rec(nch);
     for (unsigned i = 0; i < n; ++i) costs[i] = 0;
     for (unsigned k = 0; k < nch; ++k) {
-        const unsigned c0 = k * LZC_CHUNK, c1 = lzc_min(n, c0 + LZC_CHUNK);
+        const unsigned c0 = k * g_chunk, c1 = lzc_min(n, c0 + g_chunk);
         lzc_parse_chunk<false, true>(a, c0, c1, mml, nullptr, rec[k], costs, (unsigned)prefix);
     }
     LzcReq q; memset(&q, 0, sizeof q);
-    q.gstart = lead; q.n = n; q.is_rc = is_rc; q.nch = nch; q.out_cap = prefix;
+    q.gstart = lead; q.n = n; q.is_rc = is_rc; q.nch = nch; q.out_cap = prefix; q.chunk = g_chunk;
     return (long)lzc_stitch_segment<LzcView<false>, true>(a, q, mml, rec.data(), nullptr, nullptr, 0, costs, (unsigned)prefix);
 }
 }

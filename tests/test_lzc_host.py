@@ -102,6 +102,26 @@ def test_chunk_encoder_realistic_segments(lzc, p):
     assert n_seq <= 1
 
 
+def test_chunk_encoder_small_chunks(lzc):
+    """small batches use smaller chunks (LzcReq::chunk): same deltas and cost vectors"""
+    lzc.lzc_host_set_chunk.argtypes = [C.c_uint]
+    try:
+        for chunk in (512, 1024):
+            lzc.lzc_host_set_chunk(chunk)
+            n_seq = 0
+            for s in range(160):
+                rng, mml, ref, t = make_case(s)
+                z = orc.LZ(ref, mml)
+                r, got = enc(lzc, t, ref, mml, z, int(rng.random() < 0.4), int(rng.integers(0, 70)))
+                if r <= -10: n_seq += 1
+                else: assert got == z.encode(t), f"chunk {chunk} seed {s}: delta differs from the oracle"
+                r, cv = costs(lzc, t, ref, mml, z, s & 1, 0, 3)
+                if r > -10: assert np.array_equal(cv, z.cost_vector(t, s & 1)), f"chunk {chunk} seed {s}: cost vector differs"
+            assert n_seq <= 12
+    finally:
+        lzc.lzc_host_set_chunk(2048)
+
+
 def test_chunk_encoder_edges(lzc):
     rng = np.random.default_rng(3)
     ref = rng.integers(0, 4, 5000).astype(np.uint8)
