@@ -52,7 +52,8 @@ class Stats(C.Structure):
                 ("last_scan_kernel_ms", C.c_float), ("zstd_kernel_ms", C.c_float), ("zstd_input_mb", C.c_float),
                 ("lz_chunk_segments", C.c_uint64), ("lz_sequential_segments", C.c_uint64),
                 ("lz_alg_bytes_total", C.c_uint64), ("scan_bytes_total", C.c_uint64), ("lz_kernel_ms_total", C.c_float),
-                ("scan_kernel_ms_total", C.c_float), ("lz_encode_launches", C.c_uint32), ("scan_launches", C.c_uint32)]
+                ("scan_kernel_ms_total", C.c_float), ("lz_encode_launches", C.c_uint32), ("scan_launches", C.c_uint32),
+                ("zstd_wait_ms", C.c_float), ("reserved0", C.c_uint32)]
 
 
 # every symbol include/agcgpu.h declares (tests/test_abi.py checks header <-> library <-> this list)
@@ -65,7 +66,7 @@ EXPORTED_SYMBOLS = [
     "agcgpu_zstd_compress_batch_sharded", "agcgpu_comm_unique_id", "agcgpu_comm_init", "agcgpu_comm_destroy", "agcgpu_comm_get_stats",
     "agcgpu_comm_last_error", "agcgpu_comm_world", "agcgpu_comm_rank", "agcgpu_pack_ref_batch", "agcgpu_zstd_compress_batch",
     "agcgpu_find_new_splitters", "agcgpu_rescan_contigs", "agcgpu_filtered_kmers", "agcgpu_last_splitter_positions",
-    "agcgpu_zstd_decompress_batch", "agcgpu_lz_decode_batch",
+    "agcgpu_zstd_decompress_batch", "agcgpu_lz_decode_batch", "agcgpu_zstd_submit", "agcgpu_zstd_collect",
 ]
 
 
@@ -123,6 +124,8 @@ def lib():
     L.agcgpu_lz_cost_split_batch.restype = C.c_int; L.agcgpu_lz_cost_split_batch.argtypes = [vp, C.POINTER(SplitReq), C.c_uint32, u32p, u32p]
     L.agcgpu_pack_ref_batch.restype = C.c_int
     L.agcgpu_pack_ref_batch.argtypes = [vp, u32p, C.c_uint32, u8p, C.c_uint64, u64p, u8p]
+    L.agcgpu_zstd_submit.restype = C.c_int; L.agcgpu_zstd_submit.argtypes = [vp, u8p, u64p, i32p, C.c_uint32]
+    L.agcgpu_zstd_collect.restype = C.c_int; L.agcgpu_zstd_collect.argtypes = [vp, C.c_uint32, u8p, C.c_uint64, u64p]
     L.agcgpu_zstd_compress_batch.restype = C.c_int
     L.agcgpu_zstd_compress_batch.argtypes = [vp, u8p, u64p, i32p, C.c_uint32, u8p, C.c_uint64, u64p]
     _LIB = L

@@ -145,6 +145,7 @@ void agcgpu_destroy(agcgpu_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->dev);
     cudaStreamSynchronize(ctx->st);
+    agc_zstd_waves_drop(ctx);
     DevBuf* bufs[] = { &ctx->spl_keys, &ctx->spl_filter, &ctx->raw, &ctx->packed, &ctx->exc_pos, &ctx->exc_code, &ctx->tile_desc,
                        &ctx->tile_cnt, &ctx->tile_base, &ctx->d_cstart, &ctx->chunk_prefix, &ctx->hits, &ctx->counters, &ctx->map_k1,
                        &ctx->map_k2, &ctx->map_val, &ctx->d_groups, &ctx->scr_req, &ctx->scr_units, &ctx->scr_out, &ctx->scr_sizes,

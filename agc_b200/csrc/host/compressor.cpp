@@ -568,6 +568,58 @@ bool CAGCCompressor::lz_encode(std::vector<agcgpu_seg_req>& lz, std::vector<uint
     return true;
 }
 
+// The residual coder runs behind the pipeline (agcgpu_zstd_submit / agcgpu_zstd_collect), as the reference's compression threads do.
+// Not with the callback exchange of agcgpu_set_exchange (its all-gather is a host call per batch): that path keeps the drain.
+bool CAGCCompressor::async_coder() const
+{
+    static const bool drain_only = getenv("AGCGPU_ZSTD_DRAIN") != nullptr;       // diagnostics: code parts only at the drains
+    return !drain_only && (xworld <= 1 || agcgpu_comm_world() > 1);
+}
+
+bool CAGCCompressor::submit_pending(bool with_extra)
+{
+    std::vector<ZTask*> tasks;
+    for (size_t i = jobs_submitted; i < jobs.size(); ++i) for (auto& t : jobs[i].tasks) tasks.push_back(&t);
+    jobs_submitted = jobs.size();
+    if (with_extra) { for (auto* t : extra_tasks) tasks.push_back(t); extra_tasks.clear(); }
+    if (tasks.empty()) return true;
+    PhaseTimer pt("residual coder submit");
+    std::vector<uint64_t> offs(tasks.size() + 1, 0);
+    std::vector<int32_t> levels(tasks.size());
+    for (size_t i = 0; i < tasks.size(); ++i) { offs[i + 1] = offs[i] + tasks[i]->raw.size(); levels[i] = tasks[i]->level; }
+    std::vector<uint8_t> src(offs.back() + 1);
+    for (size_t i = 0; i < tasks.size(); ++i) if (!tasks[i]->raw.empty()) memcpy(src.data() + offs[i], tasks[i]->raw.data(), tasks[i]->raw.size());
+    if (!gpu_ok(agcgpu_zstd_submit(ctx, src.data(), offs.data(), levels.data(), (uint32_t)tasks.size()), "zstd_submit")) return false;
+    inflight.insert(inflight.end(), tasks.begin(), tasks.end());
+    return true;
+}
+
+bool CAGCCompressor::collect_inflight()
+{
+    if (inflight.empty()) return true;
+    PhaseTimer pt("residual coder collect");
+    std::vector<ZTask*> tasks;
+    tasks.swap(inflight);
+    std::vector<uint64_t> offs(tasks.size() + 1, 0);
+    for (size_t i = 0; i < tasks.size(); ++i) offs[i + 1] = offs[i] + tasks[i]->raw.size();
+    const uint64_t cap = offs.back() + offs.back() / 128 + 1024 * (tasks.size() + 1);
+    std::vector<uint8_t> dst(cap);
+    std::vector<uint64_t> doffs(tasks.size() + 1, 0);
+    if (!gpu_ok(agcgpu_zstd_collect(ctx, (uint32_t)tasks.size(), dst.data(), cap, doffs.data()), "zstd_collect")) return false;
+    for (size_t i = 0; i < tasks.size(); ++i) tasks[i]->packed.assign(dst.begin() + doffs[i], dst.begin() + doffs[i + 1]);
+    if (verify) {                                            // decode-and-compare: the frames must give back exactly what went in
+        PhaseTimer pv("residual coder self check");
+        std::vector<uint8_t> back(offs.back() + 1);
+        std::vector<uint64_t> boffs(tasks.size() + 1, 0);
+        if (!gpu_ok(agcgpu_zstd_decompress_batch(ctx, dst.data(), doffs.data(), (uint32_t)tasks.size(), back.data(), offs.back(), boffs.data()),
+                    "zstd_decompress_batch (self check)")) return false;
+        for (size_t i = 0; i < tasks.size(); ++i)
+            if (boffs[i + 1] - boffs[i] != tasks[i]->raw.size() || (!tasks[i]->raw.empty() && memcmp(back.data() + boffs[i], tasks[i]->raw.data(), tasks[i]->raw.size()) != 0))
+                return fail("self check: frame " + std::to_string(i) + " of a residual-coder batch does not decode to its input");
+    }
+    return true;
+}
+
 bool CAGCCompressor::compress_tasks_local(std::vector<ZTask*>& tasks)
 {
     PhaseTimer pt("residual coder batch");
@@ -608,8 +660,14 @@ static void dump_bytes(FILE* f, const void* p, size_t n) { dump_u64(f, n); if (n
 bool CAGCCompressor::flush_jobs(bool force)
 {
     if (jobs.empty() && extra_tasks.empty()) return true;
-    if (!force && !dump_f && !discard_parts && pending_job_bytes < flush_threshold) return true;
+    if (!force && !dump_f && !discard_parts) {
+        // not a drain: hand what was queued since the last call to the device (asynchronous: it is coded while the next samples
+        // are processed) and go on; the host copies stay until the drain
+        if (async_coder() && !submit_pending(false)) return false;
+        if (pending_job_bytes < flush_threshold) return true;
+    }
     pending_job_bytes = 0;
+    if (!dump_f && !discard_parts && async_coder() && !submit_pending(true)) return false;       // before the sort moves the jobs around
     std::stable_sort(jobs.begin(), jobs.end(), [](const PartJob& a, const PartJob& b) {
         if (a.epoch != b.epoch) return a.epoch < b.epoch;
         if (a.stream_id != b.stream_id) return a.stream_id < b.stream_id;
@@ -626,11 +684,18 @@ bool CAGCCompressor::flush_jobs(bool force)
         jobs.clear();
         return true;
     }
-    std::vector<ZTask*> tasks;
-    for (auto& j : jobs) for (auto& t : j.tasks) tasks.push_back(&t);
-    for (auto* t : extra_tasks) tasks.push_back(t);
-    extra_tasks.clear();
-    if (!compress_tasks(tasks)) return false;
+    if (async_coder()) {
+        // the parts queued since the last submit join the batches already in flight; one collect returns every frame
+        if (!submit_pending(true)) return false;
+        if (!collect_inflight()) return false;
+    } else {
+        std::vector<ZTask*> tasks;
+        for (auto& j : jobs) for (auto& t : j.tasks) tasks.push_back(&t);
+        for (auto* t : extra_tasks) tasks.push_back(t);
+        extra_tasks.clear();
+        if (!compress_tasks(tasks)) return false;
+    }
+    jobs_submitted = 0;
     for (auto& j : jobs) {
         if (j.kind == 0 || j.kind == 1) {                       // add_to_archive / add_to_archive_tuples (segment.h:172-215)
             auto& pk = j.tasks[0].packed;

@@ -18,6 +18,7 @@
 #include <array>
 #include <unordered_map>
 #include <vector>
+#include <type_traits>
 #include "../../../include/agcgpu.h"
 
 namespace agc_b200 {
@@ -107,6 +108,7 @@ struct PartJob {
     std::vector<uint8_t> fallback_raw;   // kinds 0/1: stored as is with metadata 0 when packed+1 >= raw (segment.h:180-187)
     std::vector<ZTask> tasks;
 };
+static_assert(std::is_nothrow_move_constructible<PartJob>::value, "ZTask pointers stay valid while the job queue grows and is sorted");
 
 class CAGCCompressor {
 public:
@@ -210,6 +212,11 @@ private:
     uint32_t processed_samples = 0;
     uint64_t epoch = 0, job_seq = 0, total_bases = 0;
     std::vector<PartJob> jobs;
+    size_t jobs_submitted = 0;                                   // jobs[0 .. jobs_submitted) are with the device already
+    std::vector<ZTask*> inflight;                                // their tasks, in submission order
+    bool async_coder() const;
+    bool submit_pending(bool with_extra);
+    bool collect_inflight();
     std::vector<ZTask*> extra_tasks;                             // coded with the next drain, written by their owner
     uint64_t pending_job_bytes = 0, flush_threshold = 1ull << 30;
     std::vector<std::pair<std::string, std::string>> cmd_lines;

@@ -161,6 +161,7 @@ struct agcgpu_ctx {
     void* pin = nullptr; size_t pin_cap = 0;   // pinned host staging
     std::vector<uint64_t> last_slab_off;       // device-only encode: slab offset of every delta (request order)
     uint64_t last_lzc_chunks = 0;              // chunk records of the last chunk-parallel encode (diagnostics)
+    std::vector<void*> zwaves;                 // residual-coder batches in flight (agcgpu_zstd_submit), in submission order
 };
 
 // ------------------------------------------------------------------------------------------------ internal API
@@ -168,6 +169,7 @@ int agc_fail(agcgpu_ctx* c, int code, const char* fmt, ...);
 int agc_reserve(agcgpu_ctx* c, DevBuf& b, size_t bytes, bool keep = false);
 void* agc_arena_alloc(agcgpu_ctx* c, size_t bytes);    // 256-byte aligned, lives until destroy
 int agc_pin_reserve(agcgpu_ctx* c, size_t bytes);
+void agc_zstd_waves_drop(agcgpu_ctx* c);      // kernels_zstd.cu: waits for and frees the waves nobody collected
 void* agc_dev_alloc(int dev, size_t bytes, size_t* cap_out);   // process-wide device-memory pool (api.cu)
 void agc_dev_free(int dev, void* p, size_t cap);
 void agc_dev_trim(int dev);

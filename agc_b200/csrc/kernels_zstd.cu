@@ -23,6 +23,8 @@
 #include <numeric>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
+#include <cstring>
 
 struct ZTaskDev {
     const uint8_t* src; uint8_t* dst; uint8_t* mem;
@@ -90,6 +92,16 @@ static uint64_t zs_narrow_max()
 {
     static const uint64_t v = getenv("AGCGPU_ZSTD_NARROW_MAX") ? strtoull(getenv("AGCGPU_ZSTD_NARROW_MAX"), nullptr, 10) : (32u << 10);
     return v;
+}
+
+// the coder's call depth needs more than the default local-memory stack; cudaDeviceSetLimit waits for the device to go idle, so it
+// is only called when the limit is not there yet (never while asynchronous waves are in flight: submit sets it first)
+static int zs_stack_limit(agcgpu_ctx* ctx)
+{
+    size_t cur = 0;
+    CK(cudaDeviceGetLimit(&cur, cudaLimitStackSize));
+    if (cur < 16384) CK(cudaDeviceSetLimit(cudaLimitStackSize, 16384));
+    return 0;
 }
 
 // keep_lead == ~0: frames go to the host (dst / dst_offsets).  Otherwise (sharded coder) they stay on the device, back to back in input
@@ -170,7 +182,7 @@ static int zstd_compress_batch_impl(agcgpu_ctx* ctx, const uint8_t* src, const u
             wo += ws[i]; oo += ob[i];
         }
         CK(cudaMemcpyAsync(ctx->scr_req.p, tasks.data(), cnt * sizeof(ZTaskDev), cudaMemcpyHostToDevice, ctx->st));
-        CK(cudaDeviceSetLimit(cudaLimitStackSize, 16384));
+        if (int r = zs_stack_limit(ctx)) return r;
         CK(cudaEventRecord(ctx->ev0, ctx->st));
         // inputs are sorted by size: the first n_wide take the wide coder, the rest the narrow one on a second stream so that
         // the two kernels share the device
@@ -273,6 +285,297 @@ static int zstd_compress_batch_impl(agcgpu_ctx* ctx, const uint8_t* src, const u
     }
     if (dst_offsets[n] > dst_cap) return agc_fail(ctx, AGCGPU_EOVERFLOW, "zstd: need %llu output bytes", (unsigned long long)dst_offsets[n]);
     for (uint32_t i = 0; i < n; ++i) if (out_size[i]) memcpy(dst + dst_offsets[i], frames[i].data(), out_size[i]);
+    return 0;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------- asynchronous waves
+// agcgpu_zstd_submit / agcgpu_zstd_collect: the same coder, but a batch ("wave") is only QUEUED -- inputs copied to the device, its
+// kernels launched on streams of its own -- and the call returns; the frames of every wave submitted so far come back from one
+// agcgpu_zstd_collect.  A pack is coded while the host and the library stream go on with the next samples (the reference overlaps
+// the same way: its compression threads run behind the segment queue, agc_compressor.cpp:1093-1272), so at Close only the last
+// packs are still to be coded.  With a communicator every rank submits the same waves and codes its share of each (largest first
+// to the least loaded rank, the same assignment on every rank); collect all-gathers the frames once.
+struct ZWave {
+    uint32_t n_in = 0;                               // inputs of the submit call
+    std::vector<std::vector<uint32_t>> of_rank;      // with a communicator: who codes which input
+    std::vector<uint32_t> mine;                      // inputs coded here, in launch order (wide first, largest first)
+    std::vector<uint64_t> in_size;                   // per input
+    uint32_t n_wide = 0;
+    void* d_src = nullptr; size_t src_cap = 0;
+    void* d_ws = nullptr; size_t ws_cap = 0;
+    void* d_out = nullptr; size_t out_cap = 0;
+    void* d_tasks = nullptr; size_t tasks_cap = 0;
+    uint64_t osum = 0;
+    std::vector<ZTaskDev> tasks;
+    cudaStream_t st_w = nullptr, st_n = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr, en = nullptr;
+    bool launched = false;
+    // no room on the device at submit time: the inputs wait on the host and are coded synchronously at collect
+    std::vector<uint8_t> h_src; std::vector<uint64_t> h_offs; std::vector<int32_t> h_levels;
+    std::vector<std::vector<uint8_t>> frames;        // results of `mine` (index = position in mine)
+};
+
+static void zwave_release(agcgpu_ctx* ctx, ZWave* w)
+{
+    if (w->st_w) { cudaStreamSynchronize(w->st_w); cudaStreamDestroy(w->st_w); }
+    if (w->st_n) { cudaStreamSynchronize(w->st_n); cudaStreamDestroy(w->st_n); }
+    if (w->e0) cudaEventDestroy(w->e0);
+    if (w->e1) cudaEventDestroy(w->e1);
+    if (w->en) cudaEventDestroy(w->en);
+    agc_dev_free(ctx->dev, w->d_src, w->src_cap); agc_dev_free(ctx->dev, w->d_ws, w->ws_cap);
+    agc_dev_free(ctx->dev, w->d_out, w->out_cap); agc_dev_free(ctx->dev, w->d_tasks, w->tasks_cap);
+    delete w;
+}
+void agc_zstd_waves_drop(agcgpu_ctx* ctx)            // destroy(): waves nobody collected
+{
+    for (void* p : ctx->zwaves) zwave_release(ctx, (ZWave*)p);
+    ctx->zwaves.clear();
+}
+
+static bool zs_is_text(const uint8_t* p, uint64_t len)
+{
+    uint32_t sym = 0; const uint32_t probe = 64;
+    for (uint32_t k = 0; k < probe; ++k) { const uint8_t c = p[(uint64_t)k * (len / probe)]; sym += c < 32u || c == 0xffu; }
+    return sym * 2 <= probe;                         // mostly printable: digits, ',', '.', letters
+}
+
+extern "C" int agcgpu_zstd_submit(agcgpu_ctx* ctx, const uint8_t* src, const uint64_t* src_offsets, const int32_t* levels, uint32_t n)
+{
+    if (!ctx || !src_offsets || (n && (!src || !levels))) return AGCGPU_EINVAL;
+    cudaSetDevice(ctx->dev);
+    if (n == 0) return 0;
+    std::vector<uint64_t> ws(n), ob(n);
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint64_t len = src_offsets[i + 1] - src_offsets[i];
+        ze::Params cp = ze::get_params(levels[i], len);
+        if (!cp.supported)
+            return agc_fail(ctx, AGCGPU_EUNSUPPORTED, "zstd: input %u (level %d, %llu bytes) is outside the implemented envelope "
+                            "(levels 13/17/18/19, inputs below 1 GiB)", i, levels[i], (unsigned long long)len);
+        ws[i] = (ze::work_sizes(cp).total + 255) / 256 * 256;
+        ob[i] = (ze::compress_bound(len) + 64 + 255) / 256 * 256;
+    }
+    ZWave* w = new ZWave;
+    w->n_in = n; w->in_size.resize(n);
+    for (uint32_t i = 0; i < n; ++i) w->in_size[i] = src_offsets[i + 1] - src_offsets[i];
+    std::vector<uint32_t> order(n);
+    std::iota(order.begin(), order.end(), 0u);
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return w->in_size[a] > w->in_size[b]; });
+    if (agc_comm_active()) {
+        const uint32_t W = agc_comm_world();
+        std::vector<uint64_t> load(W, 0);
+        w->of_rank.assign(W, {});
+        for (uint32_t i : order) {
+            const uint32_t r = (uint32_t)(std::min_element(load.begin(), load.end()) - load.begin());
+            w->of_rank[r].push_back(i); load[r] += w->in_size[i] + 512;
+        }
+        w->mine = w->of_rank[agc_comm_rank()];
+    } else w->mine = order;
+    // Delta text ("0,85.C0,33.A!!!!...": runs and a tiny alphabet cut the match-finder windows after a few dozen positions, the
+    // helper warps of the wide coder idle and the one-warp coder is faster per frame, 4.9 vs 5.8 us/B) always takes the narrow
+    // coder here; other inputs above 32 KB (packs of raw sequences) take the wide one.  Scheduling only: same bytes either way.
+    std::vector<uint8_t> wide(n, 0);
+    for (uint32_t i : w->mine)
+        if (w->in_size[i] > zs_narrow_max() && (getenv("AGCGPU_ZSTD_WIDE_ALL") || !zs_is_text(src + src_offsets[i], w->in_size[i]))) wide[i] = 1;
+    std::stable_sort(w->mine.begin(), w->mine.end(), [&](uint32_t a, uint32_t b) {
+        if (wide[a] != wide[b]) return wide[a] > wide[b];
+        return w->in_size[a] > w->in_size[b]; });
+    const uint32_t cnt = (uint32_t)w->mine.size();
+    ctx->zwaves.push_back(w);
+    if (cnt == 0) return 0;
+    uint64_t total_src = 0, wsum = 0, osum = 0;
+    for (uint32_t i : w->mine) { total_src += w->in_size[i]; wsum += ws[i]; osum += ob[i]; w->n_wide += wide[i]; }
+    ctx->stats.zstd_input_mb += (float)(total_src * 1e-6);
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    auto park = [&]() {                              // keep the inputs on the host; collect codes them with the synchronous call
+        w->h_offs.assign(1, 0); w->h_levels.clear(); w->h_src.resize(total_src);
+        for (uint32_t i : w->mine) {
+            if (w->in_size[i]) memcpy(w->h_src.data() + w->h_offs.back(), src + src_offsets[i], w->in_size[i]);
+            w->h_offs.push_back(w->h_offs.back() + w->in_size[i]); w->h_levels.push_back(levels[i]);
+        }
+        return 0;
+    };
+    if (total_src + wsum + osum + (64ull << 20) > (uint64_t)(free_b * 0.5) || getenv("AGCGPU_ZSTD_SYNC")) return park();
+    w->d_src = agc_dev_alloc(ctx->dev, total_src + 256, &w->src_cap);
+    w->d_ws = agc_dev_alloc(ctx->dev, wsum + 256, &w->ws_cap);
+    w->d_out = agc_dev_alloc(ctx->dev, osum + 256, &w->out_cap);
+    w->d_tasks = agc_dev_alloc(ctx->dev, cnt * sizeof(ZTaskDev) + 256, &w->tasks_cap);
+    if (!w->d_src || !w->d_ws || !w->d_out || !w->d_tasks) {
+        agc_dev_free(ctx->dev, w->d_src, w->src_cap); agc_dev_free(ctx->dev, w->d_ws, w->ws_cap);
+        agc_dev_free(ctx->dev, w->d_out, w->out_cap); agc_dev_free(ctx->dev, w->d_tasks, w->tasks_cap);
+        w->d_src = w->d_ws = w->d_out = w->d_tasks = nullptr;
+        return park();
+    }
+    w->osum = osum;
+    if (int r = zs_stack_limit(ctx)) return r;
+    CK(cudaStreamCreateWithFlags(&w->st_w, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&w->e0)); CK(cudaEventCreate(&w->e1));
+    w->tasks.resize(cnt);
+    {   // inputs back to back in launch order
+        std::vector<uint8_t> stage(total_src + 1);
+        uint64_t so = 0, wo = 0, oo = 0;
+        for (uint32_t j = 0; j < cnt; ++j) {
+            const uint32_t i = w->mine[j];
+            if (w->in_size[i]) memcpy(stage.data() + so, src + src_offsets[i], w->in_size[i]);
+            ZTaskDev& k = w->tasks[j];
+            k.src = (const uint8_t*)w->d_src + so; k.n = w->in_size[i];
+            k.dst = (uint8_t*)w->d_out + oo; k.dst_cap = ob[i]; k.mem = (uint8_t*)w->d_ws + wo;
+            k.level = levels[i]; k.err = 0; k.out_size = 0; k.t_start = k.t_end = 0;
+            so += w->in_size[i]; wo += ws[i]; oo += ob[i];
+        }
+        CK(cudaMemcpyAsync(w->d_src, stage.data(), total_src, cudaMemcpyHostToDevice, w->st_w));
+        CK(cudaStreamSynchronize(w->st_w));          // `stage` goes out of scope
+        ctx->stats.h2d_bytes += total_src;
+    }
+    CK(cudaMemsetAsync(w->d_ws, 0, wsum, w->st_w));
+    CK(cudaMemcpyAsync(w->d_tasks, w->tasks.data(), cnt * sizeof(ZTaskDev), cudaMemcpyHostToDevice, w->st_w));
+    CK(cudaEventRecord(w->e0, w->st_w));
+    if (w->n_wide) {
+        const uint32_t smem_bytes = ze::fast_sizes().total;
+        CK(cudaFuncSetAttribute(k_zstd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        k_zstd<<<w->n_wide, ZS_THREADS, smem_bytes, w->st_w>>>((ZTaskDev*)w->d_tasks, w->n_wide, smem_bytes);
+        CKL();
+    }
+    if (cnt > w->n_wide) {
+        const uint32_t smem_n = zen::fast_sizes().total;
+        cudaStream_t sn = w->st_w;
+        if (w->n_wide) {                             // beside the wide kernel, not behind it
+            CK(cudaStreamCreateWithFlags(&w->st_n, cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&w->en, cudaEventDisableTiming));
+            CK(cudaStreamWaitEvent(w->st_n, w->e0, 0));
+            sn = w->st_n;
+        }
+        k_zstd_narrow<<<cnt - w->n_wide, 32, smem_n, sn>>>((ZTaskDev*)w->d_tasks + w->n_wide, cnt - w->n_wide, smem_n);
+        CKL();
+        if (w->st_n) { CK(cudaEventRecord(w->en, w->st_n)); CK(cudaStreamWaitEvent(w->st_w, w->en, 0)); }
+    }
+    CK(cudaEventRecord(w->e1, w->st_w));
+    w->launched = true;
+    return 0;
+}
+
+// frames of every input submitted since the last collect, in submission order: frame i = dst[dst_offsets[i] .. dst_offsets[i+1]);
+// n_expected = total number of inputs (checked)
+extern "C" int agcgpu_zstd_collect(agcgpu_ctx* ctx, uint32_t n_expected, uint8_t* dst, uint64_t dst_cap, uint64_t* dst_offsets)
+{
+    if (!ctx || !dst_offsets || (n_expected && !dst)) return AGCGPU_EINVAL;
+    cudaSetDevice(ctx->dev);
+    std::vector<ZWave*> waves;
+    for (void* p : ctx->zwaves) waves.push_back((ZWave*)p);
+    ctx->zwaves.clear();
+    struct Guard { agcgpu_ctx* c; std::vector<ZWave*>& v; ~Guard() { for (ZWave* w : v) zwave_release(c, w); } } guard{ ctx, waves };
+    uint64_t n_total = 0;
+    for (ZWave* w : waves) n_total += w->n_in;
+    dst_offsets[0] = 0;
+    int local = 0;
+    if (n_total != n_expected) local = agc_fail(ctx, AGCGPU_EINVAL, "zstd collect: %llu inputs were submitted, the caller expects %u", (unsigned long long)n_total, n_expected);
+    const bool trace = getenv("AGCGPU_TRACE") != nullptr;
+    const auto t_wait0 = std::chrono::steady_clock::now();
+    // 1. this rank's frames of every wave, on the host
+    for (size_t wi = 0; wi < waves.size() && !local; ++wi) {
+        ZWave* w = waves[wi];
+        const uint32_t cnt = (uint32_t)w->mine.size();
+        w->frames.resize(cnt);
+        if (!cnt) continue;
+        if (!w->launched) {
+            std::vector<uint64_t> fo((size_t)cnt + 1, 0);
+            const uint64_t cap = w->h_offs.back() + w->h_offs.back() / 128 + 1024ull * (cnt + 1);
+            std::vector<uint8_t> out(cap);
+            local = zstd_compress_batch_impl(ctx, w->h_src.data(), w->h_offs.data(), w->h_levels.data(), cnt, out.data(), cap, fo.data(), ~0ull);
+            if (!local) for (uint32_t j = 0; j < cnt; ++j) w->frames[j].assign(out.begin() + fo[j], out.begin() + fo[j + 1]);
+            continue;
+        }
+        if (cudaEventSynchronize(w->e1) != cudaSuccess) { local = agc_fail(ctx, AGCGPU_ECUDA, "zstd wave %zu: %s", wi, cudaGetErrorString(cudaGetLastError())); break; }
+        float ms = 0; cudaEventElapsedTime(&ms, w->e0, w->e1);
+        ctx->stats.zstd_kernel_ms += ms;
+        if (cudaMemcpyAsync(w->tasks.data(), w->d_tasks, cnt * sizeof(ZTaskDev), cudaMemcpyDeviceToHost, w->st_w) != cudaSuccess ||
+            cudaStreamSynchronize(w->st_w) != cudaSuccess) { local = agc_fail(ctx, AGCGPU_ECUDA, "zstd wave %zu: task copy failed", wi); break; }
+        uint64_t out_total = 0;
+        for (uint32_t j = 0; j < cnt && !local; ++j) {
+            if (w->tasks[j].err) local = agc_fail(ctx, AGCGPU_EUNSUPPORTED, "zstd: device coder failed on input %u of wave %zu (code %d)", w->mine[j], wi, w->tasks[j].err);
+            out_total += w->tasks[j].out_size;
+        }
+        if (local) break;
+        if (trace) {
+            uint64_t tot = 0, big = 0; for (uint32_t j = 0; j < cnt; ++j) { tot += w->tasks[j].n; big = std::max<uint64_t>(big, w->tasks[j].n); }
+            fprintf(stderr, "[agcgpu] zstd wave %zu (async): %u inputs (%u wide), %llu bytes, largest %llu, device %.1f ms\n", wi, cnt, w->n_wide,
+                    (unsigned long long)tot, (unsigned long long)big, ms);
+        }
+        if (w->osum <= (64ull << 20) || out_total * 2 >= w->osum) {
+            std::vector<uint8_t> host(w->osum);
+            if (cudaMemcpyAsync(host.data(), w->d_out, w->osum, cudaMemcpyDeviceToHost, w->st_w) != cudaSuccess || cudaStreamSynchronize(w->st_w) != cudaSuccess) {
+                local = agc_fail(ctx, AGCGPU_ECUDA, "zstd wave %zu: frame copy failed", wi); break; }
+            ctx->stats.d2h_bytes += w->osum;
+            for (uint32_t j = 0; j < cnt; ++j) { const uint8_t* p = host.data() + (w->tasks[j].dst - (uint8_t*)w->d_out); w->frames[j].assign(p, p + w->tasks[j].out_size); }
+        } else {
+            for (uint32_t j = 0; j < cnt; ++j) {
+                w->frames[j].resize(w->tasks[j].out_size);
+                if (cudaMemcpyAsync(w->frames[j].data(), w->tasks[j].dst, w->tasks[j].out_size, cudaMemcpyDeviceToHost, w->st_w) != cudaSuccess) { local = AGCGPU_ECUDA; break; }
+                ctx->stats.d2h_bytes += w->tasks[j].out_size;
+            }
+            if (cudaStreamSynchronize(w->st_w) != cudaSuccess || local) { local = agc_fail(ctx, AGCGPU_ECUDA, "zstd wave %zu: frame copy failed", wi); break; }
+        }
+    }
+    ctx->stats.zstd_wait_ms += (float)std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_wait0).count();
+    if (!agc_comm_active()) {
+        if (local) return local;
+        uint64_t i = 0;
+        for (ZWave* w : waves) {
+            std::vector<uint64_t> sz(w->n_in, 0);
+            for (size_t j = 0; j < w->mine.size(); ++j) sz[w->mine[j]] = w->frames[j].size();
+            for (uint32_t k = 0; k < w->n_in; ++k, ++i) dst_offsets[i + 1] = dst_offsets[i] + sz[k];
+        }
+        if (dst_offsets[n_total] > dst_cap) return agc_fail(ctx, AGCGPU_EOVERFLOW, "zstd: need %llu output bytes", (unsigned long long)dst_offsets[n_total]);
+        uint64_t base = 0;
+        for (ZWave* w : waves) {
+            for (size_t j = 0; j < w->mine.size(); ++j) if (!w->frames[j].empty()) memcpy(dst + dst_offsets[base + w->mine[j]], w->frames[j].data(), w->frames[j].size());
+            base += w->n_in;
+        }
+        return 0;
+    }
+    // 2. all-gather: block of a rank = [u64 size of each of its frames, wave by wave in its launch order][the frames back to back]
+    const uint32_t W = agc_comm_world(), me = agc_comm_rank();
+    uint64_t my_cnt = 0, my_bytes = 0;
+    for (ZWave* w : waves) { my_cnt += w->mine.size(); if (!local) for (auto& f : w->frames) my_bytes += f.size(); }
+    const uint64_t hdr = (my_cnt * 8 + 15) / 16 * 16;
+    std::vector<uint8_t> blk(hdr + my_bytes + 16, 0);
+    if (!local) {
+        // frames in the order of the assignment (of_rank), which every rank can rebuild -- `mine` is in launch order
+        uint64_t* sz = (uint64_t*)blk.data(); uint64_t o = hdr, k = 0;
+        for (ZWave* w : waves) {
+            std::vector<uint32_t> at(w->n_in, 0);
+            for (size_t j = 0; j < w->mine.size(); ++j) at[w->mine[j]] = (uint32_t)j;
+            for (uint32_t i : w->of_rank[me]) { auto& f = w->frames[at[i]]; sz[k++] = f.size(); if (!f.empty()) memcpy(blk.data() + o, f.data(), f.size()); o += f.size(); }
+        }
+    }
+    if (!local) local = agc_reserve(ctx, ctx->scr_zkeep, hdr + my_bytes + 64);
+    if (!local && cudaMemcpyAsync(ctx->scr_zkeep.p, blk.data(), hdr + my_bytes, cudaMemcpyHostToDevice, ctx->st) != cudaSuccess) local = AGCGPU_ECUDA;
+    std::vector<uint64_t> sizes; uint64_t stride = 0;
+    if (int r = agc_comm_allgatherv(ctx, ctx->scr_zkeep.p, hdr + my_bytes, local, sizes, &stride)) return r;
+    std::vector<uint8_t> host((size_t)stride * W);
+    if (stride) CK(cudaMemcpyAsync(host.data(), ctx->scr_gather.p, (size_t)stride * W, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    ctx->stats.d2h_bytes += (size_t)stride * W;
+    std::vector<const uint8_t*> fptr(n_total, nullptr);
+    std::vector<uint64_t> fsize(n_total, 0);
+    for (uint32_t r = 0; r < W; ++r) {
+        uint64_t c = 0; for (ZWave* w : waves) c += w->of_rank[r].size();
+        const uint64_t h = (c * 8 + 15) / 16 * 16;
+        if (sizes[r] < h) return agc_fail(ctx, AGCGPU_ECUDA, "sharded coder: truncated block from rank %u", r);
+        const uint64_t* sz = (const uint64_t*)(host.data() + (size_t)stride * r);
+        uint64_t o = h, k = 0, base = 0;
+        for (ZWave* w : waves) {
+            for (uint32_t i : w->of_rank[r]) {
+                if (o + sz[k] > sizes[r]) return agc_fail(ctx, AGCGPU_ECUDA, "sharded coder: block of rank %u has the wrong size", r);
+                fptr[base + i] = host.data() + (size_t)stride * r + o; fsize[base + i] = sz[k]; o += sz[k]; ++k;
+            }
+            base += w->n_in;
+        }
+        if (o != sizes[r]) return agc_fail(ctx, AGCGPU_ECUDA, "sharded coder: block of rank %u has the wrong size", r);
+    }
+    for (uint64_t i = 0; i < n_total; ++i) dst_offsets[i + 1] = dst_offsets[i] + fsize[i];
+    if (dst_offsets[n_total] > dst_cap) return agc_fail(ctx, AGCGPU_EOVERFLOW, "zstd: need %llu output bytes", (unsigned long long)dst_offsets[n_total]);
+    for (uint64_t i = 0; i < n_total; ++i) if (fsize[i]) memcpy(dst + dst_offsets[i], fptr[i], fsize[i]);
     return 0;
 }
 

@@ -36,7 +36,9 @@ extern "C" int agcgpu_zstd_decompress_batch(agcgpu_ctx* ctx, const uint8_t* src,
     const uint32_t wave = 1024;                             // frames in flight: 1024 x sizeof(zd::Work) ~ 150 MB of tables and literal buffers
     if (int r = agc_reserve(ctx, ctx->scr_out, (size_t)std::min<uint32_t>(n, wave) * sizeof(zd::Work) + 256)) return r;
     if (int r = agc_reserve(ctx, ctx->scr_req, (size_t)std::min<uint32_t>(n, wave) * sizeof(ZDTaskDev))) return r;
-    CK(cudaDeviceSetLimit(cudaLimitStackSize, 16384));
+    {   size_t cur = 0;                                   // (setting the limit waits for an idle device: only when it is not there yet)
+        CK(cudaDeviceGetLimit(&cur, cudaLimitStackSize));
+        if (cur < 16384) CK(cudaDeviceSetLimit(cudaLimitStackSize, 16384)); }
     for (uint32_t pos = 0; pos < n; pos += wave) {
         const uint32_t cnt = std::min<uint32_t>(wave, n - pos);
         std::vector<ZDTaskDev> tasks(cnt);

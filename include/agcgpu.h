@@ -104,6 +104,8 @@ typedef struct {
     float    lz_kernel_ms_total;      /* device time of the encode kernels (CUDA events) */
     float    scan_kernel_ms_total;
     uint32_t lz_encode_launches, scan_launches;
+    float    zstd_wait_ms;            /* host time blocked in agcgpu_zstd_collect: the part of the residual coder that did NOT overlap */
+    uint32_t reserved0;
 } agcgpu_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------------------------------- */
@@ -249,6 +251,15 @@ int agcgpu_pack_ref_batch(agcgpu_ctx* ctx, const uint32_t* group_ids, uint32_t n
  * dst_offsets[i+1]).  Frames are byte-identical to libzstd 1.5.5's. */
 int agcgpu_zstd_compress_batch(agcgpu_ctx* ctx, const uint8_t* src, const uint64_t* src_offsets, const int32_t* levels,
                                uint32_t n, uint8_t* dst, uint64_t dst_cap, uint64_t* dst_offsets);
+/* The same coder, asynchronous -- the reference codes its packs on worker threads behind the segment queue
+ * (src/core/agc_compressor.cpp:1093-1272: store_segments -> CSegment::add -> add_to_archive) while the next contigs are read;
+ * here a batch is queued on streams of its own and the call returns once the inputs are on the device, so a pack is coded
+ * while the host and the library stream go on with the following samples.  agcgpu_zstd_collect waits for every batch
+ * submitted since the last collect and returns their frames in submission order (n_expected = their total number of
+ * inputs; frame i = dst[dst_offsets[i] .. dst_offsets[i+1])).  With a communicator (agcgpu_comm_init) every rank submits
+ * the same batches and codes its share of each; collect all-gathers the frames once. */
+int agcgpu_zstd_submit(agcgpu_ctx* ctx, const uint8_t* src, const uint64_t* src_offsets, const int32_t* levels, uint32_t n);
+int agcgpu_zstd_collect(agcgpu_ctx* ctx, uint32_t n_expected, uint8_t* dst, uint64_t dst_cap, uint64_t* dst_offsets);
 
 /* ZSTD_decompressDCtx (3rd_party/zstd/lib/decompress) for a batch of independent frames, as CSegment::unpack / get
  * (src/common/segment.cpp:500-577, 220-399) and CCollection_V3 call it: the decode side of the residual coder, used by the

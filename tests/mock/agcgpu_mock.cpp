@@ -69,6 +69,8 @@ struct agcgpu_ctx {
     std::vector<uint64_t> ref_kmers;                          // AGCGPU_F_ADAPTIVE: sorted k-mers of the reference sample
     struct SplFound { uint32_t contig; uint64_t pos, kmer; uint8_t is_last; };
     std::vector<SplFound> last_spl;
+    struct ZBatch { std::vector<uint8_t> src; std::vector<uint64_t> offs; std::vector<int32_t> levels; };
+    std::vector<ZBatch> zwaves;                               // agcgpu_zstd_submit: batches waiting for agcgpu_zstd_collect
 };
 
 static thread_local std::string g_create_err;
@@ -471,6 +473,37 @@ int agcgpu_pack_ref_batch(agcgpu_ctx* ctx, const uint32_t* group_ids, uint32_t n
         if (o + pn > out_cap) return fail(ctx, AGCGPU_EOVERFLOW, "pack_ref: output buffer too small");
         if (pn) memcpy(out + o, pay.data(), pn);
         o += pn; out_offsets[i + 1] = o;
+    }
+    return 0;
+}
+
+// the asynchronous coder: submit parks the batch, collect codes every parked batch in submission order
+int agcgpu_zstd_submit(agcgpu_ctx* ctx, const uint8_t* src, const uint64_t* so, const int32_t* levels, uint32_t n)
+{
+    COUNT("agcgpu_zstd_submit", n);
+    if (!ctx || !so || (n && (!src || !levels))) return AGCGPU_EINVAL;
+    if (!n) return 0;
+    agcgpu_ctx::ZBatch b;
+    b.src.assign(src + so[0], src + so[n]); b.offs.resize(n + 1); b.levels.assign(levels, levels + n);
+    for (uint32_t i = 0; i <= n; ++i) b.offs[i] = so[i] - so[0];
+    ctx->zwaves.push_back(std::move(b));
+    return 0;
+}
+int agcgpu_zstd_collect(agcgpu_ctx* ctx, uint32_t n_expected, uint8_t* dst, uint64_t dst_cap, uint64_t* dof)
+{
+    COUNT("agcgpu_zstd_collect", n_expected);
+    if (!ctx || !dof || (n_expected && !dst)) return AGCGPU_EINVAL;
+    std::vector<agcgpu_ctx::ZBatch> waves; waves.swap(ctx->zwaves);
+    uint64_t total = 0; for (auto& w : waves) total += w.levels.size();
+    if (total != n_expected) return fail(ctx, AGCGPU_EINVAL, "zstd collect: %llu inputs were submitted, the caller expects %u", (unsigned long long)total, n_expected);
+    uint64_t base = 0, o = 0; dof[0] = 0;
+    for (auto& w : waves) {
+        const uint32_t n = (uint32_t)w.levels.size();
+        std::vector<uint64_t> fo(n + 1, 0);
+        w.src.push_back(0);
+        if (int r = agcgpu_zstd_compress_batch(ctx, w.src.data(), w.offs.data(), w.levels.data(), n, dst + o, dst_cap - o, fo.data())) return r;
+        for (uint32_t i = 0; i < n; ++i) dof[base + i + 1] = o + fo[i + 1];
+        o += fo[n]; base += n;
     }
     return 0;
 }
