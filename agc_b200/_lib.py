@@ -53,7 +53,7 @@ class Stats(C.Structure):
                 ("lz_chunk_segments", C.c_uint64), ("lz_sequential_segments", C.c_uint64),
                 ("lz_alg_bytes_total", C.c_uint64), ("scan_bytes_total", C.c_uint64), ("lz_kernel_ms_total", C.c_float),
                 ("scan_kernel_ms_total", C.c_float), ("lz_encode_launches", C.c_uint32), ("scan_launches", C.c_uint32),
-                ("zstd_wait_ms", C.c_float), ("reserved0", C.c_uint32)]
+                ("zstd_wait_ms", C.c_float), ("lz_diag_segments", C.c_uint32)]
 
 
 # every symbol include/agcgpu.h declares (tests/test_abi.py checks header <-> library <-> this list)

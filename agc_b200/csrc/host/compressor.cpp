@@ -663,10 +663,16 @@ bool CAGCCompressor::flush_jobs(bool force)
     if (!force && !dump_f && !discard_parts) {
         // not a drain: hand what was queued since the last call to the device (asynchronous: it is coded while the next samples
         // are processed) and go on; the host copies stay until the drain
-        if (async_coder() && !submit_pending(false)) return false;
+        // (only once a worthwhile batch has gathered: a submit costs device allocations and a stream of its own, and small parts
+        // gain nothing from an early start -- AGCGPU_ZSTD_ASYNC_MIN overrides the 32 MiB)
+        static const uint64_t async_min = getenv("AGCGPU_ZSTD_ASYNC_MIN") ? strtoull(getenv("AGCGPU_ZSTD_ASYNC_MIN"), nullptr, 10) : (32ull << 20);
+        if (async_coder() && pending_job_bytes - submitted_job_bytes >= async_min) {
+            if (!submit_pending(false)) return false;
+            submitted_job_bytes = pending_job_bytes;
+        }
         if (pending_job_bytes < flush_threshold) return true;
     }
-    pending_job_bytes = 0;
+    pending_job_bytes = 0; submitted_job_bytes = 0;
     if (!dump_f && !discard_parts && async_coder() && !submit_pending(true)) return false;       // before the sort moves the jobs around
     std::stable_sort(jobs.begin(), jobs.end(), [](const PartJob& a, const PartJob& b) {
         if (a.epoch != b.epoch) return a.epoch < b.epoch;

@@ -212,6 +212,7 @@ private:
     uint32_t processed_samples = 0;
     uint64_t epoch = 0, job_seq = 0, total_bases = 0;
     std::vector<PartJob> jobs;
+    uint64_t submitted_job_bytes = 0;                            // pending_job_bytes at the last asynchronous submit
     size_t jobs_submitted = 0;                                   // jobs[0 .. jobs_submitted) are with the device already
     std::vector<ZTask*> inflight;                                // their tasks, in submission order
     bool async_coder() const;

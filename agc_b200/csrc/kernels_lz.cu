@@ -1000,6 +1000,54 @@ int agc_lz_run(agcgpu_ctx* ctx, int mode, const agcgpu_seg_req* reqs, uint32_t n
         return 0;
     };
     static const bool no_chunks = getenv("AGCGPU_LZ_SEQUENTIAL") != nullptr;          // diagnostics: force the sequential kernel
+    // ---- encode: warp per segment streaming along the diagonal (kernels_lz_diag.cu) for every segment of ordinary length; what is
+    // left (segments above LZD_MAX_N bases: contigs without splitters) takes the chunk-parallel kernels below
+    static const bool no_diag = getenv("AGCGPU_LZ_NO_DIAG") != nullptr;               // diagnostics: chunk-parallel kernels for everything
+    bool diag_timed = false;
+    if (mode == 0 && !no_chunks && !no_diag && !packed_reqs.empty()) {
+        std::vector<LzReqDev> dq, rest;
+        // reference AND hash table staged (32 warps, 1 CTA per SM).  AGCGPU_LZ_DIAG_HT=0 stages the reference alone (16 warps, 3 CTAs per
+        // SM, index probes through L2): measured no faster at 0.1 % SNPs (0.415 vs 0.423 ms) and 23 % slower at 1 % -- kept as a switch
+        static const int ht_staged = getenv("AGCGPU_LZ_DIAG_HT") ? atoi(getenv("AGCGPU_LZ_DIAG_HT")) : 1;
+        const size_t stage_max = ht_staged ? (size_t)227 * 1024 - agc_lzd_scratch_bytes(1) - 1024 : (size_t)32 * 1024;
+        const uint32_t unit_max = ht_staged ? 32u : 16u;
+        for (const LzReqDev& q : packed_reqs) {
+            // one warp walks a segment alone, with the reference (and its index) in shared memory: segments of ordinary length whose
+            // group fits there; the others (contigs without splitters, merged segments) take the chunk-parallel kernels
+            const GroupRefDev& g = ctx->h_groups[q.group];
+            const size_t need = (size_t)g.packed_bytes + (ht_staged ? (size_t)g.ht_size * ((g.flags & GRF_SHORT) ? 2 : 4) : 0);
+            (q.n <= LZD_MAX_N && need <= stage_max ? dq : rest).push_back(q);
+        }
+        if (!dq.empty()) {
+            std::vector<LzUnit> un;
+            size_t stage = 0;
+            for (size_t a = 0; a < dq.size();) {
+                size_t b = a;
+                while (b < dq.size() && dq[b].group == dq[a].group) ++b;
+                const GroupRefDev& g = ctx->h_groups[dq[a].group];
+                size_t need = (size_t)g.packed_bytes + (ht_staged ? (size_t)g.ht_size * ((g.flags & GRF_SHORT) ? 2 : 4) : 0);
+                if (need <= stage_max) stage = std::max(stage, need);
+                const size_t cnt = b - a, nun = (cnt + unit_max - 1) / unit_max, per = (cnt + nun - 1) / nun;      // one request per warp and round
+                for (size_t s0 = a; s0 < b; s0 += per) {
+                    LzUnit u; u.group = dq[a].group; u.first = (uint32_t)s0; u.count = (uint32_t)std::min(per, b - s0); u.pad = 0;
+                    un.push_back(u);
+                }
+                a = b;
+            }
+            if (int r = agc_reserve(ctx, ctx->scr_rec, dq.size() * sizeof(LzReqDev) + un.size() * sizeof(LzUnit) + 256)) return r;
+            LzReqDev* d_req = (LzReqDev*)ctx->scr_rec.p;
+            LzUnit* d_un = (LzUnit*)(d_req + dq.size());
+            CK(cudaMemcpyAsync(d_req, dq.data(), dq.size() * sizeof(LzReqDev), cudaMemcpyHostToDevice, ctx->st));
+            CK(cudaMemcpyAsync(d_un, un.data(), un.size() * sizeof(LzUnit), cudaMemcpyHostToDevice, ctx->st));
+            ctx->stats.h2d_bytes += dq.size() * sizeof(LzReqDev) + un.size() * sizeof(LzUnit);
+            CK(cudaEventRecord(ctx->ev0, ctx->st));
+            if (int r = agc_lzd_launch(ctx, d_req, d_un, (uint32_t)un.size(), stage, ht_staged, slab, res, err)) return r;
+            ctx->stats.lz_diag_segments += (uint32_t)dq.size();
+            diag_timed = true;
+            if (rest.empty()) { CK(cudaEventRecord(ctx->ev1, ctx->st)); chunk_timed = true; }
+        }
+        packed_reqs.swap(rest);
+    }
     if (!packed_reqs.empty() && (mode == 0 || mode == 2) && !no_chunks) {
         // ---- chunk-parallel encode / cost vectors (kernels_lz_chunk.cu): thread per chunk, then thread per segment; segments the
         // stitcher could not prove identical to the sequential parse are redone by the sequential kernel
@@ -1045,7 +1093,7 @@ int agc_lz_run(agcgpu_ctx* ctx, int mode, const agcgpu_seg_req* reqs, uint32_t n
         CK(cudaMemcpyAsync(ctx->scr_units.p, cu.data(), cu.size() * sizeof(LzcUnit), cudaMemcpyHostToDevice, ctx->st));
         ctx->stats.h2d_bytes += nr * sizeof(LzcReq) + cu.size() * sizeof(LzcUnit);
         if (mode == 2) CK(cudaMemsetAsync(costv, 0, slab_total * 4, ctx->st));      // the chunks only write the non-zero entries
-        CK(cudaEventRecord(ctx->ev0, ctx->st));
+        if (!diag_timed) CK(cudaEventRecord(ctx->ev0, ctx->st));
         LzcRec* d_rec = (LzcRec*)ctx->scr_rec.p;
         uint32_t* d_fb = (uint32_t*)(d_rec + n_chunks);
         uint32_t* cnt2 = (uint32_t*)ctx->counters.p;                       // [0] segments for the sequential kernel, [1] overflow
@@ -1066,7 +1114,7 @@ int agc_lz_run(agcgpu_ctx* ctx, int mode, const agcgpu_seg_req* reqs, uint32_t n
         }
         chunk_timed = true; ctx->last_lzc_chunks = n_chunks;
     } else if (!packed_reqs.empty()) {
-        CK(cudaEventRecord(ctx->ev0, ctx->st));
+        if (!diag_timed) CK(cudaEventRecord(ctx->ev0, ctx->st));
         if (int r = run_sequential(packed_reqs)) return r;
     }
     if (!chunk_timed) CK(cudaEventRecord(ctx->ev1, ctx->st));
@@ -1150,6 +1198,11 @@ int agc_lz_run(agcgpu_ctx* ctx, int mode, const agcgpu_seg_req* reqs, uint32_t n
     if (mode == 2 && !out_u32) return 0;                 // nothing was synchronised: the caller queues its reduction behind the launch
     cudaEventElapsedTime(&ctx->stats.last_lz_kernel_ms, ctx->ev0, ctx->ev1);
     ctx->stats.lz_alg_bytes = alg_bytes;
+    if (mode == 0 && getenv("AGCGPU_TRACE_LZ") && *getenv("AGCGPU_TRACE_LZ")) {
+        uint32_t mx = 0, mn = ~0u, nrc = 0; uint64_t sum = 0;
+        for (uint32_t i = 0; i < n; ++i) { mx = std::max(mx, reqs[i].len); mn = std::min(mn, reqs[i].len); sum += reqs[i].len; nrc += reqs[i].is_rc != 0; }
+        fprintf(stderr, "[agcgpu] lz encode call: %u requests (%u rc), %llu bases, len %u..%u, kernels %.3f ms\n", n, nrc, (unsigned long long)sum, mn, mx, ctx->stats.last_lz_kernel_ms);
+    }
     if (mode == 0) { ctx->stats.lz_alg_bytes_total += alg_bytes; ctx->stats.lz_kernel_ms_total += ctx->stats.last_lz_kernel_ms; ctx->stats.lz_encode_launches++; }
     return 0;
 }

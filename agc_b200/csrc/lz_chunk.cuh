@@ -49,3 +49,9 @@ struct LzcUnit { uint32_t group, first, count, item0, n_items, pad; };   // one 
 struct agcgpu_ctx;
 int agc_lzc_launch(agcgpu_ctx* ctx, const LzcReq* d_reqs, uint32_t n_req, const LzcUnit* d_units, uint32_t n_units, size_t smem,
                    uint8_t* cslab, LzcRec* recs, uint8_t* slab, uint32_t* res, uint32_t* fb, uint32_t* counters, uint32_t* costv = nullptr);
+// kernels_lz_diag.cu: warp per segment, streaming along the current diagonal (mode 0 only)
+struct LzReqDev; struct LzUnit;
+int agc_lzd_launch(agcgpu_ctx* ctx, const LzReqDev* d_reqs, const LzUnit* d_units, uint32_t n_units, size_t stage_bytes, int ht_staged,
+                   uint8_t* slab, uint32_t* res, uint32_t* err);
+size_t agc_lzd_scratch_bytes(int ht_staged);
+#define LZD_MAX_N (1u << 17)      // longer segments go to the chunk-parallel kernels (one warp would walk them alone)

@@ -120,7 +120,7 @@ LZC_HD uint32_t lzc_match_cost(uint32_t mp, uint32_t len, uint32_t pred, uint32_
 }
 
 // view of one (text segment, reference) pair for a single thread
-template <bool STAGED>
+template <bool STAGED, bool HT_STAGED = STAGED>
 struct LzcView {
     const uint64_t* T; int64_t gs; uint32_t n, rc;
     const uint64_t* R; uint32_t r_s;            // reference words: generic pointer / shared-memory address
@@ -183,8 +183,8 @@ struct LzcView {
     }
     LZC_HD uint32_t slot(uint32_t s) const
     {
-        if (is_short) { const uint32_t v = STAGED ? lzc_lds16(ht_s + 2u * s) : (uint32_t)((const uint16_t*)ht)[s]; return v == 0xffffu ? AGC_EMPTY32 : v; }
-        return STAGED ? lzc_lds32(ht_s + 4u * s) : ((const uint32_t*)ht)[s];
+        if (is_short) { const uint32_t v = HT_STAGED ? lzc_lds16(ht_s + 2u * s) : (uint32_t)((const uint16_t*)ht)[s]; return v == 0xffffu ? AGC_EMPTY32 : v; }
+        return HT_STAGED ? lzc_lds32(ht_s + 4u * s) : ((const uint32_t*)ht)[s];
     }
     LZC_HD uint32_t tsym(uint32_t q) const { return (uint32_t)(twin(q) >> 62); }
     LZC_HD uint32_t rsym(uint32_t q) const { return (uint32_t)(rwin(q) >> 62); }
@@ -210,8 +210,8 @@ struct LzcView {
 };
 
 // find_best_match16/32 (lz_diff.cpp:287-372) exactly as the sequential code evaluates it (all candidates, full extensions)
-template <bool STAGED>
-LZC_HD bool lzc_best_match_full(const LzcView<STAGED>& a, uint32_t h, uint64_t x, uint32_t p, uint32_t np, uint32_t kl, uint32_t mml,
+template <class View>
+LZC_HD bool lzc_best_match_full(const View& a, uint32_t h, uint64_t x, uint32_t p, uint32_t np, uint32_t kl, uint32_t mml,
                                     uint32_t& o_hp, uint32_t& o_b, uint32_t& o_f, bool& np_limited)
 {
     uint32_t best_b = 0, best_f = 0, best_hp = 0, mtu = mml;
@@ -325,7 +325,7 @@ LZC_HD void lzc_parse_stream(LzcView<STAGED> a, uint32_t mml, Fetch& fetch)
                 continue;
             }
             if (ncand > 1) {                                                // rare: the sequential evaluation of all candidates
-                e_ok = lzc_best_match_full<STAGED>(a, h, x, i, np, kl, mml, e_hp, e_b, e_f, e_npl);
+                e_ok = lzc_best_match_full(a, h, x, i, np, kl, mml, e_hp, e_b, e_f, e_npl);
                 e_multi = true; st = ST_RESOLVE;
                 continue;
             }

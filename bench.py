@@ -163,7 +163,8 @@ def run_reference(args, rank, world):
 
 
 STAT_KEYS = ("kernel_launches", "h2d_bytes", "d2h_bytes", "zstd_kernel_ms", "zstd_input_mb", "lz_alg_bytes_total", "lz_kernel_ms_total",
-             "scan_bytes_total", "scan_kernel_ms_total", "lz_encode_launches", "scan_launches", "lz_chunk_segments", "lz_sequential_segments")
+             "scan_bytes_total", "scan_kernel_ms_total", "lz_encode_launches", "scan_launches", "lz_chunk_segments", "lz_sequential_segments",
+             "zstd_wait_ms", "lz_diag_segments")
 
 
 class Runner:
@@ -314,7 +315,7 @@ def main():
             lz_gbs = lz_b / (lz_ms * 1e-3) / 1e9 if lz_ms else 0.0
             sc_ms, sc_b = st_res["scan_kernel_ms_total"], st_res["scan_bytes_total"]
             sc_gbs = sc_b / (sc_ms * 1e-3) / 1e9 if sc_ms else 0.0
-            prof = os.path.join(ROOT, "profiles", "r02_lz_traffic.json")
+            prof = os.path.join(ROOT, "profiles", "r02_lz_traffic.json")      # dram__bytes_read + dram__bytes_write of one ncu --set full capture
             traffic = json.load(open(prof)) if os.path.exists(prof) else {}
             line = {"metric": "input Gbp/s (agc create, bit-exact .agc)", "value": total / sec_res / 1e9, "unit": "Gbp/s", "n_gpus": world,
                     "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec_res * 1e3, "higher_is_better": True,
@@ -325,18 +326,22 @@ def main():
                             "includes": "FASTA file read + parse, H2D/D2H, archive write"},
                     "gpu_launches": int(st_res["kernel_launches"]) * args.steps,
                     "archive_sha256": sha_e2e, "reference_sha256": ref_sha, "bit_exact": True,
-                    "roofline": {"kernel": "k_lzc_parse + k_lzc_stitch (LZ-diff encode, all launches of the step)", "bound": "hbm", "achieved": lz_gbs, "peak": peak,
+                    "roofline": {"kernel": "k_lz_diag (+ k_lzc_parse / k_lzc_stitch for segments above 128 kb): LZ-diff encode, all launches of the step", "bound": "hbm", "achieved": lz_gbs, "peak": peak,
                                  "unit": "GB/s", "frac": lz_gbs / peak, "traffic": traffic.get("step_traffic_bytes_per_launch"), "peak_source": peak_src,
                                  "algorithmic_bytes_per_step": int(lz_b), "kernel_ms_per_step": lz_ms, "launches_per_step": int(st_res["lz_encode_launches"]),
-                                 "segments_chunk_parallel": int(st_res["lz_chunk_segments"]), "segments_sequential_kernel": int(st_res["lz_sequential_segments"]),
-                                 "note": "-a mode: one device batch per sample, so a launch holds ~90 segments (2.7 MB algorithmic): launch-latency bound; the HBM figure of the kernel is lz_kernel_hpp_like_batch"},
+                                 "segments_diagonal_kernel": int(st_res["lz_diag_segments"]), "segments_chunk_parallel": int(st_res["lz_chunk_segments"]),
+                                 "segments_sequential_kernel": int(st_res["lz_sequential_segments"]),
+                                 "note": "-a mode: one device batch per sample, so a launch holds ~90 segments (2.7 MB algorithmic) and lasts as long as its slowest warp: launch-latency bound; the HBM figure of the kernel is lz_kernel_hpp_like_batch (segments_chunk_parallel also counts the cost-vector requests of the missing-middle decisions)"},
                     "scan_roofline": {"kernel": "k_scan (splitter scan over 2-bit packed contigs)", "bound": "hbm", "achieved": sc_gbs, "peak": peak, "unit": "GB/s",
                                       "frac": sc_gbs / peak, "algorithmic_bytes_per_step": int(sc_b), "kernel_ms_per_step": sc_ms, "launches_per_step": int(st_res["scan_launches"])},
                     "residual_coder": {"kernel": "k_zstd / k_zstd_narrow (bit-exact zstd frames, one CTA per part)", "ms_per_step": float(st_res["zstd_kernel_ms"]),
-                                       "input_bytes_per_step": int(st_res["zstd_input_mb"] * 1e6), "share_of_step": float(st_res["zstd_kernel_ms"]) / (sec_res * 1e3)},
+                                       "input_bytes_per_step": int(st_res["zstd_input_mb"] * 1e6), "host_wait_ms_per_step": float(st_res["zstd_wait_ms"]),
+                                       "share_of_step": float(st_res["zstd_wait_ms"] or st_res["zstd_kernel_ms"]) / (sec_res * 1e3),
+                                       "note": "batches are queued behind the pipeline (agcgpu_zstd_submit); host_wait_ms = the part that did not overlap"},
                     "cpu_baseline": cpu, "clocks": sampler.summary()}
             if comm_info:
-                line["comm"] = comm_info
+                from agc_b200 import dist as agc_dist
+                line["comm"] = agc_dist.comm_stats()          # counters after the run: collectives issued by the data path
             if not args.no_extra and world == 1:
                 line["lz_kernel_hpp_like_batch"] = lz_hpp_batch(local_rank, peak, traffic)
                 line["other_workloads"] = {}
@@ -359,14 +364,39 @@ def main():
             dist.destroy_process_group()
 
 
+def cpu_lz_encode_leg(n_texts=32, reps=4):
+    """BASELINE.md section 3 per-stage CPU number: the reference's own CLZDiff_V2::Encode (oracle/_ref/liblzdiff_ref.so, index prepared
+    once) on segments of the same shape as the device batch, one thread"""
+    so = os.path.join(ROOT, "oracle", "_ref", "liblzdiff_ref.so")
+    if not os.path.exists(so):
+        return None
+    import gen_data
+    L = C.CDLL(so)
+    if not hasattr(L, "ref_lz_encode_many_ns"):
+        return None
+    L.ref_lz_encode_many_ns.restype = C.c_long
+    L.ref_lz_encode_many_ns.argtypes = [C.c_void_p, C.c_long, C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_void_p]
+    rng = np.random.default_rng(1)
+    ref = rng.integers(0, 4, 60031, dtype=np.uint8)
+    texts = [gen_data.substitute(rng, ref, 0.001) for _ in range(n_texts)]
+    cat = np.concatenate(texts); offs = np.zeros(n_texts + 1, np.int64); offs[1:] = np.cumsum([len(t) for t in texts])
+    ob = C.c_long()
+    ns = L.ref_lz_encode_many_ns(ref.ctypes.data, len(ref), cat.ctypes.data, offs.ctypes.data, n_texts, MML, reps, C.byref(ob))
+    bases = n_texts * reps * 60031
+    return {"value": bases / ns, "unit": "Gbase/s", "cores": 1, "kind": "reference",
+            "sample": f"CLZDiff_V2::Encode of {n_texts} x 60 031-base segments (0.1% SNP) x {reps} against one prepared reference, single thread"}
+
+
 def lz_hpp_batch(device, peak, traffic):
-    """the LZ-diff encode kernels on 16384 segments of 60 031 bases (0.1 % SNP, 256 reference segments; 0.98 Gbase, one HPP-scale device
-    batch): CUDA-event time of the launch (k_lzc_parse + k_lzc_stitch), L2 flushed before every launch (working set 0.5 GB > L2 anyway)"""
+    """the LZ-diff encode kernel on 16384 segments of 60 031 bases (0.1 % SNP, 256 reference segments; 0.98 Gbase, one HPP-scale device
+    batch): CUDA-event time of the launch (k_lz_diag), L2 flushed before every launch (working set 0.5 GB > L2 anyway)"""
     import lz_hpp_bench
     r = lz_hpp_bench.run(16384, 0.001, 256, reps=5, device=device, flush=True)
+    t = traffic.get("hpp_traffic_bytes_per_launch")
     return {"workload": f"{r['n_seg']} segments x {r['seg_len']} bases, 0.1% SNP, {r['groups']} reference segments (one HPP-scale device batch; working set >> L2, L2 flushed between launches)",
-            "kernel_ms": r["kernel_ms"], "algorithmic_bytes_per_launch": r["alg_bytes"], "achieved": r["GBps"], "unit": "GB/s", "frac": r["GBps"] / peak,
-            "Gbase_per_s": r["Gbase_per_s"], "segments_sequential_kernel": r["sequential_segments"], "traffic": traffic.get("hpp_traffic_bytes_per_launch")}
+            "kernel": "k_lz_diag", "kernel_ms": r["kernel_ms"], "algorithmic_bytes_per_launch": r["alg_bytes"], "achieved": r["GBps"], "unit": "GB/s", "frac": r["GBps"] / peak,
+            "Gbase_per_s": r["Gbase_per_s"], "segments_sequential_kernel": r["sequential_segments"], "traffic": t,
+            "traffic_source": traffic.get("source"), "cpu_lz_encode": cpu_lz_encode_leg()}
 
 
 if __name__ == "__main__":

@@ -105,7 +105,7 @@ typedef struct {
     float    scan_kernel_ms_total;
     uint32_t lz_encode_launches, scan_launches;
     float    zstd_wait_ms;            /* host time blocked in agcgpu_zstd_collect: the part of the residual coder that did NOT overlap */
-    uint32_t reserved0;
+    uint32_t lz_diag_segments;        /* segments encoded by the warp-per-segment diagonal kernel since agcgpu_create */
 } agcgpu_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------------------------------- */

@@ -4,6 +4,8 @@
 // and the CUDA kernels against the reference itself. Never linked into the product.
 #include "lz_diff.h"
 #include <cstring>
+#include <ctime>
+#include <vector>
 extern "C" {
 // returns encoded size; out may be NULL to query size only
 long ref_lz_encode(const uint8_t* ref, long m, const uint8_t* text, long n, int min_match_len, uint8_t* out, long cap)
@@ -15,6 +17,26 @@ long ref_lz_encode(const uint8_t* ref, long m, const uint8_t* text, long n, int 
     lz.Encode(t, e);
     if (out && (long)e.size() <= cap) memcpy(out, e.data(), e.size());
     return (long)e.size();
+}
+// per-stage CPU microbenchmark: CLZDiff_V2::Encode alone -- the index is prepared once, then every text
+// (text i = texts[offs[i] .. offs[i+1])) is encoded `reps` times; returns the nanoseconds spent in Encode, *out_bytes the delta bytes
+long ref_lz_encode_many_ns(const uint8_t* ref, long m, const uint8_t* texts, const long* offs, long n_texts, int min_match_len, int reps,
+                           long* out_bytes)
+{
+    CLZDiff_V2 lz(min_match_len);
+    lz.SetMinMatchLen(min_match_len);
+    contig_t r(ref, ref + m);
+    lz.Prepare(r);
+    lz.AssureIndex();
+    std::vector<contig_t> t;
+    for (long i = 0; i < n_texts; ++i) t.emplace_back(texts + offs[i], texts + offs[i + 1]);
+    contig_t e; long bytes = 0;
+    struct timespec a, b;
+    clock_gettime(CLOCK_MONOTONIC, &a);
+    for (int k = 0; k < reps; ++k) for (auto& x : t) { lz.Encode(x, e); bytes += (long)e.size(); }
+    clock_gettime(CLOCK_MONOTONIC, &b);
+    if (out_bytes) *out_bytes = bytes;
+    return (b.tv_sec - a.tv_sec) * 1000000000L + (b.tv_nsec - a.tv_nsec);
 }
 long ref_lz_estimate(const uint8_t* ref, long m, const uint8_t* text, long n, int min_match_len, unsigned bound)
 {
