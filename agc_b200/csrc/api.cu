@@ -95,6 +95,32 @@ void* agc_arena_alloc(agcgpu_ctx* ctx, size_t bytes)
     return r;
 }
 
+// page-locked host memory for the caller's ingest buffers (include/agcgpu.h), pooled like the contexts' staging buffers: a file read
+// straight into such a buffer goes to the device by DMA without the driver's staging copy
+extern "C" void* agcgpu_host_alloc(uint64_t bytes, uint64_t* out_cap)
+{
+    if (!out_cap) return nullptr;
+    {   std::lock_guard<std::mutex> lk(g_pool_mu);
+        int best = -1;
+        for (int i = 0; i < (int)g_pin_pool.size(); ++i)
+            if (g_pin_pool[i].cap >= bytes && (best < 0 || g_pin_pool[i].cap < g_pin_pool[best].cap)) best = i;
+        if (best >= 0) { PoolBlock b = g_pin_pool[best]; g_pin_pool.erase(g_pin_pool.begin() + best); *out_cap = b.cap; return b.p; }
+    }
+    void* p = nullptr;
+    const size_t ncap = (size_t)bytes + (size_t)bytes / 4 + 4096;
+    if (cudaMallocHost(&p, ncap) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    *out_cap = ncap;
+    return p;
+}
+extern "C" void agcgpu_host_free(void* p, uint64_t cap)
+{
+    if (!p) return;
+    {   std::lock_guard<std::mutex> lk(g_pool_mu);
+        if (g_pin_pool.size() < 6) { g_pin_pool.push_back(PoolBlock{ p, (size_t)cap }); return; }
+    }
+    cudaFreeHost(p);
+}
+
 int agc_pin_reserve(agcgpu_ctx* ctx, size_t bytes)
 {
     if (bytes <= ctx->pin_cap) return 0;
@@ -369,7 +395,7 @@ int agcgpu_map_insert(agcgpu_ctx* ctx, const uint64_t* k1, const uint64_t* k2, c
         if (gid[i] < 0) return agc_fail(ctx, AGCGPU_EINVAL, "map_insert: negative group id");
         ctx->h_map_k1.push_back(k1[i]); ctx->h_map_k2.push_back(k2[i]); ctx->h_map_val.push_back(gid[i]);
     }
-    return agc_map_rebuild(ctx);
+    return agc_map_update(ctx);
 }
 
 int agcgpu_assign_cuts(agcgpu_ctx* ctx, const agcgpu_cut* cuts, uint64_t n, agcgpu_assign* out)

@@ -1,5 +1,8 @@
 // compressor.cpp -- see compressor.h.  Reference citations are relative to /root/reference.
 #include "compressor.h"
+#include <fcntl.h>
+#include <unistd.h>
+#include <sys/stat.h>
 #include <chrono>
 #include <cstdlib>
 #include <cstdio>
@@ -325,6 +328,7 @@ CAGCCompressor::CAGCCompressor() {}
 CAGCCompressor::~CAGCCompressor()
 {
     if (working) Close(1);
+    if (arena) agcgpu_host_free(arena, arena_cap);
     if (ctx) agcgpu_destroy(ctx);
     if (dump_f) fclose(dump_f);
 }
@@ -352,6 +356,13 @@ std::string CAGCCompressor::ss_base(uint32_t n) const       // utils.cpp:30-66 (
 void CAGCCompressor::add_job(PartJob&& j)
 {
     j.seq = job_seq++;
+    // The device residual coder restates libzstd's index handling for inputs below 1 GiB only (include/agcgpu.h): a part beyond that
+    // (a pack of pack_cardinality splitter-less contigs of a large genome) is refused HERE, when it is queued, with a message that
+    // says what to do -- not at the drain after all the device work has been done.  flush_jobs reports it.
+    for (auto& t : j.tasks)
+        if (t.raw.size() >= (1ull << 30) && oversize_error.empty())
+            oversize_error = "a part of " + std::to_string(t.raw.size()) + " bytes (stream " + std::to_string(j.stream_id) + ") exceeds the residual coder's 1 GiB input limit: "
+                             "lower the pack cardinality (-b) so that a pack of raw contigs stays below 1 GiB";
     for (auto& t : j.tasks) pending_job_bytes += t.raw.size();
     jobs.emplace_back(std::move(j));
 }
@@ -659,6 +670,7 @@ static void dump_bytes(FILE* f, const void* p, size_t n) { dump_u64(f, n); if (n
 // Registration epochs only grow, so one sorted drain writes the parts in the same order as many small ones would.
 bool CAGCCompressor::flush_jobs(bool force)
 {
+    if (!oversize_error.empty()) return fail(oversize_error);
     if (jobs.empty() && extra_tasks.empty()) return true;
     if (!force && !dump_f && !discard_parts) {
         // not a drain: hand what was queued since the last call to the device (asynchronous: it is coded while the next samples
@@ -729,6 +741,7 @@ bool CAGCCompressor::AddSampleFiles(std::vector<std::pair<std::string, std::stri
 {
     if (!working) return false;
     if (files.empty()) return true;
+    if (!concatenated_genomes) return add_sample_files_arena(files);
     std::vector<std::vector<uint8_t>> raws;
     std::vector<BatchContig> owners;
     uint64_t raw_in_batch = 0;
@@ -779,6 +792,115 @@ bool CAGCCompressor::AddSampleFiles(std::vector<std::pair<std::string, std::stri
     if (!raws.empty()) if (!process_batch(raws, owners)) return false;
     if (trailing_empty_unit) { account_registration(); if (!flush_jobs(false)) return false; }
     if (concatenated_genomes) processed_samples = (uint32_t)collection.get_no_samples();        // 2255-2256
+    if (processed_samples % pack_cardinality != 0)                                     // agc_compressor.cpp:2258-2259
+        store_contig_batch((processed_samples / pack_cardinality) * pack_cardinality, processed_samples, epoch);
+    ++epoch;
+    return flush_jobs(false);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Ingest without -c: the raw contigs of a device batch gather back to back in ONE page-locked buffer (agcgpu_host_alloc) that
+// agcgpu_scan_contigs uploads by DMA.  A plain FASTA file is read() straight into that buffer and cut into records in place with
+// the rules of CGenomeIO::ReadContigRaw (the bodies slide down over the header lines); gzipped files go through ReadContigRaw.
+// ---------------------------------------------------------------------------------------------------------------------
+bool CAGCCompressor::arena_reserve(uint64_t need)
+{
+    if (need <= arena_cap) return true;
+    uint64_t cap = 0;
+    uint8_t* np = (uint8_t*)agcgpu_host_alloc(std::max<uint64_t>(need, 2 * arena_cap), &cap);
+    if (!np) return fail("agcgpu_host_alloc(" + std::to_string(need) + ") failed");
+    if (arena_used) memcpy(np, arena, arena_used);
+    if (arena) agcgpu_host_free(arena, arena_cap);
+    arena = np; arena_cap = cap;
+    return true;
+}
+
+bool CAGCCompressor::add_sample_files_arena(std::vector<std::pair<std::string, std::string>>& files)
+{
+    std::vector<BatchContig> owners;
+    std::vector<uint64_t> offs(1, 0);
+    arena_used = 0;
+    auto flush_batch = [&]() -> bool {
+        if (owners.empty()) return true;
+        const bool ok = process_batch_raw(arena, false, offs, owners);
+        owners.clear(); offs.assign(1, 0); arena_used = 0;
+        return ok;
+    };
+    for (auto& sf : files) {
+        collection.reset_prev_sample_name();
+        bool any_read = false, any_added = false, opened = false;
+        auto add_contig = [&](const std::string& id) -> bool {          // the body already lies at arena[offs.back() .. arena_used)
+            if (collection.register_sample_contig(sf.first, id)) {
+                const uint32_t sid = (uint32_t)collection.sample_desc.size() - 1;
+                owners.push_back(BatchContig{ sid, (uint32_t)collection.sample_desc[sid].contigs.size() - 1, sid });
+                offs.push_back(arena_used);
+                any_added = true;
+                return true;
+            }
+            std::cerr << "Error: Pair sample_name:contig_name " << sf.first << ":" << id << " is already in the archive!\n";
+            arena_used = offs.back();                                    // drop the body
+            return false;
+        };
+        int fd = ::open(sf.second.c_str(), O_RDONLY);
+        struct stat st;
+        uint8_t magic[2] = { 0, 0 };
+        const bool plain = fd >= 0 && fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && ::pread(fd, magic, 2, 0) >= 0 && !(magic[0] == 0x1f && magic[1] == 0x8b);
+        if (plain) {
+            opened = true;
+            const uint64_t fsize = (uint64_t)st.st_size, start = arena_used;
+            if (!arena_reserve(start + fsize + 64)) { ::close(fd); return false; }
+            uint64_t got = 0;
+            while (got < fsize) { const ssize_t r = ::read(fd, arena + start + got, (size_t)std::min<uint64_t>(fsize - got, 1ull << 30)); if (r <= 0) break; got += (uint64_t)r; }
+            ::close(fd);
+            // records in place: rd = read cursor, arena_used = write cursor (never ahead of rd)
+            const uint8_t* end = arena + start + got;
+            const uint8_t* rd = arena + start;
+            std::string id;
+            while (true) {
+                id.clear();
+                bool eof = false;
+                while (true) {                                           // header line (ReadContigRaw: up to '\n' or '\r')
+                    if (rd >= end) { eof = true; break; }
+                    const uint8_t c = *rd++;
+                    if (c == '\n' || c == '\r') break;
+                    id.push_back((char)c);
+                }
+                if (eof) break;
+                if (!id.empty()) id.erase(id.begin());
+                const uint8_t* q = (const uint8_t*)memchr(rd, '>', (size_t)(end - rd));
+                const uint8_t* body_end = q ? q : end;
+                const uint64_t blen = (uint64_t)(body_end - rd);
+                if (id.empty() || blen == 0) break;
+                any_read = true;
+                memmove(arena + arena_used, rd, blen);
+                arena_used += blen;
+                add_contig(id);
+                rd = body_end;
+            }
+            if (arena_used < start) arena_used = start;
+        } else {
+            if (fd >= 0) ::close(fd);
+            CGenomeIO gio;
+            if (gio.Open(sf.second)) {
+                opened = true;
+                std::string id; std::vector<uint8_t> contig;
+                while (gio.ReadContigRaw(id, contig)) {
+                    any_read = true;
+                    if (!arena_reserve(arena_used + contig.size() + 64)) return false;
+                    memcpy(arena + arena_used, contig.data(), contig.size());
+                    arena_used += contig.size();
+                    add_contig(id);
+                }
+            }
+        }
+        if (!opened) { std::cerr << "Cannot open file: " << sf.second << std::endl; continue; }
+        if (!any_read) std::cerr << "Warning: Pair sample_name:file_path " << sf.first << ":" << sf.second << " contains no contigs and will not be included in the archive!\n";
+        if (!any_added) std::cerr << "Warning: Pair sample_name:file_path " << sf.first << ":" << sf.second << " contains only contigs already present in the archive!\n";
+        // -a: the splitter set may grow at every sample's synchronisation point (new_splitters stage, 1187-1229), so a
+        // device batch is one sample
+        if (arena_used >= batch_bases || (adaptive_compression && !owners.empty())) if (!flush_batch()) return false;
+    }
+    if (!flush_batch()) return false;
     if (processed_samples % pack_cardinality != 0)                                     // agc_compressor.cpp:2258-2259
         store_contig_batch((processed_samples / pack_cardinality) * pack_cardinality, processed_samples, epoch);
     ++epoch;

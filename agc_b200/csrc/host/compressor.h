@@ -191,7 +191,7 @@ private:
     int device = 0;
     uint32_t xrank = 0, xworld = 1; agcgpu_allgather_fn xfn = nullptr; void* xuser = nullptr;
     uint64_t batch_bases = 1ull << 30;
-    std::string dump_path, last_error;
+    std::string dump_path, last_error, oversize_error;
     bool discard_parts = false, verify = false;
     FILE* dump_f = nullptr;
 
@@ -212,6 +212,9 @@ private:
     uint32_t processed_samples = 0;
     uint64_t epoch = 0, job_seq = 0, total_bases = 0;
     std::vector<PartJob> jobs;
+    uint8_t* arena = nullptr; uint64_t arena_cap = 0, arena_used = 0;   // page-locked ingest buffer: the raw contigs of the device batch
+    bool arena_reserve(uint64_t need);
+    bool add_sample_files_arena(std::vector<std::pair<std::string, std::string>>& files);
     uint64_t submitted_job_bytes = 0;                            // pending_job_bytes at the last asynchronous submit
     size_t jobs_submitted = 0;                                   // jobs[0 .. jobs_submitted) are with the device already
     std::vector<ZTask*> inflight;                                // their tasks, in submission order

@@ -148,6 +148,8 @@ struct agcgpu_ctx {
     DevBuf map_k1, map_k2, map_val;
     uint64_t map_mask = 0, map_count = 0;
     std::vector<uint64_t> h_map_k1, h_map_k2; std::vector<int32_t> h_map_val;   // insertion log for rebuilds
+    std::vector<uint64_t> t_k1, t_k2; std::vector<int32_t> t_val;               // host mirror of the table (places new keys)
+    uint64_t map_placed = 0;                                                    // log entries already in the mirror
 
     // reference store
     std::vector<GroupRefDev> h_groups;
@@ -191,6 +193,7 @@ int agc_enumerate_splitters(agcgpu_ctx* ctx, uint32_t c0, uint32_t nc, bool excl
 int agc_expand_segment(agcgpu_ctx* ctx, uint64_t gstart, uint32_t n, uint32_t is_rc, uint8_t* dst_dev, uint32_t pad_bytes);
 int agc_upload_splitters(agcgpu_ctx* ctx, const uint64_t* s, uint64_t n);
 int agc_map_rebuild(agcgpu_ctx* ctx);
+int agc_map_update(agcgpu_ctx* ctx);      // places the keys logged since the last call (rebuilds when the table is too full)
 int agc_assign_launch(agcgpu_ctx* ctx, const agcgpu_cut* cuts, uint64_t n, agcgpu_assign* out);
 
 // comm.cu (NCCL exchange)

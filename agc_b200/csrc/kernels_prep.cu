@@ -462,29 +462,69 @@ int agc_expand_segment(agcgpu_ctx* ctx, uint64_t gstart, uint32_t n, uint32_t is
     return 0;
 }
 
+// The (k1, k2) -> group table lives twice: the device copy k_assign reads and a host mirror that decides where a new key goes.
+// A rebuild (first use, or the load factor reached 1/4) sizes the table for twice the keys and uploads it whole; every other
+// insertion only touches the slots of the new keys: they are placed in the mirror and sent as a short update list that
+// k_map_apply writes into the device copy (one registration unit adds a handful of groups to a table of up to millions).
+struct MapUpd { uint64_t slot, k1, k2; int32_t val; int32_t pad; };
+__global__ void k_map_apply(const MapUpd* __restrict__ u, uint32_t n, uint64_t* __restrict__ mk1, uint64_t* __restrict__ mk2, int32_t* __restrict__ mval)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const MapUpd x = u[i];
+    mk1[x.slot] = x.k1; mk2[x.slot] = x.k2; mval[x.slot] = x.val;
+}
+// place key i of the insertion log in the mirror; returns the slot when the device copy has to change, ~0 otherwise
+static uint64_t map_place(agcgpu_ctx* ctx, uint64_t i)
+{
+    const uint64_t cap = ctx->t_val.size();
+    const uint64_t a = ctx->h_map_k1[i], b = ctx->h_map_k2[i];
+    const int32_t v = ctx->h_map_val[i];
+    uint64_t slot = agc_murmur_pair(a, b) & (cap - 1);
+    while (ctx->t_val[slot] >= 0 && !(ctx->t_k1[slot] == a && ctx->t_k2[slot] == b)) slot = (slot + 1) & (cap - 1);
+    if (ctx->t_val[slot] < 0) { ctx->t_k1[slot] = a; ctx->t_k2[slot] = b; ctx->t_val[slot] = v; ++ctx->map_count; return slot; }
+    if (ctx->t_val[slot] > v) { ctx->t_val[slot] = v; return slot; }      // keep the smallest id (agc_compressor.cpp:1010-1012)
+    return ~0ull;
+}
 int agc_map_rebuild(agcgpu_ctx* ctx)
 {
-    uint64_t n = ctx->h_map_k1.size();
+    const uint64_t n = ctx->h_map_k1.size();
     uint64_t cap = 1024;
-    while (cap < 4 * n + 16) cap <<= 1;
-    std::vector<uint64_t> k1(cap, 0), k2(cap, 0);
-    std::vector<int32_t> val(cap, -1);
-    uint64_t cnt = 0;
-    for (uint64_t i = 0; i < n; ++i) {
-        uint64_t slot = agc_murmur_pair(ctx->h_map_k1[i], ctx->h_map_k2[i]) & (cap - 1);
-        while (val[slot] >= 0 && !(k1[slot] == ctx->h_map_k1[i] && k2[slot] == ctx->h_map_k2[i])) slot = (slot + 1) & (cap - 1);
-        if (val[slot] < 0) { k1[slot] = ctx->h_map_k1[i]; k2[slot] = ctx->h_map_k2[i]; val[slot] = ctx->h_map_val[i]; ++cnt; }
-        else if (val[slot] > ctx->h_map_val[i]) val[slot] = ctx->h_map_val[i];      // keep the smallest id (agc_compressor.cpp:1010-1012)
-    }
+    while (cap < 8 * n + 16) cap <<= 1;                          // load <= 1/8 now, rebuilt again at 1/4
+    ctx->t_k1.assign(cap, 0); ctx->t_k2.assign(cap, 0); ctx->t_val.assign(cap, -1);
+    ctx->map_count = 0;
+    for (uint64_t i = 0; i < n; ++i) map_place(ctx, i);
+    ctx->map_placed = n;
     if (int r = agc_reserve(ctx, ctx->map_k1, cap * 8)) return r;
     if (int r = agc_reserve(ctx, ctx->map_k2, cap * 8)) return r;
     if (int r = agc_reserve(ctx, ctx->map_val, cap * 4)) return r;
-    CK(cudaMemcpyAsync(ctx->map_k1.p, k1.data(), cap * 8, cudaMemcpyHostToDevice, ctx->st));
-    CK(cudaMemcpyAsync(ctx->map_k2.p, k2.data(), cap * 8, cudaMemcpyHostToDevice, ctx->st));
-    CK(cudaMemcpyAsync(ctx->map_val.p, val.data(), cap * 4, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemcpyAsync(ctx->map_k1.p, ctx->t_k1.data(), cap * 8, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemcpyAsync(ctx->map_k2.p, ctx->t_k2.data(), cap * 8, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemcpyAsync(ctx->map_val.p, ctx->t_val.data(), cap * 4, cudaMemcpyHostToDevice, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
     ctx->stats.h2d_bytes += cap * 20;
-    ctx->map_mask = cap - 1; ctx->map_count = cnt;
+    ctx->map_mask = cap - 1;
+    return 0;
+}
+// the keys appended to the insertion log since the last call
+int agc_map_update(agcgpu_ctx* ctx)
+{
+    const uint64_t n = ctx->h_map_k1.size();
+    if (ctx->map_val.p == nullptr || ctx->t_val.empty() || 4 * n + 16 > ctx->t_val.size()) return agc_map_rebuild(ctx);
+    std::vector<MapUpd> upd;
+    for (uint64_t i = ctx->map_placed; i < n; ++i) {
+        const uint64_t slot = map_place(ctx, i);
+        if (slot != ~0ull) { MapUpd u; u.slot = slot; u.k1 = ctx->t_k1[slot]; u.k2 = ctx->t_k2[slot]; u.val = ctx->t_val[slot]; u.pad = 0; upd.push_back(u); }
+    }
+    ctx->map_placed = n;
+    if (upd.empty()) return 0;
+    if (int r = agc_reserve(ctx, ctx->scr_gsz, upd.size() * sizeof(MapUpd) + 64)) return r;
+    CK(cudaMemcpyAsync(ctx->scr_gsz.p, upd.data(), upd.size() * sizeof(MapUpd), cudaMemcpyHostToDevice, ctx->st));
+    k_map_apply<<<(uint32_t)((upd.size() + 127) / 128), 128, 0, ctx->st>>>((const MapUpd*)ctx->scr_gsz.p, (uint32_t)upd.size(),
+        (uint64_t*)ctx->map_k1.p, (uint64_t*)ctx->map_k2.p, (int32_t*)ctx->map_val.p);
+    CKL();
+    CK(cudaStreamSynchronize(ctx->st));                          // `upd` goes out of scope
+    ctx->stats.h2d_bytes += upd.size() * sizeof(MapUpd);
     return 0;
 }
 

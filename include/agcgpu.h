@@ -116,6 +116,11 @@ const char* agcgpu_last_error(const agcgpu_ctx* ctx);     /* ctx may be NULL: er
 int agcgpu_sync(agcgpu_ctx* ctx);                         /* wait for all work queued on the library stream */
 void* agcgpu_stream(agcgpu_ctx* ctx);                     /* cudaStream_t the kernels are launched on (for event timing) */
 int agcgpu_get_stats(agcgpu_ctx* ctx, agcgpu_stats* out);
+/* Page-locked host memory for ingest buffers (CGenomeIO::ReadContigRaw's destination, src/core/genome_io.cpp:206-250): raw FASTA
+ * read straight into such a buffer is uploaded by agcgpu_scan_contigs without a staging copy.  Pooled per process; *out_cap = the
+ * capacity actually handed out (>= bytes), to be passed back to agcgpu_host_free.  NULL when the allocation fails. */
+void* agcgpu_host_alloc(uint64_t bytes, uint64_t* out_cap);
+void agcgpu_host_free(void* p, uint64_t cap);
 
 /* ---- splitters -------------------------------------------------------------------------------------------------- */
 /* determine_splitters (src/core/agc_compressor.cpp:428-563): raw FASTA bodies of the reference sample in

@@ -477,6 +477,9 @@ int agcgpu_pack_ref_batch(agcgpu_ctx* ctx, const uint32_t* group_ids, uint32_t n
     return 0;
 }
 
+void* agcgpu_host_alloc(uint64_t bytes, uint64_t* out_cap) { if (!out_cap) return nullptr; *out_cap = bytes + 64; return malloc(bytes + 64); }
+void agcgpu_host_free(void* p, uint64_t) { free(p); }
+
 // the asynchronous coder: submit parks the batch, collect codes every parked batch in submission order
 int agcgpu_zstd_submit(agcgpu_ctx* ctx, const uint8_t* src, const uint64_t* so, const int32_t* levels, uint32_t n)
 {
