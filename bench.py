@@ -262,6 +262,10 @@ def bind(L):
 
 
 def main():
+    # stdout carries exactly ONE line (the JSON): whatever libraries print there (NCCL's version banner ...) goes to stderr
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)

@@ -1,2 +1,10 @@
 mkdir -p gpurun_out
-timeout 1500 python bench.py --workload c4s --steps 2 --warmup 1 --no-extra > gpurun_out/r02g_bench_c4s_n1.json 2> gpurun_out/r02g_bench_c4s_n1.err; tail -3 gpurun_out/r02g_bench_c4s_n1.err; cut -c1-3500 gpurun_out/r02g_bench_c4s_n1.json
+python - <<'PY'
+import sys; sys.path.insert(0,'tools')
+import gen_data
+files = gen_data.human_chromosome('/dev/shm/c4s', seed=3, n_samples=4, ctg_len=50_000_000, n_repeats=40)
+open('/dev/shm/c4s/list.txt','w').write("\n".join(files[1:])+"\n")
+PY
+( time AGCGPU_TRACE=1 agc_b200/bin/agc-b200 create -k 31 -o /dev/shm/c4s/our.agc -i /dev/shm/c4s/list.txt /dev/shm/c4s/ref.fa ) > gpurun_out/c4s_trace.log 2>&1
+grep -vE "zstd wave|frame " gpurun_out/c4s_trace.log | tail -40
+( time AGCGPU_TRACE=1 agc_b200/bin/agc-b200 create -k 31 -o /dev/shm/c4s/our.agc -i /dev/shm/c4s/list.txt /dev/shm/c4s/ref.fa ) 2>&1 | grep real
