@@ -6,6 +6,7 @@
 // names, the last contig batch, the references and the last pack of every group) goes through agcgpu_zstd_decompress_batch in
 // two device batches; the references are handed back to the device as LZ references (agcgpu_group_put_reference).
 #include "compressor.h"
+#include <stdexcept>
 #include <algorithm>
 #include <cstring>
 #include <iostream>
@@ -117,20 +118,25 @@ static std::string decode_split(std::vector<std::string>& prev, std::vector<std:
 {
     std::string dec, cmp;
     for (size_t i = 0; i < curr.size(); ++i) {
+        if (i >= prev.size()) throw std::runtime_error("damaged archive: contig name refers to a missing previous name");
         if (curr[i].size() == 1 && (signed char)curr[i].front() == -127) { dec.append(prev[i]); curr[i] = prev[i]; }
         else {
             cmp.clear();
-            const char* pp = prev[i].data();
+            size_t pp = 0;                                                   // position in prev[i] (a damaged archive may run past its end)
             for (signed char c : curr[i]) {
                 if (c >= 0) { cmp.push_back(c); ++pp; }
-                else { cmp.append(pp, -c); pp += -c; }
+                else {
+                    const size_t cnt = (size_t)(-(int)c);
+                    if (pp > prev[i].size() || cnt > prev[i].size() - pp) throw std::runtime_error("damaged archive: contig name copy beyond the previous name");
+                    cmp.append(prev[i], pp, cnt); pp += cnt;
+                }
             }
             dec.append(cmp);
             curr[i] = cmp;
         }
         dec.push_back(' ');
     }
-    dec.pop_back();
+    if (!dec.empty()) dec.pop_back();
     return dec;
 }
 
@@ -178,7 +184,7 @@ bool CCollection_V3::deserialize_contig_details(const std::vector<uint8_t> (&v)[
     v_in_group_ids.clear();
     auto get_igi = [&](uint32_t pos) -> int { return pos >= v_in_group_ids.size() ? -1 : v_in_group_ids[pos]; };
     auto set_igi = [&](uint32_t pos, int val) {
-        if (pos >= v_in_group_ids.size()) v_in_group_ids.resize((size_t)((int)(pos * 1.2) + 1), -1);
+        if (pos >= v_in_group_ids.size()) v_in_group_ids.resize((size_t)((double)pos * 1.2) + 1, -1);
         v_in_group_ids[pos] = val;
     };
     const uint32_t pred_raw_length = segment_size + kmer_length;
@@ -187,6 +193,7 @@ bool CCollection_V3::deserialize_contig_details(const std::vector<uint8_t> (&v)[
         for (auto& c : sample_desc[i_sample + i].contigs)
             for (auto& seg : c.segments) {
                 const uint32_t g = det[1][it], e_igi = det[2][it];
+                if (g > (1u << 28)) return false;                           // (group ids are checked against the streams once those are loaded)
                 seg.group_id = g;
                 const int prev = get_igi(g);
                 uint32_t igi;
@@ -263,6 +270,10 @@ bool CAGCCompressor::Append(const std::string& in_archive_fn, const std::string&
         std::vector<uint8_t> dst(1);
         int rc = agcgpu_zstd_decompress_batch(ctx, src.data(), so.data(), (uint32_t)todo.size(), dst.data(), 0, dof.data());
         if (rc == AGCGPU_EOVERFLOW) {
+            uint64_t announced = 0;
+            for (auto* f : todo) announced += f->raw_size + 1;
+            if (dof.back() > announced + 4 * (uint64_t)todo.size())         // frame headers of a damaged archive may claim anything
+                return fail("archive parts announce more decoded bytes than their metadata");
             dst.resize(dof.back() + 1);
             rc = agcgpu_zstd_decompress_batch(ctx, src.data(), so.data(), (uint32_t)todo.size(), dst.data(), dof.back(), dof.data());
         }
@@ -373,7 +384,10 @@ bool CAGCCompressor::Append(const std::string& in_archive_fn, const std::string&
     {   std::vector<Frame*> fr;
         std::vector<uint8_t> markers(ref_frames.size(), 0);
         for (size_t i = 0; i < ref_frames.size(); ++i)
-            if (ref_frames[i]->raw_size) { markers[i] = ref_frames[i]->packed.back(); ref_frames[i]->packed.pop_back(); }   // the marker byte follows the frame
+            if (ref_frames[i]->raw_size) {
+                if (ref_frames[i]->packed.empty()) return fail("damaged archive: empty reference part");
+                markers[i] = ref_frames[i]->packed.back(); ref_frames[i]->packed.pop_back();                                   // the marker byte follows the frame
+            }
         for (auto& f : ref_frames) fr.push_back(f.get());
         for (auto& f : pack_frames) fr.push_back(f.get());
         if (!decode_all(fr)) return false;
@@ -474,6 +488,7 @@ bool CAGCCompressor::Append(const std::string& in_archive_fn, const std::string&
         uint64_t x1 = 0, x2 = 0; uint32_t x3 = 0;
         for (int j = 0; j < 8; ++j) { x1 |= (uint64_t)d[i * 20 + j] << (8 * j); x2 |= (uint64_t)d[i * 20 + 8 + j] << (8 * j); }
         for (int j = 0; j < 4; ++j) x3 |= (uint32_t)d[i * 20 + 16 + j] << (8 * j);
+        if (x3 >= no_segments) return fail("damaged archive: segment-splitters refers to group " + std::to_string(x3) + " of " + std::to_string(no_segments));
         map_segments[std::make_pair(x1, x2)] = (int32_t)x3;
         if (x1 != EMPTY_K && x2 != EMPTY_K) {
             map_segments_terminators[x1].push_back(x2);

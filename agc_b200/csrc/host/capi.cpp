@@ -17,6 +17,12 @@ static thread_local std::string g_err;
 static agcgpu_stats g_last_stats = {};
 static struct { uint32_t rank = 0, world = 1; agcgpu_allgather_fn fn = nullptr; void* user = nullptr; } g_exchange;
 
+// No C++ exception crosses the C ABI (bad_alloc on a huge collection, out_of_range on a damaged archive fed to append ...): the
+// body of every entry point that runs compressor code is wrapped; the message lands in the last-error slot.
+#define AGC_GUARD_BEGIN try {
+#define AGC_GUARD_END(c_) } catch (const std::exception& e) { g_err = std::string("exception: ") + e.what(); if (c_) (c_)->impl.SetLastError(g_err); return AGCGPU_ECUDA; } \
+                          catch (...) { g_err = "unknown exception"; if (c_) (c_)->impl.SetLastError(g_err); return AGCGPU_ECUDA; }
+
 extern "C" {
 
 int agcgpu_set_exchange(uint32_t rank, uint32_t world, agcgpu_allgather_fn allgather, void* user)
@@ -33,7 +39,9 @@ int agcgpu_compressor_create(const char* out_file, uint32_t pack_cardinality, ui
 {
     if (!out_file || !reference_file || !out) { g_err = "null argument"; return AGCGPU_EINVAL; }
     CallTimer ct("compressor_create");
-    agcgpu_compressor* c = new agcgpu_compressor();
+    agcgpu_compressor* c = nullptr;
+    AGC_GUARD_BEGIN
+    c = new agcgpu_compressor();
     c->impl.SetAppMode(false);
     c->impl.SetDevice(device);
     c->impl.SetExchange(g_exchange.rank, g_exchange.world, g_exchange.fn, g_exchange.user);
@@ -46,6 +54,8 @@ int agcgpu_compressor_create(const char* out_file, uint32_t pack_cardinality, ui
     }
     *out = c;
     return 0;
+    } catch (const std::exception& e) { g_err = std::string("exception: ") + e.what(); delete c; return AGCGPU_ECUDA; }
+    catch (...) { g_err = "unknown exception"; delete c; return AGCGPU_ECUDA; }
 }
 
 int agcgpu_compressor_append(const char* in_archive, const char* out_file, uint32_t verbosity, int prefetch_archive, int concatenated_genomes,
@@ -53,7 +63,9 @@ int agcgpu_compressor_append(const char* in_archive, const char* out_file, uint3
 {
     if (!in_archive || !out_file || !out) { g_err = "null argument"; return AGCGPU_EINVAL; }
     CallTimer ct("compressor_append");
-    agcgpu_compressor* c = new agcgpu_compressor();
+    agcgpu_compressor* c = nullptr;
+    AGC_GUARD_BEGIN
+    c = new agcgpu_compressor();
     c->impl.SetAppMode(false);
     c->impl.SetDevice(device);
     c->impl.SetExchange(g_exchange.rank, g_exchange.world, g_exchange.fn, g_exchange.user);
@@ -64,15 +76,19 @@ int agcgpu_compressor_append(const char* in_archive, const char* out_file, uint3
     }
     *out = c;
     return 0;
+    } catch (const std::exception& e) { g_err = std::string("exception: ") + e.what(); delete c; return AGCGPU_ECUDA; }
+    catch (...) { g_err = "unknown exception"; delete c; return AGCGPU_ECUDA; }
 }
 
 int agcgpu_compressor_add_sample_files(agcgpu_compressor* c, const char* const* sample_names, const char* const* file_names,
                                        uint32_t n, uint32_t no_threads)
 {
     if (!c || (n && (!sample_names || !file_names))) return AGCGPU_EINVAL;
+    AGC_GUARD_BEGIN
     std::vector<std::pair<std::string, std::string>> v;
     for (uint32_t i = 0; i < n; ++i) v.emplace_back(sample_names[i], file_names[i]);
     return c->impl.AddSampleFiles(v, no_threads) ? 0 : AGCGPU_ECUDA;
+    AGC_GUARD_END(c)
 }
 
 int agcgpu_compressor_add_samples_memory(agcgpu_compressor* c, const char* const* sample_names, uint32_t n_samples,
@@ -81,10 +97,12 @@ int agcgpu_compressor_add_samples_memory(agcgpu_compressor* c, const char* const
 {
     if (!c || !sample_names || !sample_of_contig || !contig_ids || !raw || !offsets) return AGCGPU_EINVAL;
     CallTimer ct("add_samples_memory");
+    AGC_GUARD_BEGIN
     std::vector<std::string> sn(sample_names, sample_names + n_samples), ci(contig_ids, contig_ids + n_contigs);
     std::vector<uint32_t> soc(sample_of_contig, sample_of_contig + n_contigs);
     for (auto s : soc) if (s >= n_samples) return AGCGPU_EINVAL;
     return c->impl.AddSamplesFromMemory(sn, soc, ci, (const uint8_t*)raw, offsets, raw_is_device != 0) ? 0 : AGCGPU_ECUDA;
+    AGC_GUARD_END(c)
 }
 
 int agcgpu_compressor_set_discard_parts(agcgpu_compressor* c, int discard)
@@ -112,7 +130,10 @@ int agcgpu_compressor_close(agcgpu_compressor* c, uint32_t no_threads)
 {
     if (!c) return AGCGPU_EINVAL;
     CallTimer ct("compressor_close");
-    bool ok = c->impl.Close(no_threads);
+    bool ok = false;
+    try { ok = c->impl.Close(no_threads); }
+    catch (const std::exception& e) { c->impl.SetLastError(std::string("exception: ") + e.what()); }
+    catch (...) { c->impl.SetLastError("unknown exception"); }
     if (!ok) g_err = c->impl.LastError();
     if (c->impl.Ctx()) agcgpu_get_stats(c->impl.Ctx(), &g_last_stats);
     {   CallTimer cd("compressor delete");

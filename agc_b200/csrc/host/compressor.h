@@ -139,6 +139,7 @@ public:
     // multi-GPU (include/agcgpu.h, agcgpu_set_exchange): this object is rank `rank` of `world` identical ones
     void SetExchange(uint32_t rank, uint32_t world, agcgpu_allgather_fn fn, void* user) { xrank = rank; xworld = fn && world > 1 ? world : 1; xfn = fn; xuser = user; }
     const std::string& LastError() const { return last_error; }
+    void SetLastError(const std::string& e) { last_error = e; }
     uint64_t TotalBases() const { return total_bases; }
     agcgpu_ctx* Ctx() { return ctx; }
 

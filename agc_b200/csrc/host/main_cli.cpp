@@ -7,6 +7,7 @@
 #include <filesystem>
 #include <fstream>
 #include <iostream>
+#include <exception>
 #include <unordered_set>
 
 static void remove_common_suffixes(std::string& s)        // application.cpp:606-630
@@ -23,7 +24,15 @@ static void remove_common_suffixes(std::string& s)        // application.cpp:606
     }
 }
 
+static int run(int argc, char** argv);
 int main(int argc, char** argv)
+{
+    // a damaged input archive (append) or an allocation failure ends with a message and exit code 1, never with an abort
+    try { return run(argc, argv); }
+    catch (const std::exception& e) { std::cerr << "agc-b200: " << e.what() << std::endl; return 1; }
+    catch (...) { std::cerr << "agc-b200: unknown error" << std::endl; return 1; }
+}
+static int run(int argc, char** argv)
 {
     const bool is_append = argc >= 2 && std::string(argv[1]) == "append";
     if (argc < 3 || (std::string(argv[1]) != "create" && !is_append)) {

@@ -1005,47 +1005,64 @@ int agc_lz_run(agcgpu_ctx* ctx, int mode, const agcgpu_seg_req* reqs, uint32_t n
     static const bool no_diag = getenv("AGCGPU_LZ_NO_DIAG") != nullptr;               // diagnostics: chunk-parallel kernels for everything
     bool diag_timed = false;
     if (mode == 0 && !no_chunks && !no_diag && !packed_reqs.empty()) {
-        std::vector<LzReqDev> dq, rest;
-        // reference AND hash table staged (32 warps, 1 CTA per SM).  AGCGPU_LZ_DIAG_HT=0 stages the reference alone (16 warps, 3 CTAs per
-        // SM, index probes through L2): measured no faster at 0.1 % SNPs (0.415 vs 0.423 ms) and 23 % slower at 1 % -- kept as a switch
-        static const int ht_staged = getenv("AGCGPU_LZ_DIAG_HT") ? atoi(getenv("AGCGPU_LZ_DIAG_HT")) : 1;
-        const size_t stage_max = ht_staged ? (size_t)227 * 1024 - agc_lzd_scratch_bytes(1) - 1024 : (size_t)32 * 1024;
-        const uint32_t unit_max = ht_staged ? 32u : 16u;
+        // One warp walks a segment alone.  Launch (1): groups whose reference AND hash table fit in shared memory (32 warps, one CTA per
+        // SM) -- every ordinary 60 kb group.  Launch (2), optional: groups of which only the reference fits (references of 92 kb and more
+        // have a 128+ KB table): 16 warps per CTA, the index probes go to L2.  Segments above LZD_MAX_N bases, segments much
+        // longer than their reference and references beyond 96 KB packed take the chunk-parallel kernels.  (Variant (2) for everything: no faster at 0.1 % SNPs, 0.415 vs 0.423 ms,
+        // and 23 % slower at 1 %.)
+        static const int ht_mode = getenv("AGCGPU_LZ_DIAG_HT") ? atoi(getenv("AGCGPU_LZ_DIAG_HT")) : 1;      // 0: variant (2) for every group
+        const size_t stage_max_full = ht_mode ? (size_t)227 * 1024 - agc_lzd_scratch_bytes(1) - 1024 : 0;
+        const size_t stage_max_ref = (size_t)96 * 1024;
+        // launch (2) is OFF by default: on C3's 120-260 kb merged groups at 1 % SNPs the probes through L2 make it 3-4x slower than the
+        // chunk-parallel kernels (5-12 ms vs 2-3 ms per one-sample launch); AGCGPU_LZ_DIAG_REFONLY=1 switches it on
+        static const bool ref_only = !ht_mode || (getenv("AGCGPU_LZ_DIAG_REFONLY") && atoi(getenv("AGCGPU_LZ_DIAG_REFONLY")));
+        std::vector<LzReqDev> dq[2], rest;
         for (const LzReqDev& q : packed_reqs) {
-            // one warp walks a segment alone, with the reference (and its index) in shared memory: segments of ordinary length whose
-            // group fits there; the others (contigs without splitters, merged segments) take the chunk-parallel kernels
             const GroupRefDev& g = ctx->h_groups[q.group];
-            const size_t need = (size_t)g.packed_bytes + (ht_staged ? (size_t)g.ht_size * ((g.flags & GRF_SHORT) ? 2 : 4) : 0);
-            (q.n <= LZD_MAX_N && need <= stage_max ? dq : rest).push_back(q);
+            const size_t full = (size_t)g.packed_bytes + (size_t)g.ht_size * ((g.flags & GRF_SHORT) ? 2 : 4);
+            // (a text much longer than its reference -- a merged segment against an ordinary group -- is mostly literals: the one warp
+            // would probe them 32 at a time, ~0.1 us per position; the chunk kernels spread them over a lane per 512 positions)
+            if (q.n > LZD_MAX_N || q.n > g.m + 8192u) rest.push_back(q);
+            else if (full <= stage_max_full) dq[1].push_back(q);
+            else if (ref_only && g.packed_bytes <= stage_max_ref) dq[0].push_back(q);
+            else rest.push_back(q);
         }
-        if (!dq.empty()) {
+        size_t d_off = 0;
+        const size_t n_diag = dq[0].size() + dq[1].size();
+        if (n_diag) {
+            if (int r = agc_reserve(ctx, ctx->scr_rec, n_diag * (sizeof(LzReqDev) + sizeof(LzUnit)) + 512)) return r;
+            CK(cudaEventRecord(ctx->ev0, ctx->st));
+        }
+        for (int hs = 1; hs >= 0; --hs) {
+            const std::vector<LzReqDev>& v = dq[hs];
+            if (v.empty()) continue;
+            const uint32_t unit_max = hs ? 32u : 16u;
             std::vector<LzUnit> un;
             size_t stage = 0;
-            for (size_t a = 0; a < dq.size();) {
-                size_t b = a;
-                while (b < dq.size() && dq[b].group == dq[a].group) ++b;
-                const GroupRefDev& g = ctx->h_groups[dq[a].group];
-                size_t need = (size_t)g.packed_bytes + (ht_staged ? (size_t)g.ht_size * ((g.flags & GRF_SHORT) ? 2 : 4) : 0);
-                if (need <= stage_max) stage = std::max(stage, need);
-                const size_t cnt = b - a, nun = (cnt + unit_max - 1) / unit_max, per = (cnt + nun - 1) / nun;      // one request per warp and round
-                for (size_t s0 = a; s0 < b; s0 += per) {
-                    LzUnit u; u.group = dq[a].group; u.first = (uint32_t)s0; u.count = (uint32_t)std::min(per, b - s0); u.pad = 0;
+            for (size_t a2 = 0; a2 < v.size();) {
+                size_t b2 = a2;
+                while (b2 < v.size() && v[b2].group == v[a2].group) ++b2;
+                const GroupRefDev& g = ctx->h_groups[v[a2].group];
+                stage = std::max(stage, (size_t)g.packed_bytes + (hs ? (size_t)g.ht_size * ((g.flags & GRF_SHORT) ? 2 : 4) : 0));
+                const size_t cnt = b2 - a2, nun = (cnt + unit_max - 1) / unit_max, per = (cnt + nun - 1) / nun;      // one request per warp and round
+                for (size_t s0 = a2; s0 < b2; s0 += per) {
+                    LzUnit u; u.group = v[a2].group; u.first = (uint32_t)s0; u.count = (uint32_t)std::min(per, b2 - s0); u.pad = 0;
                     un.push_back(u);
                 }
-                a = b;
+                a2 = b2;
             }
-            if (int r = agc_reserve(ctx, ctx->scr_rec, dq.size() * sizeof(LzReqDev) + un.size() * sizeof(LzUnit) + 256)) return r;
-            LzReqDev* d_req = (LzReqDev*)ctx->scr_rec.p;
-            LzUnit* d_un = (LzUnit*)(d_req + dq.size());
-            CK(cudaMemcpyAsync(d_req, dq.data(), dq.size() * sizeof(LzReqDev), cudaMemcpyHostToDevice, ctx->st));
+            LzReqDev* d_req = (LzReqDev*)((uint8_t*)ctx->scr_rec.p + d_off);
+            LzUnit* d_un = (LzUnit*)(d_req + v.size());
+            d_off += (v.size() * sizeof(LzReqDev) + un.size() * sizeof(LzUnit) + 255) / 256 * 256;
+            CK(cudaMemcpyAsync(d_req, v.data(), v.size() * sizeof(LzReqDev), cudaMemcpyHostToDevice, ctx->st));
             CK(cudaMemcpyAsync(d_un, un.data(), un.size() * sizeof(LzUnit), cudaMemcpyHostToDevice, ctx->st));
-            ctx->stats.h2d_bytes += dq.size() * sizeof(LzReqDev) + un.size() * sizeof(LzUnit);
-            CK(cudaEventRecord(ctx->ev0, ctx->st));
-            if (int r = agc_lzd_launch(ctx, d_req, d_un, (uint32_t)un.size(), stage, ht_staged, slab, res, err)) return r;
-            ctx->stats.lz_diag_segments += (uint32_t)dq.size();
+            CK(cudaStreamSynchronize(ctx->st));                  // `un` goes out of scope (a few hundred bytes; the kernel is queued right behind)
+            ctx->stats.h2d_bytes += v.size() * sizeof(LzReqDev) + un.size() * sizeof(LzUnit);
+            if (int r = agc_lzd_launch(ctx, d_req, d_un, (uint32_t)un.size(), stage, hs, slab, res, err)) return r;
+            ctx->stats.lz_diag_segments += (uint32_t)v.size();
             diag_timed = true;
-            if (rest.empty()) { CK(cudaEventRecord(ctx->ev1, ctx->st)); chunk_timed = true; }
         }
+        if (diag_timed && rest.empty()) { CK(cudaEventRecord(ctx->ev1, ctx->st)); chunk_timed = true; }
         packed_reqs.swap(rest);
     }
     if (!packed_reqs.empty() && (mode == 0 || mode == 2) && !no_chunks) {
@@ -1198,6 +1215,11 @@ int agc_lz_run(agcgpu_ctx* ctx, int mode, const agcgpu_seg_req* reqs, uint32_t n
     if (mode == 2 && !out_u32) return 0;                 // nothing was synchronised: the caller queues its reduction behind the launch
     cudaEventElapsedTime(&ctx->stats.last_lz_kernel_ms, ctx->ev0, ctx->ev1);
     ctx->stats.lz_alg_bytes = alg_bytes;
+    if (mode == 1 && getenv("AGCGPU_TRACE_LZ") && *getenv("AGCGPU_TRACE_LZ")) {
+        fprintf(stderr, "[agcgpu] lz estimate call: %u requests, kernels %.3f ms:", n, ctx->stats.last_lz_kernel_ms);
+        for (uint32_t i = 0; i < n && i < 12; ++i) fprintf(stderr, " (n %u m %u bound %u)", reqs[i].len, ctx->h_groups[reqs[i].group_id].m, reqs[i].bound);
+        fprintf(stderr, "\n");
+    }
     if (mode == 0 && getenv("AGCGPU_TRACE_LZ") && *getenv("AGCGPU_TRACE_LZ")) {
         uint32_t mx = 0, mn = ~0u, nrc = 0; uint64_t sum = 0;
         for (uint32_t i = 0; i < n; ++i) { mx = std::max(mx, reqs[i].len); mn = std::min(mn, reqs[i].len); sum += reqs[i].len; nrc += reqs[i].is_rc != 0; }

@@ -13,10 +13,10 @@
 
 __device__ __forceinline__ uint32_t lzd_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// HT_STAGED: the hash table is staged as well (32 warps, one CTA per SM); otherwise only the reference is (16 warps, several
-// CTAs per SM; the few index probes per mismatch go to L2)
+// HT_STAGED: the hash table is staged as well (32 warps, one CTA per SM); otherwise only the reference is (16 warps, up to two
+// CTAs per SM; the few index probes per mismatch go to L2) -- the launch for groups whose table does not fit
 template <int LZD_THREADS, bool HT_STAGED>
-__global__ void __launch_bounds__(LZD_THREADS, HT_STAGED ? 1 : 3) k_lz_diag(
+__global__ void __launch_bounds__(LZD_THREADS, HT_STAGED ? 1 : 2) k_lz_diag(
     const uint64_t* __restrict__ P, const GroupRefDev* __restrict__ groups, const LzReqDev* __restrict__ reqs,
     const LzUnit* __restrict__ units, uint32_t mml, uint32_t stage_bytes, uint8_t* __restrict__ slab,
     uint32_t* __restrict__ res, uint32_t* __restrict__ err)

@@ -45,6 +45,8 @@ WORKLOADS = {
     # not part of the default run: BASELINE configs[3] in shape at 1/5 of its size (python bench.py --workload c4s)
     "c4s": ("BASELINE configs[3] in shape, scaled: 4 synthetic 50 Mb human-chromosome-like contigs (0.1% SNP, an indel every 10 kb, repeats) + "
             "50 Mb reference, seed 3, agc create -k 31 (l=20 s=60000 b=50)", dict(kind="human", seed=3, n_samples=4, ref_len=50_000_000), 31, 0),
+    "c4": ("BASELINE configs[3]: 8 synthetic 250 Mb human-chromosome-like contigs (0.1% SNP, an indel every 10 kb, repeats) + 250 Mb reference, "
+           "seed 3, agc create -k 31 (l=20 s=60000 b=50)", dict(kind="human", seed=3, n_samples=8, ref_len=250_000_000), 31, 0),
     "c2": ("BASELINE configs[1]: 1000 synthetic 30 kb viral genomes (1% SNP) + reference, seed 1, agc create -k 25 (l=20 s=60000 b=50)",
            dict(kind="viral", seed=1, n_samples=1000, ref_len=30000), 25, 0),
 }
@@ -61,7 +63,7 @@ def make_workload(tmp, name):
     if kind == "viral":
         files, _ = gen_data.viral(d, n_samples=kw["n_samples"], ref_len=kw["ref_len"], p=0.01, seed=kw["seed"])
     elif kind == "human":
-        files = gen_data.human_chromosome(d, seed=kw["seed"], n_samples=kw["n_samples"], ctg_len=kw["ref_len"], n_repeats=40)
+        files = gen_data.human_chromosome(d, seed=kw["seed"], n_samples=kw["n_samples"], ctg_len=kw["ref_len"], n_repeats=40 if kw["ref_len"] < 100_000_000 else 200)
     else:
         files = gen_data.bacterial_adaptive(d, seed=kw["seed"], n_samples=kw["n_samples"], ref_len=kw["ref_len"])
     return files, gen_data.total_bases(files)
