@@ -299,6 +299,7 @@ __device__ void lz_parse(const A& a, const HT& ht, uint32_t mml, uint32_t lane, 
         if (a.lcp_fwd(0, 0, n, lane) == n) { s.olen = 0; s.est = 0; return; }
     }
     uint32_t i = 0, pred = 0, np = 0;                // np = no_prev_literals = length of the pending literal run ending at i
+    bool lit_streak = false;                         // the previous round found no match
     while (i + kl < n) {
         uint32_t p = i + lane;
         bool active = p + kl < n;
@@ -310,16 +311,27 @@ __device__ void lz_parse(const A& a, const HT& ht, uint32_t mml, uint32_t lane, 
         // The probe walk of a round costs as many steps as the longest chain among the probing lanes, and after a mismatch the
         // next match starts within a few positions (the first one that is a multiple of 4 on the reference): the first 8
         // positions are probed on their own, the other 24 only if none of them ends the round.
-        for (uint32_t grp = 0; grp < 2 && !restart; ++grp) {
-        const bool mine = grp == 0 ? lane < 8 : lane >= 8;
+        // (inside a stretch without matches -- a text compared with the wrong candidate, a novel insertion -- the 8-lane phase only adds
+        // a round trip: after a round that found nothing all 32 lanes probe at once)
+        const uint32_t ngrp = lit_streak ? 1u : 2u;
+        for (uint32_t grp = 0; grp < ngrp && !restart; ++grp) {
+        const bool mine = lit_streak ? true : (grp == 0 ? lane < 8 : lane >= 8);
         if (grp == 1 && nact <= 8) break;
         if (active && mine && ev == 0) {
             uint32_t hp = (uint32_t)agc_murmur64(x) & ht.mask;
             const uint32_t xq = a.key_quick(x, kl);
-            for (uint32_t t = 0; t < 64; ++t) {
-                uint32_t v = ht.get((hp + t) & ht.mask);
-                if (v == AGC_EMPTY32) break;
-                if (a.rcode_quick(v, xq, kl) && a.rcode_eq(v * 4u, x, kl)) { ev = 2; break; }
+            // four slots per step: their loads are independent (one round trip to the table -- L2 for groups too large for shared
+            // memory -- instead of four), the tests keep the slot order
+            bool done = false;
+            for (uint32_t t = 0; t < 64 && !done; t += 4) {
+                const uint32_t v0 = ht.get((hp + t) & ht.mask), v1 = ht.get((hp + t + 1) & ht.mask);
+                const uint32_t v2 = ht.get((hp + t + 2) & ht.mask), v3 = ht.get((hp + t + 3) & ht.mask);
+                const uint32_t vv[4] = { v0, v1, v2, v3 };
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (vv[k] == AGC_EMPTY32) { done = true; break; }
+                    if (a.rcode_quick(vv[k], xq, kl) && a.rcode_eq(vv[k] * 4u, x, kl)) { ev = 2; done = true; break; }
+                }
             }
         }
         uint32_t evmask = __ballot_sync(FULL, mine && ev != 0);
@@ -379,6 +391,7 @@ __device__ void lz_parse(const A& a, const HT& ht, uint32_t mml, uint32_t lane, 
             break;
         }
         }
+        lit_streak = !restart;
         if (!restart) {
             uint32_t r = nact - c;
             if (MODE == 1 && r) {

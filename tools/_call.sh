@@ -1,4 +1,5 @@
 mkdir -p gpurun_out
-N_SAMPLES=12 TRACE_LZ=1 THREADS=$(nproc) timeout 600 bash tools/run_c3_cli.sh | tail -3; grep -E "lz encode call" gpurun_out/c3_trace.log | head -13 | cut -c1-200
-for w in c3; do timeout 1500 python bench.py --workload $w --steps 2 --warmup 1 --no-extra > gpurun_out/r02n_bench_${w}_n1.json 2> gpurun_out/r02n_bench_${w}_n1.err; tail -2 gpurun_out/r02n_bench_${w}_n1.err | cut -c1-300; python -c "
-import json; d=json.load(open('gpurun_out/r02n_bench_${w}_n1.json')); print('$w', round(d['value'],4), round(d['ms_per_step']), round(d['e2e']['value'],4), round(d['e2e']['ms_per_step']), round(d['cpu_baseline']['value'],4), 'zstd', round(d['residual_coder']['ms_per_step']), 'lz', round(d['roofline']['kernel_ms_per_step'],1), d['roofline']['segments_diagonal_kernel'], d['roofline']['segments_chunk_parallel'], d['roofline']['segments_sequential_kernel'])"; done
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_pipeline.py tests/test_gpu_zy_fuzz.py -m gpu -x -q 2>&1 | tail -3
+N_SAMPLES=10 TRACE_LZ=1 THREADS=$(nproc) timeout 600 bash tools/run_c3_cli.sh | tail -2; grep -E "lz estimate call" gpurun_out/c3_trace.log | sed -n '2p;8p' | cut -c1-160
+for w in c3; do timeout 1500 python bench.py --workload $w --steps 2 --warmup 1 --no-extra > gpurun_out/r02p_bench_${w}_n1.json 2> gpurun_out/r02p_bench_${w}_n1.err; tail -2 gpurun_out/r02p_bench_${w}_n1.err | cut -c1-300; python -c "
+import json; d=json.load(open('gpurun_out/r02p_bench_${w}_n1.json')); print('$w', round(d['value'],4), round(d['ms_per_step']), round(d['e2e']['value'],4), round(d['e2e']['ms_per_step']), round(d['cpu_baseline']['value'],4), 'zstd', round(d['residual_coder']['ms_per_step']), 'lz', round(d['roofline']['kernel_ms_per_step'],1))"; done
