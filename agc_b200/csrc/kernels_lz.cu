@@ -1042,37 +1042,38 @@ int agc_lz_run(agcgpu_ctx* ctx, int mode, const agcgpu_seg_req* reqs, uint32_t n
         }
         size_t d_off = 0;
         const size_t n_diag = dq[0].size() + dq[1].size();
-        if (n_diag) {
-            if (int r = agc_reserve(ctx, ctx->scr_rec, n_diag * (sizeof(LzReqDev) + sizeof(LzUnit)) + 512)) return r;
-            CK(cudaEventRecord(ctx->ev0, ctx->st));
-        }
-        for (int hs = 1; hs >= 0; --hs) {
+        if (n_diag) if (int r = agc_reserve(ctx, ctx->scr_rec, n_diag * (sizeof(LzReqDev) + sizeof(LzUnit)) + 512)) return r;
+        std::vector<LzUnit> un[2];
+        LzReqDev* d_req[2] = { nullptr, nullptr }; LzUnit* d_un[2] = { nullptr, nullptr };
+        size_t stage[2] = { 0, 0 };
+        for (int hs = 1; hs >= 0; --hs) {                          // requests and units of both launches go up first ...
             const std::vector<LzReqDev>& v = dq[hs];
             if (v.empty()) continue;
             const uint32_t unit_max = hs ? 32u : 16u;
-            std::vector<LzUnit> un;
-            size_t stage = 0;
             for (size_t a2 = 0; a2 < v.size();) {
                 size_t b2 = a2;
                 while (b2 < v.size() && v[b2].group == v[a2].group) ++b2;
                 const GroupRefDev& g = ctx->h_groups[v[a2].group];
-                stage = std::max(stage, (size_t)g.packed_bytes + (hs ? (size_t)g.ht_size * ((g.flags & GRF_SHORT) ? 2 : 4) : 0));
+                stage[hs] = std::max(stage[hs], (size_t)g.packed_bytes + (hs ? (size_t)g.ht_size * ((g.flags & GRF_SHORT) ? 2 : 4) : 0));
                 const size_t cnt = b2 - a2, nun = (cnt + unit_max - 1) / unit_max, per = (cnt + nun - 1) / nun;      // one request per warp and round
                 for (size_t s0 = a2; s0 < b2; s0 += per) {
                     LzUnit u; u.group = v[a2].group; u.first = (uint32_t)s0; u.count = (uint32_t)std::min(per, b2 - s0); u.pad = 0;
-                    un.push_back(u);
+                    un[hs].push_back(u);
                 }
                 a2 = b2;
             }
-            LzReqDev* d_req = (LzReqDev*)((uint8_t*)ctx->scr_rec.p + d_off);
-            LzUnit* d_un = (LzUnit*)(d_req + v.size());
-            d_off += (v.size() * sizeof(LzReqDev) + un.size() * sizeof(LzUnit) + 255) / 256 * 256;
-            CK(cudaMemcpyAsync(d_req, v.data(), v.size() * sizeof(LzReqDev), cudaMemcpyHostToDevice, ctx->st));
-            CK(cudaMemcpyAsync(d_un, un.data(), un.size() * sizeof(LzUnit), cudaMemcpyHostToDevice, ctx->st));
-            CK(cudaStreamSynchronize(ctx->st));                  // `un` goes out of scope (a few hundred bytes; the kernel is queued right behind)
-            ctx->stats.h2d_bytes += v.size() * sizeof(LzReqDev) + un.size() * sizeof(LzUnit);
-            if (int r = agc_lzd_launch(ctx, d_req, d_un, (uint32_t)un.size(), stage, hs, slab, res, err)) return r;
-            ctx->stats.lz_diag_segments += (uint32_t)v.size();
+            d_req[hs] = (LzReqDev*)((uint8_t*)ctx->scr_rec.p + d_off);
+            d_un[hs] = (LzUnit*)(d_req[hs] + v.size());
+            d_off += (v.size() * sizeof(LzReqDev) + un[hs].size() * sizeof(LzUnit) + 255) / 256 * 256;
+            CK(cudaMemcpyAsync(d_req[hs], v.data(), v.size() * sizeof(LzReqDev), cudaMemcpyHostToDevice, ctx->st));
+            CK(cudaMemcpyAsync(d_un[hs], un[hs].data(), un[hs].size() * sizeof(LzUnit), cudaMemcpyHostToDevice, ctx->st));
+            ctx->stats.h2d_bytes += v.size() * sizeof(LzReqDev) + un[hs].size() * sizeof(LzUnit);
+        }
+        if (n_diag) CK(cudaEventRecord(ctx->ev0, ctx->st));        // ... so that the timed interval holds the kernels only
+        for (int hs = 1; hs >= 0; --hs) {
+            if (dq[hs].empty()) continue;
+            if (int r = agc_lzd_launch(ctx, d_req[hs], d_un[hs], (uint32_t)un[hs].size(), stage[hs], hs, slab, res, err)) return r;
+            ctx->stats.lz_diag_segments += (uint32_t)dq[hs].size();
             diag_timed = true;
         }
         if (diag_timed && rest.empty()) { CK(cudaEventRecord(ctx->ev1, ctx->st)); chunk_timed = true; }

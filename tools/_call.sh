@@ -1,5 +1,9 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_pipeline.py tests/test_gpu_zy_fuzz.py -m gpu -x -q 2>&1 | tail -3
-N_SAMPLES=10 TRACE_LZ=1 THREADS=$(nproc) timeout 600 bash tools/run_c3_cli.sh | tail -2; grep -E "lz estimate call" gpurun_out/c3_trace.log | sed -n '2p;8p' | cut -c1-160
-for w in c3; do timeout 1500 python bench.py --workload $w --steps 2 --warmup 1 --no-extra > gpurun_out/r02p_bench_${w}_n1.json 2> gpurun_out/r02p_bench_${w}_n1.err; tail -2 gpurun_out/r02p_bench_${w}_n1.err | cut -c1-300; python -c "
-import json; d=json.load(open('gpurun_out/r02p_bench_${w}_n1.json')); print('$w', round(d['value'],4), round(d['ms_per_step']), round(d['e2e']['value'],4), round(d['e2e']['ms_per_step']), round(d['cpu_baseline']['value'],4), 'zstd', round(d['residual_coder']['ms_per_step']), 'lz', round(d['roofline']['kernel_ms_per_step'],1))"; done
+python - <<'PY'
+import sys; sys.path.insert(0,'tools')
+import gen_data
+files = gen_data.human_chromosome('/dev/shm/c4', seed=3, n_samples=8, ctg_len=250_000_000, n_repeats=200)
+open('/dev/shm/c4/list.txt','w').write("\n".join(files[1:])+"\n")
+PY
+( time AGCGPU_TRACE=1 agc_b200/bin/agc-b200 create -k 31 -o /dev/shm/c4/our.agc -i /dev/shm/c4/list.txt /dev/shm/c4/ref.fa ) > gpurun_out/c4_trace.log 2>&1
+grep -vE "zstd wave|frame |cost split" gpurun_out/c4_trace.log | tail -60
