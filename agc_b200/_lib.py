@@ -126,6 +126,8 @@ def lib():
     L.agcgpu_pack_ref_batch.argtypes = [vp, u32p, C.c_uint32, u8p, C.c_uint64, u64p, u8p]
     L.agcgpu_zstd_submit.restype = C.c_int; L.agcgpu_zstd_submit.argtypes = [vp, u8p, u64p, i32p, C.c_uint32]
     L.agcgpu_zstd_collect.restype = C.c_int; L.agcgpu_zstd_collect.argtypes = [vp, C.c_uint32, u8p, C.c_uint64, u64p]
+    L.agcgpu_host_alloc.restype = vp; L.agcgpu_host_alloc.argtypes = [C.c_uint64, u64p]
+    L.agcgpu_host_free.restype = None; L.agcgpu_host_free.argtypes = [vp, C.c_uint64]
     L.agcgpu_zstd_compress_batch.restype = C.c_int
     L.agcgpu_zstd_compress_batch.argtypes = [vp, u8p, u64p, i32p, C.c_uint32, u8p, C.c_uint64, u64p]
     _LIB = L
@@ -351,6 +353,27 @@ class Device:
         doffs = np.zeros(len(inputs) + 1, np.uint64)
         self._ck(self.L.agcgpu_zstd_compress_batch(self.h, _p(src, u8p), _p(offs, u64p), _p(lv, i32p), len(inputs), _p(dst, u8p), cap, _p(doffs, u64p)))
         return [dst[int(doffs[i]):int(doffs[i + 1])].tobytes() for i in range(len(inputs))]
+
+    def zstd_submit(self, inputs, levels):
+        """queue a batch for the residual coder (agcgpu_zstd_submit): returns at once, the frames come from zstd_collect"""
+        offs = np.zeros(len(inputs) + 1, np.uint64)
+        if inputs:
+            offs[1:] = np.cumsum([len(x) for x in inputs])
+        src = np.frombuffer(b"".join(inputs), np.uint8).copy() if offs[-1] else np.zeros(1, np.uint8)
+        lv = np.ascontiguousarray(levels, np.int32)
+        self._ck(self.L.agcgpu_zstd_submit(self.h, _p(src, u8p), _p(offs, u64p), _p(lv, i32p), len(inputs)))
+        self._submitted = getattr(self, "_submitted", []) + [len(x) for x in inputs]
+
+    def zstd_collect(self):
+        """frames of every batch submitted since the last collect, in submission order"""
+        sizes = getattr(self, "_submitted", [])
+        self._submitted = []
+        n = len(sizes); tot = int(sum(sizes))
+        cap = tot + tot // 128 + 1024 * (n + 1)
+        dst = np.zeros(max(cap, 1), np.uint8)
+        doffs = np.zeros(n + 1, np.uint64)
+        self._ck(self.L.agcgpu_zstd_collect(self.h, n, _p(dst, u8p), cap, _p(doffs, u64p)))
+        return [dst[int(doffs[i]):int(doffs[i + 1])].tobytes() for i in range(n)]
 
     def lz_decode(self, group_ids, deltas):
         """CLZDiff_V2::Decode of every delta against its group's resident reference -> list of symbol arrays"""

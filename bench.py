@@ -355,6 +355,10 @@ def main():
                 line["comm"] = agc_dist.comm_stats()          # counters after the run: collectives issued by the data path
             if not args.no_extra and world == 1:
                 line["lz_kernel_hpp_like_batch"] = lz_hpp_batch(local_rank, peak, traffic)
+                # the same kernel where it is not launch-latency bound (one HPP-scale device batch), next to the step's own figure
+                hb = line["lz_kernel_hpp_like_batch"]
+                line["roofline"].update({"batch_achieved": hb["achieved"], "batch_frac": hb["frac"], "batch_traffic": hb["traffic"],
+                                         "batch_workload": hb["workload"]})
                 line["other_workloads"] = {}
                 for other in ("c2", "c3"):
                     if other == args.workload:

@@ -48,3 +48,16 @@ def test_parts_match_reference(tmp_path, case):
         sample = os.path.splitext(os.path.basename(files[-1]))[0]
     out = subprocess.run([REF_AGC, "getset", our, sample], capture_output=True).stdout
     assert out == last
+
+
+@pytest.mark.skipif(not os.path.exists(REF_AGC), reason="reference binary not built (make -f oracle/Makefile.ref)")
+@pytest.mark.parametrize("case", ["complex", "adaptive"])
+def test_async_coder_every_flush(tmp_path, case):
+    """AGCGPU_ZSTD_ASYNC_MIN=1: every flush point submits its parts to the residual coder at once (many small batches in flight
+    while the next samples are processed) -- the archive is still the reference's"""
+    tmp = str(tmp_path)
+    files, flags = collection(case, tmp)
+    ref_out = os.path.join(tmp, "ref.agc"); our = os.path.join(tmp, "our.agc")
+    subprocess.check_call([REF_AGC, "create", "-t", "4", "-o", ref_out] + flags + files, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    subprocess.check_call([OUR_AGC, "create", "-o", our] + flags + files, env=dict(os.environ, AGCGPU_ZSTD_ASYNC_MIN="1"))
+    assert open(our, "rb").read() == open(ref_out, "rb").read()

@@ -118,3 +118,37 @@ def test_zstd_unsupported_is_loud(dev_factory):
     dev = dev_factory(k=21, min_match_len=20)
     with pytest.raises(agc_b200.AgcGpuError):
         dev.zstd_compress([b"abc"], [3])             # only the levels AGC uses (13 / 17 / 18 / 19) exist: refused, not approximated
+
+
+def test_zstd_async_batches(dev_factory):
+    """agcgpu_zstd_submit / agcgpu_zstd_collect: several batches in flight (wide and narrow frames, an empty input, a batch of one),
+    other device work in between, frames back in submission order and identical to libzstd's"""
+    rng = np.random.default_rng(9)
+    dev = dev_factory(k=21, min_match_len=20)
+    batches = [([_gen(rng, 2, 50000), _gen_adv(rng, 5, 70000), b"", _gen(rng, 1, 900)], [17, 17, 19, 13]),
+               ([_gen(rng, 3, 16000)], [18]),
+               ([_gen_adv(rng, k, 20000) for k in range(6)], [17, 13, 19, 18, 17, 17])]
+    assert dev.zstd_collect() == []
+    for inputs, levels in batches:
+        dev.zstd_submit(inputs, levels)
+        dev.zstd_compress([b"between the batches" * 10], [19])           # the synchronous call while batches are in flight
+    got = dev.zstd_collect()
+    exp = [agc_parts.zstd_compress(x, lv) for inputs, levels in batches for x, lv in zip(inputs, levels)]
+    assert got == exp
+    dev.zstd_submit([b"abc" * 100], [17])                                 # a second round on the same context
+    assert dev.zstd_collect() == [agc_parts.zstd_compress(b"abc" * 100, 17)]
+
+
+def test_host_alloc_roundtrip():
+    import ctypes as C
+    import agc_b200
+    L = agc_b200.lib()
+    cap = C.c_uint64(0)
+    p = L.agcgpu_host_alloc(1 << 20, C.byref(cap))
+    assert p and cap.value >= (1 << 20)
+    C.memset(p, 0x5A, 1 << 20)
+    L.agcgpu_host_free(p, cap.value)
+    cap2 = C.c_uint64(0)
+    q = L.agcgpu_host_alloc(1 << 19, C.byref(cap2))                      # comes back from the pool
+    assert q and cap2.value >= (1 << 19)
+    L.agcgpu_host_free(q, cap2.value)
