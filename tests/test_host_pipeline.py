@@ -226,3 +226,13 @@ def test_cli_clamps_options_like_the_reference(tmp_path, mock_agc):
             subprocess.check_call([exe, "create", "-o", out] + flags + files[:3], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
             outs.append(open(out, "rb").read())
     assert outs[0] == outs[1] == outs[2] == outs[3]
+
+
+def test_fasta_layout_variants(mock_agc):
+    """the in-place record cutter of the ingest path (CAGCCompressor::add_sample_files_arena) against CGenomeIO::ReadContigRaw's rules:
+    CRLF, lower case, N / IUPAC / junk symbols, tabs and spaces in headers, no final newline, blank lines, empty records, gzipped
+    members -- archives identical to the reference binary's (tools/fuzz_fasta_layout.py)"""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import fuzz_fasta_layout
+    n, bad = fuzz_fasta_layout.run(30, seed=5, our=mock_agc, verbose=False)
+    assert n == 30 and bad == 0
