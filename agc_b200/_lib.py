@@ -66,7 +66,7 @@ EXPORTED_SYMBOLS = [
     "agcgpu_zstd_compress_batch_sharded", "agcgpu_comm_unique_id", "agcgpu_comm_init", "agcgpu_comm_destroy", "agcgpu_comm_get_stats",
     "agcgpu_comm_last_error", "agcgpu_comm_world", "agcgpu_comm_rank", "agcgpu_pack_ref_batch", "agcgpu_zstd_compress_batch",
     "agcgpu_find_new_splitters", "agcgpu_rescan_contigs", "agcgpu_filtered_kmers", "agcgpu_last_splitter_positions",
-    "agcgpu_zstd_decompress_batch", "agcgpu_lz_decode_batch", "agcgpu_zstd_submit", "agcgpu_zstd_collect", "agcgpu_host_alloc", "agcgpu_host_free",
+    "agcgpu_zstd_decompress_batch", "agcgpu_lz_decode_batch", "agcgpu_zstd_submit", "agcgpu_zstd_submit_parts", "agcgpu_zstd_collect", "agcgpu_host_alloc", "agcgpu_host_free",
 ]
 
 

@@ -595,12 +595,11 @@ bool CAGCCompressor::submit_pending(bool with_extra)
     if (with_extra) { for (auto* t : extra_tasks) tasks.push_back(t); extra_tasks.clear(); }
     if (tasks.empty()) return true;
     PhaseTimer pt("residual coder submit");
-    std::vector<uint64_t> offs(tasks.size() + 1, 0);
+    std::vector<const uint8_t*> ptrs(tasks.size());
+    std::vector<uint64_t> sizes(tasks.size());
     std::vector<int32_t> levels(tasks.size());
-    for (size_t i = 0; i < tasks.size(); ++i) { offs[i + 1] = offs[i] + tasks[i]->raw.size(); levels[i] = tasks[i]->level; }
-    std::vector<uint8_t> src(offs.back() + 1);
-    for (size_t i = 0; i < tasks.size(); ++i) if (!tasks[i]->raw.empty()) memcpy(src.data() + offs[i], tasks[i]->raw.data(), tasks[i]->raw.size());
-    if (!gpu_ok(agcgpu_zstd_submit(ctx, src.data(), offs.data(), levels.data(), (uint32_t)tasks.size()), "zstd_submit")) return false;
+    for (size_t i = 0; i < tasks.size(); ++i) { ptrs[i] = tasks[i]->raw.data(); sizes[i] = tasks[i]->raw.size(); levels[i] = tasks[i]->level; }
+    if (!gpu_ok(agcgpu_zstd_submit_parts(ctx, ptrs.data(), sizes.data(), levels.data(), (uint32_t)tasks.size()), "zstd_submit")) return false;
     inflight.insert(inflight.end(), tasks.begin(), tasks.end());
     return true;
 }

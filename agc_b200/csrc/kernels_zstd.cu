@@ -340,14 +340,17 @@ static bool zs_is_text(const uint8_t* p, uint64_t len)
     return sym * 2 <= probe;                         // mostly printable: digits, ',', '.', letters
 }
 
-extern "C" int agcgpu_zstd_submit(agcgpu_ctx* ctx, const uint8_t* src, const uint64_t* src_offsets, const int32_t* levels, uint32_t n)
+extern "C" void* agcgpu_host_alloc(uint64_t bytes, uint64_t* out_cap);
+extern "C" void agcgpu_host_free(void* p, uint64_t cap);
+
+// input i = ptrs[i][0 .. sizes[i])
+static int zstd_submit_impl(agcgpu_ctx* ctx, const uint8_t* const* ptrs, const uint64_t* sizes, const int32_t* levels, uint32_t n)
 {
-    if (!ctx || !src_offsets || (n && (!src || !levels))) return AGCGPU_EINVAL;
     cudaSetDevice(ctx->dev);
     if (n == 0) return 0;
     std::vector<uint64_t> ws(n), ob(n);
     for (uint32_t i = 0; i < n; ++i) {
-        const uint64_t len = src_offsets[i + 1] - src_offsets[i];
+        const uint64_t len = sizes[i];
         ze::Params cp = ze::get_params(levels[i], len);
         if (!cp.supported)
             return agc_fail(ctx, AGCGPU_EUNSUPPORTED, "zstd: input %u (level %d, %llu bytes) is outside the implemented envelope "
@@ -357,7 +360,7 @@ extern "C" int agcgpu_zstd_submit(agcgpu_ctx* ctx, const uint8_t* src, const uin
     }
     ZWave* w = new ZWave;
     w->n_in = n; w->in_size.resize(n);
-    for (uint32_t i = 0; i < n; ++i) w->in_size[i] = src_offsets[i + 1] - src_offsets[i];
+    for (uint32_t i = 0; i < n; ++i) w->in_size[i] = sizes[i];
     std::vector<uint32_t> order(n);
     std::iota(order.begin(), order.end(), 0u);
     std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return w->in_size[a] > w->in_size[b]; });
@@ -376,7 +379,7 @@ extern "C" int agcgpu_zstd_submit(agcgpu_ctx* ctx, const uint8_t* src, const uin
     // coder here; other inputs above 32 KB (packs of raw sequences) take the wide one.  Scheduling only: same bytes either way.
     std::vector<uint8_t> wide(n, 0);
     for (uint32_t i : w->mine)
-        if (w->in_size[i] > zs_narrow_max() && (getenv("AGCGPU_ZSTD_WIDE_ALL") || !zs_is_text(src + src_offsets[i], w->in_size[i]))) wide[i] = 1;
+        if (w->in_size[i] > zs_narrow_max() && (getenv("AGCGPU_ZSTD_WIDE_ALL") || !zs_is_text(ptrs[i], w->in_size[i]))) wide[i] = 1;
     std::stable_sort(w->mine.begin(), w->mine.end(), [&](uint32_t a, uint32_t b) {
         if (wide[a] != wide[b]) return wide[a] > wide[b];
         return w->in_size[a] > w->in_size[b]; });
@@ -391,7 +394,7 @@ extern "C" int agcgpu_zstd_submit(agcgpu_ctx* ctx, const uint8_t* src, const uin
     auto park = [&]() {                              // keep the inputs on the host; collect codes them with the synchronous call
         w->h_offs.assign(1, 0); w->h_levels.clear(); w->h_src.resize(total_src);
         for (uint32_t i : w->mine) {
-            if (w->in_size[i]) memcpy(w->h_src.data() + w->h_offs.back(), src + src_offsets[i], w->in_size[i]);
+            if (w->in_size[i]) memcpy(w->h_src.data() + w->h_offs.back(), ptrs[i], w->in_size[i]);
             w->h_offs.push_back(w->h_offs.back() + w->in_size[i]); w->h_levels.push_back(levels[i]);
         }
         return 0;
@@ -412,20 +415,25 @@ extern "C" int agcgpu_zstd_submit(agcgpu_ctx* ctx, const uint8_t* src, const uin
     CK(cudaStreamCreateWithFlags(&w->st_w, cudaStreamNonBlocking));
     CK(cudaEventCreate(&w->e0)); CK(cudaEventCreate(&w->e1));
     w->tasks.resize(cnt);
-    {   // inputs back to back in launch order
-        std::vector<uint8_t> stage(total_src + 1);
+    {   // inputs back to back in launch order, gathered into a page-locked staging buffer (pooled) and sent by DMA
+        uint64_t stage_cap = 0;
+        uint8_t* stage = (uint8_t*)agcgpu_host_alloc(total_src + 64, &stage_cap);
+        std::vector<uint8_t> pageable;
+        if (!stage) { pageable.resize(total_src + 1); stage = pageable.data(); }
         uint64_t so = 0, wo = 0, oo = 0;
         for (uint32_t j = 0; j < cnt; ++j) {
             const uint32_t i = w->mine[j];
-            if (w->in_size[i]) memcpy(stage.data() + so, src + src_offsets[i], w->in_size[i]);
+            if (w->in_size[i]) memcpy(stage + so, ptrs[i], w->in_size[i]);
             ZTaskDev& k = w->tasks[j];
             k.src = (const uint8_t*)w->d_src + so; k.n = w->in_size[i];
             k.dst = (uint8_t*)w->d_out + oo; k.dst_cap = ob[i]; k.mem = (uint8_t*)w->d_ws + wo;
             k.level = levels[i]; k.err = 0; k.out_size = 0; k.t_start = k.t_end = 0;
             so += w->in_size[i]; wo += ws[i]; oo += ob[i];
         }
-        CK(cudaMemcpyAsync(w->d_src, stage.data(), total_src, cudaMemcpyHostToDevice, w->st_w));
-        CK(cudaStreamSynchronize(w->st_w));          // `stage` goes out of scope
+        cudaError_t e = cudaMemcpyAsync(w->d_src, stage, total_src, cudaMemcpyHostToDevice, w->st_w);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(w->st_w);          // the staging buffer goes back to the pool
+        if (pageable.empty()) agcgpu_host_free(stage, stage_cap);
+        if (e != cudaSuccess) return agc_fail(ctx, AGCGPU_ECUDA, "zstd submit: upload failed: %s", cudaGetErrorString(e));
         ctx->stats.h2d_bytes += total_src;
     }
     CK(cudaMemsetAsync(w->d_ws, 0, wsum, w->st_w));
@@ -452,6 +460,21 @@ extern "C" int agcgpu_zstd_submit(agcgpu_ctx* ctx, const uint8_t* src, const uin
     CK(cudaEventRecord(w->e1, w->st_w));
     w->launched = true;
     return 0;
+}
+
+extern "C" int agcgpu_zstd_submit(agcgpu_ctx* ctx, const uint8_t* src, const uint64_t* src_offsets, const int32_t* levels, uint32_t n)
+{
+    if (!ctx || !src_offsets || (n && (!src || !levels))) return AGCGPU_EINVAL;
+    std::vector<const uint8_t*> ptrs(n); std::vector<uint64_t> sizes(n);
+    for (uint32_t i = 0; i < n; ++i) { ptrs[i] = src + src_offsets[i]; sizes[i] = src_offsets[i + 1] - src_offsets[i]; }
+    return zstd_submit_impl(ctx, ptrs.data(), sizes.data(), levels, n);
+}
+// the same with one pointer per input (the parts of a pack queue are separate buffers: no concatenation on the caller's side)
+extern "C" int agcgpu_zstd_submit_parts(agcgpu_ctx* ctx, const uint8_t* const* ptrs, const uint64_t* sizes, const int32_t* levels, uint32_t n)
+{
+    if (!ctx || (n && (!ptrs || !sizes || !levels))) return AGCGPU_EINVAL;
+    for (uint32_t i = 0; i < n; ++i) if (sizes[i] && !ptrs[i]) return AGCGPU_EINVAL;
+    return zstd_submit_impl(ctx, ptrs, sizes, levels, n);
 }
 
 // frames of every input submitted since the last collect, in submission order: frame i = dst[dst_offsets[i] .. dst_offsets[i+1]);

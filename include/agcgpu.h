@@ -264,6 +264,8 @@ int agcgpu_zstd_compress_batch(agcgpu_ctx* ctx, const uint8_t* src, const uint64
  * inputs; frame i = dst[dst_offsets[i] .. dst_offsets[i+1])).  With a communicator (agcgpu_comm_init) every rank submits
  * the same batches and codes its share of each; collect all-gathers the frames once. */
 int agcgpu_zstd_submit(agcgpu_ctx* ctx, const uint8_t* src, const uint64_t* src_offsets, const int32_t* levels, uint32_t n);
+/* agcgpu_zstd_submit with one pointer per input: input i = ptrs[i][0 .. sizes[i]) (a pack queue holds separate buffers) */
+int agcgpu_zstd_submit_parts(agcgpu_ctx* ctx, const uint8_t* const* ptrs, const uint64_t* sizes, const int32_t* levels, uint32_t n);
 int agcgpu_zstd_collect(agcgpu_ctx* ctx, uint32_t n_expected, uint8_t* dst, uint64_t dst_cap, uint64_t* dst_offsets);
 
 /* ZSTD_decompressDCtx (3rd_party/zstd/lib/decompress) for a batch of independent frames, as CSegment::unpack / get

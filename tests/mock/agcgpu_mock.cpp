@@ -492,6 +492,17 @@ int agcgpu_zstd_submit(agcgpu_ctx* ctx, const uint8_t* src, const uint64_t* so, 
     ctx->zwaves.push_back(std::move(b));
     return 0;
 }
+int agcgpu_zstd_submit_parts(agcgpu_ctx* ctx, const uint8_t* const* ptrs, const uint64_t* sizes, const int32_t* levels, uint32_t n)
+{
+    COUNT("agcgpu_zstd_submit_parts", n);
+    if (!ctx || (n && (!ptrs || !sizes || !levels))) return AGCGPU_EINVAL;
+    if (!n) return 0;
+    agcgpu_ctx::ZBatch b;
+    b.offs.assign(1, 0); b.levels.assign(levels, levels + n);
+    for (uint32_t i = 0; i < n; ++i) { if (sizes[i]) b.src.insert(b.src.end(), ptrs[i], ptrs[i] + sizes[i]); b.offs.push_back(b.src.size()); }
+    ctx->zwaves.push_back(std::move(b));
+    return 0;
+}
 int agcgpu_zstd_collect(agcgpu_ctx* ctx, uint32_t n_expected, uint8_t* dst, uint64_t dst_cap, uint64_t* dof)
 {
     COUNT("agcgpu_zstd_collect", n_expected);

@@ -1,7 +1,4 @@
 mkdir -p gpurun_out
-nvidia-smi -L | wc -l
-for w in c4; do
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 4 --steps 2 --warmup 1 --workload $w > gpurun_out/r02u_bench_${w}_n4.json 2> gpurun_out/r02u_bench_${w}_n4.err
-tail -2 gpurun_out/r02u_bench_${w}_n4.err | cut -c1-200; python -c "
-import json; d=json.loads(open('gpurun_out/r02u_bench_${w}_n4.json').read().strip().splitlines()[-1]); print('$w n4', round(d['value'],4), round(d['ms_per_step']), round(d['e2e']['value'],4), round(d['e2e']['ms_per_step']), round(d['cpu_baseline']['value'],4), 'zstd', round(d['residual_coder']['ms_per_step']), 'lz', round(d['roofline']['kernel_ms_per_step'],1), d['comm']['collectives'], d['comm']['bytes_gathered'], d['bit_exact'])"
-done
+timeout 900 python -m pytest tests/test_gpu_zstd.py tests/test_gpu_pipeline.py tests/test_gpu_zz_sharded.py -m gpu -x -q 2>&1 | tail -3
+for w in c4 c3; do timeout 1500 python bench.py --workload $w --steps 2 --warmup 1 --no-extra > gpurun_out/r02v_bench_${w}_n1.json 2> gpurun_out/r02v_bench_${w}_n1.err; tail -2 gpurun_out/r02v_bench_${w}_n1.err | cut -c1-300; python -c "
+import json; d=json.load(open('gpurun_out/r02v_bench_${w}_n1.json')); print('$w', round(d['value'],4), round(d['ms_per_step']), round(d['e2e']['value'],4), round(d['e2e']['ms_per_step']), round(d['cpu_baseline']['value'],4), 'zstd', round(d['residual_coder']['ms_per_step']), round(d['residual_coder']['host_wait_ms_per_step']), 'lz', round(d['roofline']['kernel_ms_per_step'],1), d['bit_exact'])"; done
