@@ -359,19 +359,34 @@ def main():
                 hb = line["lz_kernel_hpp_like_batch"]
                 line["roofline"].update({"batch_achieved": hb["achieved"], "batch_frac": hb["frac"], "batch_traffic": hb["traffic"],
                                          "batch_workload": hb["workload"]})
+                # the other BASELINE configurations that fit one GPU, measured the same way with fewer steps (the headline stays C3):
+                # configs[1] and configs[3] at full size (2.25 Gbases -- the HPP-like regime, where the device has frames and segments
+                # by the thousand).  A failure here is reported, it does not take the headline line with it; a mismatch of an
+                # archive still aborts.
                 line["other_workloads"] = {}
-                for other in ("c2", "c3"):
+                for other, (st, wu) in (("c2", (2, 1)), ("c4", (1, 1))):
                     if other == args.workload:
                         continue
-                    r2 = Runner(L, other, tmp, local_rank, rank, world)
-                    s_res, _ = r2.timed(True, 2, 1, flush, dist)
-                    s_e2e, _ = r2.timed(False, 2, 1, flush, dist)
-                    sha2 = sha256_file(r2.out_path)
-                    rdt, rsha, _ = run_reference_once(r2.files, tmp, other, "cpu")
+                    try:
+                        r2 = Runner(L, other, tmp, local_rank, rank, world)
+                        s_res, st2 = r2.timed(True, st, wu, flush, dist)
+                        s_e2e, _ = r2.timed(False, st, wu, flush, dist)
+                        sha2 = sha256_file(r2.out_path)
+                        rdt, rsha, _ = run_reference_once(r2.files, tmp, other, "cpu")
+                    except SystemExit:
+                        raise
+                    except Exception as e:                                   # out of host memory for the 2.3 GB of FASTA, a full tmpfs ...
+                        line["other_workloads"][other] = {"workload": WORKLOADS[other][0], "error": repr(e)[:200]}
+                        continue
                     if sha2 != rsha:
                         raise SystemExit(f"bench.py: {other} archive differs from the reference's")
                     line["other_workloads"][other] = {"workload": WORKLOADS[other][0], "value": r2.total / s_res / 1e9, "e2e": r2.total / s_e2e / 1e9,
-                                                      "unit": "Gbp/s", "steps": 2, "warmup": 1, "reference_cpu": r2.total / rdt / 1e9, "bit_exact": True}
+                                                      "unit": "Gbp/s", "steps": st, "warmup": wu, "ms_per_step": s_res * 1e3, "e2e_ms_per_step": s_e2e * 1e3,
+                                                      "reference_cpu": r2.total / rdt / 1e9, "reference_ms": rdt * 1e3,
+                                                      "residual_coder_ms": float(st2["zstd_kernel_ms"]), "lz_kernel_ms": float(st2["lz_kernel_ms_total"]),
+                                                      "bit_exact": True}
+                    del r2
+                    shutil.rmtree(os.path.join(tmp, "data_" + other), ignore_errors=True)
             print(json.dumps(line))
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
