@@ -149,6 +149,15 @@ bool CCollection_V3::register_sample_contig(const std::string& sample_name, cons
         sample_desc.emplace_back();
         sample_desc.back().name = stored;
         prev_sample_name = stored;
+        cur_contig_names.clear();
+    }
+    // Two contigs of one sample with the same name: the reference accepts them, but its segment placement looks contigs up by name
+    // (first match) and its result then depends on how std::sort leaves equal keys -- data of the second contig is lost and the
+    // bytes are not reproducible.  Same treatment here (so no failure), but said out loud once per sample.
+    if (!cur_contig_names.insert(contig_name).second && !dup_warned.count(stored)) {
+        dup_warned.insert(stored);
+        std::cerr << "Warning: sample " << stored << " holds more than one contig named \"" << contig_name
+                  << "\": the archive will not contain all of them (rename the contigs)\n";
     }
     sample_desc.back().contigs.emplace_back();
     sample_desc.back().contigs.back().name = contig_name;

@@ -17,6 +17,7 @@
 #include <string>
 #include <array>
 #include <unordered_map>
+#include <unordered_set>
 #include <vector>
 #include <type_traits>
 #include "../../../include/agcgpu.h"
@@ -57,6 +58,7 @@ class CCollection_V3 {
 public:
     void set_params(uint32_t batch_size, uint32_t segment_size, uint32_t kmer_length);
     bool register_sample_contig(const std::string& sample_name, const std::string& contig_name);   // collection_v3.cpp:706-731
+    std::unordered_set<std::string> cur_contig_names, dup_warned;   // contig names of the sample being registered / samples already warned about
     void reset_prev_sample_name() { prev_sample_name.clear(); }
     void add_segment_placed(uint32_t sample_id, uint32_t contig_idx, uint32_t place, const segment_desc_t& d);
     size_t get_no_samples() const { return sample_desc.size(); }
