@@ -363,6 +363,7 @@ def main():
                 # configs[1] and configs[3] at full size (2.25 Gbases -- the HPP-like regime, where the device has frames and segments
                 # by the thousand).  A failure here is reported, it does not take the headline line with it; a mismatch of an
                 # archive still aborts.
+                line["residual_coder"]["cpu_zstd"] = cpu_zstd_leg(run, tmp)
                 line["other_workloads"] = {}
                 for other, (st, wu) in (("c2", (2, 1)), ("c4", (1, 1))):
                     if other == args.workload:
@@ -415,6 +416,50 @@ def cpu_lz_encode_leg(n_texts=32, reps=4):
     bases = n_texts * reps * 60031
     return {"value": bases / ns, "unit": "Gbase/s", "cores": 1, "kind": "reference",
             "sample": f"CLZDiff_V2::Encode of {n_texts} x 60 031-base segments (0.1% SNP) x {reps} against one prepared reference, single thread"}
+
+
+def cpu_zstd_leg(run, tmp, budget_s=15.0):
+    """BASELINE.md section 3 per-stage CPU number for the residual coder: ZSTD_compress of the reference's vendored libzstd
+    (oracle/_ref/libzstd_ref.so) over the EXACT parts of the workload -- one more create with the facade's part dump switched on
+    (parts are written to a file instead of being coded), then every part at its level on one host thread, until `budget_s`."""
+    try:
+        import agc_parts
+        if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libzstd_ref.so")):
+            return None
+        L, vp = run.L, C.c_void_p
+        dump = os.path.join(tmp, "parts.dump")
+        h = vp()
+        if L.agcgpu_compressor_create(os.path.join(tmp, "dump_out.agc").encode(), PACK, run.k, run.files[0].encode(), SEG, MML, 0, run.adaptive, 0, 1, 0.0,
+                                      run.local_rank, dump.encode(), C.byref(h)):
+            return None
+        all_files = (C.c_char_p * len(run.files))(*[f.encode() for f in run.files])
+        all_names = (C.c_char_p * len(run.files))(*[run.c_names[i] for i in range(run.n_names)])
+        rc = L.agcgpu_compressor_add_sample_files(h, all_names, all_files, len(run.files), 1)
+        rc = L.agcgpu_compressor_close(h, 1) or rc
+        if rc:
+            return None
+        _, recs = agc_parts.read_dump(dump)
+        tasks = [(int(lv), raw) for r in recs if r["kind"] != 9 for lv, raw in r["tasks"] if int(lv) in (13, 17, 18, 19)]
+        os.remove(dump)
+        tasks.sort(key=lambda t: -len(t[1]))
+        total = sum(len(t[1]) for t in tasks)
+        done_b, done_n, largest_s = 0, 0, 0.0
+        t0 = time.perf_counter()
+        for lv, raw in tasks:
+            t1 = time.perf_counter()
+            agc_parts.zstd_compress(bytes(raw), lv)
+            dt = time.perf_counter() - t1
+            if done_n == 0:
+                largest_s = dt
+            done_b += len(raw); done_n += 1
+            if time.perf_counter() - t0 > budget_s:
+                break
+        el = time.perf_counter() - t0
+        return {"value": done_b / el / 1e6, "unit": "MB/s", "cores": 1, "kind": "reference",
+                "sample": f"ZSTD_compress (vendored libzstd 1.5.5) of the workload's own parts at their levels, largest first: {done_n} of {len(tasks)} parts, "
+                          f"{done_b} of {total} bytes in {el:.1f} s on one thread; the largest part ({len(tasks[0][1])} B, level {tasks[0][0]}) took {largest_s * 1e3:.0f} ms"}
+    except Exception as e:
+        return {"error": repr(e)[:200]}
 
 
 def lz_hpp_batch(device, peak, traffic):
