@@ -10,8 +10,10 @@ the archive the reference binary writes for the same files (cpu_baseline leg) --
   e2e   : the same create from the FASTA FILES (tmpfs): file read + parse + host->device copies + device->host copies +
           archive write inside the timed region -- what `agc create` does, and what the reference arm is timed on
 Workload (config.workload): BASELINE.json configs[2] = 64 synthetic 5 Mb bacterial genomes, adaptive mode (-a), k=29 -- the
-largest single-GPU configuration of BASELINE.json.  `other_workloads` carries configs[1] (1000 x 30 kb viral, k=25) measured
-the same way with fewer steps.
+largest configuration BASELINE.json gives to one GPU.  `other_workloads` carries configs[1] (1000 x 30 kb viral, k=25) and configs[3]
+at full size (8 x 250 Mb human-like contigs + reference: 2.25 Gbases fit one B200) measured the same way with fewer steps;
+`lz_kernel_hpp_like_batch` / `roofline.batch_*` the LZ-diff encode kernel on one HPP-scale device batch with the reference's own
+Encode timed on one host core beside it; `residual_coder.cpu_zstd` the reference's libzstd over the workload's exact parts.
 N>1 (torchrun): ONE create sharded over the N GPUs (strong scaling): every rank keeps the O(#segments) bookkeeping, the
 per-base device work (LZ-diff encoding, residual coding) is split across the ranks and all-gathered over NCCL from C++
 (agc_b200/csrc/comm.cu); rank 0 writes the archive, whose sha256 is checked like at N=1.
